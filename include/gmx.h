@@ -1,0 +1,255 @@
+/* gmx.h -- C ABI of the B200-native GNUMAP hot path ("gmx" = GNUMAP mapping accelerator).
+ *
+ * This is the drop-in boundary described in DESIGN.md / INTEGRATION.md.  The reference
+ * (byucsl/gnumap 4.0.0 BETA) has no plugin or FFI layer: its hot path is reached through the
+ * abstract class `Genome` (reference inc/Genome.h:88-141), value-type `bin_seq` objects
+ * (reference inc/bin_seq.h:47-200) and `virtual ScoredSeq::score` (reference inc/ScoredSeq.h:259),
+ * driven by the two per-batch loops of the worker threads (reference src/Driver.cpp:2344-2373).
+ * Each entry point below names the reference function(s) it replaces.
+ *
+ * Rules of the boundary
+ *   - plain C: pointers + sizes, no C++/torch types, no exceptions; every call returns GMX_OK (0)
+ *     or a negative error code; per-read outcomes are data, not errors;
+ *   - the caller owns every host buffer; the library owns all device memory;
+ *   - one context drives one GPU (one process per GPU); there is NO CPU fallback: without a usable
+ *     CUDA device every call fails with GMX_ERR_NO_DEVICE.
+ */
+#ifndef GMX_H
+#define GMX_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GMX_ABI_VERSION 1
+
+/* ---- error codes ------------------------------------------------------------------------ */
+#define GMX_OK               0
+#define GMX_ERR_INVALID     -1   /* bad argument */
+#define GMX_ERR_CUDA        -2   /* CUDA runtime error, see gmx_last_error() */
+#define GMX_ERR_NOMEM       -3
+#define GMX_ERR_UNSUPPORTED -4   /* option combination not implemented on the device path */
+#define GMX_ERR_OVERFLOW    -5   /* an internal device work list overflowed even after regrowth */
+#define GMX_ERR_NO_DEVICE   -6   /* no CUDA device: there is no CPU fallback */
+#define GMX_ERR_STATE       -7   /* call sequence violated (e.g. score_batch without map_batch) */
+
+/* ---- per-read status (mirrors the sentinels the reference stores in gTopReadScore,
+ *      reference inc/const_include.h:184-188 and src/Driver.cpp:446-611) ----------------------- */
+#define GMX_READ_MAPPED     0    /* unique.size() > 0                      top = best NW score   */
+#define GMX_READ_UNMATCHED  1    /* no accepted hit                         top = 0               */
+#define GMX_READ_TOO_SHORT  2    /* length < mer            (READ_TOO_SHORT) top = -2             */
+#define GMX_READ_TOO_POOR   3    /* self score < cutoff     (READ_TOO_POOR)  top = -3             */
+#define GMX_READ_TOO_MANY   4    /* > max_matches or !unique (READ_TOO_MANY) top = 999999         */
+
+#define GMX_POS_STRAND 0         /* reference inc/const_include.h:190-191 */
+#define GMX_NEG_STRAND 1
+
+#define GMX_MODE_NORMAL 0        /* NormalScoredSeq: amount_genome only                           */
+#define GMX_MODE_BS     1        /* BSScoredSeq (-b / --b2 / -d): amount_genome + 5 base planes   */
+#define GMX_MODE_SNP    2        /* SNPScoredSeq (--snp): pair-HMM posteriors into 5 planes       */
+
+typedef struct gmx_ctx gmx_ctx;
+
+/* Borrowed host views of a loaded BWA-style index == the reference's bwaidx_t
+ * (reference inc/GenomeBwt.h:64-72; bwt_t inc/bwt.h:46-58; bntseq_t inc/bntseq.h:41-66).
+ * gmx_create() copies everything it needs to the device; the views may be freed afterwards. */
+typedef struct gmx_index {
+    const uint32_t *bwt;         /* bwt_t::bwt : occ-interleaved BWT, 64-byte blocks (bwtindex.c:128-150) */
+    uint64_t        bwt_words;   /* bwt_t::bwt_size (uint32 words)                                 */
+    uint64_t        primary;     /* bwt_t::primary                                                 */
+    uint64_t        L2[5];       /* bwt_t::L2                                                      */
+    uint64_t        seq_len;     /* bwt_t::seq_len (== l_pac: the index is forward-only)           */
+    const uint64_t *sa;          /* bwt_t::sa, n_sa entries, sa[0] == (uint64_t)-1 (bwt.c:83)      */
+    uint64_t        n_sa;
+    int32_t         sa_intv;     /* 32 in every index GNUMAP writes (bwtindex.c:286)               */
+    int32_t         n_seqs;      /* bntseq_t::n_seqs                                               */
+    const uint8_t  *pac;         /* 2-bit packed forward genome, MSB first (bntseq.c:224-225)      */
+    int64_t         l_pac;       /* bntseq_t::l_pac                                                */
+    const int64_t  *seq_offset;  /* bntann1_t::offset per sequence                                 */
+    const int32_t  *seq_len_arr; /* bntann1_t::len per sequence                                    */
+} gmx_index;
+
+/* Snapshot of the reference globals that reach the hot path, taken AFTER main()
+ * has finished editing them (reference src/Driver.cpp:1083-1315). */
+typedef struct gmx_params {
+    float    align_scores[256][4]; /* gALIGN_SCORES, already gADJUST-scaled (a_matrices.c:59-87)   */
+    float    phmm_scores[256][4];  /* gPHMM_ALIGN_SCORES (a_matrices.c:97-126)                     */
+    float    gap;                  /* gGAP (scaled)                     const_define.h:69          */
+    int32_t  max_gap;              /* gMAX_GAP                          const_define.h:86          */
+    int32_t  mer;                  /* gMER_SIZE                         const_define.h:47          */
+    int32_t  jump;                 /* gJUMP_SIZE                        const_define.h:102         */
+    int32_t  min_seed_hits;        /* gMIN_JUMP_MATCHES                 const_define.h:107         */
+    uint32_t max_kmer_hits;        /* gMAX_KMER_SIZE (0 = unlimited)    const_define.h:60          */
+    uint32_t max_matches;          /* gMAX_MATCHES                      const_define.h:49          */
+    uint32_t gen_size;             /* gGEN_SIZE (accumulator bin width) const_define.h:101         */
+    float    align_score;          /* gALIGN_SCORE                      const_define.h:61          */
+    int32_t  perc;                 /* perc                              const_define.h:62          */
+    float    cutoff;               /* gCUTOFF_SCORE                     const_define.h:63          */
+    int32_t  match_pos;            /* gMATCH_POS_STRAND                 const_define.h:94          */
+    int32_t  match_neg;            /* gMATCH_NEG_STRAND                 const_define.h:95          */
+    int32_t  unique_only;          /* gUNIQUE                           const_define.h:50          */
+    int32_t  fast;                 /* gFAST                             const_define.h:92          */
+    int32_t  use_nw;               /* gNW (only 1 is implemented on the device)                    */
+    int32_t  mode;                 /* GMX_MODE_*  (gSNP / gBISULFITE / gATOG)                      */
+    int32_t  illumina;             /* gILLUMINA: Q offset 64 + Q2Prb_ill (SeqReader.cpp:618-622)   */
+    float    adjust;               /* gADJUST (only used to print XA, Driver.cpp:2202)             */
+} gmx_params;
+
+/* Fill `p` with the reference defaults (const_define.h + setup_alignment_matrices(), Normal mode). */
+void gmx_default_params(gmx_params *p);
+
+/* One batch of reads (the reference hands its workers slices of <= 2048 Read* per thread,
+ * Driver.cpp:2339; a batch here may be any size).
+ *   seq/qual : the FASTQ sequence and quality lines, concatenated, raw ASCII (case preserved);
+ *              read r occupies [offsets[r], offsets[r+1]).  The PWM of a FASTQ read is a pure
+ *              function of (base, quality char) -- reference src/SeqReader.cpp:1155-1240.
+ *   pwm      : optional float[total_len][4] for reads whose PWM is not such a function
+ *              (PRB / INT inputs, SeqReader.cpp:541-571,901-978); NULL for FASTQ. */
+typedef struct gmx_reads {
+    int32_t        n_reads;
+    const int64_t *offsets;   /* [n_reads + 1] */
+    const uint8_t *seq;
+    const uint8_t *qual;
+    const float   *pwm;
+} gmx_reads;
+
+/* Per-read outcome of PHASE A + PHASE B  (== gTopReadScore / gReadDenominator / the best
+ * ScoredSeq chosen in create_match_output, reference src/Driver.cpp:606-611,640-716). */
+typedef struct gmx_read_result {
+    double   top_score;        /* gTopReadScore[k] incl. sentinels                                 */
+    double   denominator;      /* gReadDenominator[k]                                              */
+    float    max_align_score;  /* self-alignment score (Driver.cpp:466)                            */
+    int32_t  status;           /* GMX_READ_*                                                       */
+    int32_t  n_groups;         /* unique.size(): distinct genome strings accepted                  */
+    int32_t  n_candidates;     /* NW alignments evaluated for this read (== DEBUG_NW counter)      */
+    /* best ScoredSeq (first in key order with the largest exp(score), strict >):                 */
+    float    best_score;       /* A_SCORE                                                          */
+    float    best_posterior;   /* POST_PROB = exp(score)/denominator                               */
+    int32_t  best_n_positions; /* SIM_MATCHES (X0)                                                 */
+    int32_t  best_first_strand;
+    uint64_t best_first_pos;   /* smallest (pos,strand) of the best group, absolute 0-based        */
+    int32_t  hit_begin;        /* [hit_begin, hit_end) into the gmx_hit array of the batch         */
+    int32_t  hit_end;
+    int32_t  best_group;       /* index (key order) of the best group within this read, or -1      */
+    int32_t  best_aligned_len; /* length of the gapped `aligned` string of the best group          */
+} gmx_read_result;
+
+/* One accepted (position, strand) of one group (== one element of ScoredSeq::positions). */
+typedef struct gmx_hit {
+    uint64_t pos;              /* absolute 0-based genome position                                 */
+    float    score;            /* NW score of the group's first hit (ScoredSeq::align_score)       */
+    int32_t  read;             /* read index in the batch                                          */
+    int16_t  group;            /* group index within the read, key (lexicographic) order           */
+    uint8_t  strand;           /* GMX_POS_STRAND / GMX_NEG_STRAND                                  */
+    uint8_t  first_strand;     /* ScoredSeq::firstStrand of the group                              */
+} gmx_hit;
+
+/* ---- context ------------------------------------------------------------------------------ */
+
+/* After gGen.LoadGenome() (Driver.cpp:1428-1429): upload index + tables to GPU `device`,
+ * de-sample the suffix array, allocate zeroed accumulators. */
+int  gmx_create(gmx_ctx **ctx, const gmx_index *index, const gmx_params *params, int device);
+void gmx_destroy(gmx_ctx *ctx);
+const char *gmx_strerror(int code);
+const char *gmx_last_error(const gmx_ctx *ctx);
+int  gmx_abi_version(void);
+/* Run all subsequent work of `ctx` on this cudaStream_t (default: a private stream). */
+int  gmx_set_stream(gmx_ctx *ctx, void *cuda_stream);
+int  gmx_synchronize(gmx_ctx *ctx);
+
+/* ---- kernel-level entry points (each is also a stage of gmx_map_batch) -------------------- */
+
+/* K1: GenomeBwt::get_sa_int (GenomeBwt.cpp:438-474) -> bwt_match_exact (bwt.c:222-239).
+ * kmers: n x len ASCII.  Writes the inclusive SA interval [k,l], or (0,0) when absent / non-ACGT. */
+int gmx_fm_search(gmx_ctx *ctx, const uint8_t *kmers, int32_t len, int64_t n,
+                  uint64_t *k_out, uint64_t *l_out);
+
+/* K1b: GenomeBwt::get_sa_coord (GenomeBwt.cpp:431-436) -> bwt_sa (bwt.c:86-97).
+ * mode 0: one read of the de-sampled suffix array; mode 1: LF-walk over the sampled SA exactly as
+ * bwt_sa does (validation path). */
+int gmx_sa_locate(gmx_ctx *ctx, const uint64_t *ranks, int64_t n, int32_t mode, uint64_t *pos_out);
+
+/* GenomeBwt::GetString (GenomeBwt.cpp:384-415): n windows of `size` bases as "acgt" chars;
+ * len_out[i] = size, or 0 when the window crosses a sequence boundary / the genome end. */
+int gmx_get_windows(gmx_ctx *ctx, const uint64_t *begin, int64_t n, int32_t size,
+                    uint8_t *chars_out, int32_t *len_out);
+
+/* a3: bin_seq::get_align_score(read, consensus, 0, n-1) (bin_seq.cpp:739-759,860-893). */
+int gmx_self_score(gmx_ctx *ctx, const gmx_reads *reads, float *score_out);
+
+/* K2a: bin_seq::get_align_score(read, gen) (bin_seq.cpp:761-850): banded PWM NW, score only.
+ * Task t aligns read read_idx[t] (strand[t]: the PWM is reverse-complemented for NEG) against the
+ * explicit window `windows + t*win_stride` (ASCII, length == read length). */
+int gmx_nw_score(gmx_ctx *ctx, const gmx_reads *reads, int64_t n_tasks, const int32_t *read_idx,
+                 const uint8_t *strand, const uint8_t *windows, int32_t win_stride, float *score_out);
+
+/* K2b: bin_seq::get_align_score_w_traceback (bin_seq.cpp:445-718).  Consensus is the lower-case
+ * max_char() consensus of the (strand-oriented) PWM (ScoredSeq.h:57-103) unless `consensus` is
+ * given (n_tasks x win_stride ASCII).  aligned_out: n_tasks x aligned_stride bytes (NUL padded);
+ * cigar_out: n_tasks x cigar_stride bytes (NUL terminated, forward order as the reference builds). */
+int gmx_nw_traceback(gmx_ctx *ctx, const gmx_reads *reads, int64_t n_tasks, const int32_t *read_idx,
+                     const uint8_t *strand, const uint8_t *windows, int32_t win_stride,
+                     const uint8_t *consensus,
+                     uint8_t *aligned_out, int32_t aligned_stride, int32_t *aligned_len_out,
+                     char *cigar_out, int32_t cigar_stride);
+
+/* K2c: bin_seq::pairHMM (bin_seq.cpp:60-244).  post_out: n_tasks x win_len x 5 floats (A,C,G,T,N). */
+int gmx_pair_hmm(gmx_ctx *ctx, const gmx_reads *reads, int64_t n_tasks, const int32_t *read_idx,
+                 const uint8_t *strand, const uint8_t *windows, int32_t win_stride, float *post_out);
+
+/* ---- batch pipeline ----------------------------------------------------------------------- */
+
+/* PHASE A for a whole batch: set_top_matches (Driver.cpp:432-612) = self score, k-mer walk +
+ * backward search + locate + diagonal vote (align_seq2_raw.cpp:180-328), window fetch + banded NW
+ * + acceptance + grouping + denominator (align_seq2_raw.cpp:22-178).  Results stay on the device
+ * for gmx_score_batch; `results` (n_reads entries, may be NULL) receives the PHASE A fields. */
+int gmx_map_batch(gmx_ctx *ctx, const gmx_reads *reads, gmx_read_result *results);
+
+/* PHASE B for the batch last mapped: create_match_output (Driver.cpp:614-753) =
+ * {Normal,BS,SNP}ScoredSeq::score -- traceback / pair-HMM, posterior, atomic scatter into the
+ * genome accumulators -- and selection of the best group.  Fills the best_* fields. */
+int gmx_score_batch(gmx_ctx *ctx, gmx_read_result *results);
+
+/* gmx_map_batch + gmx_score_batch in one call with one D2H at the end. */
+int gmx_process_batch(gmx_ctx *ctx, const gmx_reads *reads, gmx_read_result *results);
+
+/* Accepted hits of the last batch, sorted by (read, group, pos, strand).  Call with hits == NULL
+ * to obtain the count. */
+int gmx_get_hits(gmx_ctx *ctx, gmx_hit *hits, int64_t capacity, int64_t *n_hits);
+
+/* CIGAR (as get_SAM builds it, ScoredSeq.h:314-372, before strand reversal) and gapped aligned
+ * string of the best group of each read of the last scored batch; stride bytes per read. */
+int gmx_get_best_alignments(gmx_ctx *ctx, char *cigar_out, int32_t cigar_stride,
+                            uint8_t *aligned_out, int32_t aligned_stride);
+
+/* Device accumulators (float): amount_genome[ceil(l_pac/gen_size)] and, in BS/SNP modes, five
+ * planes [l_pac] (A,C,G,T,N).  Exposed so the caller can run the final NCCL sum-reduce
+ * (replacing the MPI block, Driver.cpp:1615-1811) directly on them. */
+int gmx_accumulators_device(gmx_ctx *ctx, void **amount, uint64_t *n_amount,
+                            void *planes[5], uint64_t *n_plane);
+int gmx_reset_accumulators(gmx_ctx *ctx);
+
+/* Before gGen.PrintFinal (Driver.cpp:1820-1823): synchronise and download the accumulators into
+ * the host arrays GetGenomeAmtPtr() / GetGenome{A,C,G,T,N}Ptr() (GenomeBwt.h:199-209).
+ * planes may be NULL in Normal mode. */
+int gmx_finish(gmx_ctx *ctx, float *amount_genome, float *const planes[5]);
+
+/* ---- instrumentation ---------------------------------------------------------------------- */
+#define GMX_N_STAGES 12
+typedef struct gmx_stage_stats {
+    const char *name[GMX_N_STAGES];
+    float    ms[GMX_N_STAGES];        /* CUDA-event time of each stage, last batch              */
+    uint64_t units[GMX_N_STAGES];     /* work units of each stage (lookups, hits, cells, ...)   */
+    uint64_t bytes[GMX_N_STAGES];     /* algorithmic bytes of each stage  */
+    int32_t  launches[GMX_N_STAGES];  /* kernel launches of each stage                          */
+    int32_t  n_stages;
+} gmx_stage_stats;
+int gmx_get_stage_stats(gmx_ctx *ctx, gmx_stage_stats *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GMX_H */
