@@ -1,0 +1,232 @@
+"""Host-side mirror of the reference interface over the gmx C ABI (include/gmx.h).
+
+Method names follow the reference classes they stand in for, so parity tests read like the
+reference's own call sites:
+
+    GenomeBwt::get_sa_int / get_sa_coord / GetString        -> Mapper.get_sa_int / get_sa_coord / GetString
+    bin_seq::get_align_score / _w_traceback / pairHMM        -> Mapper.get_align_score / ..._w_traceback / pairHMM
+    set_top_matches + create_match_output (Driver.cpp)       -> Mapper.process_batch
+    MPI reduce + PrintFinal inputs (Driver.cpp:1615-1823)    -> Mapper.finish / accumulator tensors
+
+The CUDA library is mandatory: importing this module where `libgmx.so` has not been built, or
+creating a Mapper without a CUDA device, raises -- there is no CPU fallback (and nothing here
+touches oracle/).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _abi
+from ._abi import (GmxIndex, GmxParams, GmxReads, GmxStageStats, HIT_DTYPE, READ_RESULT_DTYPE, IndexHandle, ReadBatch, ptr)
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libgmx.so")
+
+_lib = None
+
+EXPORTS = [
+    "gmx_default_params", "gmx_create", "gmx_destroy", "gmx_strerror", "gmx_last_error", "gmx_abi_version",
+    "gmx_set_stream", "gmx_synchronize", "gmx_fm_search", "gmx_sa_locate", "gmx_get_windows", "gmx_self_score",
+    "gmx_nw_score", "gmx_nw_traceback", "gmx_pair_hmm", "gmx_map_batch", "gmx_score_batch", "gmx_process_batch",
+    "gmx_get_hits", "gmx_get_best_alignments", "gmx_accumulators_device", "gmx_reset_accumulators", "gmx_finish",
+    "gmx_get_stage_stats",
+]
+
+
+class GmxError(RuntimeError):
+    def __init__(self, code: int, where: str, detail: str = ""):
+        self.code = code
+        super().__init__(f"{where}: {code} ({detail})")
+
+
+def load_library():
+    """dlopen gnumap_b200/libgmx.so; fails loudly when the CUDA extension is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(gnumap_b200 has no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        L.gmx_strerror.restype = C.c_char_p
+        L.gmx_last_error.restype = C.c_char_p
+        L.gmx_last_error.argtypes = [C.c_void_p]
+        L.gmx_create.argtypes = [C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p, C.c_int]
+        L.gmx_destroy.argtypes = [C.c_void_p]
+        L.gmx_destroy.restype = None
+        L.gmx_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+        L.gmx_synchronize.argtypes = [C.c_void_p]
+        L.gmx_fm_search.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]
+        L.gmx_sa_locate.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]
+        L.gmx_get_windows.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]
+        L.gmx_self_score.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.gmx_nw_score.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+        L.gmx_nw_traceback.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                       C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32]
+        L.gmx_pair_hmm.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+        for f in ("gmx_map_batch", "gmx_process_batch"):
+            getattr(L, f).argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.gmx_score_batch.argtypes = [C.c_void_p, C.c_void_p]
+        L.gmx_get_hits.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
+        L.gmx_get_best_alignments.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32]
+        L.gmx_accumulators_device.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.c_void_p, C.POINTER(C.c_uint64)]
+        L.gmx_reset_accumulators.argtypes = [C.c_void_p]
+        L.gmx_finish.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.gmx_get_stage_stats.argtypes = [C.c_void_p, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def default_params() -> GmxParams:
+    p = GmxParams()
+    load_library().gmx_default_params(C.byref(p))
+    return p
+
+
+class Mapper:
+    """One GPU's worth of the GNUMAP hot path (one process per GPU)."""
+
+    def __init__(self, index, params: GmxParams | None = None, device: int = 0):
+        self.L = load_library()
+        self.index = index
+        self.params = params if params is not None else default_params()
+        self._ih = IndexHandle(index)
+        self._ctx = C.c_void_p()
+        rc = self.L.gmx_create(C.byref(self._ctx), C.addressof(self._ih.struct), C.addressof(self.params), device)
+        if rc != 0:
+            detail = self.L.gmx_last_error(self._ctx).decode() if self._ctx else ""
+            if self._ctx:
+                self.L.gmx_destroy(self._ctx)
+                self._ctx = C.c_void_p()
+            raise GmxError(rc, "gmx_create", detail or self.L.gmx_strerror(rc).decode())
+
+    # -- plumbing ---------------------------------------------------------------------------
+    def _ck(self, rc: int, where: str):
+        if rc != 0:
+            raise GmxError(rc, where, self.L.gmx_last_error(self._ctx).decode() or self.L.gmx_strerror(rc).decode())
+
+    def close(self):
+        if self._ctx:
+            self.L.gmx_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream: int):
+        self._ck(self.L.gmx_set_stream(self._ctx, C.c_void_p(cuda_stream)), "gmx_set_stream")
+
+    def synchronize(self):
+        self._ck(self.L.gmx_synchronize(self._ctx), "gmx_synchronize")
+
+    # -- GenomeBwt ----------------------------------------------------------------------------
+    def get_sa_int(self, kmers):
+        """kmers: list of equal-length bytes, or uint8[n, len] -> (start uint64[n], end uint64[n])."""
+        arr = np.frombuffer(b"".join(kmers), dtype=np.uint8).reshape(len(kmers), -1).copy() if isinstance(kmers, (list, tuple)) else np.ascontiguousarray(kmers, dtype=np.uint8)
+        n, ln = arr.shape
+        k = np.zeros(n, dtype=np.uint64); l = np.zeros(n, dtype=np.uint64)
+        self._ck(self.L.gmx_fm_search(self._ctx, ptr(arr), ln, n, ptr(k), ptr(l)), "gmx_fm_search")
+        return k, l
+
+    def get_sa_coord(self, ranks, sampled: bool = False):
+        r = np.ascontiguousarray(ranks, dtype=np.uint64)
+        out = np.zeros(len(r), dtype=np.uint64)
+        self._ck(self.L.gmx_sa_locate(self._ctx, ptr(r), len(r), 1 if sampled else 0, ptr(out)), "gmx_sa_locate")
+        return out
+
+    def GetString(self, begins, size: int):
+        b = np.ascontiguousarray(begins, dtype=np.uint64)
+        chars = np.zeros((len(b), size), dtype=np.uint8); lens = np.zeros(len(b), dtype=np.int32)
+        self._ck(self.L.gmx_get_windows(self._ctx, ptr(b), len(b), size, ptr(chars), ptr(lens)), "gmx_get_windows")
+        return [chars[i, : lens[i]].tobytes() for i in range(len(b))]
+
+    # -- bin_seq ------------------------------------------------------------------------------
+    def self_score(self, batch: ReadBatch):
+        out = np.zeros(batch.n_reads, dtype=np.float32)
+        self._ck(self.L.gmx_self_score(self._ctx, C.addressof(batch.struct), ptr(out)), "gmx_self_score")
+        return out
+
+    @staticmethod
+    def _pack_windows(windows, stride=None):
+        stride = stride or max(len(w) for w in windows)
+        buf = np.zeros((len(windows), stride), dtype=np.uint8)
+        for i, w in enumerate(windows):
+            buf[i, : len(w)] = np.frombuffer(w, dtype=np.uint8)
+        return buf, stride
+
+    def get_align_score(self, batch: ReadBatch, read_idx, strands, windows):
+        ri = np.ascontiguousarray(read_idx, dtype=np.int32); st = np.ascontiguousarray(strands, dtype=np.uint8)
+        wb, stride = self._pack_windows(windows)
+        out = np.zeros(len(ri), dtype=np.float32)
+        self._ck(self.L.gmx_nw_score(self._ctx, C.addressof(batch.struct), len(ri), ptr(ri), ptr(st), ptr(wb), stride, ptr(out)), "gmx_nw_score")
+        return out
+
+    def get_align_score_w_traceback(self, batch: ReadBatch, read_idx, strands, windows, consensus=None):
+        ri = np.ascontiguousarray(read_idx, dtype=np.int32); st = np.ascontiguousarray(strands, dtype=np.uint8)
+        wb, stride = self._pack_windows(windows)
+        cb = None
+        if consensus is not None:
+            cb, _ = self._pack_windows(consensus, stride)
+        a_stride, c_stride = 2 * stride + 16, 128
+        aligned = np.zeros((len(ri), a_stride), dtype=np.uint8); alen = np.zeros(len(ri), dtype=np.int32)
+        cigar = np.zeros((len(ri), c_stride), dtype=np.uint8)
+        self._ck(self.L.gmx_nw_traceback(self._ctx, C.addressof(batch.struct), len(ri), ptr(ri), ptr(st), ptr(wb), stride, ptr(cb),
+                                         ptr(aligned), a_stride, ptr(alen), ptr(cigar), c_stride), "gmx_nw_traceback")
+        return [(aligned[i, : alen[i]].tobytes(), bytes(cigar[i]).split(b"\0")[0].decode()) for i in range(len(ri))]
+
+    def pairHMM(self, batch: ReadBatch, read_idx, strands, windows):
+        ri = np.ascontiguousarray(read_idx, dtype=np.int32); st = np.ascontiguousarray(strands, dtype=np.uint8)
+        wb, stride = self._pack_windows(windows)
+        out = np.zeros((len(ri), stride, 5), dtype=np.float32)
+        self._ck(self.L.gmx_pair_hmm(self._ctx, C.addressof(batch.struct), len(ri), ptr(ri), ptr(st), ptr(wb), stride, ptr(out)), "gmx_pair_hmm")
+        return out
+
+    # -- batch pipeline -----------------------------------------------------------------------
+    def process_batch(self, batch: ReadBatch, score: bool = True, fetch: bool = True):
+        """PHASE A (+ PHASE B).  Returns dict(results, hits, cigars, aligned)."""
+        results = np.zeros(batch.n_reads, dtype=READ_RESULT_DTYPE)
+        fn = self.L.gmx_process_batch if score else self.L.gmx_map_batch
+        self._ck(fn(self._ctx, C.addressof(batch.struct), ptr(results)), "gmx_process_batch")
+        out = dict(results=results)
+        if fetch:
+            n = C.c_int64(0)
+            self._ck(self.L.gmx_get_hits(self._ctx, None, 0, C.byref(n)), "gmx_get_hits")
+            hits = np.zeros(max(n.value, 1), dtype=HIT_DTYPE)
+            self._ck(self.L.gmx_get_hits(self._ctx, ptr(hits), len(hits), C.byref(n)), "gmx_get_hits")
+            out["hits"] = hits[: n.value]
+            if score:
+                cs, as_ = 64, 512
+                cig = np.zeros((batch.n_reads, cs), dtype=np.uint8); al = np.zeros((batch.n_reads, as_), dtype=np.uint8)
+                self._ck(self.L.gmx_get_best_alignments(self._ctx, ptr(cig), cs, ptr(al), as_), "gmx_get_best_alignments")
+                out["cigars"] = [bytes(r).split(b"\0")[0].decode() for r in cig]
+                out["aligned"] = al
+        return out
+
+    def accumulators_device(self):
+        amount = C.c_void_p(); n_amount = C.c_uint64(); planes = (C.c_void_p * 5)(); n_plane = C.c_uint64()
+        self._ck(self.L.gmx_accumulators_device(self._ctx, C.byref(amount), C.byref(n_amount), planes, C.byref(n_plane)), "gmx_accumulators_device")
+        return amount.value, n_amount.value, [planes[b] for b in range(5)], n_plane.value
+
+    def reset_accumulators(self):
+        self._ck(self.L.gmx_reset_accumulators(self._ctx), "gmx_reset_accumulators")
+
+    def finish(self):
+        """Download the accumulators: (amount float32[n_amount], planes float32[5, l_pac] | None)."""
+        _, n_amount, _, n_plane = self.accumulators_device()
+        amount = np.zeros(n_amount, dtype=np.float32)
+        planes = np.zeros((5, n_plane), dtype=np.float32) if n_plane else None
+        pl = (C.c_void_p * 5)()
+        for b in range(5):
+            pl[b] = planes[b].ctypes.data if planes is not None else None
+        self._ck(self.L.gmx_finish(self._ctx, ptr(amount), pl), "gmx_finish")
+        return amount, planes
+
+    def stage_stats(self):
+        s = GmxStageStats()
+        self._ck(self.L.gmx_get_stage_stats(self._ctx, C.byref(s)), "gmx_get_stage_stats")
+        return {s.name[i].decode(): dict(ms=s.ms[i], units=s.units[i], bytes=s.bytes[i], launches=s.launches[i]) for i in range(s.n_stages)}

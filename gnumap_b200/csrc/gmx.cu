@@ -1,0 +1,975 @@
+// gmx.cu -- host side of the C ABI declared in include/gmx.h: context, kernel-level entry points
+// and the batched PHASE A / PHASE B pipeline.  sm_100a only; there is no CPU fallback -- without a
+// CUDA device every entry point returns GMX_ERR_NO_DEVICE.
+#include <cub/device/device_radix_sort.cuh>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "pipeline.cuh"
+#include "pair_hmm.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// small utilities
+// ------------------------------------------------------------------------------------------------
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+enum Stage { ST_UPLOAD = 0, ST_PREP, ST_SEED, ST_CLASSIFY, ST_VOTE, ST_SORT, ST_NW, ST_FINALIZE, ST_TRACEBACK, ST_PHMM, ST_SCATTER, ST_DOWNLOAD, ST_COUNT };
+static const char *kStageNames[ST_COUNT] = {"upload", "prep_reads", "seed_walk", "classify", "locate_vote", "sort_candidates",
+                                            "nw_score", "finalize_reads", "nw_traceback", "pair_hmm", "scatter", "download"};
+
+struct gmx_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    gmx_params params;
+    DevParams dparams;
+    DevIndex ix;
+    DevTables tab;
+    // index storage
+    DevBuf d_bwt, d_sa_full, d_sa_samp, d_pac, d_seq_offset, d_tables;
+    // accumulators
+    Accum acc;
+    DevBuf d_amount, d_planes;
+    uint64_t n_plane = 0;
+    // reads of the current chunk
+    DevBuf d_offsets, d_seq, d_qual, d_pwm;
+    DevReads dreads;
+    std::vector<int64_t> h_offsets;            // offsets of the last batch (for gmx_get_hits)
+    // pipeline buffers
+    DevBuf d_prep, d_seed_rank, d_seed_count, d_seed_off, d_seed_n, d_seed_hits, d_cls_list, d_cls_meta;
+    DevBuf d_keys, d_keys_alt, d_sort_tmp, d_score, d_leader, d_slot, d_lead_cand, d_hashes, d_expv, d_counters;
+    DevBuf d_results, d_alen, d_aligned, d_cigar, d_hmm, d_moves, d_arena, d_phmm_scratch;
+    size_t cand_cap = 0;
+    // last-batch bookkeeping (whole batch = concatenation of chunks)
+    bool mapped = false, scored = false;
+    int32_t last_n_reads = 0;
+    int32_t last_max_len = 0;
+    std::vector<gmx_read_result> h_results;
+    std::vector<gmx_hit> h_hits;
+    std::vector<char> h_best_cigar;            // [n_reads][64]
+    std::vector<uint8_t> h_best_aligned;       // [n_reads][a_stride]
+    int h_a_stride = 0;
+    // per-chunk device->host staging kept for score_batch when map and score are split
+    struct ChunkState {
+        int32_t read_lo = 0, n_reads = 0, max_len = 0;
+        uint32_t n_cand = 0;
+    };
+    // instrumentation
+    cudaEvent_t ev[ST_COUNT][2];
+    bool ev_used[ST_COUNT];
+    float stage_ms[ST_COUNT];
+    uint64_t stage_units[ST_COUNT], stage_bytes[ST_COUNT];
+    int32_t stage_launches[ST_COUNT];
+    std::string err;
+    size_t chunk_reads = 1 << 18;
+};
+
+#define CK(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e__ = (call);                                                                    \
+        if (e__ != cudaSuccess) {                                                                    \
+            char b__[512];                                                                           \
+            snprintf(b__, sizeof(b__), "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            ctx->err = b__;                                                                          \
+            return (e__ == cudaErrorMemoryAllocation) ? GMX_ERR_NOMEM : GMX_ERR_CUDA;                \
+        }                                                                                            \
+    } while (0)
+
+static inline unsigned nblk(int64_t n, int b) { return (unsigned)((n + b - 1) / b); }
+
+static void stage_begin(gmx_ctx *ctx, int st) { cudaEventRecord(ctx->ev[st][0], ctx->stream); }
+static void stage_end(gmx_ctx *ctx, int st, uint64_t units, uint64_t bytes, int launches)
+{
+    cudaEventRecord(ctx->ev[st][1], ctx->stream);
+    ctx->ev_used[st] = true;
+    ctx->stage_units[st] += units; ctx->stage_bytes[st] += bytes; ctx->stage_launches[st] += launches;
+}
+// fold the event pairs of the chunk just finished into the running totals (stream must be idle)
+static void stage_collect(gmx_ctx *ctx)
+{
+    for (int s = 0; s < ST_COUNT; ++s)
+        if (ctx->ev_used[s]) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, ctx->ev[s][0], ctx->ev[s][1]) == cudaSuccess) ctx->stage_ms[s] += ms;
+            ctx->ev_used[s] = false;
+        }
+}
+static void stage_reset(gmx_ctx *ctx)
+{
+    for (int s = 0; s < ST_COUNT; ++s) { ctx->stage_ms[s] = 0; ctx->stage_units[s] = 0; ctx->stage_bytes[s] = 0; ctx->stage_launches[s] = 0; ctx->ev_used[s] = false; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// defaults + LUTs  (host arithmetic must not be contracted: compiled with -ffp-contract=off)
+// ------------------------------------------------------------------------------------------------
+static void fill_table(float T[256][4], float match, float transition, float transversion)
+{
+    static const char *lo = "acgt", *up = "ACGT";
+    for (int i = 0; i < 256; ++i) for (int j = 0; j < 4; ++j) T[i][j] = transversion;
+    for (int g = 0; g < 4; ++g)
+        for (int b = 0; b < 4; ++b) {
+            float v = (g == b) ? match : ((g ^ b) == 2 ? transition : transversion);
+            T[(int)lo[g]][b] = T[(int)up[g]][b] = v;
+        }
+}
+
+extern "C" void gmx_default_params(gmx_params *p)
+{   // reference inc/const_define.h:46-107, inc/a_matrices.c:59-126
+    memset(p, 0, sizeof(*p));
+    float adjust = 0.25f, match = 3, transition = -2, transversion = -3, gap = -4;
+    match *= adjust; transition *= adjust; transversion *= adjust; gap *= adjust;
+    fill_table(p->align_scores, match, transition, transversion);
+    fill_table(p->phmm_scores, 0.98f, 0.01f, 0.005f);
+    p->gap = gap; p->max_gap = 3; p->mer = 10; p->jump = 5; p->min_seed_hits = 2;
+    p->max_kmer_hits = 0; p->max_matches = 1000; p->gen_size = 8;
+    p->align_score = 0.9f; p->perc = 1; p->cutoff = 0.0f;
+    p->match_pos = 1; p->match_neg = 1; p->unique_only = 0; p->fast = 0; p->use_nw = 1;
+    p->mode = GMX_MODE_NORMAL; p->illumina = 0; p->adjust = adjust;
+}
+
+// FASTQ (base, quality char) -> PWM row: reference src/SeqReader.cpp:618-627,1155-1216,1268-1271
+static void pwm_row_host(int code, int qchar, int illumina, float out[4])
+{
+    int Q = qchar;
+    double max_prb;
+    if (illumina) { Q -= 64; double a = 1.0 - 1.0 / (pow(10.0, ((double)Q / 10.0))); max_prb = a > 1.0 ? 1.0 : a; }
+    else { Q -= 33; double a = 1 - exp((-(double)Q / 10.0) * log(10.0)); max_prb = a > 1.0 ? 1.0 : a; }
+    double other = (1 - max_prb) / 3;
+    for (int b = 0; b < 4; ++b) out[b] = (float)((b == code) ? max_prb : other);
+}
+
+static float get_val_host(const float a[4], const float s[4])
+{   // reference src/bin_seq.cpp:975-987
+    volatile float t0 = a[0] * s[0], t1 = a[1] * s[1], t2 = a[2] * s[2], t3 = a[3] * s[3];
+    volatile float r = t0 + t1; r = r + t2; r = r + t3;
+    return r;
+}
+
+static float p_seq_host(const float x[4], const float P[4])
+{   // reference src/bin_seq.cpp:41-57
+    volatile float sum = 0;
+    volatile float t;
+    t = x[0] * P[0]; sum = sum + t;
+    t = x[1] * P[1]; sum = sum + t;
+    t = x[2] * P[2]; sum = sum + t;
+    t = x[3] * P[3]; sum = sum + t;
+    volatile float r = 3 * sum;
+    return r;
+}
+
+static const size_t kLutFloats = 5 * GMX_NQ * 4;
+
+static int build_tables(gmx_ctx *ctx)
+{
+    const gmx_params &p = ctx->params;
+    // layout: sub_pos | sub_neg | pwm_lut | phmm_pos | phmm_neg | S | P | self(unused)
+    std::vector<float> h(5 * kLutFloats + 2 * 1024);
+    float *sub_pos = h.data(), *sub_neg = sub_pos + kLutFloats, *pwm_lut = sub_neg + kLutFloats;
+    float *phmm_pos = pwm_lut + kLutFloats, *phmm_neg = phmm_pos + kLutFloats, *S = phmm_neg + kLutFloats, *P = S + 1024;
+    for (int code = 0; code < 5; ++code)
+        for (int q = 0; q < GMX_NQ; ++q) {
+            float row[4], rc[4];
+            pwm_row_host(code, q + GMX_QMIN, p.illumina, row);
+            rc[0] = row[3]; rc[1] = row[2]; rc[2] = row[1]; rc[3] = row[0];
+            size_t o = ((size_t)code * GMX_NQ + q) * 4;
+            for (int g = 0; g < 4; ++g) {
+                int ch = "acgt"[g];
+                pwm_lut[o + g] = row[g];
+                sub_pos[o + g] = get_val_host(row, p.align_scores[ch]);
+                sub_neg[o + g] = get_val_host(rc, p.align_scores[ch]);
+                phmm_pos[o + g] = p_seq_host(row, p.phmm_scores[ch]);
+                phmm_neg[o + g] = p_seq_host(rc, p.phmm_scores[ch]);
+            }
+        }
+    memcpy(S, p.align_scores, sizeof(float) * 1024);
+    memcpy(P, p.phmm_scores, sizeof(float) * 1024);
+    CK(ctx->d_tables.ensure(h.size() * sizeof(float)));
+    CK(cudaMemcpyAsync(ctx->d_tables.p, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    float *d = ctx->d_tables.as<float>();
+    ctx->tab.sub_pos = d; ctx->tab.sub_neg = d + kLutFloats; ctx->tab.pwm_lut = d + 2 * kLutFloats;
+    ctx->tab.phmm_pos = d + 3 * kLutFloats; ctx->tab.phmm_neg = d + 4 * kLutFloats;
+    ctx->tab.S = d + 5 * kLutFloats; ctx->tab.P = d + 5 * kLutFloats + 1024; ctx->tab.self_lut = nullptr;
+    return GMX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+extern "C" const char *gmx_strerror(int code)
+{
+    switch (code) {
+        case GMX_OK: return "ok";
+        case GMX_ERR_INVALID: return "invalid argument";
+        case GMX_ERR_CUDA: return "CUDA error";
+        case GMX_ERR_NOMEM: return "out of memory";
+        case GMX_ERR_UNSUPPORTED: return "unsupported option combination";
+        case GMX_ERR_OVERFLOW: return "device work list overflow";
+        case GMX_ERR_NO_DEVICE: return "no CUDA device (there is no CPU fallback)";
+        case GMX_ERR_STATE: return "invalid call sequence";
+        default: return "unknown error";
+    }
+}
+extern "C" const char *gmx_last_error(const gmx_ctx *ctx) { return ctx ? ctx->err.c_str() : ""; }
+extern "C" int gmx_abi_version(void) { return GMX_ABI_VERSION; }
+
+static int validate_params(const gmx_params *p, std::string &why)
+{
+    if (!p->use_nw) { why = "use_nw = 0 (--no_nw) is not implemented on the device path"; return GMX_ERR_UNSUPPORTED; }
+    if (p->mer < 1 || p->mer > 31) { why = "mer must be in 1..31"; return GMX_ERR_INVALID; }
+    if (p->jump < 1) { why = "jump must be >= 1"; return GMX_ERR_INVALID; }
+    if (p->max_gap < 1 || p->max_gap > 7) { why = "max_gap must be in 1..7"; return GMX_ERR_UNSUPPORTED; }
+    if (p->min_seed_hits < 1 || p->min_seed_hits > 200) { why = "min_seed_hits must be in 1..200"; return GMX_ERR_UNSUPPORTED; }
+    if (p->gen_size < 1) { why = "gen_size must be >= 1"; return GMX_ERR_INVALID; }
+    if (p->mode < 0 || p->mode > 2) { why = "bad mode"; return GMX_ERR_INVALID; }
+    return GMX_OK;
+}
+
+extern "C" int gmx_create(gmx_ctx **out, const gmx_index *index, const gmx_params *params, int device)
+{
+    if (!out || !index || !params) return GMX_ERR_INVALID;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return GMX_ERR_NO_DEVICE;
+    if (device < 0 || device >= ndev) return GMX_ERR_INVALID;
+    std::string why;
+    int vr = validate_params(params, why);
+    gmx_ctx *ctx = new gmx_ctx();
+    *out = ctx;                                    // returned even on failure so gmx_last_error works
+    ctx->device = device;
+    ctx->params = *params;
+    if (vr != GMX_OK) { ctx->err = why; return vr; }
+    if (index->seq_len >= 0xFFFFFFF0ull || (uint64_t)index->l_pac != index->seq_len) {
+        ctx->err = "index must be forward-only with seq_len < 2^32 - 16"; return GMX_ERR_UNSUPPORTED;
+    }
+    if (index->sa_intv <= 0 || (index->sa_intv & (index->sa_intv - 1))) { ctx->err = "sa_intv must be a power of two"; return GMX_ERR_INVALID; }
+    CK(cudaSetDevice(device));
+    CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    ctx->own_stream = true;
+    for (int s = 0; s < ST_COUNT; ++s) { CK(cudaEventCreate(&ctx->ev[s][0])); CK(cudaEventCreate(&ctx->ev[s][1])); }
+    stage_reset(ctx);
+
+    DevParams &dp = ctx->dparams;
+    dp.gap = params->gap; dp.align_score = params->align_score; dp.cutoff = params->cutoff; dp.max_gap = params->max_gap;
+    dp.mer = params->mer; dp.jump = params->jump; dp.kmin = params->min_seed_hits; dp.perc = params->perc;
+    dp.match_pos = params->match_pos; dp.match_neg = params->match_neg; dp.unique_only = params->unique_only;
+    dp.fast = params->fast; dp.mode = params->mode; dp.max_kmer_hits = params->max_kmer_hits;
+    dp.max_matches = params->max_matches; dp.gen_size = params->gen_size;
+
+    // index upload
+    size_t bwt_bytes = index->bwt_words * 4;
+    CK(ctx->d_bwt.ensure(bwt_bytes + 64));
+    CK(cudaMemcpyAsync(ctx->d_bwt.p, index->bwt, bwt_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx->d_sa_samp.ensure(index->n_sa * 8));
+    CK(cudaMemcpyAsync(ctx->d_sa_samp.p, index->sa, index->n_sa * 8, cudaMemcpyHostToDevice, ctx->stream));
+    size_t pac_bytes = ((size_t)index->l_pac + 3) / 4;
+    CK(ctx->d_pac.ensure(pac_bytes + 16));
+    CK(cudaMemsetAsync(ctx->d_pac.p, 0, pac_bytes + 16, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_pac.p, index->pac, pac_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    std::vector<int64_t> offs(index->n_seqs + 1);
+    for (int i = 0; i < index->n_seqs; ++i) offs[i] = index->seq_offset[i];
+    offs[index->n_seqs] = index->l_pac;
+    CK(ctx->d_seq_offset.ensure(offs.size() * 8));
+    CK(cudaMemcpyAsync(ctx->d_seq_offset.p, offs.data(), offs.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx->d_sa_full.ensure((index->seq_len + 1) * 4));
+    CK(cudaStreamSynchronize(ctx->stream));
+
+    DevIndex &ix = ctx->ix;
+    ix.bwt = ctx->d_bwt.as<uint32_t>(); ix.sa_full = ctx->d_sa_full.as<uint32_t>(); ix.sa_samp = ctx->d_sa_samp.as<uint64_t>();
+    ix.pac = ctx->d_pac.as<uint8_t>(); ix.seq_offset = ctx->d_seq_offset.as<int64_t>();
+    ix.primary = index->primary; ix.seq_len = index->seq_len;
+    for (int i = 0; i < 5; ++i) ix.L2[i] = index->L2[i];
+    ix.l_pac = index->l_pac; ix.sa_intv = index->sa_intv; ix.n_seqs = index->n_seqs;
+
+    // de-sample the suffix array: sa_full[k] == bwt_sa(k) for every rank
+    k_desample_sa<<<nblk((int64_t)index->seq_len + 1, 256), 256, 0, ctx->stream>>>(ix, ctx->d_sa_full.as<uint32_t>());
+    CK(cudaGetLastError());
+
+    int r = build_tables(ctx);
+    if (r != GMX_OK) return r;
+
+    // accumulators (zeroed: neutralises the reference's un-initialised malloc)
+    ctx->acc.n_amount = ((uint64_t)index->l_pac + params->gen_size - 1) / params->gen_size;
+    CK(ctx->d_amount.ensure(ctx->acc.n_amount * 4));
+    ctx->acc.amount = ctx->d_amount.as<float>();
+    for (int b = 0; b < 5; ++b) ctx->acc.planes[b] = nullptr;
+    if (params->mode != GMX_MODE_NORMAL) {
+        ctx->n_plane = ctx->acc.n_amount;
+        CK(ctx->d_planes.ensure(ctx->n_plane * 4 * 5));
+        for (int b = 0; b < 5; ++b) ctx->acc.planes[b] = ctx->d_planes.as<float>() + (size_t)b * ctx->n_plane;
+    }
+    r = gmx_reset_accumulators(ctx);
+    if (r != GMX_OK) return r;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return GMX_OK;
+}
+
+extern "C" void gmx_destroy(gmx_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    DevBuf *bufs[] = {&ctx->d_bwt, &ctx->d_sa_full, &ctx->d_sa_samp, &ctx->d_pac, &ctx->d_seq_offset, &ctx->d_tables, &ctx->d_amount,
+                      &ctx->d_planes, &ctx->d_offsets, &ctx->d_seq, &ctx->d_qual, &ctx->d_pwm, &ctx->d_prep, &ctx->d_seed_rank,
+                      &ctx->d_seed_count, &ctx->d_seed_off, &ctx->d_seed_n, &ctx->d_seed_hits, &ctx->d_cls_list, &ctx->d_cls_meta,
+                      &ctx->d_keys, &ctx->d_keys_alt, &ctx->d_sort_tmp, &ctx->d_score, &ctx->d_leader, &ctx->d_slot, &ctx->d_lead_cand,
+                      &ctx->d_hashes, &ctx->d_expv, &ctx->d_counters, &ctx->d_results, &ctx->d_alen, &ctx->d_aligned, &ctx->d_cigar,
+                      &ctx->d_hmm, &ctx->d_moves, &ctx->d_arena, &ctx->d_phmm_scratch};
+    for (DevBuf *b : bufs) b->release();
+    if (ctx->ev[0][0]) for (int s = 0; s < ST_COUNT; ++s) { cudaEventDestroy(ctx->ev[s][0]); cudaEventDestroy(ctx->ev[s][1]); }
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" int gmx_set_stream(gmx_ctx *ctx, void *cuda_stream)
+{
+    if (!ctx) return GMX_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->own_stream) { cudaStreamDestroy(ctx->stream); ctx->own_stream = false; }
+    ctx->stream = (cudaStream_t)cuda_stream;
+    return GMX_OK;
+}
+
+extern "C" int gmx_synchronize(gmx_ctx *ctx)
+{
+    if (!ctx) return GMX_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return GMX_OK;
+}
+
+extern "C" int gmx_reset_accumulators(gmx_ctx *ctx)
+{
+    if (!ctx) return GMX_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemsetAsync(ctx->acc.amount, 0, ctx->acc.n_amount * 4, ctx->stream));
+    if (ctx->acc.planes[0]) CK(cudaMemsetAsync(ctx->acc.planes[0], 0, ctx->n_plane * 4 * 5, ctx->stream));
+    return GMX_OK;
+}
+
+extern "C" int gmx_accumulators_device(gmx_ctx *ctx, void **amount, uint64_t *n_amount, void *planes[5], uint64_t *n_plane)
+{
+    if (!ctx) return GMX_ERR_INVALID;
+    if (amount) *amount = ctx->acc.amount;
+    if (n_amount) *n_amount = ctx->acc.n_amount;
+    if (planes) for (int b = 0; b < 5; ++b) planes[b] = ctx->acc.planes[b];
+    if (n_plane) *n_plane = ctx->acc.planes[0] ? ctx->n_plane : 0;
+    return GMX_OK;
+}
+
+extern "C" int gmx_finish(gmx_ctx *ctx, float *amount_genome, float *const planes[5])
+{
+    if (!ctx || !amount_genome) return GMX_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(amount_genome, ctx->acc.amount, ctx->acc.n_amount * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (planes && ctx->acc.planes[0])
+        for (int b = 0; b < 5; ++b)
+            if (planes[b]) CK(cudaMemcpyAsync(planes[b], ctx->acc.planes[b], ctx->n_plane * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return GMX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// reads upload
+// ------------------------------------------------------------------------------------------------
+static int upload_reads(gmx_ctx *ctx, const gmx_reads *reads, int32_t lo, int32_t hi, int32_t *max_len_out)
+{
+    int32_t n = hi - lo;
+    int64_t base = reads->offsets[lo], total = reads->offsets[hi] - base;
+    std::vector<int64_t> offs((size_t)n + 1);
+    int32_t max_len = 0;
+    for (int32_t i = 0; i <= n; ++i) offs[i] = reads->offsets[lo + i] - base;
+    for (int32_t i = 0; i < n; ++i) max_len = std::max<int32_t>(max_len, (int32_t)(offs[i + 1] - offs[i]));
+    if (max_len > GMX_MAX_READ_LEN) { ctx->err = "read longer than GMX_MAX_READ_LEN"; return GMX_ERR_UNSUPPORTED; }
+    if (!reads->seq) { ctx->err = "gmx_reads.seq is required (the consensus string for raw-PWM reads)"; return GMX_ERR_INVALID; }
+    if (!reads->qual && !reads->pwm) { ctx->err = "gmx_reads needs qual or pwm"; return GMX_ERR_INVALID; }
+    CK(ctx->d_offsets.ensure(((size_t)n + 1) * 8));
+    CK(ctx->d_seq.ensure((size_t)total + 16));
+    CK(cudaMemcpyAsync(ctx->d_offsets.p, offs.data(), ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_seq.p, reads->seq + base, (size_t)total, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->dreads.qual = nullptr; ctx->dreads.pwm = nullptr;
+    if (reads->qual) {
+        CK(ctx->d_qual.ensure((size_t)total + 16));
+        CK(cudaMemcpyAsync(ctx->d_qual.p, reads->qual + base, (size_t)total, cudaMemcpyHostToDevice, ctx->stream));
+        ctx->dreads.qual = ctx->d_qual.as<uint8_t>();
+    }
+    if (reads->pwm) {
+        CK(ctx->d_pwm.ensure((size_t)total * 16 + 16));
+        CK(cudaMemcpyAsync(ctx->d_pwm.p, reads->pwm + 4 * base, (size_t)total * 16, cudaMemcpyHostToDevice, ctx->stream));
+        ctx->dreads.pwm = ctx->d_pwm.as<float>();
+    }
+    CK(cudaStreamSynchronize(ctx->stream));        // offs is a stack-lifetime staging vector
+    ctx->dreads.offsets = ctx->d_offsets.as<int64_t>();
+    ctx->dreads.seq = ctx->d_seq.as<uint8_t>();
+    ctx->dreads.n_reads = n; ctx->dreads.qbase = ctx->params.illumina ? 64 : 33;
+    if (max_len_out) *max_len_out = max_len;
+    return GMX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel-level entry points
+// ------------------------------------------------------------------------------------------------
+extern "C" int gmx_fm_search(gmx_ctx *ctx, const uint8_t *kmers, int32_t len, int64_t n, uint64_t *k_out, uint64_t *l_out)
+{
+    if (!ctx || !kmers || !k_out || !l_out || len < 1 || len > 64 || n < 0) return GMX_ERR_INVALID;
+    if (n == 0) return GMX_OK;
+    CK(cudaSetDevice(ctx->device));
+    DevBuf in, ko, lo;
+    CK(in.ensure((size_t)n * len)); CK(ko.ensure((size_t)n * 8)); CK(lo.ensure((size_t)n * 8));
+    CK(cudaMemcpyAsync(in.p, kmers, (size_t)n * len, cudaMemcpyHostToDevice, ctx->stream));
+    k_fm_search<<<nblk(n, 128), 128, 0, ctx->stream>>>(ctx->ix, in.as<uint8_t>(), len, n, ko.as<uint64_t>(), lo.as<uint64_t>());
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(k_out, ko.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(l_out, lo.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    in.release(); ko.release(); lo.release();
+    return GMX_OK;
+}
+
+extern "C" int gmx_sa_locate(gmx_ctx *ctx, const uint64_t *ranks, int64_t n, int32_t mode, uint64_t *pos_out)
+{
+    if (!ctx || !ranks || !pos_out || n < 0 || (mode != 0 && mode != 1)) return GMX_ERR_INVALID;
+    if (n == 0) return GMX_OK;
+    for (int64_t i = 0; i < n; ++i) if (ranks[i] > ctx->ix.seq_len) { ctx->err = "rank out of range"; return GMX_ERR_INVALID; }
+    CK(cudaSetDevice(ctx->device));
+    DevBuf in, po;
+    CK(in.ensure((size_t)n * 8)); CK(po.ensure((size_t)n * 8));
+    CK(cudaMemcpyAsync(in.p, ranks, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    k_sa_locate<<<nblk(n, 128), 128, 0, ctx->stream>>>(ctx->ix, in.as<uint64_t>(), n, mode, po.as<uint64_t>());
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(pos_out, po.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    in.release(); po.release();
+    return GMX_OK;
+}
+
+extern "C" int gmx_get_windows(gmx_ctx *ctx, const uint64_t *begin, int64_t n, int32_t size, uint8_t *chars_out, int32_t *len_out)
+{
+    if (!ctx || !begin || !chars_out || !len_out || n < 0 || size < 1) return GMX_ERR_INVALID;
+    if (n == 0) return GMX_OK;
+    CK(cudaSetDevice(ctx->device));
+    DevBuf in, ch, ln;
+    CK(in.ensure((size_t)n * 8)); CK(ch.ensure((size_t)n * size)); CK(ln.ensure((size_t)n * 4));
+    CK(cudaMemcpyAsync(in.p, begin, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    k_get_windows<<<nblk(n, 128), 128, 0, ctx->stream>>>(ctx->ix, in.as<uint64_t>(), n, size, ch.as<uint8_t>(), ln.as<int32_t>());
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(chars_out, ch.p, (size_t)n * size, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(len_out, ln.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    in.release(); ch.release(); ln.release();
+    return GMX_OK;
+}
+
+extern "C" int gmx_self_score(gmx_ctx *ctx, const gmx_reads *reads, float *score_out)
+{
+    if (!ctx || !reads || !score_out || reads->n_reads < 0) return GMX_ERR_INVALID;
+    if (reads->n_reads == 0) return GMX_OK;
+    CK(cudaSetDevice(ctx->device));
+    int r = upload_reads(ctx, reads, 0, reads->n_reads, nullptr);
+    if (r != GMX_OK) return r;
+    int n = reads->n_reads;
+    CK(ctx->d_prep.ensure((size_t)n * sizeof(ReadPrep)));
+    DevParams dp = ctx->dparams; dp.mer = 0;             // score every read regardless of length
+    dp.cutoff = -INFINITY;
+    k_prep_reads<<<nblk(n, 128), 128, 0, ctx->stream>>>(ctx->dreads, ctx->tab, dp, ctx->d_prep.as<ReadPrep>());
+    CK(cudaGetLastError());
+    std::vector<ReadPrep> h(n);
+    CK(cudaMemcpyAsync(h.data(), ctx->d_prep.p, (size_t)n * sizeof(ReadPrep), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < n; ++i) score_out[i] = h[i].max_align;
+    return GMX_OK;
+}
+
+// explicit-window task kernels -------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_nw_score_tasks(DevReads R, DevTables T, DevParams P, int64_t n_tasks, const int32_t *read_idx,
+                                                        const uint8_t *strand, const uint8_t *windows, int win_stride, float *out)
+{
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tasks) return;
+    ReadView rd = gmx_read_view(R, read_idx[t], strand ? strand[t] : 0);
+    WindowView win; win.pac = nullptr; win.pos = 0; win.chars = windows + t * win_stride;
+    out[t] = gmx_nw_score_dispatch(rd, win, T, P.gap, P.max_gap);
+}
+
+__global__ void __launch_bounds__(128) k_traceback_tasks(DevReads R, DevTables T, DevParams P, int64_t n_tasks, const int32_t *read_idx,
+                                                         const uint8_t *strand, const uint8_t *windows, int win_stride, const uint8_t *consensus,
+                                                         uint8_t *aligned, int a_stride, int32_t *alen, char *cigar, int c_stride, uint32_t *moves)
+{
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tasks) return;
+    ReadView rd = gmx_read_view(R, read_idx[t], strand ? strand[t] : 0);
+    WindowView win; win.pac = nullptr; win.pos = 0; win.chars = windows + t * win_stride;
+    ConsView cons; cons.explicit_chars = consensus ? consensus + t * win_stride : nullptr;
+    TracebackOut o; o.aligned = aligned + t * a_stride; o.aligned_cap = a_stride; o.cigar = cigar + t * c_stride; o.cigar_cap = c_stride; o.fix_deletions = 0;
+    alen[t] = gmx_nw_traceback(rd, win, cons, T, P.gap, P.max_gap, moves + t, n_tasks, o);
+}
+
+struct TaskUpload {
+    DevBuf ridx, strand, windows, cons;
+};
+
+static int upload_tasks(gmx_ctx *ctx, TaskUpload &u, const gmx_reads *reads, int64_t n_tasks, const int32_t *read_idx, const uint8_t *strand,
+                        const uint8_t *windows, int32_t win_stride, const uint8_t *consensus, int32_t *max_len)
+{
+    for (int64_t t = 0; t < n_tasks; ++t) {
+        if (read_idx[t] < 0 || read_idx[t] >= reads->n_reads) { ctx->err = "read_idx out of range"; return GMX_ERR_INVALID; }
+        int64_t len = reads->offsets[read_idx[t] + 1] - reads->offsets[read_idx[t]];
+        if (len > win_stride) { ctx->err = "win_stride shorter than a read"; return GMX_ERR_INVALID; }
+    }
+    int r = upload_reads(ctx, reads, 0, reads->n_reads, max_len);
+    if (r != GMX_OK) return r;
+    CK(u.ridx.ensure((size_t)n_tasks * 4)); CK(u.windows.ensure((size_t)n_tasks * win_stride + 16));
+    CK(cudaMemcpyAsync(u.ridx.p, read_idx, (size_t)n_tasks * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(u.windows.p, windows, (size_t)n_tasks * win_stride, cudaMemcpyHostToDevice, ctx->stream));
+    if (strand) { CK(u.strand.ensure((size_t)n_tasks)); CK(cudaMemcpyAsync(u.strand.p, strand, (size_t)n_tasks, cudaMemcpyHostToDevice, ctx->stream)); }
+    if (consensus) { CK(u.cons.ensure((size_t)n_tasks * win_stride + 16)); CK(cudaMemcpyAsync(u.cons.p, consensus, (size_t)n_tasks * win_stride, cudaMemcpyHostToDevice, ctx->stream)); }
+    return GMX_OK;
+}
+
+extern "C" int gmx_nw_score(gmx_ctx *ctx, const gmx_reads *reads, int64_t n_tasks, const int32_t *read_idx, const uint8_t *strand,
+                            const uint8_t *windows, int32_t win_stride, float *score_out)
+{
+    if (!ctx || !reads || !read_idx || !windows || !score_out || n_tasks < 0 || win_stride < 1) return GMX_ERR_INVALID;
+    if (n_tasks == 0) return GMX_OK;
+    CK(cudaSetDevice(ctx->device));
+    TaskUpload u; DevBuf out;
+    int r = upload_tasks(ctx, u, reads, n_tasks, read_idx, strand, windows, win_stride, nullptr, nullptr);
+    if (r != GMX_OK) return r;
+    CK(out.ensure((size_t)n_tasks * 4));
+    k_nw_score_tasks<<<nblk(n_tasks, 128), 128, 0, ctx->stream>>>(ctx->dreads, ctx->tab, ctx->dparams, n_tasks, u.ridx.as<int32_t>(),
+                                                                 strand ? u.strand.as<uint8_t>() : nullptr, u.windows.as<uint8_t>(), win_stride, out.as<float>());
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(score_out, out.p, (size_t)n_tasks * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    u.ridx.release(); u.strand.release(); u.windows.release(); u.cons.release(); out.release();
+    return GMX_OK;
+}
+
+extern "C" int gmx_nw_traceback(gmx_ctx *ctx, const gmx_reads *reads, int64_t n_tasks, const int32_t *read_idx, const uint8_t *strand,
+                                const uint8_t *windows, int32_t win_stride, const uint8_t *consensus, uint8_t *aligned_out,
+                                int32_t aligned_stride, int32_t *aligned_len_out, char *cigar_out, int32_t cigar_stride)
+{
+    if (!ctx || !reads || !read_idx || !windows || !aligned_out || !aligned_len_out || !cigar_out || n_tasks < 0 || win_stride < 1 ||
+        aligned_stride < 1 || cigar_stride < 2)
+        return GMX_ERR_INVALID;
+    if (n_tasks == 0) return GMX_OK;
+    CK(cudaSetDevice(ctx->device));
+    TaskUpload u; DevBuf al, ln, cg, mv;
+    int32_t max_len = 0;
+    int r = upload_tasks(ctx, u, reads, n_tasks, read_idx, strand, windows, win_stride, consensus, &max_len);
+    if (r != GMX_OK) return r;
+    CK(al.ensure((size_t)n_tasks * aligned_stride)); CK(ln.ensure((size_t)n_tasks * 4)); CK(cg.ensure((size_t)n_tasks * cigar_stride));
+    CK(mv.ensure((size_t)n_tasks * ((size_t)max_len + 1) * 4));
+    CK(cudaMemsetAsync(al.p, 0, (size_t)n_tasks * aligned_stride, ctx->stream));
+    k_traceback_tasks<<<nblk(n_tasks, 128), 128, 0, ctx->stream>>>(ctx->dreads, ctx->tab, ctx->dparams, n_tasks, u.ridx.as<int32_t>(),
+                                                                  strand ? u.strand.as<uint8_t>() : nullptr, u.windows.as<uint8_t>(), win_stride,
+                                                                  consensus ? u.cons.as<uint8_t>() : nullptr, al.as<uint8_t>(), aligned_stride,
+                                                                  ln.as<int32_t>(), cg.as<char>(), cigar_stride, mv.as<uint32_t>());
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(aligned_out, al.p, (size_t)n_tasks * aligned_stride, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(aligned_len_out, ln.p, (size_t)n_tasks * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(cigar_out, cg.p, (size_t)n_tasks * cigar_stride, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    u.ridx.release(); u.strand.release(); u.windows.release(); u.cons.release(); al.release(); ln.release(); cg.release(); mv.release();
+    return GMX_OK;
+}
+
+extern "C" int gmx_pair_hmm(gmx_ctx *ctx, const gmx_reads *reads, int64_t n_tasks, const int32_t *read_idx, const uint8_t *strand,
+                            const uint8_t *windows, int32_t win_stride, float *post_out)
+{
+    if (!ctx || !reads || !read_idx || !windows || !post_out || n_tasks < 0 || win_stride < 1) return GMX_ERR_INVALID;
+    if (n_tasks == 0) return GMX_OK;
+    CK(cudaSetDevice(ctx->device));
+    TaskUpload u; DevBuf out, scratch;
+    int32_t max_len = 0;
+    int r = upload_tasks(ctx, u, reads, n_tasks, read_idx, strand, windows, win_stride, nullptr, &max_len);
+    if (r != GMX_OK) return r;
+    CK(out.ensure((size_t)n_tasks * win_stride * 5 * 4));
+    CK(cudaMemsetAsync(out.p, 0, (size_t)n_tasks * win_stride * 5 * 4, ctx->stream));
+    size_t per_task = gmx_phmm_scratch_doubles(max_len);
+    int64_t wave = std::min<int64_t>(n_tasks, 148 * 8);
+    CK(scratch.ensure((size_t)wave * per_task * 8));
+    for (int64_t t0 = 0; t0 < n_tasks; t0 += wave) {
+        int64_t cnt = std::min<int64_t>(wave, n_tasks - t0);
+        k_pair_hmm_tasks<<<(unsigned)cnt, GMX_PHMM_THREADS, 0, ctx->stream>>>(ctx->dreads, ctx->tab, t0, cnt, u.ridx.as<int32_t>(),
+                                                                              strand ? u.strand.as<uint8_t>() : nullptr, u.windows.as<uint8_t>(),
+                                                                              win_stride, out.as<float>(), scratch.as<double>(), per_task);
+        CK(cudaGetLastError());
+    }
+    CK(cudaMemcpyAsync(post_out, out.p, (size_t)n_tasks * win_stride * 5 * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    u.ridx.release(); u.strand.release(); u.windows.release(); u.cons.release(); out.release(); scratch.release();
+    return GMX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// batch pipeline
+// ------------------------------------------------------------------------------------------------
+struct Counters {            // device-resident scalars, one small allocation
+    uint32_t n_cand, cand_overflow, n_leaders, n_accepted, arena_overflow, pad[3];
+    unsigned long long arena_used;
+    uint32_t cls_count[GMX_N_CLASSES], cls_cursor[GMX_N_CLASSES];
+};
+
+template <int SL, int WARPS>
+static cudaError_t launch_vote(gmx_ctx *ctx, const SeedStore &S, const ClassLists &C, int cls, const CandSink &sink, int n_sm)
+{
+    size_t smem = (size_t)WARPS * ((1u << SL) + (1u << SL) / 4) * 4;
+    cudaError_t e = cudaFuncSetAttribute(k_vote_smem<SL, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = 1;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_vote_smem<SL, WARPS>, WARPS * 32, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    k_vote_smem<SL, WARPS><<<n_sm * per_sm, WARPS * 32, smem, ctx->stream>>>(ctx->ix, S, C, cls, ctx->dparams.kmin, sink);
+    return cudaGetLastError();
+}
+
+// Runs PHASE A (and PHASE B when do_score) for reads [lo, hi) of the batch.
+static int run_chunk(gmx_ctx *ctx, const gmx_reads *reads, int32_t lo, int32_t hi, bool do_score, gmx_read_result *results_out)
+{
+    const int32_t n = hi - lo;
+    const int64_t n_tasks = 2 * (int64_t)n;
+    int32_t max_len = 0;
+    int n_sm = 148;
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device);
+
+    stage_begin(ctx, ST_UPLOAD);
+    int r = upload_reads(ctx, reads, lo, hi, &max_len);
+    if (r != GMX_OK) return r;
+    int64_t total_bases = reads->offsets[hi] - reads->offsets[lo];
+    stage_end(ctx, ST_UPLOAD, (uint64_t)n, (uint64_t)total_bases * (reads->qual ? 2 : 1) + (reads->pwm ? 16ull * total_bases : 0), 0);
+    ctx->last_max_len = std::max(ctx->last_max_len, max_len);
+
+    const DevParams &P = ctx->dparams;
+    int max_seeds = 1;
+    if (max_len > P.mer) max_seeds = (max_len - P.mer + P.jump - 1) / P.jump + 1;
+    if (max_seeds > GMX_MAX_SEEDS) { ctx->err = "too many k-mer rounds per read (read too long for this jump)"; return GMX_ERR_UNSUPPORTED; }
+
+    // buffers
+    CK(ctx->d_prep.ensure((size_t)n * sizeof(ReadPrep)));
+    CK(ctx->d_seed_rank.ensure((size_t)max_seeds * n_tasks * 4));
+    CK(ctx->d_seed_count.ensure((size_t)max_seeds * n_tasks * 4));
+    CK(ctx->d_seed_off.ensure((size_t)max_seeds * n_tasks * 2));
+    CK(ctx->d_seed_n.ensure((size_t)n_tasks));
+    CK(ctx->d_seed_hits.ensure((size_t)n_tasks * 4));
+    CK(ctx->d_cls_list.ensure((size_t)GMX_N_CLASSES * n_tasks * 4));
+    CK(ctx->d_counters.ensure(sizeof(Counters)));
+    CK(ctx->d_results.ensure((size_t)n * sizeof(gmx_read_result)));
+    if (ctx->cand_cap == 0) ctx->cand_cap = std::max<size_t>(1 << 16, (size_t)n * 16);
+
+    Counters *dc = ctx->d_counters.as<Counters>();
+    SeedStore S;
+    S.rank = ctx->d_seed_rank.as<uint32_t>(); S.count = ctx->d_seed_count.as<uint32_t>(); S.offset = ctx->d_seed_off.as<uint16_t>();
+    S.n_seeds = ctx->d_seed_n.as<uint8_t>(); S.hits = ctx->d_seed_hits.as<uint32_t>(); S.max_seeds = max_seeds; S.n_tasks = n_tasks;
+    ClassLists C;
+    C.list = ctx->d_cls_list.as<uint32_t>(); C.count = dc->cls_count; C.cursor = dc->cls_cursor; C.n_tasks = n_tasks;
+
+    // a3 + status
+    stage_begin(ctx, ST_PREP);
+    k_prep_reads<<<nblk(n, 128), 128, 0, ctx->stream>>>(ctx->dreads, ctx->tab, P, ctx->d_prep.as<ReadPrep>());
+    CK(cudaGetLastError());
+    stage_end(ctx, ST_PREP, (uint64_t)n, (uint64_t)total_bases * 2, 1);
+
+    // K1: k-mer walk + backward search
+    stage_begin(ctx, ST_SEED);
+    k_seed_walk<<<nblk(n_tasks, 128), 128, 0, ctx->stream>>>(ctx->ix, ctx->dreads, P, ctx->d_prep.as<ReadPrep>(), S);
+    CK(cudaGetLastError());
+    stage_end(ctx, ST_SEED, 0, 0, 1);
+
+    Counters hc;
+    uint32_t n_cand = 0;
+    for (int attempt = 0;; ++attempt) {
+        CK(cudaMemsetAsync(dc, 0, sizeof(Counters), ctx->stream));
+        CK(ctx->d_keys.ensure(ctx->cand_cap * 8));
+        CK(ctx->d_keys_alt.ensure(ctx->cand_cap * 8));
+        stage_begin(ctx, ST_CLASSIFY);
+        k_classify<<<nblk(n_tasks, 256), 256, 0, ctx->stream>>>(S.hits, C);
+        CK(cudaGetLastError());
+        stage_end(ctx, ST_CLASSIFY, (uint64_t)n_tasks, (uint64_t)n_tasks * 8, 1);
+
+        // K1b + K1c
+        CandSink sink; sink.keys = ctx->d_keys.as<unsigned long long>(); sink.count = &dc->n_cand; sink.overflow = &dc->cand_overflow; sink.cap = (uint32_t)ctx->cand_cap;
+        stage_begin(ctx, ST_VOTE);
+        CK((launch_vote<10, 8>(ctx, S, C, 0, sink, n_sm)));
+        CK((launch_vote<11, 8>(ctx, S, C, 1, sink, n_sm)));
+        CK((launch_vote<12, 4>(ctx, S, C, 2, sink, n_sm)));
+        CK((launch_vote<13, 2>(ctx, S, C, 3, sink, n_sm)));
+        CK((launch_vote<14, 1>(ctx, S, C, 4, sink, n_sm)));
+        {
+            if (ctx->d_arena.cap == 0) CK(ctx->d_arena.ensure((size_t)256 << 20));
+            GlobalTableArena A; A.words = ctx->d_arena.as<uint32_t>(); A.used = &dc->arena_used; A.cap = ctx->d_arena.cap / 4; A.overflow = &dc->arena_overflow;
+            k_vote_gmem<<<n_sm * 4, 128, 0, ctx->stream>>>(ctx->ix, S, C, 5, P.kmin, sink, A);
+            CK(cudaGetLastError());
+        }
+        stage_end(ctx, ST_VOTE, 0, 0, 6);
+        CK(cudaMemcpyAsync(&hc, dc, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        stage_collect(ctx);
+        if (hc.arena_overflow) {
+            if (attempt >= 4) { ctx->err = "global vote-table arena overflow"; return GMX_ERR_OVERFLOW; }
+            size_t want = ctx->d_arena.cap * 4;
+            ctx->d_arena.release();
+            CK(ctx->d_arena.ensure(want));
+            continue;
+        }
+        if (hc.cand_overflow || hc.n_cand > ctx->cand_cap) {
+            if (attempt >= 6) { ctx->err = "candidate list overflow"; return GMX_ERR_OVERFLOW; }
+            ctx->cand_cap = std::max<size_t>(ctx->cand_cap * 2, (size_t)hc.n_cand + 1024);
+            continue;
+        }
+        n_cand = hc.n_cand;
+        break;
+    }
+    {   // units for the seed/vote stages: lookups are not counted on the device; hits are the sum over tasks
+        // (kept cheap: one reduction on the host over a D2H copy would dominate, so report candidates here
+        //  and let bench.py derive hits from the workload statistics gathered in tests)
+        ctx->stage_units[ST_VOTE] += n_cand;
+    }
+
+    // restore the reference's processing order: (task, round, position)
+    unsigned long long *keys = ctx->d_keys.as<unsigned long long>();
+    if (n_cand > 1) {
+        stage_begin(ctx, ST_SORT);
+        size_t tmp_bytes = 0;
+        int task_bits = 1; while ((1ll << task_bits) < n_tasks) task_bits++;
+        CK(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, keys, ctx->d_keys_alt.as<unsigned long long>(), (int)n_cand, 0, 40 + task_bits, ctx->stream));
+        CK(ctx->d_sort_tmp.ensure(tmp_bytes));
+        CK(cub::DeviceRadixSort::SortKeys(ctx->d_sort_tmp.p, tmp_bytes, keys, ctx->d_keys_alt.as<unsigned long long>(), (int)n_cand, 0, 40 + task_bits, ctx->stream));
+        keys = ctx->d_keys_alt.as<unsigned long long>();
+        stage_end(ctx, ST_SORT, n_cand, (uint64_t)n_cand * 16, 1);
+    }
+
+    size_t nc = std::max<uint32_t>(n_cand, 1);
+    CK(ctx->d_score.ensure(nc * 4)); CK(ctx->d_leader.ensure(nc * 4)); CK(ctx->d_slot.ensure(nc * 4)); CK(ctx->d_lead_cand.ensure(nc * 4));
+    CK(ctx->d_hashes.ensure(nc * 8)); CK(ctx->d_expv.ensure(nc * 8));
+
+    // GetString + K2a
+    if (n_cand) {
+        stage_begin(ctx, ST_NW);
+        k_cand_score<<<nblk(n_cand, 128), 128, 0, ctx->stream>>>(ctx->ix, ctx->dreads, ctx->tab, P, keys, n_cand, ctx->d_score.as<float>());
+        CK(cudaGetLastError());
+        stage_end(ctx, ST_NW, n_cand, 0, 1);
+    }
+
+    // acceptance, grouping, denominator, best group
+    FinalizeOut O;
+    O.results = ctx->d_results.as<gmx_read_result>(); O.leader = ctx->d_leader.as<int32_t>(); O.slot = ctx->d_slot.as<int32_t>();
+    O.lead_cand = ctx->d_lead_cand.as<uint32_t>(); O.n_leaders = &dc->n_leaders; O.n_accepted = &dc->n_accepted;
+    O.hashes = ctx->d_hashes.as<uint64_t>(); O.expv = ctx->d_expv.as<double>();
+    stage_begin(ctx, ST_FINALIZE);
+    k_finalize_reads<<<nblk((int64_t)n * 32, 128), 128, 0, ctx->stream>>>(ctx->ix, ctx->dreads, P, ctx->d_prep.as<ReadPrep>(), keys, ctx->d_score.as<float>(), n_cand, O);
+    CK(cudaGetLastError());
+    stage_end(ctx, ST_FINALIZE, (uint64_t)n, 0, 1);
+
+    CK(cudaMemcpyAsync(&hc, dc, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    stage_collect(ctx);
+    const uint32_t n_leaders = hc.n_leaders;
+
+    // PHASE B
+    LeaderStore L;
+    L.lead_cand = ctx->d_lead_cand.as<uint32_t>();
+    L.a_stride = max_len + 2 * P.max_gap + 8; L.c_stride = 64; L.max_len = max_len;
+    size_t nl = std::max<uint32_t>(n_leaders, 1);
+    CK(ctx->d_alen.ensure(nl * 4)); CK(ctx->d_aligned.ensure(nl * L.a_stride)); CK(ctx->d_cigar.ensure(nl * L.c_stride));
+    L.alen = ctx->d_alen.as<int32_t>(); L.aligned = ctx->d_aligned.as<uint8_t>(); L.cigar = ctx->d_cigar.as<char>(); L.hmm = nullptr;
+    if (do_score && n_leaders) {
+        // traceback is needed in every mode for the CIGAR of the best hit (get_SAM, reference inc/ScoredSeq.h:314-372)
+        CK(ctx->d_moves.ensure((size_t)n_leaders * ((size_t)max_len + 1) * 4));
+        stage_begin(ctx, ST_TRACEBACK);
+        k_traceback<<<nblk(n_leaders, 128), 128, 0, ctx->stream>>>(ctx->ix, ctx->dreads, ctx->tab, P, keys, n_leaders, L, ctx->d_moves.as<uint32_t>());
+        CK(cudaGetLastError());
+        stage_end(ctx, ST_TRACEBACK, n_leaders, 0, 1);
+        if (P.mode == GMX_MODE_SNP) {
+            CK(ctx->d_hmm.ensure((size_t)n_leaders * max_len * 5 * 4));
+            L.hmm = ctx->d_hmm.as<float>();
+            size_t per_task = gmx_phmm_scratch_doubles(max_len);
+            uint32_t wave = std::min<uint32_t>(n_leaders, (uint32_t)n_sm * 8);
+            CK(ctx->d_phmm_scratch.ensure((size_t)wave * per_task * 8));
+            stage_begin(ctx, ST_PHMM);
+            int launches = 0;
+            for (uint32_t s0 = 0; s0 < n_leaders; s0 += wave) {
+                uint32_t cnt = std::min<uint32_t>(wave, n_leaders - s0);
+                k_pair_hmm_leaders<<<cnt, GMX_PHMM_THREADS, 0, ctx->stream>>>(ctx->ix, ctx->dreads, ctx->tab, keys, L, s0, cnt,
+                                                                             ctx->d_phmm_scratch.as<double>(), per_task);
+                CK(cudaGetLastError());
+                launches++;
+            }
+            stage_end(ctx, ST_PHMM, n_leaders, 0, launches);
+        }
+        stage_begin(ctx, ST_SCATTER);
+        k_scatter<<<nblk((int64_t)n_cand * 32, 128), 128, 0, ctx->stream>>>(ctx->ix, ctx->dreads, P, keys, ctx->d_score.as<float>(), ctx->d_leader.as<int32_t>(),
+                                                                            ctx->d_slot.as<int32_t>(), n_cand, ctx->d_results.as<gmx_read_result>(), L, ctx->acc);
+        CK(cudaGetLastError());
+        stage_end(ctx, ST_SCATTER, hc.n_accepted, 0, 1);
+    }
+
+    // download: per-read results, and the accepted hits / best alignments for the SAM writer
+    stage_begin(ctx, ST_DOWNLOAD);
+    gmx_read_result *hres = ctx->h_results.data() + lo;
+    CK(cudaMemcpyAsync(hres, ctx->d_results.p, (size_t)n * sizeof(gmx_read_result), cudaMemcpyDeviceToHost, ctx->stream));
+    std::vector<unsigned long long> h_keys(n_cand);
+    std::vector<int32_t> h_leader(n_cand), h_slot(n_cand), h_alen(n_leaders);
+    std::vector<float> h_score(n_cand);
+    std::vector<char> h_cigar((size_t)n_leaders * L.c_stride);
+    std::vector<uint8_t> h_aligned((size_t)n_leaders * L.a_stride);
+    if (n_cand) {
+        CK(cudaMemcpyAsync(h_keys.data(), keys, (size_t)n_cand * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(h_leader.data(), ctx->d_leader.p, (size_t)n_cand * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(h_slot.data(), ctx->d_slot.p, (size_t)n_cand * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(h_score.data(), ctx->d_score.p, (size_t)n_cand * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (do_score && n_leaders) {
+        CK(cudaMemcpyAsync(h_alen.data(), ctx->d_alen.p, (size_t)n_leaders * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(h_cigar.data(), ctx->d_cigar.p, h_cigar.size(), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(h_aligned.data(), ctx->d_aligned.p, h_aligned.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    stage_end(ctx, ST_DOWNLOAD, (uint64_t)n, (uint64_t)n * sizeof(gmx_read_result) + (uint64_t)n_cand * 20, 0);
+    CK(cudaStreamSynchronize(ctx->stream));
+    stage_collect(ctx);
+
+    // host-side assembly of the variable-length outputs (hit list, best CIGAR): pure bookkeeping
+    const int a_out = ctx->h_a_stride;
+    for (int32_t i = 0; i < n; ++i) {
+        gmx_read_result &res = hres[i];
+        int32_t c_lo = res.hit_begin, c_hi = res.hit_end;
+        res.hit_begin = res.hit_end = (int32_t)ctx->h_hits.size();
+        if (res.status != GMX_READ_MAPPED) continue;
+        // group labels: order of first appearance of the leader (processing order)
+        std::vector<int32_t> leaders;
+        int32_t best_leader = res.best_group >= 0 ? c_lo + res.best_group : -1;
+        int best_label = -1;
+        for (int32_t c = c_lo; c < c_hi; ++c) {
+            if (h_leader[c] < 0) continue;
+            int label = -1;
+            for (size_t k = 0; k < leaders.size(); ++k) if (leaders[k] == h_leader[c]) { label = (int)k; break; }
+            if (label < 0) { label = (int)leaders.size(); leaders.push_back(h_leader[c]); }
+            if (h_leader[c] == best_leader) best_label = label;
+            gmx_hit h;
+            h.pos = (uint32_t)h_keys[c]; h.score = h_score[h_leader[c]]; h.read = lo + i; h.group = (int16_t)label;
+            h.strand = (uint8_t)((h_keys[c] >> 40) & 1); h.first_strand = (uint8_t)((h_keys[h_leader[c]] >> 40) & 1);
+            ctx->h_hits.push_back(h);
+        }
+        res.hit_end = (int32_t)ctx->h_hits.size();
+        std::sort(ctx->h_hits.begin() + res.hit_begin, ctx->h_hits.end(), [](const gmx_hit &a, const gmx_hit &b) {
+            if (a.group != b.group) return a.group < b.group;
+            if (a.pos != b.pos) return a.pos < b.pos;
+            return a.strand < b.strand;
+        });
+        res.best_group = best_label;
+        if (do_score && best_leader >= 0) {
+            int s = h_slot[best_leader];
+            res.best_aligned_len = h_alen[s];
+            memcpy(&ctx->h_best_cigar[(size_t)(lo + i) * 64], &h_cigar[(size_t)s * L.c_stride], 64);
+            int cp = std::min(a_out, L.a_stride);
+            memcpy(&ctx->h_best_aligned[(size_t)(lo + i) * a_out], &h_aligned[(size_t)s * L.a_stride], (size_t)cp);
+        }
+    }
+    if (results_out) memcpy(results_out + lo, hres, (size_t)n * sizeof(gmx_read_result));
+    return GMX_OK;
+}
+
+static int run_batch(gmx_ctx *ctx, const gmx_reads *reads, gmx_read_result *results, bool do_score)
+{
+    if (!ctx || !reads || reads->n_reads < 0 || (reads->n_reads > 0 && !reads->offsets)) return GMX_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    const int32_t n = reads->n_reads;
+    int32_t max_len = 0;
+    for (int32_t i = 0; i < n; ++i) max_len = std::max<int32_t>(max_len, (int32_t)(reads->offsets[i + 1] - reads->offsets[i]));
+    ctx->h_results.assign((size_t)n, gmx_read_result());
+    ctx->h_hits.clear();
+    ctx->h_a_stride = max_len + 2 * ctx->params.max_gap + 8;
+    ctx->h_best_cigar.assign((size_t)n * 64, 0);
+    ctx->h_best_aligned.assign((size_t)n * ctx->h_a_stride, 0);
+    ctx->last_n_reads = n; ctx->last_max_len = 0;
+    ctx->mapped = false; ctx->scored = false;
+    stage_reset(ctx);
+    for (int32_t lo = 0; lo < n; lo += (int32_t)ctx->chunk_reads) {
+        int32_t hi = (int32_t)std::min<int64_t>(n, (int64_t)lo + (int64_t)ctx->chunk_reads);
+        int r = run_chunk(ctx, reads, lo, hi, do_score, results);
+        if (r != GMX_OK) return r;
+    }
+    ctx->mapped = true; ctx->scored = do_score;
+    return GMX_OK;
+}
+
+extern "C" int gmx_process_batch(gmx_ctx *ctx, const gmx_reads *reads, gmx_read_result *results) { return run_batch(ctx, reads, results, true); }
+
+// PHASE A only: nothing is scattered; gmx_score_batch re-derives PHASE B from the same reads.
+static const gmx_reads *g_last_reads_unused = nullptr;
+extern "C" int gmx_map_batch(gmx_ctx *ctx, const gmx_reads *reads, gmx_read_result *results)
+{
+    (void)g_last_reads_unused;
+    return run_batch(ctx, reads, results, false);
+}
+
+extern "C" int gmx_score_batch(gmx_ctx *ctx, gmx_read_result *results)
+{
+    if (!ctx) return GMX_ERR_INVALID;
+    (void)results;
+    ctx->err = "gmx_score_batch: PHASE B runs fused with PHASE A; call gmx_process_batch (split mode is not kept resident yet)";
+    return GMX_ERR_STATE;
+}
+
+extern "C" int gmx_get_hits(gmx_ctx *ctx, gmx_hit *hits, int64_t capacity, int64_t *n_hits)
+{
+    if (!ctx || !n_hits) return GMX_ERR_INVALID;
+    if (!ctx->mapped) return GMX_ERR_STATE;
+    *n_hits = (int64_t)ctx->h_hits.size();
+    if (!hits) return GMX_OK;
+    if (capacity < *n_hits) return GMX_ERR_OVERFLOW;
+    memcpy(hits, ctx->h_hits.data(), ctx->h_hits.size() * sizeof(gmx_hit));
+    return GMX_OK;
+}
+
+extern "C" int gmx_get_best_alignments(gmx_ctx *ctx, char *cigar_out, int32_t cigar_stride, uint8_t *aligned_out, int32_t aligned_stride)
+{
+    if (!ctx) return GMX_ERR_INVALID;
+    if (!ctx->scored) return GMX_ERR_STATE;
+    for (int32_t i = 0; i < ctx->last_n_reads; ++i) {
+        if (cigar_out) {
+            memset(cigar_out + (size_t)i * cigar_stride, 0, (size_t)cigar_stride);
+            strncpy(cigar_out + (size_t)i * cigar_stride, &ctx->h_best_cigar[(size_t)i * 64], (size_t)std::min(cigar_stride - 1, 63));
+        }
+        if (aligned_out) {
+            memset(aligned_out + (size_t)i * aligned_stride, 0, (size_t)aligned_stride);
+            memcpy(aligned_out + (size_t)i * aligned_stride, &ctx->h_best_aligned[(size_t)i * ctx->h_a_stride], (size_t)std::min(aligned_stride, ctx->h_a_stride));
+        }
+    }
+    return GMX_OK;
+}
+
+extern "C" int gmx_get_stage_stats(gmx_ctx *ctx, gmx_stage_stats *out)
+{
+    if (!ctx || !out) return GMX_ERR_INVALID;
+    memset(out, 0, sizeof(*out));
+    out->n_stages = ST_COUNT;
+    for (int s = 0; s < ST_COUNT && s < GMX_N_STAGES; ++s) {
+        out->name[s] = kStageNames[s]; out->ms[s] = ctx->stage_ms[s]; out->units[s] = ctx->stage_units[s];
+        out->bytes[s] = ctx->stage_bytes[s]; out->launches[s] = ctx->stage_launches[s];
+    }
+    return GMX_OK;
+}

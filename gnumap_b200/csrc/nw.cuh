@@ -1,0 +1,318 @@
+// nw.cuh -- banded PWM Needleman-Wunsch (score, traceback) and the pair-HMM forward/backward
+// on the device.
+//
+//   K2a  bin_seq::get_align_score(read, gen)          reference src/bin_seq.cpp:761-850
+//   K2b  bin_seq::get_align_score_w_traceback          reference src/bin_seq.cpp:445-718
+//   K2c  bin_seq::pairHMM                              reference src/bin_seq.cpp:60-244
+//
+// FP32 arithmetic follows the reference operation by operation (separate multiply / add, left to
+// right; the file is compiled with -fmad=false), so scores are bit-identical to the CPU and the
+// acceptance test `score >= min_align_score` (reference inc/align_seq2_raw.cpp:102) cannot flip.
+// The max-plus recurrence has no contraction to feed a tensor core: this is ALU work.
+#pragma once
+
+#include "gmx_common.cuh"
+
+// ---- operand sources -------------------------------------------------------------------------
+
+// One (read, strand) as the alignment kernels see it: row i of the strand-oriented PWM.
+struct ReadView {
+    const uint8_t *seq;    // raw ASCII of the read as given (forward)
+    const uint8_t *qual;
+    const float   *pwm;    // optional raw PWM rows of the read as given
+    int n;
+    int neg;               // 1: reverse-complement orientation (reference SequenceOperations.h:149-161)
+
+    __device__ __forceinline__ int src(int i) const { return neg ? n - 1 - i : i; }
+
+    // get_val(pwm[i], g) for g = a,c,g,t   (reference src/bin_seq.cpp:975-987)
+    __device__ __forceinline__ float4 sub_row(const DevTables &T, int i) const
+    {
+        int ii = src(i);
+        if (pwm) {
+            float4 p = reinterpret_cast<const float4 *>(pwm)[ii];
+            if (neg) p = make_float4(p.w, p.z, p.y, p.x);
+            float r[4];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const float *s = T.S + 4 * (int)("acgt"[g]);
+                r[g] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(p.x, s[0]), __fmul_rn(p.y, s[1])), __fmul_rn(p.z, s[2])), __fmul_rn(p.w, s[3]));
+            }
+            return make_float4(r[0], r[1], r[2], r[3]);
+        }
+        int code = gmx_nt4(seq[ii]);
+        int q = gmx_qidx(qual[ii], 0);
+        const float4 *lut = reinterpret_cast<const float4 *>(neg ? T.sub_neg : T.sub_pos);
+        return __ldg(lut + code * GMX_NQ + q);
+    }
+
+    // get_val(pwm[i], ch) for a window character that is not a/c/g/t.  Every such row of
+    // gALIGN_SCORES is identical (reference inc/a_matrices.c:65-67); the row of 'n' stands for all.
+    __device__ __forceinline__ float sub_other(const DevTables &T, int i) const
+    {
+        float4 p = pwm_row(T, i);
+        const float *s = T.S + 4 * (int)'n';
+        return __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(p.x, s[0]), __fmul_rn(p.y, s[1])), __fmul_rn(p.z, s[2])), __fmul_rn(p.w, s[3]));
+    }
+
+    // the strand-oriented PWM row itself
+    __device__ __forceinline__ float4 pwm_row(const DevTables &T, int i) const
+    {
+        int ii = src(i);
+        float4 p;
+        if (pwm) p = reinterpret_cast<const float4 *>(pwm)[ii];
+        else p = __ldg(reinterpret_cast<const float4 *>(T.pwm_lut) + gmx_nt4(seq[ii]) * GMX_NQ + gmx_qidx(qual[ii], 0));
+        if (neg) p = make_float4(p.w, p.z, p.y, p.x);
+        return p;
+    }
+
+    // 3 * sum_b pwm[i][b] * P[g][b]  (reference src/bin_seq.cpp:41-57 p_seq) for g = a,c,g,t
+    __device__ __forceinline__ float4 phmm_row(const DevTables &T, int i) const
+    {
+        int ii = src(i);
+        if (pwm) {
+            float4 p = reinterpret_cast<const float4 *>(pwm)[ii];
+            if (neg) p = make_float4(p.w, p.z, p.y, p.x);
+            float r[4];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const float *s = T.P + 4 * (int)("acgt"[g]);
+                float sum = 0.f;
+                sum = __fadd_rn(sum, __fmul_rn(p.x, s[0]));
+                sum = __fadd_rn(sum, __fmul_rn(p.y, s[1]));
+                sum = __fadd_rn(sum, __fmul_rn(p.z, s[2]));
+                sum = __fadd_rn(sum, __fmul_rn(p.w, s[3]));
+                r[g] = __fmul_rn(3.f, sum);
+            }
+            return make_float4(r[0], r[1], r[2], r[3]);
+        }
+        const float4 *lut = reinterpret_cast<const float4 *>(neg ? T.phmm_neg : T.phmm_pos);
+        return __ldg(lut + gmx_nt4(seq[ii]) * GMX_NQ + gmx_qidx(qual[ii], 0));
+    }
+};
+
+__device__ __forceinline__ char gmx_max_char(float4 c)
+{   // reference inc/ScoredSeq.h:71-103
+    if ((c.x == c.y) && (c.x == c.z) && (c.x == c.w)) return 'n';
+    if (c.x >= c.y) {
+        if (c.x >= c.z) return (c.x >= c.w) ? 'a' : 't';
+        return (c.z >= c.w) ? 'g' : 't';
+    }
+    if (c.y >= c.z) return (c.y >= c.w) ? 'c' : 't';
+    return (c.z >= c.w) ? 'g' : 't';
+}
+
+// Genome window: either the packed genome at `pos`, or an explicit ASCII string.
+struct WindowView {
+    const uint8_t *pac;   // non-null: window = genome[pos, pos+n)
+    int64_t pos;
+    const uint8_t *chars; // else explicit "acgt..." characters
+    // base code 0..3, or 4 for a non-acgt character of an explicit window
+    __device__ __forceinline__ int base(int j) const
+    {
+        if (pac) return gmx_pac_base(pac, pos + j);
+        return gmx_nt4(chars[j]);
+    }
+};
+
+__device__ __forceinline__ float gmx_sel4(float4 v, int g, float other)
+{
+    return g == 0 ? v.x : (g == 1 ? v.y : (g == 2 ? v.z : (g == 3 ? v.w : other)));
+}
+
+// ---- K2a: score only -------------------------------------------------------------------------
+// The matrix is filled from (n,n) back to (0,0) inside the band |j-i| <= G; only two band rows
+// (2G+3 floats each, including the NEG_INF / boundary guard cells at |j-i| = G+1) are live.
+template <int G>
+__device__ float gmx_nw_band_score(const ReadView &rd, const WindowView &win, const DevTables &T, float gap)
+{
+    constexpr int W = 2 * G + 3;
+    const int n = rd.n;
+    float prev[W], cur[W];
+    int gb[W];                                    // genome bases gen[i+d], d = -G-1..G+1 (guards unused)
+    // transversion-row value for a non-acgt window character of an explicit window: every
+    // gALIGN_SCORES row that is not a/c/g/t (reference a_matrices.c:65-67) -- resolved by caller LUT
+    // row n:  nm[n][j] = gap * (n - j)  for j >= n-G-1   (reference src/bin_seq.cpp:805-807)
+#pragma unroll
+    for (int d = -G - 1; d <= G + 1; ++d) prev[d + G + 1] = (d <= 0) ? __fmul_rn(gap, (float)(-d)) : GMX_NEG_INF;
+#pragma unroll
+    for (int d = -G - 1; d <= G + 1; ++d) { int j = n - 1 + d; gb[d + G + 1] = (j >= 0 && j < n) ? win.base(j) : 0; }
+
+    for (int i = n - 1; i >= 0; --i) {
+        float4 sub = rd.sub_row(T, i);
+        const float other = win.pac ? 0.f : rd.sub_other(T, i);
+        cur[2 * G + 2] = (i + G + 1 == n) ? __fmul_rn(gap, (float)(n - i)) : GMX_NEG_INF;
+#pragma unroll
+        for (int d = G; d >= -G; --d) {
+            int j = i + d;
+            float v;
+            if (j >= n) v = (j == n) ? __fmul_rn(gap, (float)(n - i)) : GMX_NEG_INF;
+            else if (j < 0) v = GMX_NEG_INF;
+            else {
+                float m_mm = __fadd_rn(prev[d + G + 1], gmx_sel4(sub, gb[d + G + 1], other));
+                float gap1 = __fadd_rn(prev[d - 1 + G + 1], gap);
+                float gap2 = __fadd_rn(cur[d + 1 + G + 1], gap);
+                v = gmx_max3(m_mm, gap1, gap2);
+            }
+            cur[d + G + 1] = v;
+        }
+        cur[0] = GMX_NEG_INF;
+#pragma unroll
+        for (int d = 0; d < W; ++d) prev[d] = cur[d];
+        // slide the genome window: gen[(i-1)+d] = gen[i+(d-1)]
+#pragma unroll
+        for (int d = W - 1; d > 0; --d) gb[d] = gb[d - 1];
+        { int j = i - 1 - G - 1; gb[0] = (j >= 0) ? win.base(j) : 0; }
+    }
+    return prev[G + 1];
+}
+
+// Same recurrence for band half-widths without a specialisation (local-memory band rows).
+__device__ float gmx_nw_band_score_any(const ReadView &rd, const WindowView &win, const DevTables &T, float gap, int G)
+{
+    const int n = rd.n;
+    float prev[2 * GMX_MAX_GAP + 3], cur[2 * GMX_MAX_GAP + 3];
+    const int W = 2 * G + 3;
+    for (int d = -G - 1; d <= G + 1; ++d) prev[d + G + 1] = (d <= 0) ? __fmul_rn(gap, (float)(-d)) : GMX_NEG_INF;
+    for (int i = n - 1; i >= 0; --i) {
+        float4 sub = rd.sub_row(T, i);
+        const float other = win.pac ? 0.f : rd.sub_other(T, i);
+        cur[2 * G + 2] = (i + G + 1 == n) ? __fmul_rn(gap, (float)(n - i)) : GMX_NEG_INF;
+        for (int d = G; d >= -G; --d) {
+            int j = i + d;
+            float v;
+            if (j >= n) v = (j == n) ? __fmul_rn(gap, (float)(n - i)) : GMX_NEG_INF;
+            else if (j < 0) v = GMX_NEG_INF;
+            else {
+                float m_mm = __fadd_rn(prev[d + G + 1], gmx_sel4(sub, win.base(j), other));
+                float gap1 = __fadd_rn(prev[d + G], gap);
+                float gap2 = __fadd_rn(cur[d + G + 2], gap);
+                v = gmx_max3(m_mm, gap1, gap2);
+            }
+            cur[d + G + 1] = v;
+        }
+        cur[0] = GMX_NEG_INF;
+        for (int d = 0; d < W; ++d) prev[d] = cur[d];
+    }
+    return prev[G + 1];
+}
+
+__device__ __forceinline__ float gmx_nw_score_dispatch(const ReadView &rd, const WindowView &win, const DevTables &T, float gap, int G)
+{
+    if (G == 3) return gmx_nw_band_score<3>(rd, win, T, gap);
+    return gmx_nw_band_score_any(rd, win, T, gap, G);
+}
+
+// ---- K2b: forward fill with moves + traceback -------------------------------------------------
+// Moves: 2 bits per band cell (0 = D, 1 = U, 2 = L), one uint32 per row (2G+1 <= 15 cells), kept
+// in a global scratch laid out [row][task] so that the lanes of a warp write adjacent words.
+#define GMX_MV_D 0u
+#define GMX_MV_U 1u
+#define GMX_MV_L 2u
+
+struct TracebackOut {
+    uint8_t *aligned;      // this task's gapped read string (capacity aligned_cap), may be null
+    int aligned_cap;
+    char *cigar;           // this task's CIGAR text (capacity cigar_cap, NUL terminated), may be null
+    int cigar_cap;
+    int fix_deletions;     // apply fix_CIGAR_for_deletions (reference SequenceOperations.h:32-42) + "*" for empty
+};
+
+// consensus character of oriented row i; i == n yields the std::string terminator the reference
+// reads at src/bin_seq.cpp:607,660
+struct ConsView {
+    const uint8_t *explicit_chars;   // non-null: explicit consensus (length n)
+    __device__ __forceinline__ uint8_t at(const ReadView &rd, const DevTables &T, int i) const
+    {
+        if (i >= rd.n) return 0;
+        if (explicit_chars) return explicit_chars[i];
+        return (uint8_t)gmx_max_char(rd.pwm_row(T, i));
+    }
+};
+
+__device__ int gmx_nw_traceback(const ReadView &rd, const WindowView &win, const ConsView &cons, const DevTables &T,
+                                float gap, int G, uint32_t *moves, int64_t mv_stride, TracebackOut out)
+{
+    const int n = rd.n, m = rd.n;
+    float prev[2 * GMX_MAX_GAP + 3], cur[2 * GMX_MAX_GAP + 3];
+    const int W = 2 * G + 3;
+    // row 0: nm[0][j] = gap * j for j <= G+2  (reference src/bin_seq.cpp:508-511)
+    for (int d = -G - 1; d <= G + 1; ++d) prev[d + G + 1] = (d >= 0) ? __fmul_rn(gap, (float)d) : GMX_NEG_INF;
+    for (int i = 1; i <= n; ++i) {
+        float4 sub = rd.sub_row(T, i - 1);
+        const float other = win.pac ? 0.f : rd.sub_other(T, i - 1);
+        uint32_t mv = 0;
+        // guard cell left of the band: column 0 carries gap*i for i <= G+2, otherwise NEG_INF
+        cur[0] = (i - G - 1 == 0) ? __fmul_rn(gap, (float)i) : GMX_NEG_INF;
+        for (int d = -G; d <= G; ++d) {
+            int j = i + d;
+            float v;
+            if (j <= 0) v = (j == 0) ? __fmul_rn(gap, (float)i) : GMX_NEG_INF;
+            else if (j > m) v = GMX_NEG_INF;
+            else {
+                float diag = __fadd_rn(prev[d + G + 1], gmx_sel4(sub, win.base(j - 1), other));
+                float upgap = __fadd_rn(prev[d + G + 2], gap);
+                float leftgap = __fadd_rn(cur[d + G], gap);
+                uint32_t path;                         // reference src/bin_seq.cpp:989-1011
+                if (diag >= upgap) { if (diag >= leftgap) { path = GMX_MV_D; v = diag; } else { path = GMX_MV_L; v = leftgap; } }
+                else               { if (upgap >= leftgap) { path = GMX_MV_U; v = upgap; } else { path = GMX_MV_L; v = leftgap; } }
+                mv |= path << (2 * (d + G));
+            }
+            cur[d + G + 1] = v;
+        }
+        cur[2 * G + 2] = GMX_NEG_INF;
+        for (int d = 0; d < W; ++d) prev[d] = cur[d];
+        moves[(int64_t)i * mv_stride] = mv;
+    }
+
+    // pass 1: path length and run-length ops, walking back from (n, m)  (reference :571-698)
+    uint16_t ops[48];                                  // (count << 2) | type, in backward order
+    int n_ops = 0, alen = 0;
+    {
+        int i = n, j = m, c_type = 0, c_counter = 0;
+        auto push = [&](int type) {
+            if (c_type == type) c_counter++;
+            else { if (c_counter && n_ops < 48) ops[n_ops++] = (uint16_t)((c_counter << 2) | c_type); c_type = type; c_counter = 1; }
+        };
+        while (i != 0 && j != 0) {
+            uint32_t mv = (moves[(int64_t)i * mv_stride] >> (2 * (j - i + G))) & 3u;
+            if (mv == GMX_MV_D) { push(0); i--; j--; }
+            else if (mv == GMX_MV_U) { push(1); i--; }
+            else { push(2); j--; }
+            alen++;
+        }
+        while (i > 0) { push(1); i--; alen++; }
+        while (j > 0) { push(2); j--; alen++; }
+        if (c_counter > 0 && n_ops < 48) ops[n_ops++] = (uint16_t)((c_counter << 2) | c_type);
+    }
+    // pass 2: the gapped read string, written at its final (reversed) positions
+    if (out.aligned) {
+        int i = n, j = m, k = 0;
+        auto put = [&](uint8_t ch) { int at = alen - 1 - k; if (at < out.aligned_cap) out.aligned[at] = ch; k++; };
+        while (i != 0 && j != 0) {
+            uint32_t mv = (moves[(int64_t)i * mv_stride] >> (2 * (j - i + G))) & 3u;
+            if (mv == GMX_MV_D) { put(cons.at(rd, T, i - 1)); i--; j--; }
+            else if (mv == GMX_MV_U) { put(cons.at(rd, T, i)); i--; }      // sic: consense[i]
+            else { put('-'); j--; }
+        }
+        while (i > 0) { put(cons.at(rd, T, i)); i--; }
+        while (j > 0) { put('-'); j--; }
+        if (alen < out.aligned_cap) out.aligned[alen] = 0;
+    }
+    // CIGAR text, forward order = ops reversed
+    if (out.cigar) {
+        int last = 0;                                  // ops[0] is the LAST op of the forward CIGAR
+        if (out.fix_deletions && n_ops > 0 && (ops[0] & 3) == 2) last = 1;   // strip a trailing D run
+        int p = 0;
+        for (int o = n_ops - 1; o >= last; --o) {
+            int cnt = ops[o] >> 2, type = ops[o] & 3;
+            char digits[8]; int nd = 0;
+            do { digits[nd++] = (char)('0' + cnt % 10); cnt /= 10; } while (cnt);
+            while (nd && p < out.cigar_cap - 1) out.cigar[p++] = digits[--nd];
+            if (p < out.cigar_cap - 1) out.cigar[p++] = type == 0 ? 'M' : (type == 1 ? 'I' : 'D');
+        }
+        if (p == 0 && out.fix_deletions && n_ops == 0 && p < out.cigar_cap - 1) out.cigar[p++] = '*';
+        out.cigar[p] = 0;
+    }
+    return alen;
+}

@@ -1,0 +1,218 @@
+// pair_hmm.cuh -- K2c: the 3-state (M, X, Y) pair-HMM forward / backward posterior of
+// bin_seq::pairHMM (reference src/bin_seq.cpp:60-244), FP64 state with FP32 emissions exactly as
+// the reference mixes them (inc/bin_seq.h:48-69: the parameters are floats, promoted inside the
+// recurrences).  All products and sums use the reference's association order without FMA
+// contraction (__dmul_rn / __dadd_rn), so forward and backward values are bit-identical to the
+// CPU; only the order of the final per-column float accumulation differs.
+//
+// Mapping: one warp per alignment.  Lane l owns a strip of C = ceil(m/32) genome columns and the
+// warp sweeps the rows as a skewed wavefront: at step s lane l computes row (s - l) of its strip,
+// receiving the boundary cell of the strip on its left (forward) / right (backward) through warp
+// shuffles.  The forward matrix is parked in a per-warp global scratch (3 doubles per cell) and
+// re-read by the backward sweep, which forms the posteriors on the fly and reduces them per
+// genome column.  This is FP64-pipe work; there is no tensor-core formulation of this recurrence
+// that keeps FP64 state.
+#pragma once
+
+#include "pipeline.cuh"
+
+#define GMX_PHMM_THREADS 32
+#define GMX_PHMM_MAXC 8                       // columns per lane -> read length <= 256 in SNP mode
+
+__host__ __device__ inline size_t gmx_phmm_scratch_doubles(int max_len) { return (size_t)max_len * max_len * 3; }
+
+struct PhmmConst {
+    double Tmm, Tgm, Tmg, Tgg, q, t;          // floats promoted to double
+    float  fTmm, fTgm, qTmg, qTgg;            // the float products the backward pass forms first
+};
+
+__device__ __forceinline__ PhmmConst gmx_phmm_const()
+{   // reference inc/bin_seq.h:60-69
+    float q = 0.25f, t = 0.05f, d = 0.0025f, e = 0.5f;
+    float Tmm = __fsub_rn(__fsub_rn(1.0f, __fmul_rn(2.0f, d)), t);
+    float Tgm = __fsub_rn(__fsub_rn(1.0f, d), t);
+    float Tmg = d, Tgg = e;
+    PhmmConst c;
+    c.Tmm = Tmm; c.Tgm = Tgm; c.Tmg = Tmg; c.Tgg = Tgg; c.q = q; c.t = t;
+    c.fTmm = Tmm; c.fTgm = Tgm; c.qTmg = __fmul_rn(q, Tmg); c.qTgg = __fmul_rn(q, Tgg);
+    return c;
+}
+
+__device__ __forceinline__ double gmx_shfl_d(double v, int src)
+{
+    int lo = __double2loint(v), hi = __double2hiint(v);
+    lo = __shfl_sync(0xffffffffu, lo, src); hi = __shfl_sync(0xffffffffu, hi, src);
+    return __hiloint2double(hi, lo);
+}
+
+// emission p_seq(pwm[i], genome base) for a strand-oriented read row; g == 4 -> non-acgt window char
+__device__ __forceinline__ float gmx_phmm_emit(const ReadView &rd, const DevTables &T, float4 row, int i, int g)
+{
+    if (g < 4) return gmx_sel4(row, g, 0.f);
+    float4 p = rd.pwm_row(T, i);
+    const float *s = T.P + 4 * (int)'n';
+    float sum = 0.f;
+    sum = __fadd_rn(sum, __fmul_rn(p.x, s[0])); sum = __fadd_rn(sum, __fmul_rn(p.y, s[1]));
+    sum = __fadd_rn(sum, __fmul_rn(p.z, s[2])); sum = __fadd_rn(sum, __fmul_rn(p.w, s[3]));
+    return __fmul_rn(3.f, sum);
+}
+
+// One warp: posteriors of read `rd` against window `win` (m == n).  post: float[m][5], zeroed by the caller.
+__device__ void gmx_pair_hmm_warp(const ReadView &rd, const WindowView &win, const DevTables &T, double *F, float *post)
+{
+    const int lane = threadIdx.x & 31;
+    const int n = rd.n, m = rd.n;
+    const int C = (m + 31) >> 5;
+    const PhmmConst K = gmx_phmm_const();
+    const int j0 = lane * C;                                   // first 0-based genome column of the strip
+    int gb[GMX_PHMM_MAXC], gbn[GMX_PHMM_MAXC];                  // genome base of column j, and of column j+1
+#pragma unroll
+    for (int c = 0; c < GMX_PHMM_MAXC; ++c) {
+        int j = j0 + c;
+        gb[c] = (c < C && j < m) ? win.base(j) : 0;
+        gbn[c] = (c < C && j + 1 < m) ? win.base(j + 1) : 0;
+    }
+
+    // ---------------- forward (reference :141-157); f index (i, j) 1-based, strip column c <-> j = j0 + c + 1
+    double pM[GMX_PHMM_MAXC], pX[GMX_PHMM_MAXC], pY[GMX_PHMM_MAXC];     // row i-1 of the strip
+#pragma unroll
+    for (int c = 0; c < GMX_PHMM_MAXC; ++c) { pM[c] = 0; pX[c] = 0; pY[c] = 0; }
+    // boundary cells on the left of the strip: (i-1, j0) "diag" and (i, j0) "left"
+    double dM = 0, dX = 0, dY = 0, lM = 0, lY = 0;
+    double outM = 0, outX = 0, outY = 0;                         // last column of the row just computed
+    double fE_M = 0, fE_X = 0, fE_Y = 0;
+    for (int s = 1; s <= n + 31; ++s) {
+        // receive the left neighbour's last column of the row it computed in the previous step (= my row i)
+        double rM = gmx_shfl_d(outM, lane - 1), rX = gmx_shfl_d(outX, lane - 1), rY = gmx_shfl_d(outY, lane - 1);
+        int i = s - lane;                                      // 1-based read row
+        if (lane == 0) { rM = 0; rX = 0; rY = 0; }             // column 0: f[i][0] = 0 for i >= 1
+        // previous step's received row is now the diagonal row (i-1); for lane 0, (i-1, 0) is (0,0) when i == 1
+        if (i >= 1 && i <= n) {
+            if (lane == 0) { dM = (i == 1) ? 1.0 : 0.0; dX = 0; dY = 0; }
+            lM = rM; lY = rY;
+            float4 row = rd.phmm_row(T, i - 1);
+            double cM_prev = dM, cX_prev = dX, cY_prev = dY;   // (i-1, j-1) for the first column
+            double leftM = lM, leftY = lY;                     // (i, j-1)
+#pragma unroll
+            for (int c = 0; c < GMX_PHMM_MAXC; ++c) {
+                int j = j0 + c;                                // 0-based genome column
+                if (c < C && j < m) {
+                    float e = gmx_phmm_emit(rd, T, row, i - 1, gb[c]);
+                    double sum = __dadd_rn(__dadd_rn(__dmul_rn(K.Tmm, cM_prev), __dmul_rn(K.Tgm, cX_prev)), __dmul_rn(K.Tgm, cY_prev));
+                    double fM = __dmul_rn((double)e, sum);
+                    double fX = __dmul_rn(K.q, __dadd_rn(__dmul_rn(K.Tmg, pM[c]), __dmul_rn(K.Tgg, pX[c])));
+                    double fY = __dmul_rn(K.q, __dadd_rn(__dmul_rn(K.Tmg, leftM), __dmul_rn(K.Tgg, leftY)));
+                    cM_prev = pM[c]; cX_prev = pX[c]; cY_prev = pY[c];      // becomes (i-1, j) = diag of the next column
+                    pM[c] = fM; pX[c] = fX; pY[c] = fY;
+                    leftM = fM; leftY = fY;
+                    double *f = F + ((size_t)(i - 1) * m + j) * 3;
+                    f[0] = fM; f[1] = fX; f[2] = fY;
+                    if (i == n && j == m - 1) { fE_M = fM; fE_X = fX; fE_Y = fY; }
+                    outM = fM; outX = fX; outY = fY;
+                }
+            }
+            // the row received now is the diagonal boundary for the next row
+            dM = rM; dX = rX; dY = rY;
+        }
+    }
+    // fE lives in the lane that owns column m-1
+    int owner = (m - 1) / C;
+    fE_M = gmx_shfl_d(fE_M, owner); fE_X = gmx_shfl_d(fE_X, owner); fE_Y = gmx_shfl_d(fE_Y, owner);
+    const double fE = __dmul_rn(K.t, __dadd_rn(__dadd_rn(fE_M, fE_X), fE_Y));                  // reference :160
+
+    // ---------------- backward (reference :164-204) + posterior (:206-241); b index (i, j) 0-based
+    double qM[GMX_PHMM_MAXC], qX[GMX_PHMM_MAXC];               // row i+1 of the strip (bM, bX)
+    float acc[GMX_PHMM_MAXC][5];
+#pragma unroll
+    for (int c = 0; c < GMX_PHMM_MAXC; ++c) { qM[c] = 0; qX[c] = 0;
+#pragma unroll
+        for (int b = 0; b < 5; ++b) acc[c][b] = 0.f; }
+    double eM = 0;                                             // bM of (i+1, strip_end+1): diagonal boundary on the right
+    double sndM = 0, sndY = 0;                                 // first column of the row just computed
+    const int last_lane = (m - 1) / C;
+    for (int s = 0; s <= n - 1 + 31; ++s) {
+        double rM = gmx_shfl_d(sndM, lane + 1), rY = gmx_shfl_d(sndY, lane + 1);
+        int i = (n - 1) - (s - (last_lane - lane));            // lanes right of last_lane own no columns
+        bool live = lane <= last_lane && i >= 0 && i <= n - 1;
+        if (live) {
+            if (lane == last_lane) { rM = 0; rY = 0; }
+            float4 row = (i + 1 <= n - 1) ? rd.phmm_row(T, i + 1) : make_float4(0, 0, 0, 0);
+            int code = 4;
+            { char ch = gmx_max_char(rd.pwm_row(T, i)); code = ch == 'a' ? 0 : ch == 'c' ? 1 : ch == 'g' ? 2 : ch == 't' ? 3 : 4; }
+            double rightM_next = eM;                           // bM (i+1, j+1) for the last column of the strip
+            double rightY = rY;                                // bY (i, j+1)
+            double firstM = 0, firstY = 0;
+#pragma unroll
+            for (int c = GMX_PHMM_MAXC - 1; c >= 0; --c) {
+                int j = j0 + c;
+                if (c < C && j < m) {
+                    double bM, bX, bY;
+                    // (i+1, j+1): from the strip itself unless c is its last column
+                    double diagM = rightM_next;
+                    if (j == m - 1 && i == n - 1) { bM = K.t; bX = K.t; bY = K.t; }
+                    else if (j == m - 1) {
+                        bM = __dmul_rn((double)K.qTmg, qX[c]);
+                        bX = __dmul_rn((double)K.qTgg, qX[c]);
+                        bY = 0;
+                    } else if (i == n - 1) {
+                        bM = __dmul_rn((double)K.qTmg, rightY);
+                        bY = __dmul_rn((double)K.qTgg, rightY);
+                        bX = 0;
+                    } else {
+                        float e = gmx_phmm_emit(rd, T, row, i + 1, gbn[c]);
+                        float eTmm = __fmul_rn(e, K.fTmm), eTgm = __fmul_rn(e, K.fTgm);
+                        bM = __dadd_rn(__dadd_rn(__dmul_rn((double)eTmm, diagM), __dmul_rn((double)K.qTmg, qX[c])), __dmul_rn((double)K.qTmg, rightY));
+                        bX = __dadd_rn(__dmul_rn((double)eTgm, diagM), __dmul_rn((double)K.qTgg, qX[c]));
+                        bY = __dadd_rn(__dmul_rn((double)eTgm, diagM), __dmul_rn((double)K.qTgg, rightY));
+                    }
+                    // posterior of (read i, genome j): f[i+1][j+1] * b[i][j] / fE, M and Y states
+                    const double *f = F + ((size_t)i * m + j) * 3;
+                    double pMv = __ddiv_rn(__dmul_rn(f[0], bM), fE);
+                    double pYv = __ddiv_rn(__dmul_rn(f[2], bY), fE);
+                    double add = __dadd_rn(pYv, pMv);
+#pragma unroll
+                    for (int b = 0; b < 5; ++b) if (b == code) acc[c][b] = (float)__dadd_rn((double)acc[c][b], add);
+                    rightM_next = qM[c];                       // (i+1, j) = diag of the next column to the left
+                    qM[c] = bM; qX[c] = bX;
+                    rightY = bY;
+                    firstM = bM; firstY = bY;
+                }
+            }
+            eM = rM;                                           // received (i, strip_end+1).M is next row's diagonal
+            sndM = firstM; sndY = firstY;
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < GMX_PHMM_MAXC; ++c) {
+        int j = j0 + c;
+        if (c < C && j < m) {
+#pragma unroll
+            for (int b = 0; b < 5; ++b) post[(size_t)j * 5 + b] = acc[c][b];
+        }
+    }
+}
+
+// explicit-window tasks (kernel-level entry point gmx_pair_hmm)
+__global__ void __launch_bounds__(GMX_PHMM_THREADS) k_pair_hmm_tasks(DevReads R, DevTables T, int64_t t0, int64_t cnt, const int32_t *read_idx,
+                                                                     const uint8_t *strand, const uint8_t *windows, int win_stride,
+                                                                     float *post, double *scratch, size_t per_task)
+{
+    int64_t t = t0 + blockIdx.x;
+    if ((int64_t)blockIdx.x >= cnt) return;
+    ReadView rd = gmx_read_view(R, read_idx[t], strand ? strand[t] : 0);
+    WindowView win; win.pac = nullptr; win.pos = 0; win.chars = windows + t * win_stride;
+    gmx_pair_hmm_warp(rd, win, T, scratch + (size_t)blockIdx.x * per_task, post + (size_t)t * win_stride * 5);
+}
+
+// one group leader per warp (SNPScoredSeq::score, reference src/SNPScoredSeq.cpp:44-67)
+__global__ void __launch_bounds__(GMX_PHMM_THREADS) k_pair_hmm_leaders(DevIndex ix, DevReads R, DevTables T, const unsigned long long *keys,
+                                                                       LeaderStore L, uint32_t s0, uint32_t cnt, double *scratch, size_t per_task)
+{
+    if (blockIdx.x >= cnt) return;
+    uint32_t s = s0 + blockIdx.x;
+    uint32_t task, round, diag;
+    gmx_decode_key(keys[L.lead_cand[s]], task, round, diag);
+    ReadView rd = gmx_read_view(R, (int)(task >> 1), (int)(task & 1));
+    WindowView win; win.pac = ix.pac; win.pos = diag; win.chars = nullptr;
+    gmx_pair_hmm_warp(rd, win, T, scratch + (size_t)blockIdx.x * per_task, L.hmm + (size_t)s * L.max_len * 5);
+}

@@ -1,0 +1,608 @@
+// pipeline.cuh -- kernels of the batched mapping pipeline (PHASE A + PHASE B of the reference's
+// per-read loops, reference src/Driver.cpp:2344-2373) for one chunk of reads.
+//
+//   k_prep_reads      set_top_matches prologue           reference src/Driver.cpp:446-497
+//   k_seed_walk       align_sequence k-mer walk + K1     reference inc/align_seq2_raw.cpp:192-243
+//   k_vote_smem/_gmem K1b locate + K1c diagonal vote     reference inc/align_seq2_raw.cpp:262-274,28-35
+//   k_cand_score      GetString + K2a                    reference inc/align_seq2_raw.cpp:43-64
+//   k_finalize_reads  acceptance, grouping, denominator  reference inc/align_seq2_raw.cpp:95-165,
+//                     best group                          reference src/Driver.cpp:593-611,640-680
+//   k_traceback       K2b per group                      reference src/NormalScoredSeq.cpp:40-62
+//   k_scatter         K3                                 reference src/NormalScoredSeq.cpp:68-75 etc.
+#pragma once
+
+#include "fm_index.cuh"
+#include "nw.cuh"
+
+struct DevParams {
+    float gap, align_score, cutoff;
+    int max_gap, mer, jump, kmin, perc, match_pos, match_neg, unique_only, fast, mode;
+    uint32_t max_kmer_hits, max_matches, gen_size;
+};
+
+// per-read scratch produced by k_prep_reads
+struct ReadPrep {
+    double min_align;     // min_align_score
+    float  max_align;     // self score
+    int32_t status;       // GMX_READ_* (MAPPED here means "eligible", decided later)
+};
+
+__device__ __forceinline__ ReadView gmx_read_view(const DevReads &R, int r, int neg)
+{
+    ReadView v;
+    int64_t off = R.offsets[r];
+    v.n = (int)(R.offsets[r + 1] - off);
+    v.seq = R.seq + off;
+    v.qual = R.qual ? R.qual + off : nullptr;
+    v.pwm = R.pwm ? R.pwm + 4 * off : nullptr;
+    v.neg = neg;
+    return v;
+}
+
+// ---- a3 + status ------------------------------------------------------------------------------
+__global__ void k_prep_reads(DevReads R, DevTables T, DevParams P, ReadPrep *prep)
+{
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R.n_reads) return;
+    ReadView rd = gmx_read_view(R, r, 0);
+    ReadPrep out; out.min_align = 0; out.max_align = 0; out.status = GMX_READ_MAPPED;
+    if ((unsigned)rd.n < (unsigned)P.mer) { out.status = GMX_READ_TOO_SHORT; prep[r] = out; return; }
+    // get_align_score(read, consensus, 0, n-1) == get_align_score_mid  (reference src/bin_seq.cpp:860-893)
+    float score = 0.f;
+    for (int i = 0; i < rd.n; ++i) {
+        float4 p = rd.pwm_row(T, i);
+        uint8_t ch = rd.seq[i];                  // GetConsensus(): read.seq (reference src/Driver.cpp:352-356)
+        const float *s = T.S + 4 * (int)ch;
+        float t = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(p.x, s[0]), __fmul_rn(p.y, s[1])), __fmul_rn(p.z, s[2])), __fmul_rn(p.w, s[3]));
+        score = __fadd_rn(score, t);
+    }
+    out.max_align = score;
+    double max_align = (double)score;
+    if (max_align < (double)P.cutoff) { out.status = GMX_READ_TOO_POOR; prep[r] = out; return; }
+    out.min_align = P.perc ? __dmul_rn((double)P.align_score, max_align) : (double)P.align_score;
+    prep[r] = out;
+}
+
+// ---- k-mer walk ---------------------------------------------------------------------------------
+// One thread per task = (read, strand).  The walk is sequentially data dependent (the next offset
+// depends on whether the previous k-mer hit), so the parallelism is across the 2 x n_reads tasks.
+// Seeds are stored SoA with stride n_tasks so that consecutive threads write consecutive words.
+struct SeedStore {
+    uint32_t *rank;    // [max_seeds][n_tasks] first SA rank of the interval
+    uint32_t *count;   // [max_seeds][n_tasks] interval size
+    uint16_t *offset;  // [max_seeds][n_tasks] k-mer offset i in the oriented read
+    uint8_t  *n_seeds; // [n_tasks]
+    uint32_t *hits;    // [n_tasks] total SA hits of the task
+    int max_seeds;
+    int64_t n_tasks;
+};
+
+__global__ void k_seed_walk(DevIndex ix, DevReads R, DevParams P, const ReadPrep *prep, SeedStore S)
+{
+    int64_t task = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (task >= S.n_tasks) return;
+    int r = (int)(task >> 1), neg = (int)(task & 1);
+    int ns = 0; uint32_t total = 0;
+    bool active = prep[r].status == GMX_READ_MAPPED && (neg ? P.match_neg : P.match_pos);
+    if (active && !R.seq) active = false;
+    if (active) {
+        int64_t off = R.offsets[r];
+        int n = (int)(R.offsets[r + 1] - off);
+        const uint8_t *seq = R.seq + off;
+        // oriented consensus symbol: POS = nt4(seq[x]); NEG = complement of seq[n-1-x]
+        // (reverse_comp maps every non-acgt character to 'n', which never matches)
+        auto sym_at = [&](int x) -> uint32_t {
+            int c = gmx_nt4(seq[neg ? n - 1 - x : x]);
+            return (uint32_t)((neg && c < 4) ? 3 - c : c);
+        };
+        unsigned last = (unsigned)n - (unsigned)P.mer;
+        for (unsigned i = 0; i < last; i += (unsigned)P.jump) {
+            unsigned j;
+            bool found = false;
+            uint64_t k = 0, l = 0;
+            for (j = 0; j + i < last; j++) {
+                unsigned base = i + j;
+                bool hit = gmx_match_exact(ix, P.mer, [&](int t) { return sym_at((int)base + t); }, k, l);
+                if (!hit) continue;
+                if (P.max_kmer_hits > 0 && l - k + 1 > (uint64_t)P.max_kmer_hits) continue;
+                found = true;
+                break;
+            }
+            i += j;
+            if (!found) break;
+            if (ns < S.max_seeds) {
+                S.rank[(int64_t)ns * S.n_tasks + task] = (uint32_t)k;
+                S.count[(int64_t)ns * S.n_tasks + task] = (uint32_t)(l - k + 1);
+                S.offset[(int64_t)ns * S.n_tasks + task] = (uint16_t)i;
+                total += (uint32_t)(l - k + 1);
+                ns++;
+            }
+            if (P.fast) break;
+        }
+    }
+    S.n_seeds[task] = (uint8_t)ns;
+    S.hits[task] = total;
+}
+
+// ---- task classes for the vote -----------------------------------------------------------------
+#define GMX_N_CLASSES 6          // 5 shared-memory table sizes + 1 global-memory class
+__constant__ const int gmx_class_slots_log2[5] = {10, 11, 12, 13, 14};
+
+struct ClassLists {
+    uint32_t *list;     // [GMX_N_CLASSES][n_tasks]
+    uint32_t *count;    // [GMX_N_CLASSES]
+    uint32_t *cursor;   // [GMX_N_CLASSES] work-stealing cursors of the persistent vote kernels
+    int64_t n_tasks;
+};
+
+__host__ __device__ __forceinline__ uint32_t gmx_class_max_hits(int cls) { return (5u << (10 + cls)) >> 3; }   // load <= 5/8
+
+__global__ void k_classify(const uint32_t *hits, ClassLists C)
+{
+    int64_t task = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (task >= C.n_tasks) return;
+    uint32_t h = hits[task];
+    if (h == 0) return;
+    int cls = 5;
+#pragma unroll
+    for (int c = 4; c >= 0; --c) if (h <= gmx_class_max_hits(c)) cls = c;
+    uint32_t at = atomicAdd(&C.count[cls], 1u);
+    C.list[(int64_t)cls * C.n_tasks + at] = (uint32_t)task;
+}
+
+// ---- K1b + K1c: locate + diagonal vote ---------------------------------------------------------
+// One warp per task.  Rounds (= k-mers of the walk) are processed in order; within a round the 32
+// lanes stride over the SA interval, read the de-sampled suffix array (contiguous ranks: coalesced)
+// and insert diag = max(0, sa - i) into a warp-private open-addressing table in shared memory
+// (uint32 keys + packed 8-bit counters).  The insert that raises a counter to kmin emits the
+// candidate, tagged with the round so that the reference's processing order (round, then ascending
+// position; reference inc/align_seq2_raw.cpp:28-35,292) can be restored by one radix sort.
+struct CandSink {
+    unsigned long long *keys;  // (task << 40) | (round << 32) | diag
+    uint32_t *count;
+    uint32_t *overflow;
+    uint32_t cap;
+};
+
+__device__ __forceinline__ uint32_t gmx_hash32(uint32_t x) { return (x * 0x9E3779B1u) ^ (x >> 15); }
+
+template <bool GLOBAL_TABLE>
+__device__ __forceinline__ void gmx_vote_task(const DevIndex &ix, const SeedStore &S, uint32_t task, int kmin,
+                                              uint32_t *keys, uint32_t *cnts, uint32_t mask, CandSink sink, int lane)
+{
+    int ns = S.n_seeds[task];
+    for (int s = 0; s < ns; ++s) {
+        uint32_t rank0 = S.rank[(int64_t)s * S.n_tasks + task];
+        uint32_t cnt = S.count[(int64_t)s * S.n_tasks + task];
+        uint32_t off = S.offset[(int64_t)s * S.n_tasks + task];
+        for (uint32_t t0 = 0; t0 < cnt; t0 += 32) {
+            uint32_t t = t0 + lane;
+            bool valid = t < cnt;
+            bool emit = false;
+            uint32_t diag = 0;
+            if (valid) {
+                uint32_t sa = __ldg(ix.sa_full + rank0 + t);
+                diag = (sa <= off) ? 0u : sa - off;
+                uint32_t h = gmx_hash32(diag) & mask;
+                while (true) {
+                    uint32_t prev = atomicCAS(&keys[h], GMX_EMPTY_KEY, diag);
+                    if (prev == GMX_EMPTY_KEY || prev == diag) break;
+                    h = (h + 1) & mask;
+                }
+                uint32_t sh = (h & 3u) << 3;
+                uint32_t cur = (reinterpret_cast<volatile uint32_t *>(cnts)[h >> 2] >> sh) & 0xffu;
+                if ((int)cur < kmin) {
+                    uint32_t old = (atomicAdd(&cnts[h >> 2], 1u << sh) >> sh) & 0xffu;
+                    emit = ((int)old + 1 == kmin);
+                }
+            }
+            uint32_t em = __ballot_sync(0xffffffffu, emit);
+            if (em) {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(sink.count, (uint32_t)__popc(em));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (emit) {
+                    uint32_t at = base + (uint32_t)__popc(em & ((1u << lane) - 1u));
+                    if (at < sink.cap) sink.keys[at] = ((unsigned long long)task << 40) | ((unsigned long long)s << 32) | diag;
+                    else *sink.overflow = 1u;
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+template <int SLOTS_LOG2, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) k_vote_smem(DevIndex ix, SeedStore S, ClassLists C, int cls, int kmin, CandSink sink)
+{
+    constexpr uint32_t SLOTS = 1u << SLOTS_LOG2;
+    extern __shared__ __align__(16) uint32_t smem[];
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t *keys = smem + (size_t)warp * (SLOTS + SLOTS / 4);
+    uint32_t *cnts = keys + SLOTS;
+    const uint32_t n_list = C.count[cls];
+    const uint32_t *list = C.list + (int64_t)cls * C.n_tasks;
+    while (true) {
+        uint32_t w = 0;
+        if (lane == 0) w = atomicAdd(&C.cursor[cls], 1u);
+        w = __shfl_sync(0xffffffffu, w, 0);
+        if (w >= n_list) break;
+        uint32_t task = list[w];
+        uint4 *k4 = reinterpret_cast<uint4 *>(keys);
+        for (uint32_t x = lane; x < SLOTS / 4; x += 32) k4[x] = make_uint4(GMX_EMPTY_KEY, GMX_EMPTY_KEY, GMX_EMPTY_KEY, GMX_EMPTY_KEY);
+        uint4 *c4 = reinterpret_cast<uint4 *>(cnts);
+        for (uint32_t x = lane; x < SLOTS / 16; x += 32) c4[x] = make_uint4(0, 0, 0, 0);
+        __syncwarp();
+        gmx_vote_task<false>(ix, S, task, kmin, keys, cnts, SLOTS - 1, sink, lane);
+        __syncwarp();
+    }
+}
+
+// Tasks whose hit count exceeds the largest shared-memory table (repeat-rich reads): same insert
+// logic over a table carved out of a global scratch buffer by a bump allocator; one warp per task.
+struct GlobalTableArena {
+    uint32_t *words;
+    unsigned long long *used;   // in words
+    unsigned long long cap;     // in words
+    uint32_t *overflow;
+};
+
+__global__ void __launch_bounds__(128) k_vote_gmem(DevIndex ix, SeedStore S, ClassLists C, int cls, int kmin, CandSink sink, GlobalTableArena A)
+{
+    int lane = threadIdx.x & 31;
+    const uint32_t n_list = C.count[cls];
+    const uint32_t *list = C.list + (int64_t)cls * C.n_tasks;
+    while (true) {
+        uint32_t w = 0;
+        if (lane == 0) w = atomicAdd(&C.cursor[cls], 1u);
+        w = __shfl_sync(0xffffffffu, w, 0);
+        if (w >= n_list) break;
+        uint32_t task = list[w];
+        uint32_t hits = S.hits[task];
+        uint32_t slots = 1u << 15;
+        while ((unsigned long long)slots * 5ull < (unsigned long long)hits * 8ull && slots < (1u << 31)) slots <<= 1;
+        unsigned long long need = (unsigned long long)slots + slots / 4, base = 0;
+        if (lane == 0) base = atomicAdd(A.used, need);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base + need > A.cap) { if (lane == 0) *A.overflow = 1u; continue; }
+        uint32_t *keys = A.words + base, *cnts = keys + slots;
+        for (uint32_t x = lane; x < slots; x += 32) keys[x] = GMX_EMPTY_KEY;
+        for (uint32_t x = lane; x < slots / 4; x += 32) cnts[x] = 0;
+        __syncwarp();
+        gmx_vote_task<true>(ix, S, task, kmin, keys, cnts, slots - 1, sink, lane);
+        __syncwarp();
+    }
+}
+
+// ---- candidate scoring -------------------------------------------------------------------------
+__device__ __forceinline__ void gmx_decode_key(unsigned long long key, uint32_t &task, uint32_t &round, uint32_t &diag)
+{
+    task = (uint32_t)(key >> 40); round = (uint32_t)(key >> 32) & 0xffu; diag = (uint32_t)key;
+}
+
+// One thread per candidate (inter-task parallelism; the band lives in registers).
+__global__ void __launch_bounds__(128) k_cand_score(DevIndex ix, DevReads R, DevTables T, DevParams P,
+                                                    const unsigned long long *keys, uint32_t n_cand, float *score)
+{
+    uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_cand) return;
+    uint32_t task, round, diag;
+    gmx_decode_key(keys[c], task, round, diag);
+    ReadView rd = gmx_read_view(R, (int)(task >> 1), (int)(task & 1));
+    float sc = __int_as_float(0x7fc00000);                       // NaN: window is "" (chromosome boundary)
+    if (gmx_window_valid(ix, diag, rd.n)) {
+        WindowView win; win.pac = ix.pac; win.pos = diag; win.chars = nullptr;
+        sc = gmx_nw_score_dispatch(rd, win, T, P.gap, P.max_gap);
+    }
+    score[c] = sc;
+}
+
+// ---- per-read finalisation ---------------------------------------------------------------------
+__device__ __forceinline__ uint32_t gmx_lower_bound(const unsigned long long *keys, uint32_t n, unsigned long long v)
+{
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (keys[mid] < v) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+
+// base j of the read-orientation key string of candidate (diag, neg): POS = window[j];
+// NEG = complement(window[n-1-j])  (reference inc/align_seq2_raw.cpp:125-128)
+__device__ __forceinline__ int gmx_key_base(const DevIndex &ix, uint32_t diag, int neg, int n, int j)
+{
+    int b = gmx_pac_base(ix.pac, (int64_t)diag + (neg ? n - 1 - j : j));
+    return neg ? 3 - b : b;
+}
+
+__device__ uint64_t gmx_key_hash(const DevIndex &ix, uint32_t diag, int neg, int n)
+{
+    uint64_t h = 0xcbf29ce484222325ull;
+    for (int j = 0; j < n; ++j) { h ^= (uint64_t)gmx_key_base(ix, diag, neg, n, j) + 1; h *= 0x100000001b3ull; }
+    return h;
+}
+
+// lexicographic compare of two key strings (<0, 0, >0)
+__device__ int gmx_key_compare(const DevIndex &ix, uint32_t da, int na, uint32_t db, int nb, int n)
+{
+    for (int j = 0; j < n; ++j) {
+        int a = gmx_key_base(ix, da, na, n, j), b = gmx_key_base(ix, db, nb, n, j);
+        if (a != b) return a - b;
+    }
+    return 0;
+}
+
+struct FinalizeOut {
+    gmx_read_result *results;   // [n_reads]
+    int32_t *leader;            // [n_cand] candidate index of the group leader, or -1 (not accepted)
+    int32_t *slot;              // [n_cand] leader-list slot for leaders, else -1
+    uint32_t *lead_cand;        // [lead_cap] candidate index per leader slot
+    uint32_t *n_leaders;
+    uint32_t *n_accepted;
+    uint64_t *hashes;           // [n_cand] scratch: key hash of accepted candidates
+    double   *expv;             // [n_cand] scratch: exp(score) of accepted candidates
+};
+
+// One warp per read.  Candidates of the read are contiguous in the sorted list: POS strand then
+// NEG strand, each in (round, position) order -- the order in which the reference meets them.
+__global__ void __launch_bounds__(128) k_finalize_reads(DevIndex ix, DevReads R, DevParams P, const ReadPrep *prep,
+                                                        const unsigned long long *keys, const float *score, uint32_t n_cand,
+                                                        FinalizeOut O)
+{
+    int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (r >= R.n_reads) return;
+    ReadPrep pr = prep[r];
+    gmx_read_result res;
+    res.top_score = 0; res.denominator = 0; res.max_align_score = pr.max_align; res.status = pr.status;
+    res.n_groups = 0; res.n_candidates = 0; res.best_score = 0; res.best_posterior = 0; res.best_n_positions = 0;
+    res.best_first_strand = 0; res.best_first_pos = 0; res.hit_begin = 0; res.hit_end = 0; res.best_group = -1; res.best_aligned_len = 0;
+    if (pr.status == GMX_READ_TOO_SHORT) { res.top_score = -2; if (lane == 0) O.results[r] = res; return; }
+    if (pr.status == GMX_READ_TOO_POOR) { res.top_score = -3; if (lane == 0) O.results[r] = res; return; }
+    const int n = (int)(R.offsets[r + 1] - R.offsets[r]);
+    uint32_t lo = gmx_lower_bound(keys, n_cand, (unsigned long long)(2 * (uint32_t)r) << 40);
+    uint32_t hi = gmx_lower_bound(keys, n_cand, (unsigned long long)(2 * (uint32_t)r + 2) << 40);
+
+    // pass 1: validity, top score, acceptance, exp(score), key hash
+    int n_valid = 0, n_acc = 0;
+    double top = 0.0;
+    for (uint32_t c0 = lo; c0 < hi; c0 += 32) {
+        uint32_t c = c0 + lane;
+        bool in = c < hi;
+        float sc = in ? score[c] : 0.f;
+        bool valid = in && !isnan(sc);
+        bool acc = valid && ((double)sc >= pr.min_align);
+        if (valid && (double)sc > top) top = (double)sc;
+        if (in) {
+            O.leader[c] = acc ? (int32_t)c : -1;
+            O.slot[c] = -1;
+            if (acc) {
+                uint32_t task, round, diag; gmx_decode_key(keys[c], task, round, diag);
+                O.hashes[c] = gmx_key_hash(ix, diag, (int)(task & 1), n);
+                O.expv[c] = exp((double)sc);
+            }
+        }
+        n_valid += __popc(__ballot_sync(0xffffffffu, valid));
+        n_acc += __popc(__ballot_sync(0xffffffffu, acc));
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) { double t = __shfl_xor_sync(0xffffffffu, top, o); if (t > top) top = t; }
+    res.n_candidates = n_valid;
+    __syncwarp();
+
+    if (n_acc == 0) {                                    // reference src/Driver.cpp:593-602
+        res.status = GMX_READ_UNMATCHED; res.top_score = 0; res.denominator = 0;
+        if (lane == 0) O.results[r] = res;
+        return;
+    }
+
+    // pass 2: group leaders = first accepted candidate (processing order) with the same key string
+    int n_groups = 0, joined = 0;
+    for (uint32_t c0 = lo; c0 < hi; c0 += 32) {
+        uint32_t c = c0 + lane;
+        bool acc = (c < hi) && O.leader[c] >= 0;
+        bool is_leader = acc;
+        if (acc) {
+            uint32_t task, round, diag; gmx_decode_key(keys[c], task, round, diag);
+            uint64_t h = O.hashes[c];
+            for (uint32_t p = lo; p < c; ++p) {
+                if (O.leader[p] < 0 || O.hashes[p] != h) continue;     // leader[p] >= 0 <=> accepted (pass 1 complete)
+                uint32_t tp, rp, dp; gmx_decode_key(keys[p], tp, rp, dp);
+                if (gmx_key_compare(ix, diag, (int)(task & 1), dp, (int)(tp & 1), n) == 0) { is_leader = false; O.slot[c] = -2 - (int32_t)(p - lo); break; }
+            }
+        }
+        n_groups += __popc(__ballot_sync(0xffffffffu, is_leader));
+        joined += __popc(__ballot_sync(0xffffffffu, acc && !is_leader));
+    }
+    __syncwarp();
+    // resolve leader indices (slot[c] temporarily holds -2 - (first equal predecessor)); the first
+    // equal predecessor of a non-leader is always a leader because equality is transitive
+    for (uint32_t c0 = lo; c0 < hi; c0 += 32) {
+        uint32_t c = c0 + lane;
+        if (c < hi && O.leader[c] >= 0 && O.slot[c] <= -2) { O.leader[c] = (int32_t)(lo + (uint32_t)(-2 - O.slot[c])); O.slot[c] = -1; }
+    }
+    __syncwarp();
+
+    // reference inc/align_seq2_raw.cpp:151-158 (gUNIQUE) and :299 (gMAX_MATCHES)
+    if ((P.unique_only && joined > 0) || (uint32_t)n_groups > P.max_matches) {
+        res.status = GMX_READ_TOO_MANY; res.top_score = 999999; res.denominator = 0; res.n_groups = 0;
+        for (uint32_t c = lo + lane; c < hi; c += 32) { O.leader[c] = -1; O.slot[c] = -1; }
+        if (lane == 0) O.results[r] = res;
+        return;
+    }
+
+    // denominator: sum of exp(score) over accepted candidates in processing order (FP64, sequential)
+    double denom = 0.0;
+    for (uint32_t c0 = lo; c0 < hi; c0 += 32) {
+        uint32_t c = c0 + lane;
+        bool acc = (c < hi) && O.leader[c] >= 0;
+        double e = acc ? O.expv[c] : 0.0;
+        uint32_t m = __ballot_sync(0xffffffffu, acc);
+        while (m) {
+            int src = __ffs(m) - 1; m &= m - 1;
+            double v = __shfl_sync(0xffffffffu, e, src);
+            denom = __dadd_rn(denom, v);
+        }
+    }
+
+    // best group: largest exp(score) with strict >, groups visited in key (lexicographic) order,
+    // starting from the empty ScoredSeq whose score is -1  (reference src/Driver.cpp:636,672)
+    float best_sc = -1.0f; int best_c = -1;
+    for (uint32_t c0 = lo; c0 < hi; c0 += 32) {
+        uint32_t c = c0 + lane;
+        bool lead = (c < hi) && O.leader[c] == (int32_t)c;
+        float sc = lead ? score[c] : -1.0f;
+        if (lead && exp((double)sc) > exp(-1.0)) {
+            bool better = (best_c < 0) || sc > best_sc;
+            if (!better && sc == best_sc) {
+                uint32_t ta, ra, da, tb, rb, db; gmx_decode_key(keys[c], ta, ra, da); gmx_decode_key(keys[best_c], tb, rb, db);
+                better = gmx_key_compare(ix, da, (int)(ta & 1), db, (int)(tb & 1), n) < 0;
+            }
+            if (better) { best_sc = sc; best_c = (int)c; }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        float osc = __shfl_xor_sync(0xffffffffu, best_sc, o);
+        int oc = __shfl_xor_sync(0xffffffffu, best_c, o);
+        bool better = false;
+        if (oc >= 0) {
+            if (best_c < 0 || osc > best_sc) better = true;
+            else if (osc == best_sc && oc != best_c) {
+                uint32_t ta, ra, da, tb, rb, db; gmx_decode_key(keys[oc], ta, ra, da); gmx_decode_key(keys[best_c], tb, rb, db);
+                int cmp = gmx_key_compare(ix, da, (int)(ta & 1), db, (int)(tb & 1), n);
+                better = cmp < 0;
+            }
+        }
+        if (better) { best_sc = osc; best_c = oc; }
+    }
+
+    // leader slots (any order) + counts
+    for (uint32_t c0 = lo; c0 < hi; c0 += 32) {
+        uint32_t c = c0 + lane;
+        bool lead = (c < hi) && O.leader[c] == (int32_t)c;
+        uint32_t m = __ballot_sync(0xffffffffu, lead);
+        if (m) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(O.n_leaders, (uint32_t)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (lead) { uint32_t s = base + (uint32_t)__popc(m & ((1u << lane) - 1u)); O.slot[c] = (int32_t)s; O.lead_cand[s] = c; }
+        }
+    }
+    if (lane == 0) atomicAdd(O.n_accepted, (uint32_t)n_acc);
+
+    res.status = GMX_READ_MAPPED;
+    res.top_score = top; res.denominator = denom; res.n_groups = n_groups;
+    res.hit_begin = (int32_t)lo; res.hit_end = (int32_t)hi;       // candidate range; remapped to hit indices on the host
+    if (best_c >= 0) {
+        // members of the best group: count and smallest (pos, strand)
+        int cnt = 0; uint64_t first = ~0ull;
+        for (uint32_t c0 = lo; c0 < hi; c0 += 32) {
+            uint32_t c = c0 + lane;
+            bool mem = (c < hi) && O.leader[c] == best_c;
+            if (mem) { uint32_t t, rr, d; gmx_decode_key(keys[c], t, rr, d); uint64_t v = ((uint64_t)d << 1) | (t & 1); if (v < first) first = v; }
+            cnt += __popc(__ballot_sync(0xffffffffu, mem));
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) { uint64_t t = __shfl_xor_sync(0xffffffffu, first, o); if (t < first) first = t; }
+        uint32_t tb, rb, db; gmx_decode_key(keys[best_c], tb, rb, db);
+        res.best_group = best_c - (int)lo;              // label: candidate index of the leader within the read
+        res.best_score = best_sc;
+        res.best_posterior = (float)(exp((double)best_sc) / denom);
+        res.best_n_positions = cnt;
+        res.best_first_strand = (int)(tb & 1);
+        res.best_first_pos = first >> 1;
+    }
+    if (lane == 0) O.results[r] = res;
+}
+
+// ---- K2b per group leader ------------------------------------------------------------------------
+struct LeaderStore {
+    const uint32_t *lead_cand;   // [n_leaders]
+    int32_t *alen;               // [n_leaders] length of the gapped `aligned` string
+    uint8_t *aligned;            // [n_leaders][a_stride] (BS mode, and for gmx_get_best_alignments)
+    char    *cigar;              // [n_leaders][c_stride]
+    float   *hmm;                // [n_leaders][max_len][5]   (SNP mode)
+    int a_stride, c_stride, max_len;
+};
+
+__global__ void __launch_bounds__(128) k_traceback(DevIndex ix, DevReads R, DevTables T, DevParams P,
+                                                   const unsigned long long *keys, uint32_t n_leaders, LeaderStore L,
+                                                   uint32_t *moves)
+{
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_leaders) return;
+    uint32_t task, round, diag;
+    gmx_decode_key(keys[L.lead_cand[s]], task, round, diag);
+    ReadView rd = gmx_read_view(R, (int)(task >> 1), (int)(task & 1));
+    WindowView win; win.pac = ix.pac; win.pos = diag; win.chars = nullptr;
+    ConsView cons; cons.explicit_chars = nullptr;          // score(): max_char consensus of the oriented PWM
+    TracebackOut out;
+    out.aligned = L.aligned + (size_t)s * L.a_stride; out.aligned_cap = L.a_stride;
+    out.cigar = L.cigar + (size_t)s * L.c_stride; out.cigar_cap = L.c_stride; out.fix_deletions = 1;
+    L.alen[s] = gmx_nw_traceback(rd, win, cons, T, P.gap, P.max_gap, moves + s, (int64_t)n_leaders, out);
+}
+
+// ---- K3: posterior scatter -----------------------------------------------------------------------
+// One warp per accepted (position, strand).  total = exp(score_of_group) / denominator as a float
+// (reference src/NormalScoredSeq.cpp:29,71: double -> `const float&`).  Lanes cover consecutive
+// genome positions; positions falling into the same accumulator bin are combined with
+// __match_any_sync before the atomic, so Normal mode (8 bases per bin) issues one RED per bin.
+struct Accum {
+    float *amount;          // [n_amount]
+    float *planes[5];       // [l_pac] each, BS / SNP
+    uint64_t n_amount;
+};
+
+__global__ void __launch_bounds__(128) k_scatter(DevIndex ix, DevReads R, DevParams P, const unsigned long long *keys,
+                                                 const float *score, const int32_t *leader, const int32_t *slot, uint32_t n_cand,
+                                                 const gmx_read_result *results, LeaderStore L, Accum A)
+{
+    uint32_t c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (c >= n_cand) return;
+    int32_t ld = leader[c];
+    if (ld < 0) return;
+    uint32_t task, round, diag, tl, rl, dl;
+    gmx_decode_key(keys[c], task, round, diag);
+    gmx_decode_key(keys[ld], tl, rl, dl);
+    int r = (int)(task >> 1);
+    int s = slot[ld];
+    double denom = results[r].denominator;
+    float total = (float)(exp((double)score[ld]) / denom);
+    int same = ((task & 1) == (tl & 1));                 // strand == firstStrand of the group
+    if (P.mode == GMX_MODE_SNP) {
+        int n = (int)(R.offsets[r + 1] - R.offsets[r]);
+        const float *hmm = L.hmm + (size_t)s * L.max_len * 5;
+        for (int i = lane; i < n; i += 32) {
+            int64_t p = (int64_t)diag + i;
+            if (p >= ix.l_pac) continue;
+            atomicAdd(&A.amount[p / P.gen_size], total);
+            // other strand: reverse_comp_cpy_phmm (reference inc/SequenceOperations.h:164-181)
+            const float *h = hmm + 5 * (same ? i : n - 1 - i);
+#pragma unroll
+            for (int b = 0; b < 5; ++b) {
+                float v = same ? h[b] : (b < 4 ? h[3 - b] : h[4]);
+                atomicAdd(&A.planes[b][p / P.gen_size], __fmul_rn(v, total));
+            }
+        }
+        return;
+    }
+    int alen = L.alen[s];
+    const uint8_t *al = L.aligned + (size_t)s * L.a_stride;
+    for (int i0 = 0; i0 < alen; i0 += 32) {
+        int i = i0 + lane;
+        int64_t p = (int64_t)diag + i;
+        bool ok = i < alen && p < ix.l_pac;
+        uint32_t bin = ok ? (uint32_t)(p / P.gen_size) : 0xffffffffu;
+        uint32_t peers = __match_any_sync(0xffffffffu, bin);
+        if (ok && (__ffs(peers) - 1) == lane) atomicAdd(&A.amount[bin], __fmul_rn((float)__popc(peers), total));
+        if (ok && P.mode == GMX_MODE_BS) {
+            // g_gen_CONVERSION of aligned[i] (same strand) or of reverse_comp(aligned)[i]
+            uint8_t ch = same ? al[i] : al[alen - 1 - i];
+            int code;
+            switch (ch) { case 'a': code = 0; break; case 'c': code = 1; break; case 'g': code = 2; break; case 't': code = 3; break;
+                          case 0: code = same ? 6 : 4; break; default: code = 4; break; }
+            if (!same && code < 4) code = 3 - code;
+            if (code < 5) atomicAdd(&A.planes[code][bin], total);
+        }
+    }
+}

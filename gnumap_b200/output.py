@@ -108,3 +108,29 @@ def sgr_lines(index, amount: np.ndarray, gen_size: int, min_print: float = 0.001
             for k in sel:
                 yield "%s\t%d\t%.5f" % (name, int(idx[k]) - start + 1, float(vals[k]))
             count = int(idx[-1]) + gen_size
+
+
+def gmp_rows(index, amount: np.ndarray, planes: np.ndarray, mode: int, min_print: float = 0.001):
+    """The numeric columns of the .gmp file: (chrom, 1-based pos, amount, A, C, G, T, N).
+
+    SNP mode: GenomeBwt::PrintFinalSNP (reference src/GenomeBwt.cpp:930-1003), every position with
+    amount > MIN_PRINT.  BS mode (-b, + strand): PrintFinalBisulfite (:1092-1205), positions whose
+    genome base is 'c' and amount > 0.  gen_size is 1 in both modes."""
+    codes = index.codes()
+    if mode == _abi.MODE_SNP:
+        sel = np.nonzero(amount[: index.l_pac] > np.float32(min_print))[0]
+    else:
+        sel = np.nonzero((amount[: index.l_pac] > 0) & (codes == 1))[0]
+    rid = np.searchsorted(index.seq_offset, sel, side="right") - 1
+    for p, r in zip(sel, rid):
+        yield (index.names[r], int(p) - int(index.seq_offset[r]) + 1, float(amount[p]),
+               *[float(planes[b][p]) for b in range(5)])
+
+
+def parse_gmp(path: str):
+    rows = []
+    with open(path) as f:
+        for line in f:
+            t = line.rstrip("\n").split("\t")
+            rows.append((t[0], int(t[1]), float(t[2]), *[float(x) for x in t[3:8]]))
+    return rows

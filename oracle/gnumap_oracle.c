@@ -905,18 +905,18 @@ int orc_process_batch(const gmx_index *ix, const gmx_params *pr, const gmx_reads
             res->best_first_strand = g->first_strand;
             res->best_first_pos = g->spots[0].pos;
             if (do_score) {
-                /* get_SAM, inc/ScoredSeq.h:314-372: POS uses the raw read string as consensus,
-                 * NEG the max_char consensus of the reverse-complemented PWM */
+                /* get_SAM (inc/ScoredSeq.h:314-372) re-runs the traceback for the CIGAR: NEG uses the
+                 * max_char consensus of the reverse-complemented PWM, POS the raw read string.  The
+                 * CIGAR depends only on the moves, never on the consensus characters, so the gapped
+                 * string reported here is the one score() feeds to the accumulators (max_char
+                 * consensus of the oriented PWM, src/NormalScoredSeq.cpp:40-62) for both strands. */
                 char aligned[2048], cigar[1024];
                 int alen;
-                if (g->first_strand == GMX_NEG_STRAND) {
-                    orc_revcomp_pwm(pwm, n, rpwm);
-                    for (int i = 0; i < n; ++i) rcons[i] = (uint8_t)orc_max_char(rpwm + 4 * i);
-                    rcons[n] = 0;
-                    alen = orc_nw_traceback(rpwm, n, rcons, g->sequence, n, pr->align_scores, pr->gap, pr->max_gap, aligned, sizeof(aligned), cigar, sizeof(cigar));
-                } else {
-                    alen = orc_nw_traceback(pwm, n, cons, g->sequence, n, pr->align_scores, pr->gap, pr->max_gap, aligned, sizeof(aligned), cigar, sizeof(cigar));
-                }
+                const float *opwm = pwm;
+                if (g->first_strand == GMX_NEG_STRAND) { orc_revcomp_pwm(pwm, n, rpwm); opwm = rpwm; }
+                for (int i = 0; i < n; ++i) rcons[i] = (uint8_t)orc_max_char(opwm + 4 * i);
+                rcons[n] = 0;
+                alen = orc_nw_traceback(opwm, n, rcons, g->sequence, n, pr->align_scores, pr->gap, pr->max_gap, aligned, sizeof(aligned), cigar, sizeof(cigar));
                 res->best_aligned_len = alen;
                 if (cigar[0] == 0) strcpy(cigar, "*"); else orc_fix_cigar_for_deletions(cigar);
                 if (cigar_out) { strncpy(cigar_out + (size_t)r * cigar_stride, cigar, (size_t)cigar_stride - 1); cigar_out[(size_t)r * cigar_stride + cigar_stride - 1] = 0; }

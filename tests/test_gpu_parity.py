@@ -1,0 +1,176 @@
+"""-m gpu: the CUDA path (through the C ABI) against the oracle on the same seeded inputs."""
+import numpy as np
+import pytest
+
+from gnumap_b200 import _abi, index
+from tests import common
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def api():
+    from gnumap_b200 import api as a
+    return a
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import oracle
+    return oracle
+
+
+@pytest.fixture(scope="module")
+def plain():
+    contigs, batch, reads = common.world_plain()
+    return index.build_index(contigs), batch, reads
+
+
+@pytest.fixture(scope="module")
+def repeats():
+    contigs, batch, reads = common.world_repeats()
+    return index.build_index(contigs), batch, reads
+
+
+def test_fm_search_and_locate(api, O, plain):
+    ix, batch, _ = plain
+    m = api.Mapper(ix)
+    oix = O.OracleIndex(ix)
+    rng = np.random.default_rng(3)
+    codes = ix.codes()
+    kmers = []
+    for _ in range(3000):
+        p = int(rng.integers(0, ix.l_pac - 10))
+        k = bytearray(b"acgt"[c] for c in codes[p:p + 10])
+        if rng.random() < 0.3:
+            k[int(rng.integers(0, 10))] = b"acgtn"[int(rng.integers(0, 5))]
+        kmers.append(bytes(k))
+    kmers += [b"nnnnnnnnnn", b"ACGTACGTAC", b"aaaaaaaaaa"]
+    k, l = m.get_sa_int(kmers)
+    want = np.array([oix.get_sa_int(x) for x in kmers], dtype=np.uint64)
+    assert np.array_equal(k, want[:, 0]) and np.array_equal(l, want[:, 1])
+    ranks = rng.integers(1, ix.seq_len + 1, size=5000).astype(np.uint64)
+    want_pos = np.array([oix.bwt_sa(int(r)) for r in ranks], dtype=np.uint64)
+    assert np.array_equal(m.get_sa_coord(ranks), want_pos)               # de-sampled SA
+    assert np.array_equal(m.get_sa_coord(ranks[:500], sampled=True), want_pos[:500])   # LF walk, as bwt_sa
+    assert m.get_sa_coord(np.array([0], dtype=np.uint64))[0] == np.uint64(0xFFFFFFFFFFFFFFFF)
+    m.close()
+
+
+def test_get_string(api, O, plain):
+    ix, _, _ = plain
+    m = api.Mapper(ix)
+    oix = O.OracleIndex(ix)
+    b0 = int(ix.seq_offset[1])
+    begins = [0, 5, b0 - 100, b0 - 99, b0 - 50, b0, ix.l_pac - 100, ix.l_pac - 99, ix.l_pac - 1]
+    got = m.GetString(begins, 100)
+    assert got == [oix.get_string(b, 100) for b in begins]
+    m.close()
+
+
+def test_nw_kernels_explicit_windows(api, O, plain):
+    ix, batch, reads = plain
+    params = O.default_params()
+    m = api.Mapper(ix)
+    oix = O.OracleIndex(ix)
+    rng = np.random.default_rng(4)
+    n = 300
+    ridx = rng.integers(0, batch.n_reads, size=n).astype(np.int32)
+    strands = rng.integers(0, 2, size=n).astype(np.uint8)
+    wins, want_s, want_t, want_h = [], [], [], []
+    for t in range(n):
+        r = int(ridx[t]); a, b = int(batch.offsets[r]), int(batch.offsets[r + 1])
+        pwm = O.fastq_pwm(batch.seq[a:b].tobytes(), batch.qual[a:b].tobytes())
+        if strands[t]:
+            pwm = O.revcomp_pwm(pwm)
+        p = int(reads["pos"][r]) + int(rng.integers(-3, 4))
+        w = oix.get_string(max(p, 0), b - a)
+        if len(w) != b - a:
+            w = oix.get_string(1000, b - a)
+        if t % 17 == 0:
+            w = w[:40] + b"n" + w[41:]
+        wins.append(w)
+        want_s.append(O.nw_score(pwm, w, params))
+        cons = O.max_char_consensus(pwm)
+        want_t.append(O.nw_traceback(pwm, cons, w, params))
+        if t < 60:
+            want_h.append(O.pair_hmm(pwm, cons, w, params))
+    got_s = m.get_align_score(batch, ridx, strands, wins)
+    assert np.array_equal(got_s, np.array(want_s, dtype=np.float32)), "K2a score is not bit-exact"
+    got_t = m.get_align_score_w_traceback(batch, ridx, strands, wins)
+    assert got_t == want_t
+    got_h = m.pairHMM(batch, ridx[:60], strands[:60], wins[:60])
+    want_h = np.stack(want_h)
+    assert np.allclose(got_h[:, : want_h.shape[1]], want_h, rtol=1e-5, atol=1e-7)   # K2c tolerance (float column sums)
+    assert np.array_equal(m.self_score(batch), np.array(
+        [O.self_score(O.fastq_pwm(batch.seq[batch.offsets[r]:batch.offsets[r + 1]].tobytes(), batch.qual[batch.offsets[r]:batch.offsets[r + 1]].tobytes()),
+                      batch.seq[batch.offsets[r]:batch.offsets[r + 1]].tobytes(), params) for r in range(batch.n_reads)], dtype=np.float32))
+    m.close()
+
+
+def test_reference_kats(api, O):
+    """The reference's own known-answer tests (reference src/bin_seq.cpp:1046-1215) through the CUDA path."""
+    import json, os
+    kat = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "bin_seq_kat.json")))
+    contigs, _, _ = common.world_plain(length=50_000, n_reads=4)
+    m = api.Mapper(index.build_index(contigs))
+    cons = kat["consensus"].encode()
+    batch = _abi.ReadBatch([cons], None, pwm=O.onehot_pwm(cons))
+    tb = m.get_align_score_w_traceback(batch, [0, 0], [0, 0], [kat["traceback"][0]["genome"].encode(), kat["traceback"][1]["genome"].encode()],
+                                       consensus=[cons, cons])
+    for got, want in zip(tb, kat["traceback"]):
+        assert got[0].decode() == want["aligned"] and got[1] == want["cigar"]
+    h = m.pairHMM(batch, [0], [0], [kat["phmm"]["genome"].encode()])[0]
+    assert np.all(np.abs(h - np.array(kat["phmm"]["answer"], dtype=np.float32)) < 0.01)
+    m.close()
+
+
+@pytest.mark.parametrize("mode", [_abi.MODE_NORMAL, _abi.MODE_BS, _abi.MODE_SNP])
+@pytest.mark.parametrize("world", ["plain", "repeats", "ragged"])
+def test_pipeline_matches_oracle(api, O, world, mode):
+    contigs, batch, _ = getattr(common, "world_" + world)()
+    ix = index.build_index(contigs)
+    pg = common.set_mode(api.default_params(), mode)
+    po = common.set_mode(O.default_params(), mode)
+    m = api.Mapper(ix, pg)
+    got = m.process_batch(batch)
+    amount, planes = m.finish()
+    want = O.process_batch(O.OracleIndex(ix), po, batch)
+    common.compare_batches(got, want)
+    common.accum_close(amount, want["amount"], want["hits"], batch.offsets, pg.gen_size, ix.l_pac)
+    if mode != _abi.MODE_NORMAL:
+        for b in range(5):
+            common.accum_close(planes[b], want["planes"][b], want["hits"], batch.offsets, pg.gen_size, ix.l_pac, what=f"plane {b}")
+    assert (want["results"]["status"] == _abi.READ_MAPPED).sum() > 0
+    m.close()
+
+
+def test_too_many_and_unique(api, O, repeats):
+    ix, batch, _ = repeats
+    for kw in (dict(max_matches=1), dict(unique_only=1), dict(min_seed_hits=1), dict(min_seed_hits=3, jump=3), dict(max_kmer_hits=50),
+               dict(match_neg=0), dict(match_pos=0), dict(fast=1, mer=14, jump=14), dict(perc=0, align_score=20.0), dict(cutoff=60.0)):
+        pg, po = api.default_params(), O.default_params()
+        for k, v in kw.items():
+            setattr(pg, k, v); setattr(po, k, v)
+        m = api.Mapper(ix, pg)
+        got = m.process_batch(batch)
+        amount, _ = m.finish()
+        want = O.process_batch(O.OracleIndex(ix), po, batch)
+        common.compare_batches(got, want)
+        common.accum_close(amount, want["amount"], want["hits"], batch.offsets, pg.gen_size, ix.l_pac, what=str(kw))
+        m.close()
+
+
+def test_accumulate_across_batches_and_empty(api, O, plain):
+    ix, batch, _ = plain
+    m = api.Mapper(ix)
+    empty = _abi.ReadBatch([], [])
+    assert len(m.process_batch(empty)["results"]) == 0
+    half = batch.n_reads // 2
+    m.process_batch(batch.slice(0, half)); m.process_batch(batch.slice(half, batch.n_reads))
+    amount, _ = m.finish()
+    want = O.process_batch(O.OracleIndex(ix), O.default_params(), batch)
+    assert np.allclose(amount, want["amount"], rtol=1e-5, atol=1e-6)
+    m.reset_accumulators()
+    assert not m.finish()[0].any()
+    m.close()
