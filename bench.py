@@ -1,0 +1,443 @@
+#!/usr/bin/env python
+"""bench.py -- reads/sec of the GNUMAP hot path (seed -> probabilistic NW -> posterior scatter).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one pass of the hot path over one batch of synthetic reads: at N=1 the batch is BASELINE.json
+configs[1] (synthetic 100 Mb genome, 1 M simulated 100-bp reads with Phred qualities, Normal mode);
+with N ranks every rank maps its own 1 M-read shard against its own replica of the index (weak scaling) and
+the step ends with the one collective of the path, the NCCL sum-reduce of the accumulators.
+
+Own arm (JSON keys, see DESIGN.md "Measurement"):
+  value        reads/s, inputs resident in HBM when the timed region starts (device-resident gmx_reads)
+  e2e          reads/s through the C ABI with HOST (pinned) buffers: H2D of the reads and D2H of the per-read
+               results + best CIGARs inside the timed region
+  roofline     dominant kernel: algorithmic bytes / CUDA-event time of that stage vs MEASURED_PEAKS.json
+  cpu_baseline the unmodified reference (oracle/_ref/gnumap) on a bounded sample, all host cores
+Reference arm (--impl reference): the unmodified reference on bounded samples of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import shutil
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+CACHE = os.environ.get("GMX_BENCH_CACHE", "/tmp/gnumap_b200_bench")
+MODES = {"normal": 0, "bs": 1, "snp": 2}
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# workload: i.i.d. genome seed 100, reads seed 101, 1 % substitutions, Q15..40
+# ------------------------------------------------------------------------------------------------
+def workload_name(a):
+    return f"synthetic {a.genome // 1_000_000} Mb genome, {a.reads} x {a.read_len} bp reads, {a.mode} mode (BASELINE configs[1] shape)"
+
+
+def get_index(a, device):
+    """Build (GPU suffix sort) or load the cached index, in the reference's on-disk format."""
+    from gnumap_b200 import index, synth
+    os.makedirs(CACHE, exist_ok=True)
+    prefix = os.path.join(CACHE, f"g{a.genome}_s{a.genome_seed}.fa")
+    if index.index_files_exist(prefix):
+        t = time.time()
+        ix = index.load_index(prefix)
+        log(f"[bench] index loaded from {prefix} in {time.time() - t:.1f}s")
+        return ix, prefix
+    t = time.time()
+    contigs = synth.make_genome(a.genome, a.genome_seed)
+    ix = index.build_index(contigs, device=device)
+    log(f"[bench] index built in {time.time() - t:.1f}s")
+    tmp = prefix + f".tmp{os.getpid()}"
+    index.save_index(ix, tmp)
+    for ext in (".gnumap.bwt", ".gnumap.sa", ".gnumap.pac", ".gnumap.ann", ".gnumap.amb"):
+        os.replace(tmp + ext, prefix + ext)
+    if not os.path.exists(prefix):
+        with open(prefix, "w") as f:          # the reference never opens the FASTA once the index files exist
+            f.write(">chrS\n")
+    return ix, prefix
+
+
+def get_reads(a, ix, shard: int):
+    from gnumap_b200 import synth
+    t = time.time()
+    codes = ix.codes()
+    reads = synth.simulate_reads(codes, a.reads, a.read_len, a.reads_seed + 1000 * shard, sub_rate=0.01, qlo=15, qhi=40,
+                                 bisulfite=0.95 if a.mode == "bs" else 0.0)
+    log(f"[bench] {a.reads} reads simulated in {time.time() - t:.1f}s")
+    return reads
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference on a bounded sample: P single-threaded processes of the unmodified binary
+# ------------------------------------------------------------------------------------------------
+class ReferenceRunner:
+    def __init__(self, a, prefix, reads):
+        from oracle import oracle as O
+        if not O.have_ref_binary():
+            raise RuntimeError("oracle/_ref/gnumap is missing (built by __graft_entry__.build() where /root/reference exists)")
+        self.bin = O.REF_BIN
+        self.prefix = prefix
+        self.reads = reads
+        self.a = a
+        self.cores = os.cpu_count() or 1
+        self.dir = tempfile.mkdtemp(prefix="gmx_ref_", dir=CACHE)
+        self.cursor = 0
+        self.load_s = None
+
+    def close(self):
+        shutil.rmtree(self.dir, ignore_errors=True)
+
+    def _fastq(self, path, lo, hi):
+        from gnumap_b200 import synth
+        sub = {k: v[lo:hi] for k, v in self.reads.items()}
+        synth.write_fastq(path, sub, prefix=f"r{lo}_")
+
+    def run(self, n_reads: int, procs: int | None = None):
+        """Map `n_reads` reads of the workload with `procs` concurrent `gnumap -c 1` processes (the reference deals
+        work to its own threads only in 2048-read slices, so small samples would idle a `-c N` run).  Returns
+        (seconds of mapping, reads mapped by the sample, reads in the sample)."""
+        procs = procs or self.cores
+        procs = max(1, min(procs, n_reads))
+        total = len(self.reads["pos"])
+        per = n_reads // procs
+        jobs = []
+        env = dict(os.environ, MALLOC_MMAP_THRESHOLD_="65536")
+        extra = {"normal": [], "bs": ["-b"], "snp": ["--snp"]}[self.a.mode]
+        for p in range(procs):
+            lo = self.cursor % max(total - per, 1)
+            self.cursor += per
+            fq = os.path.join(self.dir, f"s{p}.fq")
+            self._fastq(fq, lo, lo + per)
+            jobs.append((fq, os.path.join(self.dir, f"o{p}")))
+        if self.load_s is None:                       # index load + start-up, measured once on an empty read file
+            empty = os.path.join(self.dir, "empty.fq")
+            open(empty, "w").close()
+            t = time.time()
+            subprocess.run([self.bin, "-g", self.prefix, "-o", os.path.join(self.dir, "oe"), "-a", ".9", "-c", "1", *extra, empty],
+                           env=env, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            t = time.time()                           # second run: page cache warm
+            subprocess.run([self.bin, "-g", self.prefix, "-o", os.path.join(self.dir, "oe"), "-a", ".9", "-c", "1", *extra, empty],
+                           env=env, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            self.load_s = time.time() - t
+        t0 = time.time()
+        ps = [subprocess.Popen([self.bin, "-g", self.prefix, "-o", out, "-a", ".9", "-c", "1", "--no_gmp", *extra, fq], env=env,
+                               stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True) for fq, out in jobs]
+        mapped = 0
+        for p in ps:
+            outp, _ = p.communicate()
+            if p.returncode != 0:
+                raise RuntimeError(f"reference run failed ({p.returncode}): {outp[-500:]}")
+            for line in outp.splitlines():
+                if "equences matched" in line or "Sequences Matched" in line:
+                    pass
+        wall = time.time() - t0
+        # matched reads = SAM records' distinct read names
+        for _, out in jobs:
+            sam = out + ".sam"
+            if os.path.exists(sam):
+                names = set()
+                with open(sam) as f:
+                    for ln in f:
+                        if ln and ln[0] != "@":
+                            names.add(ln.split("\t", 1)[0])
+                mapped += len(names)
+        return max(wall - self.load_s, 1e-6), mapped, per * procs, procs
+
+
+def reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    dev = "cuda" if torch.cuda.is_available() else "cpu"
+    ix, prefix = get_index(a, dev)
+    reads = get_reads(a, ix, 0)
+    rr = ReferenceRunner(a, prefix, reads)
+    try:
+        budget_s = float(os.environ.get("GMX_REF_BUDGET_S", "150"))
+        t, _, n, procs = rr.run(max(rr.cores * 8, 64))            # calibration (always untimed)
+        rate = n / t
+        per_step = max(int(rate * budget_s / max(a.steps + a.warmup, 1)), rr.cores)
+        per_step = min(per_step, a.reads)
+        log(f"[bench] reference calibration: {rate:.1f} reads/s on {procs} processes; {per_step} reads per step")
+        for _ in range(a.warmup):
+            rr.run(per_step)
+        times, done, mapped = [], 0, 0
+        for _ in range(a.steps):
+            t, m, n, procs = rr.run(per_step)
+            times.append(t); done += n; mapped += m
+        total = sum(times)
+        value = done / total
+        sample = f"{done // a.steps} reads per step ({procs} concurrent `gnumap -c 1` processes, index pre-built, start-up {rr.load_s:.2f}s subtracted)"
+        line = {
+            "metric": "reads/sec (probabilistic-NW mapping)", "value": value, "unit": "reads/s", "impl": "reference",
+            "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * total / a.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(a), "sample": sample, "mapped_fraction": mapped / max(done, 1)},
+            "cpu_baseline": {"value": value, "unit": "reads/s", "cores": procs, "kind": "reference", "sample": sample},
+            "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }
+        print(json.dumps(line), flush=True)
+    finally:
+        rr.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# own arm
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index: int):
+        self.path = tempfile.mktemp(prefix="gmx_clocks_", suffix=".csv")
+        self.f = open(self.path, "w")
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p:
+            self.p.terminate()
+            try:
+                self.p.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.p.kill()
+        self.f.close()
+        sm, mx, reasons = [], 0.0, set()
+        try:
+            for ln in open(self.path):
+                parts = [x.strip() for x in ln.split(",")]
+                if len(parts) < 7:
+                    continue
+                try:
+                    sm.append(float(parts[0])); mx = max(mx, float(parts[1]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except OSError:
+            pass
+        busy = [x for x in sm if x >= 0.5 * max(sm)] if sm else []
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def own_arm(a):
+    import torch
+    import torch.distributed as dist
+    from gnumap_b200 import _abi, api
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: gnumap_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # index: rank 0 builds and caches it, the others load the cache
+    if rank == 0:
+        ix, prefix = get_index(a, dev)
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        ix, prefix = get_index(a, dev)
+    reads = get_reads(a, ix, rank)
+
+    params = api.default_params()
+    params.mode = MODES[a.mode]
+    if a.mode != "normal":
+        params.gen_size = 1
+    if a.mode == "bs":
+        params.align_scores[ord("c")][3] = params.align_scores[ord("a")][0]
+    t = time.time()
+    m = api.Mapper(ix, params, device=local)
+    m.synchronize()
+    log(f"[bench] context created (index upload + SA de-sampling) in {time.time() - t:.1f}s")
+    m.set_option(api.OPT_COLLECT_HITS, 0)
+    stream = torch.cuda.Stream(device=dev)
+    m.set_stream(stream.cuda_stream)
+
+    n, L = a.reads, a.read_len
+    # host (pinned) batch for the end-to-end leg
+    seq_h = torch.from_numpy(np.frombuffer(b"ACGTN", dtype=np.uint8)[reads["bases"]].reshape(-1).copy()).pin_memory()
+    qual_h = torch.from_numpy((reads["quals"].astype(np.uint8) + 33).reshape(-1).copy()).pin_memory()
+    off_h = torch.from_numpy(np.arange(n + 1, dtype=np.int64) * L).pin_memory()
+    res_h = torch.zeros(n * _abi.READ_RESULT_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+    res_np = res_h.numpy().view(_abi.READ_RESULT_DTYPE)
+
+    class Batch:
+        def __init__(self, off, seq, qual, on_device):
+            s = _abi.GmxReads()
+            s.n_reads = n; s.offsets = off.data_ptr(); s.seq = seq.data_ptr(); s.qual = qual.data_ptr(); s.pwm = None
+            s.on_device = on_device; s.max_len = L
+            self.struct = s; self.n_reads = n; self.keep = (off, seq, qual)
+
+    host_batch = Batch(off_h, seq_h, qual_h, 0)
+    dev_batch = Batch(off_h.to(dev), seq_h.to(dev), qual_h.to(dev), 1)
+
+    # accumulators as torch tensors (for the NCCL reduce)
+    amount_ptr, n_amount, plane_ptrs, n_plane = m.accumulators_device()
+
+    class _Arr:
+        def __init__(self, ptr, n_el):
+            self.__cuda_array_interface__ = {"shape": (n_el,), "typestr": "<f4", "data": (ptr, False), "version": 3, "strides": None}
+
+    acc = [torch.as_tensor(_Arr(amount_ptr, n_amount), device=dev)]
+    if n_plane:
+        acc.append(torch.as_tensor(_Arr(plane_ptrs[0], 5 * n_plane), device=dev))
+
+    def step(batch):
+        m.process_batch(batch, fetch=False, results=res_np)
+        if world > 1:
+            with torch.cuda.stream(stream):
+                for t_ in acc:
+                    dist.all_reduce(t_)      # ncclAllReduce(sum, f32): reference src/Driver.cpp:1672,1719-1767
+
+    def timed(batch, steps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        stage_ms, stage_units, stage_bytes, stage_launch = {}, {}, {}, {}
+        e0.record(stream)
+        t0 = time.time()
+        for _ in range(steps):
+            step(batch)
+            for k, v in m.stage_stats().items():
+                stage_ms[k] = stage_ms.get(k, 0.0) + v["ms"]; stage_units[k] = stage_units.get(k, 0) + v["units"]
+                stage_bytes[k] = stage_bytes.get(k, 0) + v["bytes"]; stage_launch[k] = stage_launch.get(k, 0) + v["launches"]
+        e1.record(stream)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = max(e0.elapsed_time(e1), 0.0)
+        wall_ms = (time.time() - t0) * 1e3
+        ms = max(ms, wall_ms) if a.wall else ms
+        if world > 1:
+            tt = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt.item())
+        return ms, wall_ms, dict(ms=stage_ms, units=stage_units, bytes=stage_bytes, launches=stage_launch)
+
+    for _ in range(a.warmup):
+        step(dev_batch)
+    for _ in range(max(a.warmup // 2, 1)):
+        step(host_batch)
+    m.reset_accumulators()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms_dev, wall_dev, st = timed(dev_batch, a.steps)
+    clocks = sampler.stop() if sampler else None
+    ms_e2e, wall_e2e, _ = timed(host_batch, a.steps)
+    mapped = int((res_np["status"] == 0).sum())
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        # dominant stage by CUDA-event time
+        kstages = [k for k in st["ms"] if k not in ("upload", "download") and st["launches"].get(k, 0) > 0]
+        top = max(kstages, key=lambda k: st["ms"][k])
+        launches = st["launches"][top]
+        achieved = st["bytes"][top] / (st["ms"][top] * 1e-3) / 1e9 if st["ms"][top] > 0 else 0.0
+        roofline = {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": None, "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback",
+                    "algorithmic_bytes_per_step": st["bytes"][top] / a.steps, "ms_per_step": st["ms"][top] / a.steps,
+                    "launches_per_step": launches / a.steps,
+                    "stages_ms_per_step": {k: round(v / a.steps, 3) for k, v in st["ms"].items()},
+                    "stages_units_per_step": {k: v // a.steps for k, v in st["units"].items()}}
+        nw_cells = st["units"].get("nw_score", 0)
+        gcups = nw_cells / (st["ms"]["nw_score"] * 1e-3) / 1e9 if st["ms"].get("nw_score", 0) > 0 else None
+        cpu = None
+        if not a.no_cpu:
+            try:
+                rr = ReferenceRunner(a, prefix, reads)
+                try:
+                    t, _, nn, procs = rr.run(max(rr.cores * 4, 32))
+                    rate = nn / t
+                    nn2 = min(max(int(rate * float(os.environ.get("GMX_CPU_BASELINE_S", "20"))), rr.cores), a.reads)
+                    t, mp, nn2, procs = rr.run(nn2)
+                    cpu = {"value": nn2 / t, "unit": "reads/s", "cores": procs, "kind": "reference",
+                           "sample": f"{nn2} reads of the same workload ({procs} concurrent `gnumap -c 1` processes of the unmodified reference, "
+                                     f"index pre-built, start-up {rr.load_s:.2f}s subtracted), mapped fraction {mp / max(nn2, 1):.3f}"}
+                finally:
+                    rr.close()
+            except Exception as e:  # the baseline is reported, never required
+                cpu = {"value": None, "unit": "reads/s", "cores": 0, "kind": "reference", "sample": f"unavailable: {e}"}
+        total_reads = n * world * a.steps
+        line = {
+            "metric": "reads/sec (probabilistic-NW mapping)", "value": total_reads / (ms_dev * 1e-3), "unit": "reads/s",
+            "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_dev / a.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(a), "reads_per_gpu_per_step": n, "l2": "inputs_exceed_l2 (reads 200 MB + suffix array 400 MB per step)",
+                       "collective": "ncclAllReduce(sum,f32) of the accumulators every step" if world > 1 else "none (1 GPU)",
+                       "mapped_fraction": mapped / n, "nw_gcups": gcups},
+            "clocks": clocks,
+            "e2e": {"value": total_reads / (ms_e2e * 1e-3), "unit": "reads/s", "h2d_bytes_per_step": int(2 * n * L + 8 * (n + 1)),
+                    "d2h_bytes_per_step": int(n * (_abi.READ_RESULT_DTYPE.itemsize + 64)), "ms_per_step": ms_e2e / a.steps},
+            "gpu_launches": int(sum(st["launches"].values())),
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    m.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--genome", type=int, default=100_000_000)
+    ap.add_argument("--reads", type=int, default=1_000_000)
+    ap.add_argument("--read-len", type=int, default=100)
+    ap.add_argument("--mode", default="normal", choices=list(MODES))
+    ap.add_argument("--genome-seed", type=int, default=100)
+    ap.add_argument("--reads-seed", type=int, default=101)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--wall", action="store_true", help="use max(event, wall) time")
+    a = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if a.impl == "reference":
+        return reference_arm(a)
+    if world == 1 and a.gpus > 1:
+        # convenience: re-launch under torchrun
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={a.gpus}", "--master-addr", "127.0.0.1",
+               "--master-port", "29517", os.path.abspath(__file__), *sys.argv[1:]]
+        raise SystemExit(subprocess.call(cmd))
+    import __graft_entry__ as g
+    if int(os.environ.get("LOCAL_RANK", "0")) == 0:
+        g.build()
+    own_arm(a)
+
+
+if __name__ == "__main__":
+    main()

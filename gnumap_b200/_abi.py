@@ -39,7 +39,7 @@ class GmxParams(C.Structure):
 
 class GmxReads(C.Structure):
     _fields_ = [("n_reads", C.c_int32), ("offsets", C.c_void_p), ("seq", C.c_void_p),
-                ("qual", C.c_void_p), ("pwm", C.c_void_p)]
+                ("qual", C.c_void_p), ("pwm", C.c_void_p), ("on_device", C.c_int32), ("max_len", C.c_int32)]
 
 
 class GmxStageStats(C.Structure):

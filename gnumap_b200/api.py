@@ -32,8 +32,10 @@ EXPORTS = [
     "gmx_set_stream", "gmx_synchronize", "gmx_fm_search", "gmx_sa_locate", "gmx_get_windows", "gmx_self_score",
     "gmx_nw_score", "gmx_nw_traceback", "gmx_pair_hmm", "gmx_map_batch", "gmx_score_batch", "gmx_process_batch",
     "gmx_get_hits", "gmx_get_best_alignments", "gmx_accumulators_device", "gmx_reset_accumulators", "gmx_finish",
-    "gmx_get_stage_stats",
+    "gmx_get_stage_stats", "gmx_set_option",
 ]
+
+OPT_COLLECT_HITS, OPT_CHUNK_READS = 1, 2
 
 
 class GmxError(RuntimeError):
@@ -75,6 +77,7 @@ def load_library():
         L.gmx_reset_accumulators.argtypes = [C.c_void_p]
         L.gmx_finish.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.gmx_get_stage_stats.argtypes = [C.c_void_p, C.c_void_p]
+        L.gmx_set_option.argtypes = [C.c_void_p, C.c_int, C.c_int64]
         _lib = L
     return _lib
 
@@ -120,6 +123,9 @@ class Mapper:
 
     def set_stream(self, cuda_stream: int):
         self._ck(self.L.gmx_set_stream(self._ctx, C.c_void_p(cuda_stream)), "gmx_set_stream")
+
+    def set_option(self, option: int, value: int):
+        self._ck(self.L.gmx_set_option(self._ctx, option, value), "gmx_set_option")
 
     def synchronize(self):
         self._ck(self.L.gmx_synchronize(self._ctx), "gmx_synchronize")
@@ -187,25 +193,42 @@ class Mapper:
         return out
 
     # -- batch pipeline -----------------------------------------------------------------------
-    def process_batch(self, batch: ReadBatch, score: bool = True, fetch: bool = True):
-        """PHASE A (+ PHASE B).  Returns dict(results, hits, cigars, aligned)."""
-        results = np.zeros(batch.n_reads, dtype=READ_RESULT_DTYPE)
-        fn = self.L.gmx_process_batch if score else self.L.gmx_map_batch
-        self._ck(fn(self._ctx, C.addressof(batch.struct), ptr(results)), "gmx_process_batch")
-        out = dict(results=results)
-        if fetch:
-            n = C.c_int64(0)
-            self._ck(self.L.gmx_get_hits(self._ctx, None, 0, C.byref(n)), "gmx_get_hits")
-            hits = np.zeros(max(n.value, 1), dtype=HIT_DTYPE)
-            self._ck(self.L.gmx_get_hits(self._ctx, ptr(hits), len(hits), C.byref(n)), "gmx_get_hits")
-            out["hits"] = hits[: n.value]
-            if score:
-                cs, as_ = 64, 512
-                cig = np.zeros((batch.n_reads, cs), dtype=np.uint8); al = np.zeros((batch.n_reads, as_), dtype=np.uint8)
-                self._ck(self.L.gmx_get_best_alignments(self._ctx, ptr(cig), cs, ptr(al), as_), "gmx_get_best_alignments")
-                out["cigars"] = [bytes(r).split(b"\0")[0].decode() for r in cig]
-                out["aligned"] = al
+    def _fetch(self, batch, out, scored: bool):
+        n = C.c_int64(0)
+        self._ck(self.L.gmx_get_hits(self._ctx, None, 0, C.byref(n)), "gmx_get_hits")
+        hits = np.zeros(max(n.value, 1), dtype=HIT_DTYPE)
+        self._ck(self.L.gmx_get_hits(self._ctx, ptr(hits), len(hits), C.byref(n)), "gmx_get_hits")
+        out["hits"] = hits[: n.value]
+        if scored:
+            cs, as_ = 64, 512
+            cig = np.zeros((batch.n_reads, cs), dtype=np.uint8); al = np.zeros((batch.n_reads, as_), dtype=np.uint8)
+            self._ck(self.L.gmx_get_best_alignments(self._ctx, ptr(cig), cs, ptr(al), as_), "gmx_get_best_alignments")
+            out["cigars"] = [bytes(r).split(b"\0")[0].decode() for r in cig]
+            out["aligned"] = al
         return out
+
+    def process_batch(self, batch, score: bool = True, fetch: bool = True, results: np.ndarray | None = None):
+        """PHASE A (+ PHASE B).  Returns dict(results, hits, cigars, aligned).  `batch` is a host ReadBatch or any
+        object with a `.struct` gmx_reads (e.g. DeviceReadBatch); `results` may be a caller-owned (pinned) array."""
+        if results is None:
+            results = np.zeros(batch.n_reads, dtype=READ_RESULT_DTYPE)
+        fn = self.L.gmx_process_batch if score else self.L.gmx_map_batch
+        self._ck(fn(self._ctx, C.addressof(batch.struct), C.c_void_p(results.ctypes.data)), "gmx_process_batch" if score else "gmx_map_batch")
+        out = dict(results=results)
+        return self._fetch(batch, out, score) if fetch else out
+
+    def score_batch(self, batch, results: np.ndarray | None = None, fetch: bool = True):
+        """PHASE B for the batch last passed to process_batch(score=False) (gmx_map_batch)."""
+        if results is None:
+            results = np.zeros(batch.n_reads, dtype=READ_RESULT_DTYPE)
+        self._ck(self.L.gmx_score_batch(self._ctx, C.c_void_p(results.ctypes.data)), "gmx_score_batch")
+        out = dict(results=results)
+        return self._fetch(batch, out, True) if fetch else out
+
+    def best_cigars(self, n_reads: int, stride: int = 64) -> np.ndarray:
+        cig = np.zeros((n_reads, stride), dtype=np.uint8)
+        self._ck(self.L.gmx_get_best_alignments(self._ctx, ptr(cig), stride, None, 0), "gmx_get_best_alignments")
+        return cig
 
     def accumulators_device(self):
         amount = C.c_void_p(); n_amount = C.c_uint64(); planes = (C.c_void_p * 5)(); n_plane = C.c_uint64()

@@ -71,12 +71,13 @@ __device__ __forceinline__ uint64_t gmx_bwt_sa_sampled(const DevIndex &ix, uint6
 // bwt_match_exact (reference src/bwt.c:222-239) with the symbols supplied by `sym(i)`, i in [0,len).
 // Returns true and the inclusive interval [k,l] on a hit.
 template <class SymFn>
-__device__ __forceinline__ bool gmx_match_exact(const DevIndex &ix, int len, SymFn sym, uint64_t &k_out, uint64_t &l_out)
+__device__ __forceinline__ bool gmx_match_exact(const DevIndex &ix, int len, SymFn sym, uint64_t &k_out, uint64_t &l_out, uint32_t &n_steps)
 {
     uint64_t k = 0, l = ix.seq_len;
     for (int i = len - 1; i >= 0; --i) {
         uint32_t c = sym(i);
         if (c > 3) return false;
+        n_steps++;
         uint64_t ok = gmx_bwt_occ(ix, k - 1, c);
         uint64_t ol = gmx_bwt_occ(ix, l, c);
         k = ix.L2[c] + ok + 1;
@@ -96,7 +97,8 @@ __global__ void k_fm_search(DevIndex ix, const uint8_t *kmers, int len, int64_t 
     if (t >= n) return;
     const uint8_t *s = kmers + t * len;
     uint64_t k = 0, l = 0;
-    bool hit = gmx_match_exact(ix, len, [&](int i) { uint8_t ch = s[i]; return (uint32_t)(ch < 4 ? ch : gmx_nt4(ch)); }, k, l);
+    uint32_t steps = 0;
+    bool hit = gmx_match_exact(ix, len, [&](int i) { uint8_t ch = s[i]; return (uint32_t)(ch < 4 ? ch : gmx_nt4(ch)); }, k, l, steps);
     k_out[t] = hit ? k : 0;
     l_out[t] = hit ? l : 0;
 }

@@ -34,6 +34,25 @@ struct DevBuf {
     template <class T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
+struct HostBuf {                                   // pinned host staging
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+#define GMX_CIGAR_STRIDE 64
+
 enum Stage { ST_UPLOAD = 0, ST_PREP, ST_SEED, ST_CLASSIFY, ST_VOTE, ST_SORT, ST_NW, ST_FINALIZE, ST_TRACEBACK, ST_PHMM, ST_SCATTER, ST_DOWNLOAD, ST_COUNT };
 static const char *kStageNames[ST_COUNT] = {"upload", "prep_reads", "seed_walk", "classify", "locate_vote", "sort_candidates",
                                             "nw_score", "finalize_reads", "nw_traceback", "pair_hmm", "scatter", "download"};
@@ -67,14 +86,18 @@ struct gmx_ctx {
     int32_t last_max_len = 0;
     std::vector<gmx_read_result> h_results;
     std::vector<gmx_hit> h_hits;
-    std::vector<char> h_best_cigar;            // [n_reads][64]
-    std::vector<uint8_t> h_best_aligned;       // [n_reads][a_stride]
+    HostBuf h_best_cigar;                      // pinned [n_reads][GMX_CIGAR_STRIDE]
+    std::vector<uint8_t> h_best_aligned;       // [n_reads][a_stride]  (collect_hits only)
     int h_a_stride = 0;
-    // per-chunk device->host staging kept for score_batch when map and score are split
+    // state of the chunk whose PHASE A results are resident on the device
     struct ChunkState {
-        int32_t read_lo = 0, n_reads = 0, max_len = 0;
-        uint32_t n_cand = 0;
-    };
+        bool valid = false;
+        int32_t lo = 0, n = 0, max_len = 0;
+        int64_t total_bases = 0;
+        uint32_t n_cand = 0, n_leaders = 0, n_accepted = 0;
+        unsigned long long *keys = nullptr;    // sorted candidate keys (d_keys or d_keys_alt)
+        LeaderStore L;
+    } cs;
     // instrumentation
     cudaEvent_t ev[ST_COUNT][2];
     bool ev_used[ST_COUNT];
@@ -83,6 +106,12 @@ struct gmx_ctx {
     int32_t stage_launches[ST_COUNT];
     std::string err;
     size_t chunk_reads = 1 << 18;
+    bool collect_hits = true;
+    int n_sm = 148;
+    DevBuf d_best_cigar;
+    // input of the last multi-chunk gmx_map_batch (gmx_score_batch re-runs the batch from it)
+    gmx_reads keep; bool keep_valid = false;
+    std::vector<int64_t> keep_offsets; std::vector<uint8_t> keep_seq, keep_qual; std::vector<float> keep_pwm;
 };
 
 #define CK(call)                                                                                     \
@@ -269,6 +298,7 @@ extern "C" int gmx_create(gmx_ctx **out, const gmx_index *index, const gmx_param
     ctx->own_stream = true;
     for (int s = 0; s < ST_COUNT; ++s) { CK(cudaEventCreate(&ctx->ev[s][0])); CK(cudaEventCreate(&ctx->ev[s][1])); }
     stage_reset(ctx);
+    cudaDeviceGetAttribute(&ctx->n_sm, cudaDevAttrMultiProcessorCount, device);
 
     DevParams &dp = ctx->dparams;
     dp.gap = params->gap; dp.align_score = params->align_score; dp.cutoff = params->cutoff; dp.max_gap = params->max_gap;
@@ -335,8 +365,9 @@ extern "C" void gmx_destroy(gmx_ctx *ctx)
                       &ctx->d_seed_count, &ctx->d_seed_off, &ctx->d_seed_n, &ctx->d_seed_hits, &ctx->d_cls_list, &ctx->d_cls_meta,
                       &ctx->d_keys, &ctx->d_keys_alt, &ctx->d_sort_tmp, &ctx->d_score, &ctx->d_leader, &ctx->d_slot, &ctx->d_lead_cand,
                       &ctx->d_hashes, &ctx->d_expv, &ctx->d_counters, &ctx->d_results, &ctx->d_alen, &ctx->d_aligned, &ctx->d_cigar,
-                      &ctx->d_hmm, &ctx->d_moves, &ctx->d_arena, &ctx->d_phmm_scratch};
+                      &ctx->d_hmm, &ctx->d_moves, &ctx->d_arena, &ctx->d_phmm_scratch, &ctx->d_best_cigar};
     for (DevBuf *b : bufs) b->release();
+    ctx->h_best_cigar.release();
     if (ctx->ev[0][0]) for (int s = 0; s < ST_COUNT; ++s) { cudaEventDestroy(ctx->ev[s][0]); cudaEventDestroy(ctx->ev[s][1]); }
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -394,36 +425,53 @@ extern "C" int gmx_finish(gmx_ctx *ctx, float *amount_genome, float *const plane
 // ------------------------------------------------------------------------------------------------
 // reads upload
 // ------------------------------------------------------------------------------------------------
+static int scan_max_len(gmx_ctx *ctx, const gmx_reads *reads, int32_t lo, int32_t hi, int32_t *max_len_out)
+{
+    int32_t max_len = reads->max_len;
+    if (!reads->on_device) {
+        max_len = 0;
+        for (int32_t i = lo; i < hi; ++i) max_len = std::max<int32_t>(max_len, (int32_t)(reads->offsets[i + 1] - reads->offsets[i]));
+    } else if (max_len <= 0) { ctx->err = "device-resident gmx_reads need max_len"; return GMX_ERR_INVALID; }
+    if (max_len > GMX_MAX_READ_LEN) { ctx->err = "read longer than GMX_MAX_READ_LEN"; return GMX_ERR_UNSUPPORTED; }
+    *max_len_out = max_len;
+    return GMX_OK;
+}
+
+// Make reads [lo, hi) visible to the kernels.  Offsets stay absolute (relative to the start of the
+// batch's seq/qual arrays); for host batches only the chunk's slice is copied and the device base
+// pointers are biased so that the same offsets index it.
 static int upload_reads(gmx_ctx *ctx, const gmx_reads *reads, int32_t lo, int32_t hi, int32_t *max_len_out)
 {
     int32_t n = hi - lo;
-    int64_t base = reads->offsets[lo], total = reads->offsets[hi] - base;
-    std::vector<int64_t> offs((size_t)n + 1);
-    int32_t max_len = 0;
-    for (int32_t i = 0; i <= n; ++i) offs[i] = reads->offsets[lo + i] - base;
-    for (int32_t i = 0; i < n; ++i) max_len = std::max<int32_t>(max_len, (int32_t)(offs[i + 1] - offs[i]));
-    if (max_len > GMX_MAX_READ_LEN) { ctx->err = "read longer than GMX_MAX_READ_LEN"; return GMX_ERR_UNSUPPORTED; }
     if (!reads->seq) { ctx->err = "gmx_reads.seq is required (the consensus string for raw-PWM reads)"; return GMX_ERR_INVALID; }
     if (!reads->qual && !reads->pwm) { ctx->err = "gmx_reads needs qual or pwm"; return GMX_ERR_INVALID; }
-    CK(ctx->d_offsets.ensure(((size_t)n + 1) * 8));
-    CK(ctx->d_seq.ensure((size_t)total + 16));
-    CK(cudaMemcpyAsync(ctx->d_offsets.p, offs.data(), ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->d_seq.p, reads->seq + base, (size_t)total, cudaMemcpyHostToDevice, ctx->stream));
-    ctx->dreads.qual = nullptr; ctx->dreads.pwm = nullptr;
-    if (reads->qual) {
-        CK(ctx->d_qual.ensure((size_t)total + 16));
-        CK(cudaMemcpyAsync(ctx->d_qual.p, reads->qual + base, (size_t)total, cudaMemcpyHostToDevice, ctx->stream));
-        ctx->dreads.qual = ctx->d_qual.as<uint8_t>();
-    }
-    if (reads->pwm) {
-        CK(ctx->d_pwm.ensure((size_t)total * 16 + 16));
-        CK(cudaMemcpyAsync(ctx->d_pwm.p, reads->pwm + 4 * base, (size_t)total * 16, cudaMemcpyHostToDevice, ctx->stream));
-        ctx->dreads.pwm = ctx->d_pwm.as<float>();
-    }
-    CK(cudaStreamSynchronize(ctx->stream));        // offs is a stack-lifetime staging vector
-    ctx->dreads.offsets = ctx->d_offsets.as<int64_t>();
-    ctx->dreads.seq = ctx->d_seq.as<uint8_t>();
+    int32_t max_len = 0;
+    int r = scan_max_len(ctx, reads, lo, hi, &max_len);
+    if (r != GMX_OK) return r;
     ctx->dreads.n_reads = n; ctx->dreads.qbase = ctx->params.illumina ? 64 : 33;
+    ctx->dreads.qual = nullptr; ctx->dreads.pwm = nullptr;
+    if (reads->on_device) {
+        ctx->dreads.offsets = reads->offsets + lo;
+        ctx->dreads.seq = reads->seq; ctx->dreads.qual = reads->qual; ctx->dreads.pwm = reads->pwm;
+    } else {
+        int64_t base = reads->offsets[lo], total = reads->offsets[hi] - base;
+        CK(ctx->d_offsets.ensure(((size_t)n + 1) * 8));
+        CK(ctx->d_seq.ensure((size_t)total + 16));
+        CK(cudaMemcpyAsync(ctx->d_offsets.p, reads->offsets + lo, ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->d_seq.p, reads->seq + base, (size_t)total, cudaMemcpyHostToDevice, ctx->stream));
+        ctx->dreads.offsets = ctx->d_offsets.as<int64_t>();
+        ctx->dreads.seq = ctx->d_seq.as<uint8_t>() - base;
+        if (reads->qual) {
+            CK(ctx->d_qual.ensure((size_t)total + 16));
+            CK(cudaMemcpyAsync(ctx->d_qual.p, reads->qual + base, (size_t)total, cudaMemcpyHostToDevice, ctx->stream));
+            ctx->dreads.qual = ctx->d_qual.as<uint8_t>() - base;
+        }
+        if (reads->pwm) {
+            CK(ctx->d_pwm.ensure((size_t)total * 16 + 16));
+            CK(cudaMemcpyAsync(ctx->d_pwm.p, reads->pwm + 4 * base, (size_t)total * 16, cudaMemcpyHostToDevice, ctx->stream));
+            ctx->dreads.pwm = ctx->d_pwm.as<float>() - 4 * base;
+        }
+    }
     if (max_len_out) *max_len_out = max_len;
     return GMX_OK;
 }
@@ -627,10 +675,13 @@ extern "C" int gmx_pair_hmm(gmx_ctx *ctx, const gmx_reads *reads, int64_t n_task
 // ------------------------------------------------------------------------------------------------
 // batch pipeline
 // ------------------------------------------------------------------------------------------------
-struct Counters {            // device-resident scalars, one small allocation
+struct Counters {            // device-resident scalars, reset before every vote attempt
     uint32_t n_cand, cand_overflow, n_leaders, n_accepted, arena_overflow, pad[3];
     unsigned long long arena_used;
     uint32_t cls_count[GMX_N_CLASSES], cls_cursor[GMX_N_CLASSES];
+};
+struct ChunkStats {          // device-resident, reset once per chunk: lookups, search steps, SA hits
+    unsigned long long v[4];
 };
 
 template <int SL, int WARPS>
@@ -647,20 +698,22 @@ static cudaError_t launch_vote(gmx_ctx *ctx, const SeedStore &S, const ClassList
     return cudaGetLastError();
 }
 
-// Runs PHASE A (and PHASE B when do_score) for reads [lo, hi) of the batch.
-static int run_chunk(gmx_ctx *ctx, const gmx_reads *reads, int32_t lo, int32_t hi, bool do_score, gmx_read_result *results_out)
+// PHASE A for reads [lo, hi) of the batch; leaves its results resident on the device (ctx->cs).
+static int phase_a(gmx_ctx *ctx, const gmx_reads *reads, int32_t lo, int32_t hi)
 {
+    gmx_ctx::ChunkState &cs = ctx->cs;
+    cs.valid = false;
     const int32_t n = hi - lo;
     const int64_t n_tasks = 2 * (int64_t)n;
     int32_t max_len = 0;
-    int n_sm = 148;
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device);
+    const int n_sm = ctx->n_sm;
 
     stage_begin(ctx, ST_UPLOAD);
     int r = upload_reads(ctx, reads, lo, hi, &max_len);
     if (r != GMX_OK) return r;
-    int64_t total_bases = reads->offsets[hi] - reads->offsets[lo];
-    stage_end(ctx, ST_UPLOAD, (uint64_t)n, (uint64_t)total_bases * (reads->qual ? 2 : 1) + (reads->pwm ? 16ull * total_bases : 0), 0);
+    int64_t total_bases = reads->on_device ? (int64_t)n * max_len : reads->offsets[hi] - reads->offsets[lo];
+    uint64_t up_bytes = reads->on_device ? 0 : (uint64_t)total_bases * (reads->qual ? 2 : 1) + (reads->pwm ? 16ull * total_bases : 0) + 8ull * n;
+    stage_end(ctx, ST_UPLOAD, (uint64_t)n, up_bytes, 0);
     ctx->last_max_len = std::max(ctx->last_max_len, max_len);
 
     const DevParams &P = ctx->dparams;
@@ -676,11 +729,12 @@ static int run_chunk(gmx_ctx *ctx, const gmx_reads *reads, int32_t lo, int32_t h
     CK(ctx->d_seed_n.ensure((size_t)n_tasks));
     CK(ctx->d_seed_hits.ensure((size_t)n_tasks * 4));
     CK(ctx->d_cls_list.ensure((size_t)GMX_N_CLASSES * n_tasks * 4));
-    CK(ctx->d_counters.ensure(sizeof(Counters)));
+    CK(ctx->d_counters.ensure(sizeof(Counters) + sizeof(ChunkStats)));
     CK(ctx->d_results.ensure((size_t)n * sizeof(gmx_read_result)));
     if (ctx->cand_cap == 0) ctx->cand_cap = std::max<size_t>(1 << 16, (size_t)n * 16);
 
     Counters *dc = ctx->d_counters.as<Counters>();
+    ChunkStats *ds = reinterpret_cast<ChunkStats *>(dc + 1);
     SeedStore S;
     S.rank = ctx->d_seed_rank.as<uint32_t>(); S.count = ctx->d_seed_count.as<uint32_t>(); S.offset = ctx->d_seed_off.as<uint16_t>();
     S.n_seeds = ctx->d_seed_n.as<uint8_t>(); S.hits = ctx->d_seed_hits.as<uint32_t>(); S.max_seeds = max_seeds; S.n_tasks = n_tasks;
@@ -689,17 +743,18 @@ static int run_chunk(gmx_ctx *ctx, const gmx_reads *reads, int32_t lo, int32_t h
 
     // a3 + status
     stage_begin(ctx, ST_PREP);
+    CK(cudaMemsetAsync(ds, 0, sizeof(ChunkStats), ctx->stream));
     k_prep_reads<<<nblk(n, 128), 128, 0, ctx->stream>>>(ctx->dreads, ctx->tab, P, ctx->d_prep.as<ReadPrep>());
     CK(cudaGetLastError());
     stage_end(ctx, ST_PREP, (uint64_t)n, (uint64_t)total_bases * 2, 1);
 
     // K1: k-mer walk + backward search
     stage_begin(ctx, ST_SEED);
-    k_seed_walk<<<nblk(n_tasks, 128), 128, 0, ctx->stream>>>(ctx->ix, ctx->dreads, P, ctx->d_prep.as<ReadPrep>(), S);
+    k_seed_walk<<<nblk(n_tasks, 128), 128, 0, ctx->stream>>>(ctx->ix, ctx->dreads, P, ctx->d_prep.as<ReadPrep>(), S, ds->v);
     CK(cudaGetLastError());
     stage_end(ctx, ST_SEED, 0, 0, 1);
 
-    Counters hc;
+    struct { Counters c; ChunkStats s; } hc;
     uint32_t n_cand = 0;
     for (int attempt = 0;; ++attempt) {
         CK(cudaMemsetAsync(dc, 0, sizeof(Counters), ctx->stream));
@@ -725,29 +780,28 @@ static int run_chunk(gmx_ctx *ctx, const gmx_reads *reads, int32_t lo, int32_t h
             CK(cudaGetLastError());
         }
         stage_end(ctx, ST_VOTE, 0, 0, 6);
-        CK(cudaMemcpyAsync(&hc, dc, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(&hc, dc, sizeof(hc), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         stage_collect(ctx);
-        if (hc.arena_overflow) {
+        if (hc.c.arena_overflow) {
             if (attempt >= 4) { ctx->err = "global vote-table arena overflow"; return GMX_ERR_OVERFLOW; }
             size_t want = ctx->d_arena.cap * 4;
             ctx->d_arena.release();
             CK(ctx->d_arena.ensure(want));
             continue;
         }
-        if (hc.cand_overflow || hc.n_cand > ctx->cand_cap) {
+        if (hc.c.cand_overflow || hc.c.n_cand > ctx->cand_cap) {
             if (attempt >= 6) { ctx->err = "candidate list overflow"; return GMX_ERR_OVERFLOW; }
-            ctx->cand_cap = std::max<size_t>(ctx->cand_cap * 2, (size_t)hc.n_cand + 1024);
+            ctx->cand_cap = std::max<size_t>(ctx->cand_cap * 2, (size_t)hc.c.n_cand + 1024);
             continue;
         }
-        n_cand = hc.n_cand;
+        n_cand = hc.c.n_cand;
         break;
     }
-    {   // units for the seed/vote stages: lookups are not counted on the device; hits are the sum over tasks
-        // (kept cheap: one reduction on the host over a D2H copy would dominate, so report candidates here
-        //  and let bench.py derive hits from the workload statistics gathered in tests)
-        ctx->stage_units[ST_VOTE] += n_cand;
-    }
+    // algorithmic work of the seed / vote stages (DESIGN.md "Roofline"): every backward-search step reads two
+    // 64-byte occ blocks; every SA hit reads one 4-byte entry of the de-sampled suffix array
+    ctx->stage_units[ST_SEED] += hc.s.v[0]; ctx->stage_bytes[ST_SEED] += hc.s.v[1] * 128ull;
+    ctx->stage_units[ST_VOTE] += hc.s.v[2]; ctx->stage_bytes[ST_VOTE] += hc.s.v[2] * 4ull;
 
     // restore the reference's processing order: (task, round, position)
     unsigned long long *keys = ctx->d_keys.as<unsigned long long>();
@@ -771,7 +825,8 @@ static int run_chunk(gmx_ctx *ctx, const gmx_reads *reads, int32_t lo, int32_t h
         stage_begin(ctx, ST_NW);
         k_cand_score<<<nblk(n_cand, 128), 128, 0, ctx->stream>>>(ctx->ix, ctx->dreads, ctx->tab, P, keys, n_cand, ctx->d_score.as<float>());
         CK(cudaGetLastError());
-        stage_end(ctx, ST_NW, n_cand, 0, 1);
+        // per candidate: 2-bit window (n/4 B) + read bases and qualities (2n B) + key (8 B) + score (4 B)
+        stage_end(ctx, ST_NW, (uint64_t)n_cand * (uint64_t)std::max(7 * max_len - 12, 0), (uint64_t)n_cand * (uint64_t)(max_len / 4 + 2 * max_len + 12), 1);
     }
 
     // acceptance, grouping, denominator, best group
@@ -784,51 +839,91 @@ static int run_chunk(gmx_ctx *ctx, const gmx_reads *reads, int32_t lo, int32_t h
     CK(cudaGetLastError());
     stage_end(ctx, ST_FINALIZE, (uint64_t)n, 0, 1);
 
-    CK(cudaMemcpyAsync(&hc, dc, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(&hc.c, dc, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     stage_collect(ctx);
-    const uint32_t n_leaders = hc.n_leaders;
 
-    // PHASE B
-    LeaderStore L;
+    cs.lo = lo; cs.n = n; cs.max_len = max_len; cs.total_bases = total_bases;
+    cs.n_cand = n_cand; cs.n_leaders = hc.c.n_leaders; cs.n_accepted = hc.c.n_accepted; cs.keys = keys;
+    LeaderStore &L = cs.L;
     L.lead_cand = ctx->d_lead_cand.as<uint32_t>();
-    L.a_stride = max_len + 2 * P.max_gap + 8; L.c_stride = 64; L.max_len = max_len;
-    size_t nl = std::max<uint32_t>(n_leaders, 1);
+    L.a_stride = max_len + 2 * P.max_gap + 8; L.c_stride = GMX_CIGAR_STRIDE; L.max_len = max_len;
+    size_t nl = std::max<uint32_t>(cs.n_leaders, 1);
     CK(ctx->d_alen.ensure(nl * 4)); CK(ctx->d_aligned.ensure(nl * L.a_stride)); CK(ctx->d_cigar.ensure(nl * L.c_stride));
     L.alen = ctx->d_alen.as<int32_t>(); L.aligned = ctx->d_aligned.as<uint8_t>(); L.cigar = ctx->d_cigar.as<char>(); L.hmm = nullptr;
-    if (do_score && n_leaders) {
-        // traceback is needed in every mode for the CIGAR of the best hit (get_SAM, reference inc/ScoredSeq.h:314-372)
-        CK(ctx->d_moves.ensure((size_t)n_leaders * ((size_t)max_len + 1) * 4));
-        stage_begin(ctx, ST_TRACEBACK);
-        k_traceback<<<nblk(n_leaders, 128), 128, 0, ctx->stream>>>(ctx->ix, ctx->dreads, ctx->tab, P, keys, n_leaders, L, ctx->d_moves.as<uint32_t>());
-        CK(cudaGetLastError());
-        stage_end(ctx, ST_TRACEBACK, n_leaders, 0, 1);
-        if (P.mode == GMX_MODE_SNP) {
-            CK(ctx->d_hmm.ensure((size_t)n_leaders * max_len * 5 * 4));
-            L.hmm = ctx->d_hmm.as<float>();
-            size_t per_task = gmx_phmm_scratch_doubles(max_len);
-            uint32_t wave = std::min<uint32_t>(n_leaders, (uint32_t)n_sm * 8);
-            CK(ctx->d_phmm_scratch.ensure((size_t)wave * per_task * 8));
-            stage_begin(ctx, ST_PHMM);
-            int launches = 0;
-            for (uint32_t s0 = 0; s0 < n_leaders; s0 += wave) {
-                uint32_t cnt = std::min<uint32_t>(wave, n_leaders - s0);
-                k_pair_hmm_leaders<<<cnt, GMX_PHMM_THREADS, 0, ctx->stream>>>(ctx->ix, ctx->dreads, ctx->tab, keys, L, s0, cnt,
-                                                                             ctx->d_phmm_scratch.as<double>(), per_task);
-                CK(cudaGetLastError());
-                launches++;
-            }
-            stage_end(ctx, ST_PHMM, n_leaders, 0, launches);
-        }
-        stage_begin(ctx, ST_SCATTER);
-        k_scatter<<<nblk((int64_t)n_cand * 32, 128), 128, 0, ctx->stream>>>(ctx->ix, ctx->dreads, P, keys, ctx->d_score.as<float>(), ctx->d_leader.as<int32_t>(),
-                                                                            ctx->d_slot.as<int32_t>(), n_cand, ctx->d_results.as<gmx_read_result>(), L, ctx->acc);
-        CK(cudaGetLastError());
-        stage_end(ctx, ST_SCATTER, hc.n_accepted, 0, 1);
-    }
+    cs.valid = true;
+    return GMX_OK;
+}
 
-    // download: per-read results, and the accepted hits / best alignments for the SAM writer
+// PHASE B for the resident chunk: K2b (+ K2c) per group leader, then K3.
+static int phase_b(gmx_ctx *ctx)
+{
+    gmx_ctx::ChunkState &cs = ctx->cs;
+    if (!cs.valid) { ctx->err = "no mapped chunk is resident on the device"; return GMX_ERR_STATE; }
+    const DevParams &P = ctx->dparams;
+    LeaderStore &L = cs.L;
+    const uint32_t n_leaders = cs.n_leaders, n_cand = cs.n_cand;
+    const int max_len = cs.max_len;
+    if (!n_leaders) return GMX_OK;
+    // traceback is needed in every mode for the CIGAR of the best hit (get_SAM, reference inc/ScoredSeq.h:314-372)
+    CK(ctx->d_moves.ensure((size_t)n_leaders * ((size_t)max_len + 1) * 4));
+    stage_begin(ctx, ST_TRACEBACK);
+    k_traceback<<<nblk(n_leaders, 128), 128, 0, ctx->stream>>>(ctx->ix, ctx->dreads, ctx->tab, P, cs.keys, n_leaders, L, ctx->d_moves.as<uint32_t>());
+    CK(cudaGetLastError());
+    stage_end(ctx, ST_TRACEBACK, (uint64_t)n_leaders * (uint64_t)std::max(7 * max_len - 12, 0), 0, 1);
+    if (P.mode == GMX_MODE_SNP) {
+        CK(ctx->d_hmm.ensure((size_t)n_leaders * max_len * 5 * 4));
+        L.hmm = ctx->d_hmm.as<float>();
+        size_t per_task = gmx_phmm_scratch_doubles(max_len);
+        uint32_t wave = std::min<uint32_t>(n_leaders, (uint32_t)ctx->n_sm * 8);
+        CK(ctx->d_phmm_scratch.ensure((size_t)wave * per_task * 8));
+        stage_begin(ctx, ST_PHMM);
+        int launches = 0;
+        for (uint32_t s0 = 0; s0 < n_leaders; s0 += wave) {
+            uint32_t cnt = std::min<uint32_t>(wave, n_leaders - s0);
+            k_pair_hmm_leaders<<<cnt, GMX_PHMM_THREADS, 0, ctx->stream>>>(ctx->ix, ctx->dreads, ctx->tab, cs.keys, L, s0, cnt,
+                                                                         ctx->d_phmm_scratch.as<double>(), per_task);
+            CK(cudaGetLastError());
+            launches++;
+        }
+        stage_end(ctx, ST_PHMM, (uint64_t)n_leaders * (uint64_t)max_len * (uint64_t)max_len, 0, launches);
+    }
+    stage_begin(ctx, ST_SCATTER);
+    k_scatter<<<nblk((int64_t)n_cand * 32, 128), 128, 0, ctx->stream>>>(ctx->ix, ctx->dreads, P, cs.keys, ctx->d_score.as<float>(), ctx->d_leader.as<int32_t>(),
+                                                                        ctx->d_slot.as<int32_t>(), n_cand, ctx->d_results.as<gmx_read_result>(), L, ctx->acc);
+    CK(cudaGetLastError());
+    // per accepted (position, strand): one float RMW per aligned base and plane, Normal mode
+    // after bin aggregation: ceil(len / gen_size) RMWs
+    uint64_t per_hit = P.mode == GMX_MODE_NORMAL ? 8ull * ((uint64_t)(max_len + P.gen_size - 1) / P.gen_size)
+                                                  : (P.mode == GMX_MODE_BS ? 16ull : 48ull) * (uint64_t)max_len;
+    stage_end(ctx, ST_SCATTER, cs.n_accepted, (uint64_t)cs.n_accepted * per_hit, 1);
+    return GMX_OK;
+}
+
+// Per-read results (+ hit list / best alignments) of the resident chunk -> host.
+static int download_chunk(gmx_ctx *ctx, bool scored, gmx_read_result *results_out)
+{
+    gmx_ctx::ChunkState &cs = ctx->cs;
+    if (!cs.valid) { ctx->err = "no mapped chunk is resident on the device"; return GMX_ERR_STATE; }
+    const int32_t n = cs.n, lo = cs.lo;
+    const uint32_t n_cand = cs.n_cand, n_leaders = cs.n_leaders;
+    LeaderStore &L = cs.L;
     stage_begin(ctx, ST_DOWNLOAD);
+    if (!ctx->collect_hits) {
+        // fast path: fixed-size records only
+        CK(ctx->d_best_cigar.ensure((size_t)std::max(n, 1) * GMX_CIGAR_STRIDE));
+        k_gather_best<<<nblk(n, 128), 128, 0, ctx->stream>>>(ctx->d_results.as<gmx_read_result>(), n, ctx->d_slot.as<int32_t>(), L,
+                                                           ctx->d_best_cigar.as<char>(), GMX_CIGAR_STRIDE, scored && n_leaders ? 1 : 0, scored ? 1 : 0);
+        CK(cudaGetLastError());
+        gmx_read_result *dst = results_out ? results_out + lo : ctx->h_results.data() + lo;
+        CK(cudaMemcpyAsync(dst, ctx->d_results.p, (size_t)n * sizeof(gmx_read_result), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->h_best_cigar.as<char>() + (size_t)lo * GMX_CIGAR_STRIDE, ctx->d_best_cigar.p, (size_t)n * GMX_CIGAR_STRIDE,
+                           cudaMemcpyDeviceToHost, ctx->stream));
+        stage_end(ctx, ST_DOWNLOAD, (uint64_t)n, (uint64_t)n * (sizeof(gmx_read_result) + GMX_CIGAR_STRIDE), 1);
+        CK(cudaStreamSynchronize(ctx->stream));
+        stage_collect(ctx);
+        return GMX_OK;
+    }
     gmx_read_result *hres = ctx->h_results.data() + lo;
     CK(cudaMemcpyAsync(hres, ctx->d_results.p, (size_t)n * sizeof(gmx_read_result), cudaMemcpyDeviceToHost, ctx->stream));
     std::vector<unsigned long long> h_keys(n_cand);
@@ -837,12 +932,12 @@ static int run_chunk(gmx_ctx *ctx, const gmx_reads *reads, int32_t lo, int32_t h
     std::vector<char> h_cigar((size_t)n_leaders * L.c_stride);
     std::vector<uint8_t> h_aligned((size_t)n_leaders * L.a_stride);
     if (n_cand) {
-        CK(cudaMemcpyAsync(h_keys.data(), keys, (size_t)n_cand * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(h_keys.data(), cs.keys, (size_t)n_cand * 8, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaMemcpyAsync(h_leader.data(), ctx->d_leader.p, (size_t)n_cand * 4, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaMemcpyAsync(h_slot.data(), ctx->d_slot.p, (size_t)n_cand * 4, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaMemcpyAsync(h_score.data(), ctx->d_score.p, (size_t)n_cand * 4, cudaMemcpyDeviceToHost, ctx->stream));
     }
-    if (do_score && n_leaders) {
+    if (scored && n_leaders) {
         CK(cudaMemcpyAsync(h_alen.data(), ctx->d_alen.p, (size_t)n_leaders * 4, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaMemcpyAsync(h_cigar.data(), ctx->d_cigar.p, h_cigar.size(), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaMemcpyAsync(h_aligned.data(), ctx->d_aligned.p, h_aligned.size(), cudaMemcpyDeviceToHost, ctx->stream));
@@ -853,6 +948,7 @@ static int run_chunk(gmx_ctx *ctx, const gmx_reads *reads, int32_t lo, int32_t h
 
     // host-side assembly of the variable-length outputs (hit list, best CIGAR): pure bookkeeping
     const int a_out = ctx->h_a_stride;
+    char *best_cigar = ctx->h_best_cigar.as<char>();
     for (int32_t i = 0; i < n; ++i) {
         gmx_read_result &res = hres[i];
         int32_t c_lo = res.hit_begin, c_hi = res.hit_end;
@@ -880,10 +976,10 @@ static int run_chunk(gmx_ctx *ctx, const gmx_reads *reads, int32_t lo, int32_t h
             return a.strand < b.strand;
         });
         res.best_group = best_label;
-        if (do_score && best_leader >= 0) {
+        if (scored && best_leader >= 0) {
             int s = h_slot[best_leader];
             res.best_aligned_len = h_alen[s];
-            memcpy(&ctx->h_best_cigar[(size_t)(lo + i) * 64], &h_cigar[(size_t)s * L.c_stride], 64);
+            memcpy(best_cigar + (size_t)(lo + i) * GMX_CIGAR_STRIDE, &h_cigar[(size_t)s * L.c_stride], GMX_CIGAR_STRIDE);
             int cp = std::min(a_out, L.a_stride);
             memcpy(&ctx->h_best_aligned[(size_t)(lo + i) * a_out], &h_aligned[(size_t)s * L.a_stride], (size_t)cp);
         }
@@ -892,52 +988,109 @@ static int run_chunk(gmx_ctx *ctx, const gmx_reads *reads, int32_t lo, int32_t h
     return GMX_OK;
 }
 
+static int batch_max_len(gmx_ctx *ctx, const gmx_reads *reads, int32_t *out)
+{
+    return scan_max_len(ctx, reads, 0, reads->n_reads, out);
+}
+
+// phases: 1 = PHASE A only, 3 = PHASE A + PHASE B
 static int run_batch(gmx_ctx *ctx, const gmx_reads *reads, gmx_read_result *results, bool do_score)
 {
     if (!ctx || !reads || reads->n_reads < 0 || (reads->n_reads > 0 && !reads->offsets)) return GMX_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
     const int32_t n = reads->n_reads;
     int32_t max_len = 0;
-    for (int32_t i = 0; i < n; ++i) max_len = std::max<int32_t>(max_len, (int32_t)(reads->offsets[i + 1] - reads->offsets[i]));
-    ctx->h_results.assign((size_t)n, gmx_read_result());
+    if (n > 0) { int r = batch_max_len(ctx, reads, &max_len); if (r != GMX_OK) return r; }
+    ctx->h_results.assign(ctx->collect_hits || !results ? (size_t)n : 0, gmx_read_result());
     ctx->h_hits.clear();
     ctx->h_a_stride = max_len + 2 * ctx->params.max_gap + 8;
-    ctx->h_best_cigar.assign((size_t)n * 64, 0);
-    ctx->h_best_aligned.assign((size_t)n * ctx->h_a_stride, 0);
+    CK(ctx->h_best_cigar.ensure((size_t)std::max(n, 1) * GMX_CIGAR_STRIDE));
+    if (ctx->collect_hits) {
+        memset(ctx->h_best_cigar.p, 0, (size_t)std::max(n, 1) * GMX_CIGAR_STRIDE);
+        ctx->h_best_aligned.assign((size_t)n * ctx->h_a_stride, 0);
+    }
     ctx->last_n_reads = n; ctx->last_max_len = 0;
-    ctx->mapped = false; ctx->scored = false;
+    ctx->mapped = false; ctx->scored = false; ctx->cs.valid = false;
     stage_reset(ctx);
     for (int32_t lo = 0; lo < n; lo += (int32_t)ctx->chunk_reads) {
         int32_t hi = (int32_t)std::min<int64_t>(n, (int64_t)lo + (int64_t)ctx->chunk_reads);
-        int r = run_chunk(ctx, reads, lo, hi, do_score, results);
+        int r = phase_a(ctx, reads, lo, hi);
         if (r != GMX_OK) return r;
+        const bool last_and_split = !do_score && hi == n && lo == 0;       // single-chunk map_batch: PHASE B may follow
+        if (do_score) { r = phase_b(ctx); if (r != GMX_OK) return r; }
+        r = download_chunk(ctx, do_score, results);
+        if (r != GMX_OK) return r;
+        if (!last_and_split && !do_score) ctx->cs.valid = false;
     }
+    if (do_score) ctx->cs.valid = false;
     ctx->mapped = true; ctx->scored = do_score;
     return GMX_OK;
 }
 
 extern "C" int gmx_process_batch(gmx_ctx *ctx, const gmx_reads *reads, gmx_read_result *results) { return run_batch(ctx, reads, results, true); }
 
-// PHASE A only: nothing is scattered; gmx_score_batch re-derives PHASE B from the same reads.
-static const gmx_reads *g_last_reads_unused = nullptr;
+// PHASE A only.  When the batch fits one internal chunk (GMX_OPT_CHUNK_READS, default 262144 -- the reference
+// hands its workers 2048 reads at a time) its candidates stay resident and gmx_score_batch continues from them;
+// larger batches are remembered by value (host input) or by reference (device input) and re-run.
 extern "C" int gmx_map_batch(gmx_ctx *ctx, const gmx_reads *reads, gmx_read_result *results)
 {
-    (void)g_last_reads_unused;
-    return run_batch(ctx, reads, results, false);
+    int r = run_batch(ctx, reads, results, false);
+    if (r != GMX_OK) return r;
+    ctx->keep_valid = false;
+    if (!ctx->cs.valid && reads->n_reads > 0) {
+        ctx->keep = *reads;
+        if (!reads->on_device) {
+            const int32_t n = reads->n_reads;
+            const int64_t total = reads->offsets[n];
+            ctx->keep_offsets.assign(reads->offsets, reads->offsets + n + 1);
+            ctx->keep_seq.assign(reads->seq, reads->seq + total);
+            ctx->keep.offsets = ctx->keep_offsets.data(); ctx->keep.seq = ctx->keep_seq.data();
+            if (reads->qual) { ctx->keep_qual.assign(reads->qual, reads->qual + total); ctx->keep.qual = ctx->keep_qual.data(); }
+            if (reads->pwm) { ctx->keep_pwm.assign(reads->pwm, reads->pwm + 4 * total); ctx->keep.pwm = ctx->keep_pwm.data(); }
+        }
+        ctx->keep_valid = true;
+    }
+    return GMX_OK;
 }
 
 extern "C" int gmx_score_batch(gmx_ctx *ctx, gmx_read_result *results)
 {
     if (!ctx) return GMX_ERR_INVALID;
-    (void)results;
-    ctx->err = "gmx_score_batch: PHASE B runs fused with PHASE A; call gmx_process_batch (split mode is not kept resident yet)";
-    return GMX_ERR_STATE;
+    if (!ctx->mapped || ctx->scored) { ctx->err = "gmx_score_batch needs a preceding gmx_map_batch"; return GMX_ERR_STATE; }
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->last_n_reads == 0) { ctx->scored = true; return GMX_OK; }
+    if (ctx->cs.valid) {
+        ctx->h_hits.clear();
+        int r = phase_b(ctx);
+        if (r != GMX_OK) return r;
+        r = download_chunk(ctx, true, results);
+        if (r != GMX_OK) return r;
+        ctx->cs.valid = false; ctx->scored = true;
+        return GMX_OK;
+    }
+    if (!ctx->keep_valid) { ctx->err = "the mapped batch is no longer available"; return GMX_ERR_STATE; }
+    gmx_reads again = ctx->keep;
+    ctx->keep_valid = false;
+    return run_batch(ctx, &again, results, true);
+}
+
+extern "C" int gmx_set_option(gmx_ctx *ctx, int option, int64_t value)
+{
+    if (!ctx) return GMX_ERR_INVALID;
+    switch (option) {
+        case GMX_OPT_COLLECT_HITS: ctx->collect_hits = value != 0; return GMX_OK;
+        case GMX_OPT_CHUNK_READS:
+            if (value < 1 || value > (1 << 22)) { ctx->err = "chunk_reads must be in 1..4194304"; return GMX_ERR_INVALID; }
+            ctx->chunk_reads = (size_t)value; return GMX_OK;
+        default: ctx->err = "unknown option"; return GMX_ERR_INVALID;
+    }
 }
 
 extern "C" int gmx_get_hits(gmx_ctx *ctx, gmx_hit *hits, int64_t capacity, int64_t *n_hits)
 {
     if (!ctx || !n_hits) return GMX_ERR_INVALID;
     if (!ctx->mapped) return GMX_ERR_STATE;
+    if (!ctx->collect_hits) { ctx->err = "hit collection is disabled (GMX_OPT_COLLECT_HITS = 0)"; return GMX_ERR_STATE; }
     *n_hits = (int64_t)ctx->h_hits.size();
     if (!hits) return GMX_OK;
     if (capacity < *n_hits) return GMX_ERR_OVERFLOW;
@@ -949,10 +1102,12 @@ extern "C" int gmx_get_best_alignments(gmx_ctx *ctx, char *cigar_out, int32_t ci
 {
     if (!ctx) return GMX_ERR_INVALID;
     if (!ctx->scored) return GMX_ERR_STATE;
+    if (aligned_out && !ctx->collect_hits) { ctx->err = "aligned strings need GMX_OPT_COLLECT_HITS = 1"; return GMX_ERR_STATE; }
+    const char *best_cigar = ctx->h_best_cigar.as<char>();
     for (int32_t i = 0; i < ctx->last_n_reads; ++i) {
         if (cigar_out) {
             memset(cigar_out + (size_t)i * cigar_stride, 0, (size_t)cigar_stride);
-            strncpy(cigar_out + (size_t)i * cigar_stride, &ctx->h_best_cigar[(size_t)i * 64], (size_t)std::min(cigar_stride - 1, 63));
+            strncpy(cigar_out + (size_t)i * cigar_stride, best_cigar + (size_t)i * GMX_CIGAR_STRIDE, (size_t)std::min(cigar_stride - 1, GMX_CIGAR_STRIDE - 1));
         }
         if (aligned_out) {
             memset(aligned_out + (size_t)i * aligned_stride, 0, (size_t)aligned_stride);

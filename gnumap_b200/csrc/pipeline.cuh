@@ -77,13 +77,14 @@ struct SeedStore {
     int64_t n_tasks;
 };
 
-__global__ void k_seed_walk(DevIndex ix, DevReads R, DevParams P, const ReadPrep *prep, SeedStore S)
+// stats[0] += k-mer lookups, stats[1] += backward-search steps (one bwt_2occ each), stats[2] += SA hits
+__global__ void k_seed_walk(DevIndex ix, DevReads R, DevParams P, const ReadPrep *prep, SeedStore S, unsigned long long *stats)
 {
     int64_t task = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (task >= S.n_tasks) return;
-    int r = (int)(task >> 1), neg = (int)(task & 1);
-    int ns = 0; uint32_t total = 0;
-    bool active = prep[r].status == GMX_READ_MAPPED && (neg ? P.match_neg : P.match_pos);
+    const bool in_range = task < S.n_tasks;
+    int r = in_range ? (int)(task >> 1) : 0, neg = (int)(task & 1);
+    int ns = 0; uint32_t total = 0, n_lookups = 0, n_steps = 0;
+    bool active = in_range && prep[r].status == GMX_READ_MAPPED && (neg ? P.match_neg : P.match_pos);
     if (active && !R.seq) active = false;
     if (active) {
         int64_t off = R.offsets[r];
@@ -102,7 +103,8 @@ __global__ void k_seed_walk(DevIndex ix, DevReads R, DevParams P, const ReadPrep
             uint64_t k = 0, l = 0;
             for (j = 0; j + i < last; j++) {
                 unsigned base = i + j;
-                bool hit = gmx_match_exact(ix, P.mer, [&](int t) { return sym_at((int)base + t); }, k, l);
+                bool hit = gmx_match_exact(ix, P.mer, [&](int t) { return sym_at((int)base + t); }, k, l, n_steps);
+                n_lookups++;
                 if (!hit) continue;
                 if (P.max_kmer_hits > 0 && l - k + 1 > (uint64_t)P.max_kmer_hits) continue;
                 found = true;
@@ -120,8 +122,20 @@ __global__ void k_seed_walk(DevIndex ix, DevReads R, DevParams P, const ReadPrep
             if (P.fast) break;
         }
     }
-    S.n_seeds[task] = (uint8_t)ns;
-    S.hits[task] = total;
+    if (in_range) { S.n_seeds[task] = (uint8_t)ns; S.hits[task] = total; }
+    if (stats) {
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            n_lookups += __shfl_xor_sync(0xffffffffu, n_lookups, o);
+            n_steps += __shfl_xor_sync(0xffffffffu, n_steps, o);
+            total += __shfl_xor_sync(0xffffffffu, total, o);
+        }
+        if ((threadIdx.x & 31) == 0) {
+            if (n_lookups) atomicAdd(&stats[0], (unsigned long long)n_lookups);
+            if (n_steps) atomicAdd(&stats[1], (unsigned long long)n_steps);
+            if (total) atomicAdd(&stats[2], (unsigned long long)total);
+        }
+    }
 }
 
 // ---- task classes for the vote -----------------------------------------------------------------
@@ -605,4 +619,27 @@ __global__ void __launch_bounds__(128) k_scatter(DevIndex ix, DevReads R, DevPar
             if (code < 5) atomicAdd(&A.planes[code][bin], total);
         }
     }
+}
+
+// ---- best alignment per read (fast download path) ------------------------------------------------
+// One thread per read: copies the CIGAR of the best group next to the per-read result so that only
+// [n_reads] fixed-size records leave the device when the caller does not ask for the hit list.
+__global__ void __launch_bounds__(128) k_gather_best(gmx_read_result *results, int n_reads, const int32_t *slot, LeaderStore L,
+                                                     char *best_cigar, int stride, int have_traceback, int final_pass)
+{
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_reads) return;
+    uint4 *dst = reinterpret_cast<uint4 *>(best_cigar + (size_t)r * stride);
+    gmx_read_result res = results[r];
+    const bool has = have_traceback && res.status == GMX_READ_MAPPED && res.best_group >= 0;
+    if (has) {
+        int s = slot[res.hit_begin + res.best_group];
+        results[r].best_aligned_len = L.alen[s];
+        const uint4 *src = reinterpret_cast<const uint4 *>(L.cigar + (size_t)s * L.c_stride);
+        for (int k = 0; k < stride / 16; ++k) dst[k] = src[k];
+    } else {
+        for (int k = 0; k < stride / 16; ++k) dst[k] = make_uint4(0, 0, 0, 0);
+    }
+    // the candidate range / leader index are device-internal; a later PHASE B pass still needs them
+    if (final_pass) { results[r].hit_begin = 0; results[r].hit_end = 0; results[r].best_group = -1; }
 }

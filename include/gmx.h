@@ -114,6 +114,9 @@ typedef struct gmx_reads {
     const uint8_t *seq;
     const uint8_t *qual;
     const float   *pwm;
+    int32_t        on_device; /* 0: the four arrays are host memory (copied to the GPU inside the call);
+                                 1: they already live in the memory of the context's GPU             */
+    int32_t        max_len;   /* longest read of the batch; 0 = let the library scan offsets (host only) */
 } gmx_reads;
 
 /* Per-read outcome of PHASE A + PHASE B  (== gTopReadScore / gReadDenominator / the best
@@ -236,6 +239,12 @@ int gmx_reset_accumulators(gmx_ctx *ctx);
  * the host arrays GetGenomeAmtPtr() / GetGenome{A,C,G,T,N}Ptr() (GenomeBwt.h:199-209).
  * planes may be NULL in Normal mode. */
 int gmx_finish(gmx_ctx *ctx, float *amount_genome, float *const planes[5]);
+
+/* ---- options ----------------------------------------------------------------------------- */
+#define GMX_OPT_COLLECT_HITS 1   /* 1 (default): keep every accepted (pos,strand) for gmx_get_hits; 0: only the
+                                    per-read results and the best group's CIGAR leave the device           */
+#define GMX_OPT_CHUNK_READS  2   /* reads processed per internal chunk (default 262144)                     */
+int gmx_set_option(gmx_ctx *ctx, int option, int64_t value);
 
 /* ---- instrumentation ---------------------------------------------------------------------- */
 #define GMX_N_STAGES 12
