@@ -107,6 +107,7 @@ struct gmx_ctx {
     std::string err;
     size_t chunk_reads = 1 << 18;
     bool collect_hits = true;
+    bool use_filter = true;                    // GMX_OPT_VOTE_FILTER
     int n_sm = 148;
     DevBuf d_best_cigar;
     // input of the last multi-chunk gmx_map_batch (gmx_score_batch re-runs the batch from it)
@@ -678,7 +679,8 @@ extern "C" int gmx_pair_hmm(gmx_ctx *ctx, const gmx_reads *reads, int64_t n_task
 struct Counters {            // device-resident scalars, reset before every vote attempt
     uint32_t n_cand, cand_overflow, n_leaders, n_accepted, arena_overflow, pad[3];
     unsigned long long arena_used;
-    uint32_t cls_count[GMX_N_CLASSES], cls_cursor[GMX_N_CLASSES];
+    uint32_t cls_count[GMX_N_CLASSES], cls_cursor[GMX_N_CLASSES];        // exact classes
+    uint32_t fcls_count[GMX_N_CLASSES], fcls_cursor[GMX_N_CLASSES];      // filter classes
 };
 struct ChunkStats {          // device-resident, reset once per chunk: lookups, search steps, SA hits
     unsigned long long v[4];
@@ -695,6 +697,22 @@ static cudaError_t launch_vote(gmx_ctx *ctx, const SeedStore &S, const ClassList
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
     k_vote_smem<SL, WARPS><<<n_sm * per_sm, WARPS * 32, smem, ctx->stream>>>(ctx->ix, S, C, cls, ctx->dparams.kmin, sink);
+    return cudaGetLastError();
+}
+
+template <int FL, int WARPS>
+static cudaError_t launch_filter(gmx_ctx *ctx, const SeedStore &S, const ClassLists &F, const ClassLists &E, int cls, const CandSink &sink, int n_sm,
+                                 uint32_t pac_words)
+{
+    size_t smem = (size_t)WARPS * gmx_filter_warp_bytes(FL);
+    cudaError_t e = cudaFuncSetAttribute(k_vote_filter<FL, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = 1;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_vote_filter<FL, WARPS>, WARPS * 32, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    k_vote_filter<FL, WARPS><<<n_sm * per_sm, WARPS * 32, smem, ctx->stream>>>(ctx->ix, pac_words, ctx->dreads, S, F, E, cls, ctx->dparams.kmin,
+                                                                              ctx->dparams.mer, sink);
     return cudaGetLastError();
 }
 
@@ -728,7 +746,7 @@ static int phase_a(gmx_ctx *ctx, const gmx_reads *reads, int32_t lo, int32_t hi)
     CK(ctx->d_seed_off.ensure((size_t)max_seeds * n_tasks * 2));
     CK(ctx->d_seed_n.ensure((size_t)n_tasks));
     CK(ctx->d_seed_hits.ensure((size_t)n_tasks * 4));
-    CK(ctx->d_cls_list.ensure((size_t)GMX_N_CLASSES * n_tasks * 4));
+    CK(ctx->d_cls_list.ensure((size_t)2 * GMX_N_CLASSES * n_tasks * 4));
     CK(ctx->d_counters.ensure(sizeof(Counters) + sizeof(ChunkStats)));
     CK(ctx->d_results.ensure((size_t)n * sizeof(gmx_read_result)));
     if (ctx->cand_cap == 0) ctx->cand_cap = std::max<size_t>(1 << 16, (size_t)n * 16);
@@ -740,6 +758,10 @@ static int phase_a(gmx_ctx *ctx, const gmx_reads *reads, int32_t lo, int32_t hi)
     S.n_seeds = ctx->d_seed_n.as<uint8_t>(); S.hits = ctx->d_seed_hits.as<uint32_t>(); S.max_seeds = max_seeds; S.n_tasks = n_tasks;
     ClassLists C;
     C.list = ctx->d_cls_list.as<uint32_t>(); C.count = dc->cls_count; C.cursor = dc->cls_cursor; C.n_tasks = n_tasks;
+    ClassLists F;
+    F.list = C.list + (size_t)GMX_N_CLASSES * n_tasks; F.count = dc->fcls_count; F.cursor = dc->fcls_cursor; F.n_tasks = n_tasks;
+    const int use_filter = (P.kmin >= 2 && ctx->use_filter) ? 1 : 0;
+    const uint32_t pac_words = (uint32_t)((((size_t)ctx->ix.l_pac + 3) / 4 + 16) / 4);
 
     // a3 + status
     stage_begin(ctx, ST_PREP);
@@ -761,17 +783,25 @@ static int phase_a(gmx_ctx *ctx, const gmx_reads *reads, int32_t lo, int32_t hi)
         CK(ctx->d_keys.ensure(ctx->cand_cap * 8));
         CK(ctx->d_keys_alt.ensure(ctx->cand_cap * 8));
         stage_begin(ctx, ST_CLASSIFY);
-        k_classify<<<nblk(n_tasks, 256), 256, 0, ctx->stream>>>(S.hits, C);
+        k_classify<<<nblk(n_tasks, 256), 256, 0, ctx->stream>>>(S.hits, F, C, use_filter);
         CK(cudaGetLastError());
         stage_end(ctx, ST_CLASSIFY, (uint64_t)n_tasks, (uint64_t)n_tasks * 8, 1);
 
         // K1b + K1c
         CandSink sink; sink.keys = ctx->d_keys.as<unsigned long long>(); sink.count = &dc->n_cand; sink.overflow = &dc->cand_overflow; sink.cap = (uint32_t)ctx->cand_cap;
         stage_begin(ctx, ST_VOTE);
-        CK((launch_vote<10, 8>(ctx, S, C, 0, sink, n_sm)));
-        CK((launch_vote<11, 8>(ctx, S, C, 1, sink, n_sm)));
-        CK((launch_vote<12, 4>(ctx, S, C, 2, sink, n_sm)));
-        CK((launch_vote<13, 2>(ctx, S, C, 3, sink, n_sm)));
+        if (use_filter) {
+            CK((launch_filter<12, 8>(ctx, S, F, C, 0, sink, n_sm, pac_words)));
+            CK((launch_filter<13, 4>(ctx, S, F, C, 1, sink, n_sm, pac_words)));
+            CK((launch_filter<14, 2>(ctx, S, F, C, 2, sink, n_sm, pac_words)));
+            CK((launch_filter<15, 1>(ctx, S, F, C, 3, sink, n_sm, pac_words)));
+            CK((launch_filter<16, 1>(ctx, S, F, C, 4, sink, n_sm, pac_words)));
+            CK((launch_filter<17, 1>(ctx, S, F, C, 5, sink, n_sm, pac_words)));
+        }
+        CK((launch_vote<10, 2>(ctx, S, C, 0, sink, n_sm)));
+        CK((launch_vote<11, 1>(ctx, S, C, 1, sink, n_sm)));
+        CK((launch_vote<12, 1>(ctx, S, C, 2, sink, n_sm)));
+        CK((launch_vote<13, 1>(ctx, S, C, 3, sink, n_sm)));
         CK((launch_vote<14, 1>(ctx, S, C, 4, sink, n_sm)));
         {
             if (ctx->d_arena.cap == 0) CK(ctx->d_arena.ensure((size_t)256 << 20));
@@ -779,7 +809,7 @@ static int phase_a(gmx_ctx *ctx, const gmx_reads *reads, int32_t lo, int32_t hi)
             k_vote_gmem<<<n_sm * 4, 128, 0, ctx->stream>>>(ctx->ix, S, C, 5, P.kmin, sink, A);
             CK(cudaGetLastError());
         }
-        stage_end(ctx, ST_VOTE, 0, 0, 6);
+        stage_end(ctx, ST_VOTE, 0, 0, use_filter ? 12 : 6);
         CK(cudaMemcpyAsync(&hc, dc, sizeof(hc), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         stage_collect(ctx);
@@ -1082,6 +1112,7 @@ extern "C" int gmx_set_option(gmx_ctx *ctx, int option, int64_t value)
         case GMX_OPT_CHUNK_READS:
             if (value < 1 || value > (1 << 22)) { ctx->err = "chunk_reads must be in 1..4194304"; return GMX_ERR_INVALID; }
             ctx->chunk_reads = (size_t)value; return GMX_OK;
+        case GMX_OPT_VOTE_FILTER: ctx->use_filter = value != 0; return GMX_OK;
         default: ctx->err = "unknown option"; return GMX_ERR_INVALID;
     }
 }

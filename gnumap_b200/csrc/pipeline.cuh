@@ -139,8 +139,12 @@ __global__ void k_seed_walk(DevIndex ix, DevReads R, DevParams P, const ReadPrep
 }
 
 // ---- task classes for the vote -----------------------------------------------------------------
-#define GMX_N_CLASSES 6          // 5 shared-memory table sizes + 1 global-memory class
-__constant__ const int gmx_class_slots_log2[5] = {10, 11, 12, 13, 14};
+// Two families of lists: `filter` classes (counting-filter kernel, the fast path, sized by SA hits) and
+// `exact` classes (exact hash-table kernels: 5 shared-memory table sizes + 1 global-memory class), which
+// take the tasks the filter kernel cannot handle (vote-queue overflow on repeat-rich reads, very long reads,
+// kmin == 1, more hits than the largest filter).
+#define GMX_N_CLASSES 6
+#define GMX_FILTER_LOG2_MIN 12   // filter class c uses a (1 << (12 + c))-byte counting filter, hits <= 512 << c
 
 struct ClassLists {
     uint32_t *list;     // [GMX_N_CLASSES][n_tasks]
@@ -150,18 +154,35 @@ struct ClassLists {
 };
 
 __host__ __device__ __forceinline__ uint32_t gmx_class_max_hits(int cls) { return (5u << (10 + cls)) >> 3; }   // load <= 5/8
+__host__ __device__ __forceinline__ uint32_t gmx_filter_max_hits(int cls) { return 512u << cls; }
 
-__global__ void k_classify(const uint32_t *hits, ClassLists C)
+__device__ __forceinline__ int gmx_exact_class(uint32_t h)
 {
-    int64_t task = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (task >= C.n_tasks) return;
-    uint32_t h = hits[task];
-    if (h == 0) return;
     int cls = 5;
 #pragma unroll
     for (int c = 4; c >= 0; --c) if (h <= gmx_class_max_hits(c)) cls = c;
+    return cls;
+}
+
+__device__ __forceinline__ void gmx_class_append(const ClassLists &C, int cls, uint32_t task)
+{
     uint32_t at = atomicAdd(&C.count[cls], 1u);
-    C.list[(int64_t)cls * C.n_tasks + at] = (uint32_t)task;
+    C.list[(int64_t)cls * C.n_tasks + at] = task;
+}
+
+__global__ void k_classify(const uint32_t *hits, ClassLists F, ClassLists E, int use_filter)
+{
+    int64_t task = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (task >= E.n_tasks) return;
+    uint32_t h = hits[task];
+    if (h == 0) return;
+    int fc = -1;
+    if (use_filter) {
+#pragma unroll
+        for (int c = GMX_N_CLASSES - 1; c >= 0; --c) if (h <= gmx_filter_max_hits(c)) fc = c;
+    }
+    if (fc >= 0) gmx_class_append(F, fc, (uint32_t)task);
+    else gmx_class_append(E, gmx_exact_class(h), (uint32_t)task);
 }
 
 // ---- K1b + K1c: locate + diagonal vote ---------------------------------------------------------
@@ -226,12 +247,68 @@ __device__ __forceinline__ void gmx_vote_task(const DevIndex &ix, const SeedStor
     }
 }
 
+// Shared-memory variant, no atomics.  The table is private to one warp, and within one warp step all
+// 32 lanes hold hits of the SAME k-mer: their suffix-array values are distinct, hence so are their
+// diagonals (after the lanes clamped to diagonal 0 have been folded into one).  Distinct keys can only
+// race for an empty slot; that race is settled by "store, __syncwarp, re-read": the lane that reads
+// its own key back owns the slot, every other lane moves on.  Counters are one byte per slot and
+// are written by the slot's owner of the step only, so plain LDS/STS replace the ATOMS.CAS +
+// ATOMS.ADD pair of the generic path (2 cycles per lane each on this part: profiles/r01_*).
+#define GMX_VOTE_UNROLL 4
+#define GMX_SA_INVALID 0xFFFFFFFFu
+
+template <int SLOTS_LOG2>
+__device__ __forceinline__ void gmx_vote_step(uint32_t sa, uint32_t off, int kmin, volatile uint32_t *keys, volatile uint8_t *cnt8,
+                                              uint32_t task, int round, CandSink sink, int lane)
+{
+    bool valid = sa != GMX_SA_INVALID;
+    const bool clamp = valid && sa <= off;                    // diag = max(0, sa - off) (reference inc/align_seq2_raw.cpp:270)
+    uint32_t diag = clamp ? 0u : sa - off;
+    uint32_t inc = 1;
+    const uint32_t cm = __ballot_sync(0xffffffffu, clamp);
+    if (cm && clamp) {                                        // several hits of this k-mer on diagonal 0: one lane votes for all
+        if (lane != __ffs(cm) - 1) valid = false; else inc = (uint32_t)__popc(cm);
+    }
+    uint32_t h = (diag * 0x9E3779B1u) >> (32 - SLOTS_LOG2);
+    bool pending = valid, claimed = false;
+    while (__any_sync(0xffffffffu, pending)) {
+        if (pending) {
+            uint32_t k = keys[h];
+            if (k == diag) pending = false;
+            else if (k == GMX_EMPTY_KEY) { keys[h] = diag; claimed = true; }
+            else { h = (h + 1) & ((1u << SLOTS_LOG2) - 1u); claimed = false; }
+        }
+        __syncwarp();
+    }
+    bool emit = false;
+    if (valid) {
+        uint32_t old = claimed ? 0u : (uint32_t)cnt8[h];
+        if ((int)old < kmin) {
+            uint32_t nw = old + inc; if (nw > 255u) nw = 255u;
+            cnt8[h] = (uint8_t)nw;
+            emit = (int)nw >= kmin;
+        }
+    }
+    const uint32_t em = __ballot_sync(0xffffffffu, emit);
+    if (em) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(sink.count, (uint32_t)__popc(em));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (emit) {
+            uint32_t at = base + (uint32_t)__popc(em & ((1u << lane) - 1u));
+            if (at < sink.cap) sink.keys[at] = ((unsigned long long)task << 40) | ((unsigned long long)round << 32) | diag;
+            else *sink.overflow = 1u;
+        }
+    }
+    __syncwarp();
+}
+
 template <int SLOTS_LOG2, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) k_vote_smem(DevIndex ix, SeedStore S, ClassLists C, int cls, int kmin, CandSink sink)
 {
     constexpr uint32_t SLOTS = 1u << SLOTS_LOG2;
     extern __shared__ __align__(16) uint32_t smem[];
-    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t *keys = smem + (size_t)warp * (SLOTS + SLOTS / 4);
     uint32_t *cnts = keys + SLOTS;
     const uint32_t n_list = C.count[cls];
@@ -241,13 +318,246 @@ __global__ void __launch_bounds__(WARPS * 32) k_vote_smem(DevIndex ix, SeedStore
         if (lane == 0) w = atomicAdd(&C.cursor[cls], 1u);
         w = __shfl_sync(0xffffffffu, w, 0);
         if (w >= n_list) break;
-        uint32_t task = list[w];
+        const uint32_t task = list[w];
+        const int ns = S.n_seeds[task];
+        // pull every suffix-array line this task will read into L2 while the table is being cleared
+        for (int s = 0; s < ns; ++s) {
+            const uint32_t rank0 = S.rank[(int64_t)s * S.n_tasks + task], cnt = S.count[(int64_t)s * S.n_tasks + task];
+            for (uint32_t t = (uint32_t)lane * 32u; t < cnt; t += 1024u)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(ix.sa_full + rank0 + t));
+        }
         uint4 *k4 = reinterpret_cast<uint4 *>(keys);
         for (uint32_t x = lane; x < SLOTS / 4; x += 32) k4[x] = make_uint4(GMX_EMPTY_KEY, GMX_EMPTY_KEY, GMX_EMPTY_KEY, GMX_EMPTY_KEY);
         uint4 *c4 = reinterpret_cast<uint4 *>(cnts);
         for (uint32_t x = lane; x < SLOTS / 16; x += 32) c4[x] = make_uint4(0, 0, 0, 0);
         __syncwarp();
-        gmx_vote_task<false>(ix, S, task, kmin, keys, cnts, SLOTS - 1, sink, lane);
+        for (int s = 0; s < ns; ++s) {
+            const uint32_t rank0 = S.rank[(int64_t)s * S.n_tasks + task];
+            const uint32_t cnt = S.count[(int64_t)s * S.n_tasks + task];
+            const uint32_t off = S.offset[(int64_t)s * S.n_tasks + task];
+            for (uint32_t t0 = 0; t0 < cnt; t0 += 32u * GMX_VOTE_UNROLL) {
+                uint32_t sa[GMX_VOTE_UNROLL];
+#pragma unroll
+                for (int u = 0; u < GMX_VOTE_UNROLL; ++u) {
+                    const uint32_t t = t0 + 32u * u + lane;
+                    sa[u] = t < cnt ? __ldg(ix.sa_full + rank0 + t) : GMX_SA_INVALID;
+                }
+#pragma unroll
+                for (int u = 0; u < GMX_VOTE_UNROLL; ++u)
+                    if (t0 + 32u * u < cnt)
+                        gmx_vote_step<SLOTS_LOG2>(sa[u], off, kmin, keys, reinterpret_cast<volatile uint8_t *>(cnts), task, s, sink, lane);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ---- K1b + K1c, fast path: counting filter + exact verification against the packed genome ---------
+// A diagonal becomes a candidate when `kmin` k-mers of the walk hit it.  Instead of counting every one of
+// the ~L/4^mer hits per k-mer exactly, each warp keeps a counting filter (one byte per bucket, two probes per
+// hit, plain LDS/STS: within a warp step the 32 lanes hold distinct diagonals of ONE k-mer, so a lost update
+// between lanes can only under-count a bucket shared by two DIFFERENT diagonals, never a diagonal's own
+// votes).  A hit whose two buckets already held kmin-1 votes is queued.  The queue is a superset of the
+// reference's candidates; each queued diagonal d is then verified exactly: k-mer s of the walk hits d iff
+// genome[d+off_s, d+off_s+mer) equals the k-mer (that is what membership of d+off_s in the k-mer's SA
+// interval means), so one coalesced load of the 2-bit genome window and a few shuffles give the exact vote
+// mask over all k-mers, hence the exact count and the exact round at which the reference's counter reaches
+// kmin (inc/align_seq2_raw.cpp:28-35,262-274).  The entry queued by that very round's hit emits the candidate,
+// which also de-duplicates without any exact table.
+#define GMX_FQ_CAP 256           // vote-queue entries per task; overflow -> exact path
+#define GMX_FILTER_MAX_SEEDS 64
+#define GMX_FILTER_MAX_READ 448  // window words must fit the 32 lanes: (15 + n) / 16 + 2 < 32
+
+struct FilterSmem {              // per-warp layout behind the filter bytes
+    uint32_t queue[GMX_FQ_CAP];
+    unsigned long long codes[GMX_FILTER_MAX_SEEDS];
+    uint16_t offs[GMX_FILTER_MAX_SEEDS];
+    uint8_t qseed[GMX_FQ_CAP];
+    unsigned long long outb[32];     // emitted keys, flushed to the candidate list 32 at a time
+};
+
+__host__ __device__ constexpr size_t gmx_filter_warp_bytes(int f_log2) { return ((size_t)1 << f_log2) + sizeof(FilterSmem); }
+
+// exact vote mask of diagonal d > 0 over the k-mers of the walk (bit s <=> k-mer s hits d)
+__device__ __forceinline__ unsigned long long gmx_exact_mask(const DevIndex &ix, uint32_t pac_words, uint32_t d, int ns, int mer,
+                                                             const FilterSmem *fs, int lane)
+{
+    const uint32_t *pac32 = reinterpret_cast<const uint32_t *>(ix.pac);
+    const uint32_t idx = (d >> 4) + (uint32_t)lane;
+    uint32_t w = idx < pac_words ? __ldg(pac32 + idx) : 0u;
+    w = __byte_perm(w, 0, 0x0123);                                   // bases are packed most significant first
+    unsigned long long mask = 0;
+    for (int g = 0; g < ns; g += 32) {
+        const int s = g + lane;
+        const bool active = s < ns;
+        const uint32_t off = active ? fs->offs[s] : 0u;
+        const uint32_t bit = 2u * ((d & 15u) + off);
+        const int wi = (int)(bit >> 5); const uint32_t sh = bit & 31u;
+        const uint32_t a = __shfl_sync(0xffffffffu, w, wi & 31), b = __shfl_sync(0xffffffffu, w, (wi + 1) & 31),
+                       c = __shfl_sync(0xffffffffu, w, (wi + 2) & 31);
+        unsigned long long top = ((unsigned long long)a << 32) | b;
+        if (sh) top = (top << sh) | (unsigned long long)(c >> (32u - sh));
+        const unsigned long long kmer = top >> (64 - 2 * mer);
+        const bool hit = active && kmer == fs->codes[s] && (unsigned long long)d + off + (unsigned)mer <= ix.seq_len;
+        mask |= (unsigned long long)__ballot_sync(0xffffffffu, hit) << g;
+    }
+    return mask;
+}
+
+// votes k-mer s gives diagonal 0: every occurrence at a position p <= off_s (the reference clamps sa - i at 0)
+__device__ __forceinline__ uint32_t gmx_votes_diag0(const DevIndex &ix, int s, int mer, const FilterSmem *fs)
+{
+    const uint32_t off = fs->offs[s];
+    const unsigned long long code = fs->codes[s];
+    uint32_t votes = 0;
+    for (uint32_t p = 0; p <= off; ++p) {
+        if ((unsigned long long)p + (unsigned)mer > ix.seq_len) break;
+        unsigned long long k = 0;
+        for (int t = 0; t < mer; ++t) k = (k << 2) | (unsigned long long)gmx_pac_base(ix.pac, (int64_t)p + t);
+        votes += (k == code);
+    }
+    return votes;
+}
+
+template <int F_LOG2, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) k_vote_filter(DevIndex ix, uint32_t pac_words, DevReads R, SeedStore S, ClassLists F, ClassLists E,
+                                                            int cls, int kmin, int mer, CandSink sink)
+{
+    constexpr uint32_t FBYTES = 1u << F_LOG2;
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t *filt = smem_raw + (size_t)warp * gmx_filter_warp_bytes(F_LOG2);
+    FilterSmem *fs = reinterpret_cast<FilterSmem *>(filt + FBYTES);
+    const uint32_t n_list = F.count[cls];
+    const uint32_t *list = F.list + (int64_t)cls * F.n_tasks;
+    const uint32_t lt = (1u << lane) - 1u;
+    const int need = kmin - 1;                                       // votes a bucket must already hold
+    while (true) {
+        uint32_t w = 0;
+        if (lane == 0) w = atomicAdd(&F.cursor[cls], 1u);
+        w = __shfl_sync(0xffffffffu, w, 0);
+        if (w >= n_list) break;
+        const uint32_t task = list[w];
+        const int ns = S.n_seeds[task];
+        const int r = (int)(task >> 1), neg = (int)(task & 1);
+        const int64_t roff = R.offsets[r];
+        const int n = (int)(R.offsets[r + 1] - roff);
+        if (ns > GMX_FILTER_MAX_SEEDS || n > GMX_FILTER_MAX_READ) {
+            if (lane == 0) gmx_class_append(E, gmx_exact_class(S.hits[task]), task);
+            continue;
+        }
+        // pull every suffix-array line this task will read into L2 while the filter is being cleared
+        for (int s = 0; s < ns; ++s) {
+            const uint32_t rank0 = S.rank[(int64_t)s * S.n_tasks + task], cnt = S.count[(int64_t)s * S.n_tasks + task];
+            for (uint32_t t = (uint32_t)lane * 32u; t < cnt; t += 1024u)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(ix.sa_full + rank0 + t));
+        }
+        uint4 *f4 = reinterpret_cast<uint4 *>(filt);
+        for (uint32_t x = lane; x < FBYTES / 16; x += 32) f4[x] = make_uint4(0, 0, 0, 0);
+        // 2-bit codes of the k-mers of the walk (oriented read, as k_seed_walk searched them)
+        for (int s = lane; s < ns; s += 32) {
+            const uint32_t off = S.offset[(int64_t)s * S.n_tasks + task];
+            unsigned long long code = 0;
+            for (int t = 0; t < mer; ++t) {
+                const int x = (int)off + t;
+                int c = gmx_nt4(R.seq[roff + (neg ? n - 1 - x : x)]);
+                if (neg) c = 3 - c;
+                code = (code << 2) | (unsigned long long)(c & 3);
+            }
+            fs->codes[s] = code; fs->offs[s] = (uint16_t)off;
+        }
+        __syncwarp();
+
+        // pass 1: count votes approximately, queue the hits that may complete kmin votes
+        uint32_t qn = 0;
+        for (int s = 0; s < ns; ++s) {
+            const uint32_t rank0 = S.rank[(int64_t)s * S.n_tasks + task];
+            const uint32_t cnt = S.count[(int64_t)s * S.n_tasks + task];
+            const uint32_t off = fs->offs[s];
+            for (uint32_t t0 = 0; t0 < cnt; t0 += 32u * GMX_VOTE_UNROLL) {
+                uint32_t sa[GMX_VOTE_UNROLL];
+#pragma unroll
+                for (int u = 0; u < GMX_VOTE_UNROLL; ++u) {
+                    const uint32_t t = t0 + 32u * u + lane;
+                    sa[u] = t < cnt ? __ldg(ix.sa_full + rank0 + t) : GMX_SA_INVALID;
+                }
+#pragma unroll
+                for (int u = 0; u < GMX_VOTE_UNROLL; ++u) {
+                    if (t0 + 32u * u >= cnt) break;
+                    bool valid = sa[u] != GMX_SA_INVALID;
+                    const bool clamp = valid && sa[u] <= off;
+                    const uint32_t diag = clamp ? 0u : sa[u] - off;
+                    uint32_t inc = 1;
+                    const uint32_t cm = __ballot_sync(0xffffffffu, clamp);
+                    if (cm && clamp) { if (lane != __ffs(cm) - 1) valid = false; else inc = (uint32_t)__popc(cm); }
+                    const uint32_t h1 = (diag * 0x9E3779B1u) >> (32 - F_LOG2), h2 = (diag * 0x85EBCA77u + 0x27D4EB2Fu) >> (32 - F_LOG2);
+                    bool flag = false;
+                    if (valid) {
+                        const uint32_t c1 = filt[h1], c2 = filt[h2];
+                        flag = (int)(min(c1, c2) + inc) > need;
+                        filt[h1] = (uint8_t)min(c1 + inc, 255u);
+                        filt[h2] = (uint8_t)min((h2 == h1 ? c1 : c2) + inc, 255u);
+                    }
+                    const uint32_t fm = __ballot_sync(0xffffffffu, flag);
+                    if (fm) {
+                        if (flag) {
+                            const uint32_t at = qn + (uint32_t)__popc(fm & lt);
+                            if (at < GMX_FQ_CAP) { fs->queue[at] = diag; fs->qseed[at] = (uint8_t)s; }
+                        }
+                        qn += (uint32_t)__popc(fm);
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+        if (qn > GMX_FQ_CAP) {                                         // repeat-rich read: exact tables take over
+            if (lane == 0) gmx_class_append(E, gmx_exact_class(S.hits[task]), task);
+            continue;
+        }
+
+        // pass 2: exact verification of the queued diagonals
+        uint32_t ne = 0;
+        uint32_t d_prev = GMX_EMPTY_KEY; unsigned long long m_prev = 0;
+        auto flush = [&]() {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(sink.count, ne);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            __syncwarp();
+            if ((uint32_t)lane < ne) {
+                if (base + lane < sink.cap) sink.keys[base + lane] = fs->outb[lane];
+                else *sink.overflow = 1u;
+            }
+            __syncwarp();
+            ne = 0;
+        };
+        for (uint32_t q = 0; q < qn; ++q) {
+            const uint32_t d = fs->queue[q];
+            const int sf = fs->qseed[q];
+            bool emit = false;
+            if (d != 0) {
+                if (d != d_prev) { m_prev = gmx_exact_mask(ix, pac_words, d, ns, mer, fs, lane); d_prev = d; }
+                const unsigned long long before = m_prev & ((1ull << sf) - 1ull);
+                emit = ((m_prev >> sf) & 1ull) && __popcll(before) == need;
+            } else {
+                // diagonal 0 collects every hit with sa <= off (several per k-mer): cumulative votes, lanes = k-mers
+                uint32_t cum_before = 0, own = 0;
+                for (int g = 0; g < ns; g += 32) {
+                    const int s = g + lane;
+                    const uint32_t v = s < ns ? gmx_votes_diag0(ix, s, mer, fs) : 0u;
+                    uint32_t below = (s < sf) ? v : 0u, mine = (s == sf) ? v : 0u;
+#pragma unroll
+                    for (int o = 16; o; o >>= 1) { below += __shfl_xor_sync(0xffffffffu, below, o); mine += __shfl_xor_sync(0xffffffffu, mine, o); }
+                    cum_before += below; own += mine;
+                }
+                emit = (int)cum_before < kmin && (int)(cum_before + own) >= kmin;
+            }
+            if (emit) {
+                if (lane == 0) fs->outb[ne] = ((unsigned long long)task << 40) | ((unsigned long long)sf << 32) | d;
+                ne++;
+                if (ne == 32) flush();
+            }
+        }
+        if (ne) flush();
         __syncwarp();
     }
 }

@@ -244,6 +244,8 @@ int gmx_finish(gmx_ctx *ctx, float *amount_genome, float *const planes[5]);
 #define GMX_OPT_COLLECT_HITS 1   /* 1 (default): keep every accepted (pos,strand) for gmx_get_hits; 0: only the
                                     per-read results and the best group's CIGAR leave the device           */
 #define GMX_OPT_CHUNK_READS  2   /* reads processed per internal chunk (default 262144)                     */
+#define GMX_OPT_VOTE_FILTER  3   /* 1 (default): counting-filter + exact-verification vote kernel with the exact
+                                    hash-table kernels as its overflow path; 0: exact hash tables for every task  */
 int gmx_set_option(gmx_ctx *ctx, int option, int64_t value);
 
 /* ---- instrumentation ---------------------------------------------------------------------- */

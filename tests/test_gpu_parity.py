@@ -138,6 +138,12 @@ def test_pipeline_matches_oracle(api, O, world, mode):
     want = O.process_batch(O.OracleIndex(ix), po, batch)
     common.compare_batches(got, want)
     common.accum_close(amount, want["amount"], want["hits"], batch.offsets, pg.gen_size, ix.l_pac)
+    if mode == _abi.MODE_NORMAL:
+        # the exact hash-table vote kernels alone (the filter kernel's overflow path) must give the same answer
+        m.reset_accumulators()
+        m.set_option(api.OPT_VOTE_FILTER, 0)
+        common.compare_batches(m.process_batch(batch), want)
+        m.set_option(api.OPT_VOTE_FILTER, 1)
     if mode != _abi.MODE_NORMAL:
         for b in range(5):
             common.accum_close(planes[b], want["planes"][b], want["hits"], batch.offsets, pg.gen_size, ix.l_pac, what=f"plane {b}")
