@@ -76,6 +76,7 @@ struct gmx_ctx {
     DevReads dreads;
     std::vector<int64_t> h_offsets;            // offsets of the last batch (for gmx_get_hits)
     // pipeline buffers
+    DevBuf d_seed_code;
     DevBuf d_prep, d_seed_rank, d_seed_count, d_seed_off, d_seed_n, d_seed_hits, d_cls_list, d_cls_meta;
     DevBuf d_keys, d_keys_alt, d_sort_tmp, d_score, d_leader, d_slot, d_lead_cand, d_hashes, d_expv, d_counters;
     DevBuf d_results, d_alen, d_aligned, d_cigar, d_hmm, d_moves, d_arena, d_phmm_scratch;
@@ -366,7 +367,7 @@ extern "C" void gmx_destroy(gmx_ctx *ctx)
                       &ctx->d_seed_count, &ctx->d_seed_off, &ctx->d_seed_n, &ctx->d_seed_hits, &ctx->d_cls_list, &ctx->d_cls_meta,
                       &ctx->d_keys, &ctx->d_keys_alt, &ctx->d_sort_tmp, &ctx->d_score, &ctx->d_leader, &ctx->d_slot, &ctx->d_lead_cand,
                       &ctx->d_hashes, &ctx->d_expv, &ctx->d_counters, &ctx->d_results, &ctx->d_alen, &ctx->d_aligned, &ctx->d_cigar,
-                      &ctx->d_hmm, &ctx->d_moves, &ctx->d_arena, &ctx->d_phmm_scratch, &ctx->d_best_cigar};
+                      &ctx->d_hmm, &ctx->d_moves, &ctx->d_arena, &ctx->d_phmm_scratch, &ctx->d_best_cigar, &ctx->d_seed_code};
     for (DevBuf *b : bufs) b->release();
     ctx->h_best_cigar.release();
     if (ctx->ev[0][0]) for (int s = 0; s < ST_COUNT; ++s) { cudaEventDestroy(ctx->ev[s][0]); cudaEventDestroy(ctx->ev[s][1]); }
@@ -711,7 +712,7 @@ static cudaError_t launch_filter(gmx_ctx *ctx, const SeedStore &S, const ClassLi
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_vote_filter<FL, WARPS>, WARPS * 32, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
-    k_vote_filter<FL, WARPS><<<n_sm * per_sm, WARPS * 32, smem, ctx->stream>>>(ctx->ix, pac_words, ctx->dreads, S, F, E, cls, ctx->dparams.kmin,
+    k_vote_filter<FL, WARPS><<<n_sm * per_sm, WARPS * 32, smem, ctx->stream>>>(ctx->ix, pac_words, S, F, E, cls, ctx->dparams.kmin,
                                                                               ctx->dparams.mer, sink);
     return cudaGetLastError();
 }
@@ -744,6 +745,7 @@ static int phase_a(gmx_ctx *ctx, const gmx_reads *reads, int32_t lo, int32_t hi)
     CK(ctx->d_seed_rank.ensure((size_t)max_seeds * n_tasks * 4));
     CK(ctx->d_seed_count.ensure((size_t)max_seeds * n_tasks * 4));
     CK(ctx->d_seed_off.ensure((size_t)max_seeds * n_tasks * 2));
+    CK(ctx->d_seed_code.ensure((size_t)max_seeds * n_tasks * 8));
     CK(ctx->d_seed_n.ensure((size_t)n_tasks));
     CK(ctx->d_seed_hits.ensure((size_t)n_tasks * 4));
     CK(ctx->d_cls_list.ensure((size_t)2 * GMX_N_CLASSES * n_tasks * 4));
@@ -754,7 +756,7 @@ static int phase_a(gmx_ctx *ctx, const gmx_reads *reads, int32_t lo, int32_t hi)
     Counters *dc = ctx->d_counters.as<Counters>();
     ChunkStats *ds = reinterpret_cast<ChunkStats *>(dc + 1);
     SeedStore S;
-    S.rank = ctx->d_seed_rank.as<uint32_t>(); S.count = ctx->d_seed_count.as<uint32_t>(); S.offset = ctx->d_seed_off.as<uint16_t>();
+    S.rank = ctx->d_seed_rank.as<uint32_t>(); S.count = ctx->d_seed_count.as<uint32_t>(); S.offset = ctx->d_seed_off.as<uint16_t>(); S.code = ctx->d_seed_code.as<unsigned long long>();
     S.n_seeds = ctx->d_seed_n.as<uint8_t>(); S.hits = ctx->d_seed_hits.as<uint32_t>(); S.max_seeds = max_seeds; S.n_tasks = n_tasks;
     ClassLists C;
     C.list = ctx->d_cls_list.as<uint32_t>(); C.count = dc->cls_count; C.cursor = dc->cls_cursor; C.n_tasks = n_tasks;

@@ -66,15 +66,17 @@ __global__ void k_prep_reads(DevReads R, DevTables T, DevParams P, ReadPrep *pre
 // ---- k-mer walk ---------------------------------------------------------------------------------
 // One thread per task = (read, strand).  The walk is sequentially data dependent (the next offset
 // depends on whether the previous k-mer hit), so the parallelism is across the 2 x n_reads tasks.
-// Seeds are stored SoA with stride n_tasks so that consecutive threads write consecutive words.
 struct SeedStore {
-    uint32_t *rank;    // [max_seeds][n_tasks] first SA rank of the interval
-    uint32_t *count;   // [max_seeds][n_tasks] interval size
-    uint16_t *offset;  // [max_seeds][n_tasks] k-mer offset i in the oriented read
+    uint32_t *rank;    // [n_tasks][max_seeds] first SA rank of the interval
+    uint32_t *count;   // [n_tasks][max_seeds] interval size
+    uint16_t *offset;  // [n_tasks][max_seeds] k-mer offset i in the oriented read
+    unsigned long long *code;  // [n_tasks][max_seeds] the k-mer itself, 2 bits per base, first base most significant
     uint8_t  *n_seeds; // [n_tasks]
     uint32_t *hits;    // [n_tasks] total SA hits of the task
     int max_seeds;
     int64_t n_tasks;
+    // one task's seeds are contiguous: the vote kernels read them with the lanes of one warp
+    __host__ __device__ __forceinline__ int64_t at(int64_t task, int s) const { return task * max_seeds + s; }
 };
 
 // stats[0] += k-mer lookups, stats[1] += backward-search steps (one bwt_2occ each), stats[2] += SA hits
@@ -113,9 +115,12 @@ __global__ void k_seed_walk(DevIndex ix, DevReads R, DevParams P, const ReadPrep
             i += j;
             if (!found) break;
             if (ns < S.max_seeds) {
-                S.rank[(int64_t)ns * S.n_tasks + task] = (uint32_t)k;
-                S.count[(int64_t)ns * S.n_tasks + task] = (uint32_t)(l - k + 1);
-                S.offset[(int64_t)ns * S.n_tasks + task] = (uint16_t)i;
+                S.rank[S.at(task, ns)] = (uint32_t)k;
+                S.count[S.at(task, ns)] = (uint32_t)(l - k + 1);
+                S.offset[S.at(task, ns)] = (uint16_t)i;
+                unsigned long long code = 0;
+                for (int t = 0; t < P.mer; ++t) code = (code << 2) | (unsigned long long)(sym_at((int)i + t) & 3u);
+                S.code[S.at(task, ns)] = code;
                 total += (uint32_t)(l - k + 1);
                 ns++;
             }
@@ -207,9 +212,9 @@ __device__ __forceinline__ void gmx_vote_task(const DevIndex &ix, const SeedStor
 {
     int ns = S.n_seeds[task];
     for (int s = 0; s < ns; ++s) {
-        uint32_t rank0 = S.rank[(int64_t)s * S.n_tasks + task];
-        uint32_t cnt = S.count[(int64_t)s * S.n_tasks + task];
-        uint32_t off = S.offset[(int64_t)s * S.n_tasks + task];
+        uint32_t rank0 = S.rank[S.at(task, s)];
+        uint32_t cnt = S.count[S.at(task, s)];
+        uint32_t off = S.offset[S.at(task, s)];
         for (uint32_t t0 = 0; t0 < cnt; t0 += 32) {
             uint32_t t = t0 + lane;
             bool valid = t < cnt;
@@ -322,7 +327,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_vote_smem(DevIndex ix, SeedStore
         const int ns = S.n_seeds[task];
         // pull every suffix-array line this task will read into L2 while the table is being cleared
         for (int s = 0; s < ns; ++s) {
-            const uint32_t rank0 = S.rank[(int64_t)s * S.n_tasks + task], cnt = S.count[(int64_t)s * S.n_tasks + task];
+            const uint32_t rank0 = S.rank[S.at(task, s)], cnt = S.count[S.at(task, s)];
             for (uint32_t t = (uint32_t)lane * 32u; t < cnt; t += 1024u)
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(ix.sa_full + rank0 + t));
         }
@@ -332,9 +337,9 @@ __global__ void __launch_bounds__(WARPS * 32) k_vote_smem(DevIndex ix, SeedStore
         for (uint32_t x = lane; x < SLOTS / 16; x += 32) c4[x] = make_uint4(0, 0, 0, 0);
         __syncwarp();
         for (int s = 0; s < ns; ++s) {
-            const uint32_t rank0 = S.rank[(int64_t)s * S.n_tasks + task];
-            const uint32_t cnt = S.count[(int64_t)s * S.n_tasks + task];
-            const uint32_t off = S.offset[(int64_t)s * S.n_tasks + task];
+            const uint32_t rank0 = S.rank[S.at(task, s)];
+            const uint32_t cnt = S.count[S.at(task, s)];
+            const uint32_t off = S.offset[S.at(task, s)];
             for (uint32_t t0 = 0; t0 < cnt; t0 += 32u * GMX_VOTE_UNROLL) {
                 uint32_t sa[GMX_VOTE_UNROLL];
 #pragma unroll
@@ -366,26 +371,31 @@ __global__ void __launch_bounds__(WARPS * 32) k_vote_smem(DevIndex ix, SeedStore
 // which also de-duplicates without any exact table.
 #define GMX_FQ_CAP 256           // vote-queue entries per task; overflow -> exact path
 #define GMX_FILTER_MAX_SEEDS 64
-#define GMX_FILTER_MAX_READ 448  // window words must fit the 32 lanes: (15 + n) / 16 + 2 < 32
+#define GMX_FILTER_MAX_SPAN 448  // max k-mer offset + mer: the window words must fit the 32 lanes ((15 + span) / 16 + 2 < 32)
 
 struct FilterSmem {              // per-warp layout behind the filter bytes
     uint32_t queue[GMX_FQ_CAP];
     unsigned long long codes[GMX_FILTER_MAX_SEEDS];
-    uint16_t offs[GMX_FILTER_MAX_SEEDS];
-    uint8_t qseed[GMX_FQ_CAP];
     unsigned long long outb[32];     // emitted keys, flushed to the candidate list 32 at a time
+    uint32_t rank[GMX_FILTER_MAX_SEEDS];
+    uint32_t cnt[GMX_FILTER_MAX_SEEDS];
+    uint16_t offs[GMX_FILTER_MAX_SEEDS];
 };
 
 __host__ __device__ constexpr size_t gmx_filter_warp_bytes(int f_log2) { return ((size_t)1 << f_log2) + sizeof(FilterSmem); }
 
-// exact vote mask of diagonal d > 0 over the k-mers of the walk (bit s <=> k-mer s hits d)
-__device__ __forceinline__ unsigned long long gmx_exact_mask(const DevIndex &ix, uint32_t pac_words, uint32_t d, int ns, int mer,
+// the 2-bit genome window of diagonal d: lane l holds 16 bases starting at 16 * (d / 16 + l), first base most significant
+__device__ __forceinline__ uint32_t gmx_window_word(const DevIndex &ix, uint32_t pac_words, uint32_t d, int lane)
+{
+    const uint32_t idx = (d >> 4) + (uint32_t)lane;
+    const uint32_t w = idx < pac_words ? __ldg(reinterpret_cast<const uint32_t *>(ix.pac) + idx) : 0u;
+    return __byte_perm(w, 0, 0x0123);
+}
+
+// exact vote mask of diagonal d > 0 over the k-mers of the walk (bit s <=> k-mer s hits d), from its window words
+__device__ __forceinline__ unsigned long long gmx_exact_mask(const DevIndex &ix, uint32_t w, uint32_t d, int ns, int mer,
                                                              const FilterSmem *fs, int lane)
 {
-    const uint32_t *pac32 = reinterpret_cast<const uint32_t *>(ix.pac);
-    const uint32_t idx = (d >> 4) + (uint32_t)lane;
-    uint32_t w = idx < pac_words ? __ldg(pac32 + idx) : 0u;
-    w = __byte_perm(w, 0, 0x0123);                                   // bases are packed most significant first
     unsigned long long mask = 0;
     for (int g = 0; g < ns; g += 32) {
         const int s = g + lane;
@@ -404,26 +414,40 @@ __device__ __forceinline__ unsigned long long gmx_exact_mask(const DevIndex &ix,
     return mask;
 }
 
-// votes k-mer s gives diagonal 0: every occurrence at a position p <= off_s (the reference clamps sa - i at 0)
-__device__ __forceinline__ uint32_t gmx_votes_diag0(const DevIndex &ix, int s, int mer, const FilterSmem *fs)
+// round at which diagonal 0 reaches kmin votes, or -1.  Diagonal 0 collects every occurrence of k-mer s at a
+// position p <= off_s (the reference clamps sa - i at 0, inc/align_seq2_raw.cpp:270), several per k-mer.
+__device__ int gmx_round_diag0(const DevIndex &ix, int ns, int mer, int kmin, const FilterSmem *fs, int lane)
 {
-    const uint32_t off = fs->offs[s];
-    const unsigned long long code = fs->codes[s];
-    uint32_t votes = 0;
-    for (uint32_t p = 0; p <= off; ++p) {
-        if ((unsigned long long)p + (unsigned)mer > ix.seq_len) break;
-        unsigned long long k = 0;
-        for (int t = 0; t < mer; ++t) k = (k << 2) | (unsigned long long)gmx_pac_base(ix.pac, (int64_t)p + t);
-        votes += (k == code);
+    uint32_t carry = 0;
+    for (int g = 0; g < ns; g += 32) {
+        const int s = g + lane;
+        uint32_t v = 0;
+        if (s < ns) {
+            const uint32_t off = fs->offs[s];
+            const unsigned long long code = fs->codes[s];
+            for (uint32_t p = 0; p <= off && (unsigned long long)p + (unsigned)mer <= ix.seq_len; ++p) {
+                unsigned long long k = 0;
+                for (int t = 0; t < mer; ++t) k = (k << 2) | (unsigned long long)gmx_pac_base(ix.pac, (int64_t)p + t);
+                v += (k == code);
+            }
+        }
+        uint32_t cum = v;                                            // inclusive scan over the lanes
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, cum, o); if (lane >= o) cum += t; }
+        cum += carry;
+        const uint32_t reached = __ballot_sync(0xffffffffu, (int)cum >= kmin);
+        if (reached) return g + __ffs(reached) - 1;
+        carry = __shfl_sync(0xffffffffu, cum, 31);
     }
-    return votes;
+    return -1;
 }
 
 template <int F_LOG2, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) k_vote_filter(DevIndex ix, uint32_t pac_words, DevReads R, SeedStore S, ClassLists F, ClassLists E,
+__global__ void __launch_bounds__(WARPS * 32, 1) k_vote_filter(DevIndex ix, uint32_t pac_words, SeedStore S, ClassLists F, ClassLists E,
                                                             int cls, int kmin, int mer, CandSink sink)
 {
     constexpr uint32_t FBYTES = 1u << F_LOG2;
+    constexpr int U = GMX_VOTE_UNROLL;
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint8_t *filt = smem_raw + (size_t)warp * gmx_filter_warp_bytes(F_LOG2);
@@ -432,92 +456,144 @@ __global__ void __launch_bounds__(WARPS * 32) k_vote_filter(DevIndex ix, uint32_
     const uint32_t *list = F.list + (int64_t)cls * F.n_tasks;
     const uint32_t lt = (1u << lane) - 1u;
     const int need = kmin - 1;                                       // votes a bucket must already hold
-    while (true) {
+
+    // seeds of a task in registers: seed `lane` and seed `lane + 32`; fetched one task ahead
+    struct Meta { uint32_t task; int ns; uint32_t rank[2], cnt[2], off[2]; unsigned long long code[2]; };
+    auto next_work = [&]() -> uint32_t {
         uint32_t w = 0;
         if (lane == 0) w = atomicAdd(&F.cursor[cls], 1u);
-        w = __shfl_sync(0xffffffffu, w, 0);
-        if (w >= n_list) break;
-        const uint32_t task = list[w];
-        const int ns = S.n_seeds[task];
-        const int r = (int)(task >> 1), neg = (int)(task & 1);
-        const int64_t roff = R.offsets[r];
-        const int n = (int)(R.offsets[r + 1] - roff);
-        if (ns > GMX_FILTER_MAX_SEEDS || n > GMX_FILTER_MAX_READ) {
+        return __shfl_sync(0xffffffffu, w, 0);
+    };
+    auto fetch = [&](uint32_t w, Meta &m) {
+        m.task = list[w];
+        m.ns = S.n_seeds[m.task];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int s = lane + 32 * h;
+            const bool in = s < m.ns && s < GMX_FILTER_MAX_SEEDS;
+            const int64_t at = S.at(m.task, in ? s : 0);
+            m.rank[h] = in ? S.rank[at] : 0u; m.cnt[h] = in ? S.count[at] : 0u; m.off[h] = in ? S.offset[at] : 0u;
+            m.code[h] = in ? S.code[at] : 0ull;
+        }
+    };
+
+    Meta cur, nxt;
+    uint32_t w = next_work();
+    if (w < n_list) fetch(w, cur);
+    while (w < n_list) {
+        const uint32_t task = cur.task;
+        const int ns = cur.ns;
+        bool unsupported = ns > GMX_FILTER_MAX_SEEDS;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int s = lane + 32 * h;
+            if (s < GMX_FILTER_MAX_SEEDS) { fs->rank[s] = cur.rank[h]; fs->cnt[s] = cur.cnt[h]; fs->offs[s] = (uint16_t)cur.off[h]; fs->codes[s] = cur.code[h]; }
+            if (s < ns && cur.off[h] + (uint32_t)mer > GMX_FILTER_MAX_SPAN) unsupported = true;
+        }
+        unsupported = __any_sync(0xffffffffu, unsupported);
+        // the next task's seeds travel while this one is processed
+        w = next_work();
+        if (w < n_list) fetch(w, nxt);
+        if (unsupported) {
             if (lane == 0) gmx_class_append(E, gmx_exact_class(S.hits[task]), task);
+            cur = nxt;
             continue;
         }
         // pull every suffix-array line this task will read into L2 while the filter is being cleared
-        for (int s = 0; s < ns; ++s) {
-            const uint32_t rank0 = S.rank[(int64_t)s * S.n_tasks + task], cnt = S.count[(int64_t)s * S.n_tasks + task];
-            for (uint32_t t = (uint32_t)lane * 32u; t < cnt; t += 1024u)
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(ix.sa_full + rank0 + t));
-        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+            for (uint32_t t = 0; t < cur.cnt[h]; t += 32u)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(ix.sa_full + cur.rank[h] + t));
         uint4 *f4 = reinterpret_cast<uint4 *>(filt);
         for (uint32_t x = lane; x < FBYTES / 16; x += 32) f4[x] = make_uint4(0, 0, 0, 0);
-        // 2-bit codes of the k-mers of the walk (oriented read, as k_seed_walk searched them)
-        for (int s = lane; s < ns; s += 32) {
-            const uint32_t off = S.offset[(int64_t)s * S.n_tasks + task];
-            unsigned long long code = 0;
-            for (int t = 0; t < mer; ++t) {
-                const int x = (int)off + t;
-                int c = gmx_nt4(R.seq[roff + (neg ? n - 1 - x : x)]);
-                if (neg) c = 3 - c;
-                code = (code << 2) | (unsigned long long)(c & 3);
-            }
-            fs->codes[s] = code; fs->offs[s] = (uint16_t)off;
-        }
         __syncwarp();
 
-        // pass 1: count votes approximately, queue the hits that may complete kmin votes
+        // pass 1: count votes approximately, queue the hits that may complete kmin votes.  The hits of ONE k-mer
+        // are distinct diagonals, so up to 32 * U of them are handled as one step: all loads, then all stores.
         uint32_t qn = 0;
         for (int s = 0; s < ns; ++s) {
-            const uint32_t rank0 = S.rank[(int64_t)s * S.n_tasks + task];
-            const uint32_t cnt = S.count[(int64_t)s * S.n_tasks + task];
-            const uint32_t off = fs->offs[s];
-            for (uint32_t t0 = 0; t0 < cnt; t0 += 32u * GMX_VOTE_UNROLL) {
-                uint32_t sa[GMX_VOTE_UNROLL];
+            const uint32_t rank0 = fs->rank[s], cnt = fs->cnt[s], off = fs->offs[s];
+            for (uint32_t t0 = 0; t0 < cnt; t0 += 32u * U) {
+                uint32_t sa[U], diag[U], inc[U];
+                bool valid[U];
 #pragma unroll
-                for (int u = 0; u < GMX_VOTE_UNROLL; ++u) {
+                for (int u = 0; u < U; ++u) {
                     const uint32_t t = t0 + 32u * u + lane;
-                    sa[u] = t < cnt ? __ldg(ix.sa_full + rank0 + t) : GMX_SA_INVALID;
+                    valid[u] = t < cnt;
+                    sa[u] = valid[u] ? __ldg(ix.sa_full + rank0 + t) : GMX_SA_INVALID;
+                }
+                bool any_clamp = false;
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const bool clamp = valid[u] && sa[u] <= off;
+                    any_clamp |= clamp;
+                    diag[u] = clamp ? 0u : sa[u] - off;
+                    inc[u] = 1;
+                }
+                if (__any_sync(0xffffffffu, any_clamp)) {              // hits on diagonal 0: one lane votes for all of them
+                    uint32_t total = 0; int first_u = -1, first_lane = -1;
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const uint32_t cm = __ballot_sync(0xffffffffu, valid[u] && sa[u] <= off);
+                        if (cm && first_u < 0) { first_u = u; first_lane = __ffs(cm) - 1; }
+                        total += (uint32_t)__popc(cm);
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+                        if (valid[u] && sa[u] <= off) { valid[u] = (u == first_u && lane == first_lane); inc[u] = total; }
+                }
+                uint32_t h1[U], h2[U], c1[U], c2[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    h1[u] = (diag[u] * 0x9E3779B1u) >> (32 - F_LOG2); h2[u] = (diag[u] * 0x85EBCA77u + 0x27D4EB2Fu) >> (32 - F_LOG2);
                 }
 #pragma unroll
-                for (int u = 0; u < GMX_VOTE_UNROLL; ++u) {
-                    if (t0 + 32u * u >= cnt) break;
-                    bool valid = sa[u] != GMX_SA_INVALID;
-                    const bool clamp = valid && sa[u] <= off;
-                    const uint32_t diag = clamp ? 0u : sa[u] - off;
-                    uint32_t inc = 1;
-                    const uint32_t cm = __ballot_sync(0xffffffffu, clamp);
-                    if (cm && clamp) { if (lane != __ffs(cm) - 1) valid = false; else inc = (uint32_t)__popc(cm); }
-                    const uint32_t h1 = (diag * 0x9E3779B1u) >> (32 - F_LOG2), h2 = (diag * 0x85EBCA77u + 0x27D4EB2Fu) >> (32 - F_LOG2);
-                    bool flag = false;
-                    if (valid) {
-                        const uint32_t c1 = filt[h1], c2 = filt[h2];
-                        flag = (int)(min(c1, c2) + inc) > need;
-                        filt[h1] = (uint8_t)min(c1 + inc, 255u);
-                        filt[h2] = (uint8_t)min((h2 == h1 ? c1 : c2) + inc, 255u);
+                for (int u = 0; u < U; ++u) { c1[u] = valid[u] ? filt[h1[u]] : 0u; c2[u] = valid[u] ? filt[h2[u]] : 0u; }
+                bool flag[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    flag[u] = valid[u] && (int)(min(c1[u], c2[u]) + inc[u]) > need;
+                    if (valid[u]) {
+                        filt[h1[u]] = (uint8_t)min(c1[u] + inc[u], 255u);
+                        filt[h2[u]] = (uint8_t)min(c2[u] + inc[u], 255u);
                     }
-                    const uint32_t fm = __ballot_sync(0xffffffffu, flag);
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const uint32_t fm = __ballot_sync(0xffffffffu, flag[u]);
                     if (fm) {
-                        if (flag) {
+                        if (flag[u]) {
                             const uint32_t at = qn + (uint32_t)__popc(fm & lt);
-                            if (at < GMX_FQ_CAP) { fs->queue[at] = diag; fs->qseed[at] = (uint8_t)s; }
+                            if (at < GMX_FQ_CAP) fs->queue[at] = diag[u];
                         }
                         qn += (uint32_t)__popc(fm);
                     }
-                    __syncwarp();
                 }
+                __syncwarp();
             }
         }
         if (qn > GMX_FQ_CAP) {                                         // repeat-rich read: exact tables take over
             if (lane == 0) gmx_class_append(E, gmx_exact_class(S.hits[task]), task);
+            cur = nxt;
             continue;
         }
 
-        // pass 2: exact verification of the queued diagonals
+        // distinct queued diagonals, compacted in place (a diagonal is queued once per k-mer that hits it)
+        uint32_t n2 = 0;
+        for (uint32_t q0 = 0; q0 < qn; q0 += 32) {
+            const uint32_t q = q0 + lane;
+            const uint32_t d = q < qn ? fs->queue[q] : 0u;
+            bool first = q < qn;
+            for (uint32_t j = 0; j < q0 + 32 && j < qn; ++j) first = first && !(fs->queue[j] == d && j < q);
+            __syncwarp();
+            const uint32_t fm = __ballot_sync(0xffffffffu, first);
+            if (first) fs->queue[n2 + (uint32_t)__popc(fm & lt)] = d;   // n2 + rank <= q: never overtakes unread entries
+            n2 += (uint32_t)__popc(fm);
+            __syncwarp();
+        }
+
+        // pass 2: exact votes of each distinct diagonal from its genome window, four windows in flight
         uint32_t ne = 0;
-        uint32_t d_prev = GMX_EMPTY_KEY; unsigned long long m_prev = 0;
         auto flush = [&]() {
             uint32_t base = 0;
             if (lane == 0) base = atomicAdd(sink.count, ne);
@@ -530,35 +606,37 @@ __global__ void __launch_bounds__(WARPS * 32) k_vote_filter(DevIndex ix, uint32_
             __syncwarp();
             ne = 0;
         };
-        for (uint32_t q = 0; q < qn; ++q) {
-            const uint32_t d = fs->queue[q];
-            const int sf = fs->qseed[q];
-            bool emit = false;
-            if (d != 0) {
-                if (d != d_prev) { m_prev = gmx_exact_mask(ix, pac_words, d, ns, mer, fs, lane); d_prev = d; }
-                const unsigned long long before = m_prev & ((1ull << sf) - 1ull);
-                emit = ((m_prev >> sf) & 1ull) && __popcll(before) == need;
-            } else {
-                // diagonal 0 collects every hit with sa <= off (several per k-mer): cumulative votes, lanes = k-mers
-                uint32_t cum_before = 0, own = 0;
-                for (int g = 0; g < ns; g += 32) {
-                    const int s = g + lane;
-                    const uint32_t v = s < ns ? gmx_votes_diag0(ix, s, mer, fs) : 0u;
-                    uint32_t below = (s < sf) ? v : 0u, mine = (s == sf) ? v : 0u;
+        for (uint32_t q0 = 0; q0 < n2; q0 += 4) {
+            uint32_t d[4], ww[4];
 #pragma unroll
-                    for (int o = 16; o; o >>= 1) { below += __shfl_xor_sync(0xffffffffu, below, o); mine += __shfl_xor_sync(0xffffffffu, mine, o); }
-                    cum_before += below; own += mine;
-                }
-                emit = (int)cum_before < kmin && (int)(cum_before + own) >= kmin;
+            for (int i = 0; i < 4; ++i) {
+                d[i] = q0 + i < n2 ? fs->queue[q0 + i] : GMX_EMPTY_KEY;
+                ww[i] = (d[i] != GMX_EMPTY_KEY && d[i] != 0u) ? gmx_window_word(ix, pac_words, d[i], lane) : 0u;
             }
-            if (emit) {
-                if (lane == 0) fs->outb[ne] = ((unsigned long long)task << 40) | ((unsigned long long)sf << 32) | d;
-                ne++;
-                if (ne == 32) flush();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (d[i] == GMX_EMPTY_KEY) continue;
+                int round = -1;
+                if (d[i] != 0u) {
+                    const unsigned long long m = gmx_exact_mask(ix, ww[i], d[i], ns, mer, fs, lane);
+                    if (__popcll(m) >= kmin) {
+                        const uint32_t lo = (uint32_t)m, hi = (uint32_t)(m >> 32);
+                        const int pl = __popc(lo);
+                        round = kmin <= pl ? (int)__fns(lo, 0, kmin) : 32 + (int)__fns(hi, 0, kmin - pl);
+                    }
+                } else {
+                    round = gmx_round_diag0(ix, ns, mer, kmin, fs, lane);
+                }
+                if (round >= 0) {
+                    if (lane == 0) fs->outb[ne] = ((unsigned long long)task << 40) | ((unsigned long long)round << 32) | d[i];
+                    ne++;
+                    if (ne == 32) flush();
+                }
             }
         }
         if (ne) flush();
         __syncwarp();
+        cur = nxt;
     }
 }
 
