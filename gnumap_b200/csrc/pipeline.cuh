@@ -384,32 +384,32 @@ struct FilterSmem {              // per-warp layout behind the filter bytes
 
 __host__ __device__ constexpr size_t gmx_filter_warp_bytes(int f_log2) { return ((size_t)1 << f_log2) + sizeof(FilterSmem); }
 
-// the 2-bit genome window of diagonal d: lane l holds 16 bases starting at 16 * (d / 16 + l), first base most significant
-__device__ __forceinline__ uint32_t gmx_window_word(const DevIndex &ix, uint32_t pac_words, uint32_t d, int lane)
-{
-    const uint32_t idx = (d >> 4) + (uint32_t)lane;
-    const uint32_t w = idx < pac_words ? __ldg(reinterpret_cast<const uint32_t *>(ix.pac) + idx) : 0u;
-    return __byte_perm(w, 0, 0x0123);
-}
-
-// exact vote mask of diagonal d > 0 over the k-mers of the walk (bit s <=> k-mer s hits d), from its window words
-__device__ __forceinline__ unsigned long long gmx_exact_mask(const DevIndex &ix, uint32_t w, uint32_t d, int ns, int mer,
-                                                             const FilterSmem *fs, int lane)
+// exact vote mask of diagonal d > 0 over the k-mers of the walk (bit s <=> k-mer s hits d), from its window words.
+// Lane l holds k-mers l and l + 32 of the walk in registers: offset, code, and the last diagonal at which the
+// k-mer still fits the genome (seq_len - off - mer).
+template <bool SHORT_MER>
+__device__ __forceinline__ unsigned long long gmx_exact_mask(uint32_t w, uint32_t d, int ns, int mer, const uint32_t off[2],
+                                                             const unsigned long long code[2], const uint32_t limit[2], int lane)
 {
     unsigned long long mask = 0;
-    for (int g = 0; g < ns; g += 32) {
-        const int s = g + lane;
-        const bool active = s < ns;
-        const uint32_t off = active ? fs->offs[s] : 0u;
-        const uint32_t bit = 2u * ((d & 15u) + off);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        if (h == 1 && ns <= 32) break;
+        const bool active = lane + 32 * h < ns;
+        const uint32_t bit = 2u * ((d & 15u) + off[h]);
         const int wi = (int)(bit >> 5); const uint32_t sh = bit & 31u;
-        const uint32_t a = __shfl_sync(0xffffffffu, w, wi & 31), b = __shfl_sync(0xffffffffu, w, (wi + 1) & 31),
-                       c = __shfl_sync(0xffffffffu, w, (wi + 2) & 31);
-        unsigned long long top = ((unsigned long long)a << 32) | b;
-        if (sh) top = (top << sh) | (unsigned long long)(c >> (32u - sh));
-        const unsigned long long kmer = top >> (64 - 2 * mer);
-        const bool hit = active && kmer == fs->codes[s] && (unsigned long long)d + off + (unsigned)mer <= ix.seq_len;
-        mask |= (unsigned long long)__ballot_sync(0xffffffffu, hit) << g;
+        const uint32_t a = __shfl_sync(0xffffffffu, w, wi & 31), b = __shfl_sync(0xffffffffu, w, (wi + 1) & 31);
+        bool hit;
+        if (SHORT_MER) {                                             // mer <= 16: the k-mer fits one word
+            const uint32_t top = __funnelshift_l(b, a, sh);
+            hit = (top >> (32 - 2 * mer)) == (uint32_t)code[h];
+        } else {
+            const uint32_t c = __shfl_sync(0xffffffffu, w, (wi + 2) & 31);
+            const unsigned long long top = ((unsigned long long)__funnelshift_l(b, a, sh) << 32) | __funnelshift_l(c, b, sh);
+            hit = (top >> (64 - 2 * mer)) == code[h];
+        }
+        hit = hit && active && d <= limit[h];
+        mask |= (unsigned long long)__ballot_sync(0xffffffffu, hit) << (32 * h);
     }
     return mask;
 }
@@ -510,67 +510,82 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_vote_filter(DevIndex ix, uint
 
         // pass 1: count votes approximately, queue the hits that may complete kmin votes.  The hits of ONE k-mer
         // are distinct diagonals, so up to 32 * U of them are handled as one step: all loads, then all stores.
+        // The suffix-array words of the next step are requested before the current one is processed.
         uint32_t qn = 0;
-        for (int s = 0; s < ns; ++s) {
-            const uint32_t rank0 = fs->rank[s], cnt = fs->cnt[s], off = fs->offs[s];
-            for (uint32_t t0 = 0; t0 < cnt; t0 += 32u * U) {
-                uint32_t sa[U], diag[U], inc[U];
-                bool valid[U];
+        int s_cur = 0; uint32_t t_cur = 0;
+        while (s_cur < ns && fs->cnt[s_cur] == 0) s_cur++;
+        uint32_t sa_nxt[U];
+        auto issue = [&](int s, uint32_t t0, uint32_t (&dst)[U]) {
+            const uint32_t rank0 = fs->rank[s], cnt = fs->cnt[s];
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const uint32_t t = t0 + 32u * u + lane;
-                    valid[u] = t < cnt;
-                    sa[u] = valid[u] ? __ldg(ix.sa_full + rank0 + t) : GMX_SA_INVALID;
-                }
-                bool any_clamp = false;
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const bool clamp = valid[u] && sa[u] <= off;
-                    any_clamp |= clamp;
-                    diag[u] = clamp ? 0u : sa[u] - off;
-                    inc[u] = 1;
-                }
-                if (__any_sync(0xffffffffu, any_clamp)) {              // hits on diagonal 0: one lane votes for all of them
-                    uint32_t total = 0; int first_u = -1, first_lane = -1;
-#pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        const uint32_t cm = __ballot_sync(0xffffffffu, valid[u] && sa[u] <= off);
-                        if (cm && first_u < 0) { first_u = u; first_lane = __ffs(cm) - 1; }
-                        total += (uint32_t)__popc(cm);
-                    }
-#pragma unroll
-                    for (int u = 0; u < U; ++u)
-                        if (valid[u] && sa[u] <= off) { valid[u] = (u == first_u && lane == first_lane); inc[u] = total; }
-                }
-                uint32_t h1[U], h2[U], c1[U], c2[U];
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    h1[u] = (diag[u] * 0x9E3779B1u) >> (32 - F_LOG2); h2[u] = (diag[u] * 0x85EBCA77u + 0x27D4EB2Fu) >> (32 - F_LOG2);
-                }
-#pragma unroll
-                for (int u = 0; u < U; ++u) { c1[u] = valid[u] ? filt[h1[u]] : 0u; c2[u] = valid[u] ? filt[h2[u]] : 0u; }
-                bool flag[U];
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    flag[u] = valid[u] && (int)(min(c1[u], c2[u]) + inc[u]) > need;
-                    if (valid[u]) {
-                        filt[h1[u]] = (uint8_t)min(c1[u] + inc[u], 255u);
-                        filt[h2[u]] = (uint8_t)min(c2[u] + inc[u], 255u);
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const uint32_t fm = __ballot_sync(0xffffffffu, flag[u]);
-                    if (fm) {
-                        if (flag[u]) {
-                            const uint32_t at = qn + (uint32_t)__popc(fm & lt);
-                            if (at < GMX_FQ_CAP) fs->queue[at] = diag[u];
-                        }
-                        qn += (uint32_t)__popc(fm);
-                    }
-                }
-                __syncwarp();
+            for (int u = 0; u < U; ++u) {
+                const uint32_t t = t0 + 32u * u + lane;
+                dst[u] = t < cnt ? __ldg(ix.sa_full + rank0 + t) : GMX_SA_INVALID;
             }
+        };
+        if (s_cur < ns) issue(s_cur, 0, sa_nxt);
+        while (s_cur < ns) {
+            uint32_t sa[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) sa[u] = sa_nxt[u];
+            const uint32_t off = fs->offs[s_cur];
+            // advance to the next step and request its words
+            int s_n = s_cur; uint32_t t_n = t_cur + 32u * U;
+            if (t_n >= fs->cnt[s_cur]) { s_n = s_cur + 1; t_n = 0; while (s_n < ns && fs->cnt[s_n] == 0) s_n++; }
+            if (s_n < ns) issue(s_n, t_n, sa_nxt);
+
+            uint32_t diag[U], inc[U];
+            bool valid[U];
+            bool any_clamp = false;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                valid[u] = sa[u] != GMX_SA_INVALID;
+                const bool clamp = valid[u] && sa[u] <= off;
+                any_clamp |= clamp;
+                diag[u] = clamp ? 0u : sa[u] - off;
+                inc[u] = 1;
+            }
+            if (__any_sync(0xffffffffu, any_clamp)) {              // hits on diagonal 0: one lane votes for all of them
+                uint32_t total = 0; int first_u = -1, first_lane = -1;
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const uint32_t cm = __ballot_sync(0xffffffffu, valid[u] && sa[u] <= off);
+                    if (cm && first_u < 0) { first_u = u; first_lane = __ffs(cm) - 1; }
+                    total += (uint32_t)__popc(cm);
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    if (valid[u] && sa[u] <= off) { valid[u] = (u == first_u && lane == first_lane); inc[u] = total; }
+            }
+            uint32_t h1[U], h2[U], c1[U], c2[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                h1[u] = (diag[u] * 0x9E3779B1u) >> (32 - F_LOG2); h2[u] = (diag[u] * 0x85EBCA77u + 0x27D4EB2Fu) >> (32 - F_LOG2);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) { c1[u] = valid[u] ? filt[h1[u]] : 0u; c2[u] = valid[u] ? filt[h2[u]] : 0u; }
+            bool flag[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                flag[u] = valid[u] && (int)(min(c1[u], c2[u]) + inc[u]) > need;
+                if (valid[u]) {
+                    filt[h1[u]] = (uint8_t)min(c1[u] + inc[u], 255u);
+                    filt[h2[u]] = (uint8_t)min(c2[u] + inc[u], 255u);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const uint32_t fm = __ballot_sync(0xffffffffu, flag[u]);
+                if (fm) {
+                    if (flag[u]) {
+                        const uint32_t at = qn + (uint32_t)__popc(fm & lt);
+                        if (at < GMX_FQ_CAP) fs->queue[at] = diag[u];
+                    }
+                    qn += (uint32_t)__popc(fm);
+                }
+            }
+            __syncwarp();
+            s_cur = s_n; t_cur = t_n;
         }
         if (qn > GMX_FQ_CAP) {                                         // repeat-rich read: exact tables take over
             if (lane == 0) gmx_class_append(E, gmx_exact_class(S.hits[task]), task);
@@ -582,9 +597,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_vote_filter(DevIndex ix, uint
         uint32_t n2 = 0;
         for (uint32_t q0 = 0; q0 < qn; q0 += 32) {
             const uint32_t q = q0 + lane;
-            const uint32_t d = q < qn ? fs->queue[q] : 0u;
-            bool first = q < qn;
-            for (uint32_t j = 0; j < q0 + 32 && j < qn; ++j) first = first && !(fs->queue[j] == d && j < q);
+            const bool in = q < qn;
+            const uint32_t d = in ? fs->queue[q] : (GMX_EMPTY_KEY - (uint32_t)lane);      // padding lanes never match
+            const uint32_t peers = __match_any_sync(0xffffffffu, d);
+            bool first = in && (__ffs(peers) - 1 == lane);
+            for (uint32_t j = 0; j < n2; ++j) first = first && fs->queue[j] != d;
             __syncwarp();
             const uint32_t fm = __ballot_sync(0xffffffffu, first);
             if (first) fs->queue[n2 + (uint32_t)__popc(fm & lt)] = d;   // n2 + rank <= q: never overtakes unread entries
@@ -593,6 +610,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_vote_filter(DevIndex ix, uint
         }
 
         // pass 2: exact votes of each distinct diagonal from its genome window, four windows in flight
+        uint32_t limit[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) limit[h] = (uint32_t)ix.seq_len - cur.off[h] - (uint32_t)mer;
         uint32_t ne = 0;
         auto flush = [&]() {
             uint32_t base = 0;
@@ -606,19 +626,24 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_vote_filter(DevIndex ix, uint
             __syncwarp();
             ne = 0;
         };
+        const uint32_t *pac32 = reinterpret_cast<const uint32_t *>(ix.pac);
         for (uint32_t q0 = 0; q0 < n2; q0 += 4) {
-            uint32_t d[4], ww[4];
+            uint32_t d[4], raw[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) d[i] = q0 + i < n2 ? fs->queue[q0 + i] : GMX_EMPTY_KEY;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                d[i] = q0 + i < n2 ? fs->queue[q0 + i] : GMX_EMPTY_KEY;
-                ww[i] = (d[i] != GMX_EMPTY_KEY && d[i] != 0u) ? gmx_window_word(ix, pac_words, d[i], lane) : 0u;
+                const uint32_t idx = min((d[i] >> 4) + (uint32_t)lane, pac_words - 1u);   // the pad words are zero
+                raw[i] = __ldg(pac32 + idx);
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 if (d[i] == GMX_EMPTY_KEY) continue;
                 int round = -1;
                 if (d[i] != 0u) {
-                    const unsigned long long m = gmx_exact_mask(ix, ww[i], d[i], ns, mer, fs, lane);
+                    const uint32_t ww = __byte_perm(raw[i], 0, 0x0123);   // bases are packed most significant first
+                    const unsigned long long m = mer <= 16 ? gmx_exact_mask<true>(ww, d[i], ns, mer, cur.off, cur.code, limit, lane)
+                                                           : gmx_exact_mask<false>(ww, d[i], ns, mer, cur.off, cur.code, limit, lane);
                     if (__popcll(m) >= kmin) {
                         const uint32_t lo = (uint32_t)m, hi = (uint32_t)(m >> 32);
                         const int pl = __popc(lo);
