@@ -195,9 +195,11 @@ def have_ref_binary() -> bool:
     return os.path.exists(REF_BIN)
 
 
-def run_reference(genome_fa: str, reads_fq: str, out_prefix: str, threads: int = 1, extra=(), timeout=None):
-    """Run oracle/_ref/gnumap with the hygiene SURVEY.md §8(c) requires (zeroed accumulators)."""
-    env = dict(os.environ, MALLOC_MMAP_THRESHOLD_="65536")
+def run_reference(genome_fa: str, reads_fq: str, out_prefix: str, threads: int = 1, extra=(), timeout=None, mmap_threshold: int = 65536):
+    """Run oracle/_ref/gnumap with the hygiene SURVEY.md §8(c) requires: amount_genome is malloc'd and never
+    zeroed (reference src/GenomeBwt.cpp:323); a malloc threshold at or below the array size makes glibc serve it
+    from fresh zero pages.  Small test genomes need a small `mmap_threshold`."""
+    env = dict(os.environ, MALLOC_MMAP_THRESHOLD_=str(mmap_threshold))
     cmd = [REF_BIN, "-g", genome_fa, "-o", out_prefix, "-a", ".9", "-c", str(threads), *extra, reads_fq]
     p = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=timeout)
     if p.returncode != 0:

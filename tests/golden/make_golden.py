@@ -1,0 +1,210 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures under tests/golden/ from the UNMODIFIED reference.
+
+Run in the build container (needs /root/reference and oracle/_ref/, built by `make -C oracle ref`):
+
+    python tests/golden/make_golden.py
+
+Outputs (committed; the GPU box has no /root/reference and only reads these files):
+
+  ref_functions.npz     function-level vectors produced by oracle/_ref/libref_probe.so, i.e. by the reference's own
+                        bin_seq / GenomeBwt objects: self score, banded NW score (exact float bits), traceback strings
+                        and CIGARs, pair-HMM posteriors, FM-index intervals, SA coordinates, GetString windows,
+                        ScoredSeq::score() accumulator footprints for the three modes;
+  ref_index.npz         the index files the reference's bwa_index wrote for a small two-contig FASTA (bytes), next
+                        to the FASTA's bases -- pins gnumap_b200/index.py byte for byte;
+  ref_program_<mode>.json.gz   whole-program runs of oracle/_ref/gnumap (`-c 1`, zero-initialised accumulators):
+                        the reads, the sorted SAM body and the .sgr / .gmp rows.
+
+Everything is seeded; re-running reproduces the files bit for bit.
+"""
+from __future__ import annotations
+
+import gzip
+import json
+import os
+import shutil
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from gnumap_b200 import synth  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+
+BASES = b"acgt"
+
+
+def random_cases(rng, n_cases):
+    """(seq, qual, strand, window) tuples: windows are the read's source with substitutions / indels / an 'n'."""
+    cases = []
+    for k in range(n_cases):
+        n = int(rng.integers(20, 151))
+        src = rng.integers(0, 4, size=n + 8)
+        seq = bytearray(b"ACGT"[c] for c in src[:n])
+        if k % 5 == 0:
+            seq[int(rng.integers(0, n))] = ord("N")
+        if k % 9 == 0:
+            seq = bytearray(bytes(seq).lower())
+        qual = bytes(int(q) + 33 for q in rng.integers(2, 41, size=n))
+        win = list(src[:n])
+        for _ in range(int(rng.integers(0, 4))):
+            win[int(rng.integers(0, n))] = int(rng.integers(0, 4))
+        kind = k % 4
+        if kind == 1:                                  # deletion in the window (read has an extra base)
+            p = int(rng.integers(5, n - 5)); del win[p]; win.append(int(src[n]))
+        elif kind == 2:                                # insertion in the window
+            p = int(rng.integers(5, n - 5)); win.insert(p, int(rng.integers(0, 4))); win = win[:n]
+        elif kind == 3 and n > 40:                     # two-base gap
+            p = int(rng.integers(5, n - 8)); del win[p:p + 2]; win += [int(src[n]), int(src[n + 1])]
+        w = bytearray(BASES[c] for c in win)
+        if k % 7 == 0:
+            w[int(rng.integers(0, n))] = ord("n")
+        strand = int(rng.integers(0, 2))
+        cases.append((bytes(seq), qual, strand, bytes(w)))
+    return cases
+
+
+def make_functions(tmp):
+    rp = O.RefProbe()
+    rng = np.random.default_rng(20260101)
+    out = {}
+    cases = random_cases(rng, 48)
+    seqs, quals, strands, wins = zip(*cases)
+    out["seq"] = np.array(seqs, dtype=object); out["qual"] = np.array(quals, dtype=object)
+    out["strand"] = np.array(strands, dtype=np.uint8); out["window"] = np.array(wins, dtype=object)
+    for mode, tag in ((0, "normal"), (1, "bs")):
+        rp.set_mode(mode)
+        a, p, sc = rp.tables()
+        out[f"align_scores_{tag}"] = a; out[f"phmm_scores_{tag}"] = p; out[f"scalars_{tag}"] = sc
+        selfs, scores, aligned, cigars, hmms = [], [], [], [], []
+        for seq, qual, strand, win in cases:
+            pwm = O.fastq_pwm(seq, qual)
+            selfs.append(rp.self_score(pwm, seq))
+            if strand:
+                pwm = O.revcomp_pwm(pwm)
+            cons = O.max_char_consensus(pwm)
+            scores.append(rp.nw_score(pwm, win))
+            al, cg = rp.nw_traceback(pwm, cons, win)
+            aligned.append(al); cigars.append(cg)
+            if mode == 0:
+                hmms.append(rp.pair_hmm(pwm, cons, win))
+        out[f"self_{tag}"] = np.array(selfs, dtype=np.float32); out[f"score_{tag}"] = np.array(scores, dtype=np.float32)
+        out[f"aligned_{tag}"] = np.array(aligned, dtype=object); out[f"cigar_{tag}"] = np.array(cigars, dtype=object)
+        if mode == 0:
+            out["phmm_flat"] = np.concatenate([h.reshape(-1) for h in hmms]).astype(np.float32)
+    rp.set_mode(0)
+    # PWM rows of FASTQ (base, quality) pairs as the reference's reader builds them are covered by the whole-program runs.
+
+    # genome-backed probes on a small two-contig genome
+    contigs = synth.make_genome(6000, 11, n_contigs=2)
+    fa = os.path.join(tmp, "probe.fa")
+    synth.write_fasta(fa, contigs)
+    rp.load_genome(fa)
+    codes = np.concatenate([c for _, c in contigs])
+    kmers = []
+    for _ in range(200):
+        p = int(rng.integers(0, len(codes) - 12)); ln = int(rng.integers(4, 13))
+        k = bytearray(BASES[c] for c in codes[p:p + ln])
+        if rng.random() < 0.3:
+            k[int(rng.integers(0, ln))] = b"acgtn"[int(rng.integers(0, 5))]
+        if rng.random() < 0.2:
+            k = bytearray(bytes(k).upper())
+        kmers.append(bytes(k))
+    kmers += [b"nnnnnnnnnn", b"a", b"acgtacgtacgtacgtacgtacgt"]
+    out["kmer"] = np.array(kmers, dtype=object)
+    out["sa_int"] = np.array([rp.get_sa_int(k) for k in kmers], dtype=np.uint64)
+    out["sa_coord"] = np.array([rp.get_sa_coord(k) for k in range(1, len(codes) + 1)], dtype=np.uint64)
+    begins = [0, 1, 2999 - 50, 3000 - 40, 3000 - 39, 3000, 5999 - 40, 6000 - 40, 6000 - 39, 5999]
+    out["string_begin"] = np.array(begins, dtype=np.uint64)
+    out["string_40"] = np.array([rp.get_string(b, 40) for b in begins], dtype=object)
+
+    # ScoredSeq::score footprints: one group with two positions on opposite strands, per mode
+    seq, qual, _, _ = cases[1]
+    seq = seq[:50]; qual = qual[:50]
+    pwm = O.fastq_pwm(seq, qual)
+    gen_string = rp.get_string(1000, 50)
+    for kind, tag in ((0, "normal"), (1, "bs"), (2, "snp")):
+        rp.set_mode(kind)
+        rp.load_genome(fa)                               # re-allocates the accumulators for the mode's bin size
+        gs = 1 if kind else 8
+        amount, planes = rp.score_once(kind, pwm, gen_string, 30.5, [(1000, 0), (2100, 1)], 3.0 * np.exp(30.5), 6000 // gs)
+        out[f"score_once_amount_{tag}"] = amount
+        if planes is not None:
+            out[f"score_once_planes_{tag}"] = planes
+    out["score_once_seq"] = np.array([seq, qual, gen_string], dtype=object)
+    rp.set_mode(0)
+    np.savez_compressed(os.path.join(HERE, "ref_functions.npz"), **out)
+    print("ref_functions.npz:", len(cases), "alignment cases,", len(kmers), "k-mers")
+
+
+def make_index(tmp):
+    contigs = synth.make_genome(5003, 21, n_contigs=3)         # odd length: exercises the pac tail byte
+    fa = os.path.join(tmp, "ix.fa")
+    synth.write_fasta(fa, contigs)
+    fq = os.path.join(tmp, "none.fq")
+    open(fq, "w").close()
+    O.run_reference(fa, fq, os.path.join(tmp, "ixout"), threads=1, mmap_threshold=1024)
+    out = {"lens": np.array([len(c) for _, c in contigs], dtype=np.int64), "codes": np.concatenate([c for _, c in contigs])}
+    for ext in ("bwt", "sa", "pac", "ann", "amb"):
+        out[ext] = np.fromfile(fa + ".gnumap." + ext, dtype=np.uint8)
+    np.savez_compressed(os.path.join(HERE, "ref_index.npz"), **out)
+    print("ref_index.npz written")
+
+
+def make_program(tmp):
+    for mode, extra, seed in (("normal", [], 31), ("snp", ["--snp"], 32), ("bs", ["-b"], 33)):
+        d = os.path.join(tmp, mode)
+        os.makedirs(d)
+        contigs = synth.make_genome(24000, seed, n_contigs=2)
+        codes = np.concatenate([c for _, c in contigs])
+        # plant a repeat so that multi-position groups and X0 > 1 occur
+        codes[15000:15400] = codes[3000:3400]
+        contigs = [("chrS1", codes[:12000]), ("chrS2", codes[12000:])]
+        fa = os.path.join(d, "g.fa"); fq = os.path.join(d, "r.fq")
+        synth.write_fasta(fa, contigs)
+        reads = synth.simulate_reads(codes, 400, 62, seed + 100, indel_rate=0.15, n_rate=0.003, bisulfite=0.6 if mode == "bs" else 0.0)
+        reads["pos"][:40] = np.arange(3000, 3400 - 62, 8)[:40]            # reads inside the repeat
+        fwd = codes[reads["pos"][:40, None] + np.arange(62)[None, :]]
+        reads["bases"][:40] = np.where((reads["strand"][:40] == 1)[:, None], (3 - fwd[:, ::-1]), fwd)
+        synth.write_fastq(fq, reads)
+        # first run only builds the index: a process that has run bwa_index hands the accumulators recycled
+        # (non-zero) heap memory whatever the malloc threshold (reference src/GenomeBwt.cpp:323 never zeroes them)
+        empty = os.path.join(d, "empty.fq")
+        open(empty, "w").close()
+        O.run_reference(fa, empty, os.path.join(d, "warm"), threads=1, extra=extra, mmap_threshold=1024)
+        log = O.run_reference(fa, fq, os.path.join(d, "out"), threads=1, extra=extra, mmap_threshold=1024)
+        sam = [ln.rstrip("\n") for ln in open(os.path.join(d, "out.sam")) if not ln.startswith("@")]
+        rec = {"mode": mode, "extra": extra, "genome_seed": seed,
+               "contigs": [[n, "".join("ACGT"[c] for c in cs)] for n, cs in contigs],
+               "reads": [[nm, s.decode(), q.decode()] for nm, (s, q) in zip(*synth.read_fastq(fq))],
+               "sam": sam,
+               "matched": int([ln for ln in log.splitlines() if "Sequences matched" in ln][0].split(":")[1])}
+        if mode == "normal":
+            rec["sgr"] = [ln.rstrip("\n") for ln in open(os.path.join(d, "out.sgr"))]
+        else:
+            rec["gmp"] = [ln.rstrip("\n") for ln in open(os.path.join(d, "out.gmp"))]
+        with gzip.GzipFile(os.path.join(HERE, f"ref_program_{mode}.json.gz"), "wb", mtime=0) as f:
+            f.write(json.dumps(rec).encode())
+        print(f"ref_program_{mode}.json.gz: {len(sam)} SAM records, matched {rec['matched']}")
+
+
+def main():
+    O.build()
+    if not (O.have_ref_binary() and os.path.exists(O.REF_PROBE)):
+        raise SystemExit("oracle/_ref is missing: run `make -C oracle ref` where /root/reference exists")
+    tmp = tempfile.mkdtemp(prefix="gmx_golden_")
+    try:
+        make_functions(tmp)
+        make_index(tmp)
+        make_program(tmp)
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+if __name__ == "__main__":
+    main()

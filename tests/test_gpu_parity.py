@@ -180,3 +180,101 @@ def test_accumulate_across_batches_and_empty(api, O, plain):
     m.reset_accumulators()
     assert not m.finish()[0].any()
     m.close()
+
+
+@pytest.mark.parametrize("mode", ["normal", "snp", "bs"])
+def test_whole_program_fixture_through_cuda(api, mode):
+    """The CUDA path against the UNMODIFIED reference binary's SAM / SGR / GMP (tests/golden/ref_program_*.json.gz)."""
+    from gnumap_b200 import output
+    from tests import test_oracle_golden as G
+    rec = G.load_program(mode)
+    lut = {c: i for i, c in enumerate("ACGT")}
+    contigs = [(n, np.array([lut[c] for c in s], dtype=np.uint8)) for n, s in rec["contigs"]]
+    ix = index.build_index(contigs)
+    names = [r[0] for r in rec["reads"]]
+    batch = _abi.ReadBatch([r[1].encode() for r in rec["reads"]], [r[2].encode() for r in rec["reads"]])
+    p = common.set_mode(api.default_params(), {"normal": _abi.MODE_NORMAL, "bs": _abi.MODE_BS, "snp": _abi.MODE_SNP}[mode])
+    m = api.Mapper(ix, p)
+    got = m.process_batch(batch)
+    amount, planes = m.finish()
+    assert int((got["results"]["status"] == _abi.READ_MAPPED).sum()) == rec["matched"]
+    sam = list(output.sam_records(ix, names, batch, got["results"], got["hits"], got["cigars"], p.adjust))
+    assert sorted(sam) == sorted(rec["sam"]), "SAM body differs from the reference binary's"
+    if mode == "normal":
+        want = {}
+        for ln in rec["sgr"]:
+            c, pos, v = ln.split("\t"); want[(c, int(pos))] = float(v)
+        mine = {}
+        for ln in output.sgr_lines(ix, amount, p.gen_size, min_print=0.0005):
+            c, pos, v = ln.split("\t"); mine[(c, int(pos))] = float(v)
+        for k, v in want.items():
+            assert k in mine and abs(mine[k] - v) <= 1e-5 * abs(v) + 1.1e-5, (k, v, mine.get(k))
+    else:
+        want = [ln.split("\t") for ln in rec["gmp"]]
+        rows = {(r[0], r[1]): r for r in output.gmp_rows(ix, amount, planes, p.mode, min_print=0.0005)}
+        for w in want:
+            g = rows[(w[0], int(w[1]))]
+            assert np.allclose(np.array(g[2:8], dtype=np.float64), np.array([float(x) for x in w[2:8]]), rtol=1e-5, atol=1.1e-5), (g, w)
+    m.close()
+
+
+def test_fast_path_split_phases_chunking_and_device_input(api, O, plain):
+    """Every way of driving the batch pipeline gives the per-read results of the default one."""
+    import torch
+    ix, batch, _ = plain
+    want = O.process_batch(O.OracleIndex(ix), O.default_params(), batch)
+    fields = ("status", "n_groups", "top_score", "denominator", "best_score", "best_posterior", "best_first_pos", "best_n_positions",
+              "best_first_strand", "best_aligned_len", "n_candidates")
+
+    def same(res, what):
+        for f in fields:
+            assert np.array_equal(res[f], want["results"][f]), f"{what}: {f}"
+
+    m = api.Mapper(ix)
+    # (1) fast download path: no hit list, CIGARs still available
+    m.set_option(api_mod(api).OPT_COLLECT_HITS, 0)
+    out = m.process_batch(batch, fetch=False)
+    same(out["results"], "fast path")
+    cig = [bytes(r).split(b"\0")[0].decode() for r in m.best_cigars(batch.n_reads)]
+    assert cig == want["cigars"]
+    amount_fast, _ = m.finish()
+    # (2) small chunks
+    m.reset_accumulators()
+    m.set_option(api_mod(api).OPT_CHUNK_READS, 257)
+    out = m.process_batch(batch, fetch=False)
+    same(out["results"], "chunked")
+    assert [bytes(r).split(b"\0")[0].decode() for r in m.best_cigars(batch.n_reads)] == want["cigars"]
+    amount_chunked, _ = m.finish()
+    assert np.allclose(amount_chunked, amount_fast, rtol=1e-5, atol=1e-6)
+    m.set_option(api_mod(api).OPT_CHUNK_READS, 1 << 18)
+    m.set_option(api_mod(api).OPT_COLLECT_HITS, 1)
+    # (3) gmx_map_batch + gmx_score_batch (resident single chunk) and (4) multi-chunk split (re-run from the kept copy)
+    for chunk in (1 << 18, 300):
+        m.reset_accumulators()
+        m.set_option(api_mod(api).OPT_CHUNK_READS, chunk)
+        a = m.process_batch(batch, score=False)
+        assert np.array_equal(a["results"]["status"], want["results"]["status"])
+        assert np.array_equal(a["results"]["denominator"], want["results"]["denominator"])
+        assert not m.finish()[0].any(), "PHASE A must not touch the accumulators"
+        b = m.score_batch(batch)
+        common.compare_batches(b, want)
+        assert np.allclose(m.finish()[0], want["amount"], rtol=1e-5, atol=1e-6)
+    m.set_option(api_mod(api).OPT_CHUNK_READS, 1 << 18)
+    # (5) device-resident reads
+    m.reset_accumulators()
+    dev = torch.device("cuda", 0)
+    off = torch.from_numpy(batch.offsets).to(dev); seq = torch.from_numpy(batch.seq).to(dev); qual = torch.from_numpy(batch.qual).to(dev)
+
+    class DevBatch:
+        pass
+    db = DevBatch(); db.n_reads = batch.n_reads
+    s = _abi.GmxReads(); s.n_reads = batch.n_reads; s.offsets = off.data_ptr(); s.seq = seq.data_ptr(); s.qual = qual.data_ptr()
+    s.pwm = None; s.on_device = 1; s.max_len = int(np.diff(batch.offsets).max())
+    db.struct = s
+    out = m.process_batch(db, fetch=True)
+    common.compare_batches(out, want)
+    m.close()
+
+
+def api_mod(api):
+    return api

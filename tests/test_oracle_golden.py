@@ -1,0 +1,156 @@
+"""CPU suite, part 1: pins the oracle (oracle/gnumap_oracle.c) to the reference.
+
+Three layers of evidence, all readable without /root/reference:
+  * the reference's own known-answer tests (src/bin_seq.cpp:1046-1215)         -> tests/golden/bin_seq_kat.json
+  * function-level outputs of the unmodified reference objects                   -> tests/golden/ref_functions.npz
+  * index files written by the reference's bwa_index                             -> tests/golden/ref_index.npz
+  * whole-program SAM / SGR / GMP of the unmodified reference binary (`-c 1`)    -> tests/golden/ref_program_*.json.gz
+(tests/golden/make_golden.py regenerates the last three from oracle/_ref.)
+"""
+import gzip
+import json
+import os
+
+import numpy as np
+import pytest
+
+from gnumap_b200 import _abi, index, output, synth
+from oracle import oracle as O
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def fx():
+    return np.load(os.path.join(GOLD, "ref_functions.npz"), allow_pickle=True)
+
+
+def params_for(tag):
+    p = O.default_params()
+    if tag == "bs":
+        p.align_scores[ord("c")][3] = p.align_scores[ord("a")][0]       # reference src/Driver.cpp:1266
+    return p
+
+
+# ---- the reference's own KATs ---------------------------------------------------------------------
+def test_reference_kats():
+    kat = json.load(open(os.path.join(GOLD, "bin_seq_kat.json")))
+    p = O.default_params()
+    cons = kat["consensus"].encode()
+    pwm = O.onehot_pwm(cons)
+    for tb in kat["traceback"]:
+        aligned, cigar = O.nw_traceback(pwm, cons, tb["genome"].encode(), p)
+        assert aligned.decode() == tb["aligned"] and cigar == tb["cigar"], tb["ref_line"]
+    rs = kat["range_score"]
+    got = O.align_score_range(pwm, rs["genome"].encode(), rs["begin"], rs["end"], p)
+    match, gap = float(p.align_scores[ord("a")][0]), float(p.gap)
+    want = np.float32(np.float32(np.float32(rs["n_match_1"] * np.float32(match)) + np.float32(rs["n_gap"] * np.float32(gap))) +
+                      np.float32(rs["n_match_2"] * np.float32(match))) if "n_match_1" in rs else None
+    if want is not None:
+        assert np.float32(got) == want
+    else:
+        assert np.float32(got) == np.float32(rs["value"])
+    h = O.pair_hmm(pwm, cons, kat["phmm"]["genome"].encode(), p)
+    assert np.all(np.abs(h - np.array(kat["phmm"]["answer"], dtype=np.float32)) < 0.01)     # CLOSE_ENOUGH, bin_seq.cpp:1028
+
+
+# ---- function level ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag", ["normal", "bs"])
+def test_tables_match_reference(fx, tag):
+    p = params_for(tag)
+    assert np.array_equal(O.table_np(p.align_scores), fx[f"align_scores_{tag}"])
+    assert np.array_equal(O.table_np(p.phmm_scores), fx[f"phmm_scores_{tag}"])
+    assert np.float32(p.gap) == fx[f"scalars_{tag}"][0]
+
+
+@pytest.mark.parametrize("tag", ["normal", "bs"])
+def test_alignment_functions_match_reference(fx, tag):
+    p = params_for(tag)
+    off = 0
+    for k in range(len(fx["seq"])):
+        seq, qual, strand, win = fx["seq"][k], fx["qual"][k], int(fx["strand"][k]), fx["window"][k]
+        pwm = O.fastq_pwm(seq, qual)
+        assert np.float32(O.self_score(pwm, seq, p)) == fx[f"self_{tag}"][k], f"self score, case {k}"
+        if strand:
+            pwm = O.revcomp_pwm(pwm)
+        cons = O.max_char_consensus(pwm)
+        assert np.float32(O.nw_score(pwm, win, p)) == fx[f"score_{tag}"][k], f"NW score is not bit-exact, case {k}"
+        aligned, cigar = O.nw_traceback(pwm, cons, win, p)
+        assert aligned == fx[f"aligned_{tag}"][k] and cigar == fx[f"cigar_{tag}"][k], f"traceback, case {k}"
+        if tag == "normal":
+            want = fx["phmm_flat"][off:off + 5 * len(seq)].reshape(len(seq), 5)
+            off += 5 * len(seq)
+            got = O.pair_hmm(pwm, cons, win, p)
+            assert np.array_equal(got, want), f"pair-HMM posteriors differ, case {k}: max |d| = {np.abs(got - want).max()}"
+
+
+def test_fm_index_matches_reference(fx):
+    contigs = synth.make_genome(6000, 11, n_contigs=2)              # the genome make_golden.py loaded into the reference
+    ix = index.build_index(contigs)
+    oix = O.OracleIndex(ix)
+    got = np.array([oix.get_sa_int(k) for k in fx["kmer"]], dtype=np.uint64)
+    assert np.array_equal(got, fx["sa_int"])
+    assert np.array_equal(np.array([oix.bwt_sa(k) for k in range(1, ix.seq_len + 1)], dtype=np.uint64), fx["sa_coord"])
+    assert [oix.get_string(int(b), 40) for b in fx["string_begin"]] == list(fx["string_40"])
+    # de-sampled suffix array of the builder == bwt_sa at every rank
+    full = index.full_suffix_array(contigs)
+    assert np.array_equal(full[1:], fx["sa_coord"])
+
+
+def test_index_files_match_reference(tmp_path):
+    g = np.load(os.path.join(GOLD, "ref_index.npz"))
+    codes, lens = g["codes"], g["lens"]
+    bounds = np.concatenate([[0], np.cumsum(lens)])
+    contigs = [(f"chrS{i + 1}", codes[bounds[i]:bounds[i + 1]]) for i in range(len(lens))]
+    ix = index.build_index(contigs)
+    prefix = str(tmp_path / "ix.fa")
+    index.save_index(ix, prefix)
+    for ext in ("bwt", "sa", "pac", "ann", "amb"):
+        mine = np.fromfile(prefix + ".gnumap." + ext, dtype=np.uint8)
+        assert np.array_equal(mine, g[ext]), f".gnumap.{ext} differs from the file bwa_index wrote"
+    back = index.load_index(prefix)
+    assert np.array_equal(back.bwt, ix.bwt) and np.array_equal(back.sa, ix.sa) and np.array_equal(back.pac, ix.pac)
+    assert back.primary == ix.primary and back.l_pac == ix.l_pac and back.names == ix.names
+
+
+# ---- whole program -----------------------------------------------------------------------------------
+def load_program(mode):
+    with gzip.open(os.path.join(GOLD, f"ref_program_{mode}.json.gz")) as f:
+        return json.loads(f.read().decode())
+
+
+def run_oracle_program(rec):
+    lut = {c: i for i, c in enumerate("ACGT")}
+    contigs = [(n, np.array([lut[c] for c in s], dtype=np.uint8)) for n, s in rec["contigs"]]
+    ix = index.build_index(contigs)
+    names = [r[0] for r in rec["reads"]]
+    batch = _abi.ReadBatch([r[1].encode() for r in rec["reads"]], [r[2].encode() for r in rec["reads"]])
+    mode = {"normal": _abi.MODE_NORMAL, "bs": _abi.MODE_BS, "snp": _abi.MODE_SNP}[rec["mode"]]
+    p = O.default_params()
+    p.mode = mode
+    if mode != _abi.MODE_NORMAL:
+        p.gen_size = 1
+    if mode == _abi.MODE_BS:
+        p.align_scores[ord("c")][3] = p.align_scores[ord("a")][0]
+    res = O.process_batch(O.OracleIndex(ix), p, batch)
+    return ix, names, batch, p, res
+
+
+@pytest.mark.parametrize("mode", ["normal", "snp", "bs"])
+def test_whole_program_matches_reference(mode):
+    rec = load_program(mode)
+    ix, names, batch, p, res = run_oracle_program(rec)
+    assert int((res["results"]["status"] == _abi.READ_MAPPED).sum()) == rec["matched"]
+    sam = list(output.sam_records(ix, names, batch, res["results"], res["hits"], res["cigars"], p.adjust))
+    assert sorted(sam) == sorted(rec["sam"]), "SAM body differs from the reference binary's"
+    if mode == "normal":
+        assert list(output.sgr_lines(ix, res["amount"], p.gen_size)) == rec["sgr"], ".sgr differs"
+    else:
+        want = [ln.split("\t") for ln in rec["gmp"]]
+        got = list(output.gmp_rows(ix, res["amount"], res["planes"], p.mode))
+        assert len(got) == len(want)
+        for g, w in zip(got, want):
+            assert g[0] == w[0] and g[1] == int(w[1])
+            # accumulators: posteriors and accumulated scores within 1e-5 relative; the text
+            # file is printed with five decimals (half a unit of the last place = 5e-6)
+            assert np.allclose(np.array(g[2:8], dtype=np.float64), np.array([float(x) for x in w[2:8]]), rtol=1e-5, atol=6e-6), (g, w)
