@@ -245,7 +245,7 @@ class ClockSampler:
 def own_arm(a):
     import torch
     import torch.distributed as dist
-    from gnumap_b200 import _abi, api
+    from gnumap_b200 import _abi, api, sharding
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -297,23 +297,14 @@ def own_arm(a):
     host_batch = Batch(off_h, seq_h, qual_h, 0)
     dev_batch = Batch(off_h.to(dev), seq_h.to(dev), qual_h.to(dev), 1)
 
-    # accumulators as torch tensors (for the NCCL reduce)
-    amount_ptr, n_amount, plane_ptrs, n_plane = m.accumulators_device()
-
-    class _Arr:
-        def __init__(self, ptr, n_el):
-            self.__cuda_array_interface__ = {"shape": (n_el,), "typestr": "<f4", "data": (ptr, False), "version": 3, "strides": None}
-
-    acc = [torch.as_tensor(_Arr(amount_ptr, n_amount), device=dev)]
-    if n_plane:
-        acc.append(torch.as_tensor(_Arr(plane_ptrs[0], 5 * n_plane), device=dev))
+    # accumulators as torch tensors over the context's own device memory (for the NCCL reduce)
+    acc = sharding.device_accumulators(m, dev)
 
     def step(batch):
         m.process_batch(batch, fetch=False, results=res_np)
         if world > 1:
             with torch.cuda.stream(stream):
-                for t_ in acc:
-                    dist.all_reduce(t_)      # ncclAllReduce(sum, f32): reference src/Driver.cpp:1672,1719-1767
+                sharding.all_reduce_accumulators(acc)      # ncclAllReduce(sum, f32): reference src/Driver.cpp:1672,1719-1767
 
     def timed(batch, steps):
         if world > 1:

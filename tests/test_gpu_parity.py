@@ -223,12 +223,15 @@ def test_fast_path_split_phases_chunking_and_device_input(api, O, plain):
     import torch
     ix, batch, _ = plain
     want = O.process_batch(O.OracleIndex(ix), O.default_params(), batch)
-    fields = ("status", "n_groups", "top_score", "denominator", "best_score", "best_posterior", "best_first_pos", "best_n_positions",
+    fields = ("status", "n_groups", "top_score", "best_score", "best_first_pos", "best_n_positions",
               "best_first_strand", "best_aligned_len", "n_candidates")
 
     def same(res, what):
         for f in fields:
             assert np.array_equal(res[f], want["results"][f]), f"{what}: {f}"
+        # exp() of the device and of libm may differ in the last place
+        assert np.allclose(res["denominator"], want["results"]["denominator"], rtol=1e-12, atol=0), what
+        assert np.allclose(res["best_posterior"], want["results"]["best_posterior"], rtol=1e-6, atol=1e-12), what
 
     m = api.Mapper(ix)
     # (1) fast download path: no hit list, CIGARs still available
@@ -254,7 +257,7 @@ def test_fast_path_split_phases_chunking_and_device_input(api, O, plain):
         m.set_option(api_mod(api).OPT_CHUNK_READS, chunk)
         a = m.process_batch(batch, score=False)
         assert np.array_equal(a["results"]["status"], want["results"]["status"])
-        assert np.array_equal(a["results"]["denominator"], want["results"]["denominator"])
+        assert np.allclose(a["results"]["denominator"], want["results"]["denominator"], rtol=1e-12, atol=0)
         assert not m.finish()[0].any(), "PHASE A must not touch the accumulators"
         b = m.score_batch(batch)
         common.compare_batches(b, want)
