@@ -88,7 +88,46 @@ __device__ __forceinline__ bool gmx_match_exact(const DevIndex &ix, int len, Sym
     return true;
 }
 
+// bwt_match_exact with its first `tab_len` steps (the LAST tab_len symbols of the string) looked up in the
+// memoised table; identical intervals by construction (the table is filled by gmx_match_exact itself).
+template <class SymFn>
+__device__ __forceinline__ bool gmx_match_exact_tab(const DevIndex &ix, int len, SymFn sym, uint64_t &k_out, uint64_t &l_out, uint32_t &n_steps)
+{
+    const int T = ix.tab_len;
+    if (T <= 0 || len < T) return gmx_match_exact(ix, len, sym, k_out, l_out, n_steps);
+    uint32_t code = 0; bool ok = true;
+    for (int i = len - T; i < len; ++i) { uint32_t c = sym(i); ok = ok && c <= 3; code = (code << 2) | (c & 3u); }
+    // the reference walks from the last symbol backwards and stops at the first non-ACGT symbol or empty interval;
+    // either way the answer is "absent"
+    for (int i = 0; i < len - T; ++i) ok = ok && sym(i) <= 3;
+    if (!ok) return false;
+    const uint2 kl = __ldg(ix.kmer_tab + code);
+    if (kl.x > kl.y) return false;
+    uint64_t k = kl.x, l = kl.y;
+    for (int i = len - T - 1; i >= 0; --i) {
+        uint32_t c = sym(i);
+        n_steps++;
+        uint64_t ok2 = gmx_bwt_occ(ix, k - 1, c);
+        uint64_t ol = gmx_bwt_occ(ix, l, c);
+        k = ix.L2[c] + ok2 + 1;
+        l = ix.L2[c] + ol;
+        if (k > l) return false;
+    }
+    k_out = k; l_out = l;
+    return true;
+}
+
 // ---- kernels ---------------------------------------------------------------------------------
+
+// fill the memoised table: entry `code` = interval of the T-mer whose symbols are the base-4 digits of `code`
+__global__ void k_build_kmer_table(DevIndex ix, int T, uint2 *tab)
+{
+    uint32_t code = blockIdx.x * blockDim.x + threadIdx.x;
+    if (code >= (1u << (2 * T))) return;
+    uint64_t k = 0, l = 0; uint32_t steps = 0;
+    bool hit = gmx_match_exact(ix, T, [&](int i) { return (code >> (2 * (T - 1 - i))) & 3u; }, k, l, steps);
+    tab[code] = hit ? make_uint2((uint32_t)k, (uint32_t)l) : make_uint2(1u, 0u);
+}
 
 // K1 (primitive form): one k-mer per thread.  GenomeBwt::get_sa_int (reference src/GenomeBwt.cpp:438-474)
 __global__ void k_fm_search(DevIndex ix, const uint8_t *kmers, int len, int64_t n, uint64_t *k_out, uint64_t *l_out)

@@ -66,7 +66,7 @@ struct gmx_ctx {
     DevIndex ix;
     DevTables tab;
     // index storage
-    DevBuf d_bwt, d_sa_full, d_sa_samp, d_pac, d_seq_offset, d_tables;
+    DevBuf d_bwt, d_sa_full, d_sa_samp, d_pac, d_seq_offset, d_tables, d_kmer_tab;
     // accumulators
     Accum acc;
     DevBuf d_amount, d_planes;
@@ -338,6 +338,18 @@ extern "C" int gmx_create(gmx_ctx **out, const gmx_index *index, const gmx_param
     k_desample_sa<<<nblk((int64_t)index->seq_len + 1, 256), 256, 0, ctx->stream>>>(ix, ctx->d_sa_full.as<uint32_t>());
     CK(cudaGetLastError());
 
+    // memoise the first min(mer, 12) backward-search steps of every k-mer lookup
+    ix.kmer_tab = nullptr; ix.tab_len = 0;
+    {
+        const int T = std::min<int>(params->mer, GMX_KMER_TAB_MAX);
+        const size_t n_tab = (size_t)1 << (2 * T);
+        CK(ctx->d_kmer_tab.ensure(n_tab * sizeof(uint2)));
+        k_build_kmer_table<<<nblk((int64_t)n_tab, 256), 256, 0, ctx->stream>>>(ix, T, ctx->d_kmer_tab.as<uint2>());
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(ctx->stream));
+        ix.kmer_tab = ctx->d_kmer_tab.as<uint2>(); ix.tab_len = T;
+    }
+
     int r = build_tables(ctx);
     if (r != GMX_OK) return r;
 
@@ -367,7 +379,7 @@ extern "C" void gmx_destroy(gmx_ctx *ctx)
                       &ctx->d_seed_count, &ctx->d_seed_off, &ctx->d_seed_n, &ctx->d_seed_hits, &ctx->d_cls_list, &ctx->d_cls_meta,
                       &ctx->d_keys, &ctx->d_keys_alt, &ctx->d_sort_tmp, &ctx->d_score, &ctx->d_leader, &ctx->d_slot, &ctx->d_lead_cand,
                       &ctx->d_hashes, &ctx->d_expv, &ctx->d_counters, &ctx->d_results, &ctx->d_alen, &ctx->d_aligned, &ctx->d_cigar,
-                      &ctx->d_hmm, &ctx->d_moves, &ctx->d_arena, &ctx->d_phmm_scratch, &ctx->d_best_cigar, &ctx->d_seed_code};
+                      &ctx->d_hmm, &ctx->d_moves, &ctx->d_arena, &ctx->d_phmm_scratch, &ctx->d_best_cigar, &ctx->d_seed_code, &ctx->d_kmer_tab};
     for (DevBuf *b : bufs) b->release();
     ctx->h_best_cigar.release();
     if (ctx->ev[0][0]) for (int s = 0; s < ST_COUNT; ++s) { cudaEventDestroy(ctx->ev[s][0]); cudaEventDestroy(ctx->ev[s][1]); }
@@ -832,7 +844,7 @@ static int phase_a(gmx_ctx *ctx, const gmx_reads *reads, int32_t lo, int32_t hi)
     }
     // algorithmic work of the seed / vote stages (DESIGN.md "Roofline"): every backward-search step reads two
     // 64-byte occ blocks; every SA hit reads one 4-byte entry of the de-sampled suffix array
-    ctx->stage_units[ST_SEED] += hc.s.v[0]; ctx->stage_bytes[ST_SEED] += hc.s.v[1] * 128ull;
+    ctx->stage_units[ST_SEED] += hc.s.v[0]; ctx->stage_bytes[ST_SEED] += hc.s.v[1] * 128ull + (ctx->ix.tab_len > 0 ? hc.s.v[0] * 8ull : 0ull);
     ctx->stage_units[ST_VOTE] += hc.s.v[2]; ctx->stage_bytes[ST_VOTE] += hc.s.v[2] * 4ull;
 
     // restore the reference's processing order: (task, round, position)
@@ -899,8 +911,11 @@ static int phase_b(gmx_ctx *ctx)
     if (!n_leaders) return GMX_OK;
     // traceback is needed in every mode for the CIGAR of the best hit (get_SAM, reference inc/ScoredSeq.h:314-372)
     CK(ctx->d_moves.ensure((size_t)n_leaders * ((size_t)max_len + 1) * 4));
+    // the gapped read strings themselves are only consumed by the BS scatter and by gmx_get_best_alignments
+    const int want_aligned = (P.mode == GMX_MODE_BS || ctx->collect_hits) ? 1 : 0;
     stage_begin(ctx, ST_TRACEBACK);
-    k_traceback<<<nblk(n_leaders, 128), 128, 0, ctx->stream>>>(ctx->ix, ctx->dreads, ctx->tab, P, cs.keys, n_leaders, L, ctx->d_moves.as<uint32_t>());
+    k_traceback<<<nblk(n_leaders, 128), 128, 0, ctx->stream>>>(ctx->ix, ctx->dreads, ctx->tab, P, cs.keys, n_leaders, L,
+                                                              ctx->d_moves.as<uint32_t>(), want_aligned);
     CK(cudaGetLastError());
     stage_end(ctx, ST_TRACEBACK, (uint64_t)n_leaders * (uint64_t)std::max(7 * max_len - 12, 0), 0, 1);
     if (P.mode == GMX_MODE_SNP) {

@@ -12,6 +12,7 @@
 #define GMX_NQ 94                          // quality chars 33..126
 #define GMX_MAX_READ_LEN 1024
 #define GMX_MAX_GAP 8                      // compile-time cap of the band half-width
+#define GMX_KMER_TAB_MAX 12                // 4^12 x 8 B = 128 MB at most
 #define GMX_MAX_SEEDS 255                  // seeds (rounds) per (read, strand): 8 bits of the sort key
 
 // Device view of the index (kernel parameter, passed by value).
@@ -21,6 +22,9 @@ struct DevIndex {
     const uint64_t *sa_samp;    // the reference's sampled SA (validation path)
     const uint8_t  *pac;        // 2-bit packed genome
     const int64_t  *seq_offset; // [n_seqs + 1], last = l_pac
+    const uint2    *kmer_tab;   // [4^tab_len] SA interval (k, l) of every tab_len-mer, k > l when absent: the first
+                                // tab_len backward-search steps of bwt_match_exact, memoised at load
+    int32_t  tab_len;           // min(mer, GMX_KMER_TAB_MAX)
     uint64_t primary, seq_len;
     uint64_t L2[5];
     int64_t  l_pac;

@@ -230,40 +230,64 @@ struct ConsView {
     }
 };
 
-__device__ int gmx_nw_traceback(const ReadView &rd, const WindowView &win, const ConsView &cons, const DevTables &T,
-                                float gap, int G, uint32_t *moves, int64_t mv_stride, TracebackOut out)
+// forward fill of the band, one move word per row.  G_T > 0: band half-width known at compile time (rows live in
+// registers); G_T == 0: run-time G (local-memory rows).
+template <int G_T>
+__device__ __forceinline__ void gmx_nw_fill_moves(const ReadView &rd, const WindowView &win, const DevTables &T, float gap, int G_rt,
+                                                  uint32_t *moves, int64_t mv_stride)
 {
+    constexpr int GMAX = G_T > 0 ? G_T : GMX_MAX_GAP;
+    const int G = G_T > 0 ? G_T : G_rt;
     const int n = rd.n, m = rd.n;
-    float prev[2 * GMX_MAX_GAP + 3], cur[2 * GMX_MAX_GAP + 3];
-    const int W = 2 * G + 3;
+    float prev[2 * GMAX + 3], cur[2 * GMAX + 3];
     // row 0: nm[0][j] = gap * j for j <= G+2  (reference src/bin_seq.cpp:508-511)
-    for (int d = -G - 1; d <= G + 1; ++d) prev[d + G + 1] = (d >= 0) ? __fmul_rn(gap, (float)d) : GMX_NEG_INF;
+#pragma unroll
+    for (int x = 0; x < 2 * GMAX + 3; ++x) { int d = x - G - 1; prev[x] = (x < 2 * G + 3 && d >= 0) ? __fmul_rn(gap, (float)d) : GMX_NEG_INF; }
+    // window bases of the band cells of row i: gb[x] = base(i + (x - G - 1) - 1), slid by one per row
+    int gb[2 * GMAX + 3];
+#pragma unroll
+    for (int x = 0; x < 2 * GMAX + 3; ++x) { int j = 1 + (x - G - 1) - 1; gb[x] = (x <= 2 * G + 1 && j >= 0 && j < m) ? win.base(j) : 0; }
     for (int i = 1; i <= n; ++i) {
         float4 sub = rd.sub_row(T, i - 1);
         const float other = win.pac ? 0.f : rd.sub_other(T, i - 1);
         uint32_t mv = 0;
         // guard cell left of the band: column 0 carries gap*i for i <= G+2, otherwise NEG_INF
         cur[0] = (i - G - 1 == 0) ? __fmul_rn(gap, (float)i) : GMX_NEG_INF;
-        for (int d = -G; d <= G; ++d) {
-            int j = i + d;
-            float v;
-            if (j <= 0) v = (j == 0) ? __fmul_rn(gap, (float)i) : GMX_NEG_INF;
-            else if (j > m) v = GMX_NEG_INF;
-            else {
-                float diag = __fadd_rn(prev[d + G + 1], gmx_sel4(sub, win.base(j - 1), other));
-                float upgap = __fadd_rn(prev[d + G + 2], gap);
-                float leftgap = __fadd_rn(cur[d + G], gap);
-                uint32_t path;                         // reference src/bin_seq.cpp:989-1011
-                if (diag >= upgap) { if (diag >= leftgap) { path = GMX_MV_D; v = diag; } else { path = GMX_MV_L; v = leftgap; } }
-                else               { if (upgap >= leftgap) { path = GMX_MV_U; v = upgap; } else { path = GMX_MV_L; v = leftgap; } }
-                mv |= path << (2 * (d + G));
+#pragma unroll
+        for (int x = 1; x <= 2 * GMAX + 1; ++x) {
+            if (x <= 2 * G + 1) {
+                const int d = x - G - 1;
+                const int j = i + d;
+                float v;
+                if (j <= 0) v = (j == 0) ? __fmul_rn(gap, (float)i) : GMX_NEG_INF;
+                else if (j > m) v = GMX_NEG_INF;
+                else {
+                    float diag = __fadd_rn(prev[x], gmx_sel4(sub, gb[x], other));
+                    float upgap = __fadd_rn(prev[x + 1], gap);
+                    float leftgap = __fadd_rn(cur[x - 1], gap);
+                    uint32_t path;                         // reference src/bin_seq.cpp:989-1011
+                    if (diag >= upgap) { if (diag >= leftgap) { path = GMX_MV_D; v = diag; } else { path = GMX_MV_L; v = leftgap; } }
+                    else               { if (upgap >= leftgap) { path = GMX_MV_U; v = upgap; } else { path = GMX_MV_L; v = leftgap; } }
+                    mv |= path << (2 * (x - 1));
+                }
+                cur[x] = v;
             }
-            cur[d + G + 1] = v;
         }
-        cur[2 * G + 2] = GMX_NEG_INF;
-        for (int d = 0; d < W; ++d) prev[d] = cur[d];
+#pragma unroll
+        for (int x = 0; x < 2 * GMAX + 3; ++x) { if (x == 2 * G + 2) cur[x] = GMX_NEG_INF; if (x <= 2 * G + 2) prev[x] = cur[x]; }
+#pragma unroll
+        for (int x = 0; x < 2 * GMAX + 2; ++x) gb[x] = gb[x + 1];
+        { int j = (i + 1) + G - 1; if (2 * G + 1 < 2 * GMAX + 3) gb[2 * G + 1] = j < m ? win.base(j) : 0; }
         moves[(int64_t)i * mv_stride] = mv;
     }
+}
+
+__device__ int gmx_nw_traceback(const ReadView &rd, const WindowView &win, const ConsView &cons, const DevTables &T,
+                                float gap, int G, uint32_t *moves, int64_t mv_stride, TracebackOut out)
+{
+    const int n = rd.n, m = rd.n;
+    if (G == 3) gmx_nw_fill_moves<3>(rd, win, T, gap, G, moves, mv_stride);
+    else gmx_nw_fill_moves<0>(rd, win, T, gap, G, moves, mv_stride);
 
     // pass 1: path length and run-length ops, walking back from (n, m)  (reference :571-698)
     uint16_t ops[48];                                  // (count << 2) | type, in backward order

@@ -105,7 +105,7 @@ __global__ void k_seed_walk(DevIndex ix, DevReads R, DevParams P, const ReadPrep
             uint64_t k = 0, l = 0;
             for (j = 0; j + i < last; j++) {
                 unsigned base = i + j;
-                bool hit = gmx_match_exact(ix, P.mer, [&](int t) { return sym_at((int)base + t); }, k, l, n_steps);
+                bool hit = gmx_match_exact_tab(ix, P.mer, [&](int t) { return sym_at((int)base + t); }, k, l, n_steps);
                 n_lookups++;
                 if (!hit) continue;
                 if (P.max_kmer_hits > 0 && l - k + 1 > (uint64_t)P.max_kmer_hits) continue;
@@ -178,16 +178,26 @@ __device__ __forceinline__ void gmx_class_append(const ClassLists &C, int cls, u
 __global__ void k_classify(const uint32_t *hits, ClassLists F, ClassLists E, int use_filter)
 {
     int64_t task = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (task >= E.n_tasks) return;
-    uint32_t h = hits[task];
-    if (h == 0) return;
-    int fc = -1;
-    if (use_filter) {
+    const int lane = threadIdx.x & 31;
+    uint32_t h = task < E.n_tasks ? hits[task] : 0u;
+    int cls = -1;                                   // 0..5 filter classes, 6..11 exact classes
+    if (h) {
+        if (use_filter) {
 #pragma unroll
-        for (int c = GMX_N_CLASSES - 1; c >= 0; --c) if (h <= gmx_filter_max_hits(c)) fc = c;
+            for (int c = GMX_N_CLASSES - 1; c >= 0; --c) if (h <= gmx_filter_max_hits(c)) cls = c;
+        }
+        if (cls < 0) cls = GMX_N_CLASSES + gmx_exact_class(h);
     }
-    if (fc >= 0) gmx_class_append(F, fc, (uint32_t)task);
-    else gmx_class_append(E, gmx_exact_class(h), (uint32_t)task);
+    // one atomic per (warp, class) instead of one per task
+    const uint32_t peers = __match_any_sync(0xffffffffu, cls);
+    if (cls < 0) return;
+    const ClassLists &C = cls < GMX_N_CLASSES ? F : E;
+    const int c = cls < GMX_N_CLASSES ? cls : cls - GMX_N_CLASSES;
+    const int leader = __ffs(peers) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(&C.count[c], (uint32_t)__popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    C.list[(int64_t)c * C.n_tasks + base + (uint32_t)__popc(peers & ((1u << lane) - 1u))] = (uint32_t)task;
 }
 
 // ---- K1b + K1c: locate + diagonal vote ---------------------------------------------------------
@@ -801,11 +811,7 @@ __global__ void __launch_bounds__(128) k_finalize_reads(DevIndex ix, DevReads R,
         if (in) {
             O.leader[c] = acc ? (int32_t)c : -1;
             O.slot[c] = -1;
-            if (acc) {
-                uint32_t task, round, diag; gmx_decode_key(keys[c], task, round, diag);
-                O.hashes[c] = gmx_key_hash(ix, diag, (int)(task & 1), n);
-                O.expv[c] = exp((double)sc);
-            }
+            if (acc) O.expv[c] = exp((double)sc);
         }
         n_valid += __popc(__ballot_sync(0xffffffffu, valid));
         n_acc += __popc(__ballot_sync(0xffffffffu, acc));
@@ -819,6 +825,16 @@ __global__ void __launch_bounds__(128) k_finalize_reads(DevIndex ix, DevReads R,
         res.status = GMX_READ_UNMATCHED; res.top_score = 0; res.denominator = 0;
         if (lane == 0) O.results[r] = res;
         return;
+    }
+
+    // key-string hashes are only needed to group several accepted candidates
+    if (n_acc > 1) {
+        for (uint32_t c = lo + lane; c < hi; c += 32)
+            if (O.leader[c] >= 0) {
+                uint32_t task, round, diag; gmx_decode_key(keys[c], task, round, diag);
+                O.hashes[c] = gmx_key_hash(ix, diag, (int)(task & 1), n);
+            }
+        __syncwarp();
     }
 
     // pass 2: group leaders = first accepted candidate (processing order) with the same key string
@@ -951,9 +967,11 @@ struct LeaderStore {
     int a_stride, c_stride, max_len;
 };
 
+// moves: one word per (row, group) in a global scratch laid out [row][group], so the lanes of a warp write
+// adjacent words (404 MB per million 100-bp groups: noise next to the ALU work)
 __global__ void __launch_bounds__(128) k_traceback(DevIndex ix, DevReads R, DevTables T, DevParams P,
                                                    const unsigned long long *keys, uint32_t n_leaders, LeaderStore L,
-                                                   uint32_t *moves)
+                                                   uint32_t *moves, int want_aligned)
 {
     uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n_leaders) return;
@@ -963,7 +981,7 @@ __global__ void __launch_bounds__(128) k_traceback(DevIndex ix, DevReads R, DevT
     WindowView win; win.pac = ix.pac; win.pos = diag; win.chars = nullptr;
     ConsView cons; cons.explicit_chars = nullptr;          // score(): max_char consensus of the oriented PWM
     TracebackOut out;
-    out.aligned = L.aligned + (size_t)s * L.a_stride; out.aligned_cap = L.a_stride;
+    out.aligned = want_aligned ? L.aligned + (size_t)s * L.a_stride : nullptr; out.aligned_cap = L.a_stride;
     out.cigar = L.cigar + (size_t)s * L.c_stride; out.cigar_cap = L.c_stride; out.fix_deletions = 1;
     L.alen[s] = gmx_nw_traceback(rd, win, cons, T, P.gap, P.max_gap, moves + s, (int64_t)n_leaders, out);
 }
