@@ -523,25 +523,23 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_vote_filter(DevIndex ix, uint
         // The suffix-array words of the next step are requested before the current one is processed.
         uint32_t qn = 0;
         int s_cur = 0; uint32_t t_cur = 0;
-        while (s_cur < ns && fs->cnt[s_cur] == 0) s_cur++;
         uint32_t sa_nxt[U];
         auto issue = [&](int s, uint32_t t0, uint32_t (&dst)[U]) {
-            const uint32_t rank0 = fs->rank[s], cnt = fs->cnt[s];
+            const uint32_t cnt = fs->cnt[s];
+            const uint32_t *p = ix.sa_full + (fs->rank[s] + t0 + (uint32_t)lane);     // one address, U loads at +128 B
+            const uint32_t t = t0 + (uint32_t)lane;
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const uint32_t t = t0 + 32u * u + lane;
-                dst[u] = t < cnt ? __ldg(ix.sa_full + rank0 + t) : GMX_SA_INVALID;
-            }
+            for (int u = 0; u < U; ++u) dst[u] = t + 32u * u < cnt ? __ldg(p + 32 * u) : GMX_SA_INVALID;
         };
-        if (s_cur < ns) issue(s_cur, 0, sa_nxt);
+        if (ns > 0) issue(0, 0, sa_nxt);
         while (s_cur < ns) {
             uint32_t sa[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) sa[u] = sa_nxt[u];
             const uint32_t off = fs->offs[s_cur];
-            // advance to the next step and request its words
+            // advance to the next step and request its words (every stored k-mer has at least one hit)
             int s_n = s_cur; uint32_t t_n = t_cur + 32u * U;
-            if (t_n >= fs->cnt[s_cur]) { s_n = s_cur + 1; t_n = 0; while (s_n < ns && fs->cnt[s_n] == 0) s_n++; }
+            if (t_n >= fs->cnt[s_cur]) { s_n = s_cur + 1; t_n = 0; }
             if (s_n < ns) issue(s_n, t_n, sa_nxt);
 
             uint32_t diag[U], inc[U];
