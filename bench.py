@@ -42,6 +42,25 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """Libraries (NCCL's version banner, for one) write to fd 1; the contract is ONE JSON line on stdout.  Point fd 1
+    at stderr for the run and keep the real stdout for the result line."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 # ------------------------------------------------------------------------------------------------
 # workload (SURVEY.md §8d config 2): i.i.d. genome seed 100, reads seed 101, 1 % substitutions, Q15..40
 # ------------------------------------------------------------------------------------------------
@@ -194,7 +213,7 @@ def reference_arm(a):
             "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     finally:
         rr.close()
 
@@ -395,7 +414,7 @@ def own_arm(a):
             "roofline": roofline,
             "cpu_baseline": cpu,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     m.close()
     if world > 1:
         dist.destroy_process_group()
@@ -417,6 +436,8 @@ def main():
     ap.add_argument("--wall", action="store_true", help="use max(event, wall) time")
     a = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not (a.impl == "ours" and world == 1 and a.gpus > 1):
+        claim_stdout()
     if a.impl == "reference":
         return reference_arm(a)
     if world == 1 and a.gpus > 1:

@@ -72,7 +72,11 @@ struct gmx_ctx {
     DevBuf d_amount, d_planes;
     uint64_t n_plane = 0;
     // reads of the current chunk
-    DevBuf d_offsets, d_seq, d_qual, d_pwm;
+    DevBuf d_offsets[2], d_seq[2], d_qual[2], d_pwm[2];     // double-buffered: chunk i+1 uploads while chunk i computes
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t up_ev[2] = {nullptr, nullptr};
+    DevReads up_view[2];
+    int32_t up_max_len[2] = {0, 0};
     DevReads dreads;
     std::vector<int64_t> h_offsets;            // offsets of the last batch (for gmx_get_hits)
     // pipeline buffers
@@ -298,6 +302,8 @@ extern "C" int gmx_create(gmx_ctx **out, const gmx_index *index, const gmx_param
     CK(cudaSetDevice(device));
     CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     ctx->own_stream = true;
+    CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    for (int b = 0; b < 2; ++b) CK(cudaEventCreateWithFlags(&ctx->up_ev[b], cudaEventDisableTiming));
     for (int s = 0; s < ST_COUNT; ++s) { CK(cudaEventCreate(&ctx->ev[s][0])); CK(cudaEventCreate(&ctx->ev[s][1])); }
     stage_reset(ctx);
     cudaDeviceGetAttribute(&ctx->n_sm, cudaDevAttrMultiProcessorCount, device);
@@ -375,7 +381,7 @@ extern "C" void gmx_destroy(gmx_ctx *ctx)
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     DevBuf *bufs[] = {&ctx->d_bwt, &ctx->d_sa_full, &ctx->d_sa_samp, &ctx->d_pac, &ctx->d_seq_offset, &ctx->d_tables, &ctx->d_amount,
-                      &ctx->d_planes, &ctx->d_offsets, &ctx->d_seq, &ctx->d_qual, &ctx->d_pwm, &ctx->d_prep, &ctx->d_seed_rank,
+                      &ctx->d_planes, &ctx->d_offsets[0], &ctx->d_seq[0], &ctx->d_qual[0], &ctx->d_pwm[0], &ctx->d_offsets[1], &ctx->d_seq[1], &ctx->d_qual[1], &ctx->d_pwm[1], &ctx->d_prep, &ctx->d_seed_rank,
                       &ctx->d_seed_count, &ctx->d_seed_off, &ctx->d_seed_n, &ctx->d_seed_hits, &ctx->d_cls_list, &ctx->d_cls_meta,
                       &ctx->d_keys, &ctx->d_keys_alt, &ctx->d_sort_tmp, &ctx->d_score, &ctx->d_leader, &ctx->d_slot, &ctx->d_lead_cand,
                       &ctx->d_hashes, &ctx->d_expv, &ctx->d_counters, &ctx->d_results, &ctx->d_alen, &ctx->d_aligned, &ctx->d_cigar,
@@ -383,6 +389,8 @@ extern "C" void gmx_destroy(gmx_ctx *ctx)
     for (DevBuf *b : bufs) b->release();
     ctx->h_best_cigar.release();
     if (ctx->ev[0][0]) for (int s = 0; s < ST_COUNT; ++s) { cudaEventDestroy(ctx->ev[s][0]); cudaEventDestroy(ctx->ev[s][1]); }
+    if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+    for (int b = 0; b < 2; ++b) if (ctx->up_ev[b]) cudaEventDestroy(ctx->up_ev[b]);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -451,10 +459,11 @@ static int scan_max_len(gmx_ctx *ctx, const gmx_reads *reads, int32_t lo, int32_
     return GMX_OK;
 }
 
-// Make reads [lo, hi) visible to the kernels.  Offsets stay absolute (relative to the start of the
-// batch's seq/qual arrays); for host batches only the chunk's slice is copied and the device base
-// pointers are biased so that the same offsets index it.
-static int upload_reads(gmx_ctx *ctx, const gmx_reads *reads, int32_t lo, int32_t hi, int32_t *max_len_out)
+// Make reads [lo, hi) visible to the kernels through buffer set `slot`.  Offsets stay absolute (relative to the
+// start of the batch's seq/qual arrays); for host batches only the chunk's slice is copied and the device base
+// pointers are biased so that the same offsets index it.  Copies are issued on `stream`; the view is left in
+// ctx->up_view[slot] and ctx->up_ev[slot] is recorded behind them.
+static int issue_upload(gmx_ctx *ctx, const gmx_reads *reads, int32_t lo, int32_t hi, int slot, cudaStream_t stream)
 {
     int32_t n = hi - lo;
     if (!reads->seq) { ctx->err = "gmx_reads.seq is required (the consensus string for raw-PWM reads)"; return GMX_ERR_INVALID; }
@@ -462,31 +471,43 @@ static int upload_reads(gmx_ctx *ctx, const gmx_reads *reads, int32_t lo, int32_
     int32_t max_len = 0;
     int r = scan_max_len(ctx, reads, lo, hi, &max_len);
     if (r != GMX_OK) return r;
-    ctx->dreads.n_reads = n; ctx->dreads.qbase = ctx->params.illumina ? 64 : 33;
-    ctx->dreads.qual = nullptr; ctx->dreads.pwm = nullptr;
+    DevReads &v = ctx->up_view[slot];
+    v.n_reads = n; v.qbase = ctx->params.illumina ? 64 : 33;
+    v.qual = nullptr; v.pwm = nullptr;
     if (reads->on_device) {
-        ctx->dreads.offsets = reads->offsets + lo;
-        ctx->dreads.seq = reads->seq; ctx->dreads.qual = reads->qual; ctx->dreads.pwm = reads->pwm;
+        v.offsets = reads->offsets + lo;
+        v.seq = reads->seq; v.qual = reads->qual; v.pwm = reads->pwm;
     } else {
         int64_t base = reads->offsets[lo], total = reads->offsets[hi] - base;
-        CK(ctx->d_offsets.ensure(((size_t)n + 1) * 8));
-        CK(ctx->d_seq.ensure((size_t)total + 16));
-        CK(cudaMemcpyAsync(ctx->d_offsets.p, reads->offsets + lo, ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaMemcpyAsync(ctx->d_seq.p, reads->seq + base, (size_t)total, cudaMemcpyHostToDevice, ctx->stream));
-        ctx->dreads.offsets = ctx->d_offsets.as<int64_t>();
-        ctx->dreads.seq = ctx->d_seq.as<uint8_t>() - base;
+        CK(ctx->d_offsets[slot].ensure(((size_t)n + 1) * 8));
+        CK(ctx->d_seq[slot].ensure((size_t)total + 16));
+        CK(cudaMemcpyAsync(ctx->d_offsets[slot].p, reads->offsets + lo, ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, stream));
+        CK(cudaMemcpyAsync(ctx->d_seq[slot].p, reads->seq + base, (size_t)total, cudaMemcpyHostToDevice, stream));
+        v.offsets = ctx->d_offsets[slot].as<int64_t>();
+        v.seq = ctx->d_seq[slot].as<uint8_t>() - base;
         if (reads->qual) {
-            CK(ctx->d_qual.ensure((size_t)total + 16));
-            CK(cudaMemcpyAsync(ctx->d_qual.p, reads->qual + base, (size_t)total, cudaMemcpyHostToDevice, ctx->stream));
-            ctx->dreads.qual = ctx->d_qual.as<uint8_t>() - base;
+            CK(ctx->d_qual[slot].ensure((size_t)total + 16));
+            CK(cudaMemcpyAsync(ctx->d_qual[slot].p, reads->qual + base, (size_t)total, cudaMemcpyHostToDevice, stream));
+            v.qual = ctx->d_qual[slot].as<uint8_t>() - base;
         }
         if (reads->pwm) {
-            CK(ctx->d_pwm.ensure((size_t)total * 16 + 16));
-            CK(cudaMemcpyAsync(ctx->d_pwm.p, reads->pwm + 4 * base, (size_t)total * 16, cudaMemcpyHostToDevice, ctx->stream));
-            ctx->dreads.pwm = ctx->d_pwm.as<float>() - 4 * base;
+            CK(ctx->d_pwm[slot].ensure((size_t)total * 16 + 16));
+            CK(cudaMemcpyAsync(ctx->d_pwm[slot].p, reads->pwm + 4 * base, (size_t)total * 16, cudaMemcpyHostToDevice, stream));
+            v.pwm = ctx->d_pwm[slot].as<float>() - 4 * base;
         }
     }
-    if (max_len_out) *max_len_out = max_len;
+    ctx->up_max_len[slot] = max_len;
+    CK(cudaEventRecord(ctx->up_ev[slot], stream));
+    return GMX_OK;
+}
+
+// kernel-level entry points: upload on the compute stream into slot 0
+static int upload_reads(gmx_ctx *ctx, const gmx_reads *reads, int32_t lo, int32_t hi, int32_t *max_len_out)
+{
+    int r = issue_upload(ctx, reads, lo, hi, 0, ctx->stream);
+    if (r != GMX_OK) return r;
+    ctx->dreads = ctx->up_view[0];
+    if (max_len_out) *max_len_out = ctx->up_max_len[0];
     return GMX_OK;
 }
 
@@ -730,7 +751,7 @@ static cudaError_t launch_filter(gmx_ctx *ctx, const SeedStore &S, const ClassLi
 }
 
 // PHASE A for reads [lo, hi) of the batch; leaves its results resident on the device (ctx->cs).
-static int phase_a(gmx_ctx *ctx, const gmx_reads *reads, int32_t lo, int32_t hi)
+static int phase_a(gmx_ctx *ctx, const gmx_reads *reads, int32_t lo, int32_t hi, int slot)
 {
     gmx_ctx::ChunkState &cs = ctx->cs;
     cs.valid = false;
@@ -739,9 +760,11 @@ static int phase_a(gmx_ctx *ctx, const gmx_reads *reads, int32_t lo, int32_t hi)
     int32_t max_len = 0;
     const int n_sm = ctx->n_sm;
 
+    // the chunk's reads were put in flight by run_batch (copy stream, buffer set `slot`); this stage is the wait
     stage_begin(ctx, ST_UPLOAD);
-    int r = upload_reads(ctx, reads, lo, hi, &max_len);
-    if (r != GMX_OK) return r;
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->up_ev[slot], 0));
+    ctx->dreads = ctx->up_view[slot];
+    max_len = ctx->up_max_len[slot];
     int64_t total_bases = reads->on_device ? (int64_t)n * max_len : reads->offsets[hi] - reads->offsets[lo];
     uint64_t up_bytes = reads->on_device ? 0 : (uint64_t)total_bases * (reads->qual ? 2 : 1) + (reads->pwm ? 16ull * total_bases : 0) + 8ull * n;
     stage_end(ctx, ST_UPLOAD, (uint64_t)n, up_bytes, 0);
@@ -1059,9 +1082,19 @@ static int run_batch(gmx_ctx *ctx, const gmx_reads *reads, gmx_read_result *resu
     ctx->last_n_reads = n; ctx->last_max_len = 0;
     ctx->mapped = false; ctx->scored = false; ctx->cs.valid = false;
     stage_reset(ctx);
-    for (int32_t lo = 0; lo < n; lo += (int32_t)ctx->chunk_reads) {
-        int32_t hi = (int32_t)std::min<int64_t>(n, (int64_t)lo + (int64_t)ctx->chunk_reads);
-        int r = phase_a(ctx, reads, lo, hi);
+    const int32_t step = (int32_t)ctx->chunk_reads;
+    if (n > 0) {   // first chunk's upload; every later one is issued while its predecessor computes
+        int r = issue_upload(ctx, reads, 0, std::min<int32_t>(n, step), 0, ctx->copy_stream);
+        if (r != GMX_OK) return r;
+    }
+    int slot = 0;
+    for (int32_t lo = 0; lo < n; lo += step, slot ^= 1) {
+        int32_t hi = (int32_t)std::min<int64_t>(n, (int64_t)lo + (int64_t)step);
+        if (hi < n) {   // buffer set slot^1 was last read by chunk i-1, which has been synchronised
+            int r = issue_upload(ctx, reads, hi, (int32_t)std::min<int64_t>(n, (int64_t)hi + (int64_t)step), slot ^ 1, ctx->copy_stream);
+            if (r != GMX_OK) return r;
+        }
+        int r = phase_a(ctx, reads, lo, hi, slot);
         if (r != GMX_OK) return r;
         const bool last_and_split = !do_score && hi == n && lo == 0;       // single-chunk map_batch: PHASE B may follow
         if (do_score) { r = phase_b(ctx); if (r != GMX_OK) return r; }
