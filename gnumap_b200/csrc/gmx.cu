@@ -734,18 +734,18 @@ static cudaError_t launch_vote(gmx_ctx *ctx, const SeedStore &S, const ClassList
     return cudaGetLastError();
 }
 
-template <int FL, int WARPS>
+template <int FL, int WARPS, bool BITS>
 static cudaError_t launch_filter(gmx_ctx *ctx, const SeedStore &S, const ClassLists &F, const ClassLists &E, int cls, const CandSink &sink, int n_sm,
                                  uint32_t pac_words)
 {
     size_t smem = (size_t)WARPS * gmx_filter_warp_bytes(FL);
-    cudaError_t e = cudaFuncSetAttribute(k_vote_filter<FL, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k_vote_filter<FL, WARPS, BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 1;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_vote_filter<FL, WARPS>, WARPS * 32, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_vote_filter<FL, WARPS, BITS>, WARPS * 32, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
-    k_vote_filter<FL, WARPS><<<n_sm * per_sm, WARPS * 32, smem, ctx->stream>>>(ctx->ix, pac_words, S, F, E, cls, ctx->dparams.kmin,
+    k_vote_filter<FL, WARPS, BITS><<<n_sm * per_sm, WARPS * 32, smem, ctx->stream>>>(ctx->ix, pac_words, S, F, E, cls, ctx->dparams.kmin,
                                                                               ctx->dparams.mer, sink);
     return cudaGetLastError();
 }
@@ -828,12 +828,21 @@ static int phase_a(gmx_ctx *ctx, const gmx_reads *reads, int32_t lo, int32_t hi,
         CandSink sink; sink.keys = ctx->d_keys.as<unsigned long long>(); sink.count = &dc->n_cand; sink.overflow = &dc->cand_overflow; sink.cap = (uint32_t)ctx->cand_cap;
         stage_begin(ctx, ST_VOTE);
         if (use_filter) {
-            CK((launch_filter<12, 8>(ctx, S, F, C, 0, sink, n_sm, pac_words)));
-            CK((launch_filter<13, 4>(ctx, S, F, C, 1, sink, n_sm, pac_words)));
-            CK((launch_filter<14, 2>(ctx, S, F, C, 2, sink, n_sm, pac_words)));
-            CK((launch_filter<15, 1>(ctx, S, F, C, 3, sink, n_sm, pac_words)));
-            CK((launch_filter<16, 1>(ctx, S, F, C, 4, sink, n_sm, pac_words)));
-            CK((launch_filter<17, 1>(ctx, S, F, C, 5, sink, n_sm, pac_words)));
+            if (P.kmin == 2) {       // Bloom filter over bits: 4 bytes of filter per SA hit of the class
+                CK((launch_filter<11, 8, true>(ctx, S, F, C, 0, sink, n_sm, pac_words)));
+                CK((launch_filter<12, 8, true>(ctx, S, F, C, 1, sink, n_sm, pac_words)));
+                CK((launch_filter<13, 4, true>(ctx, S, F, C, 2, sink, n_sm, pac_words)));
+                CK((launch_filter<14, 2, true>(ctx, S, F, C, 3, sink, n_sm, pac_words)));
+                CK((launch_filter<15, 1, true>(ctx, S, F, C, 4, sink, n_sm, pac_words)));
+                CK((launch_filter<16, 1, true>(ctx, S, F, C, 5, sink, n_sm, pac_words)));
+            } else {                  // byte counters: 8 bytes of filter per SA hit of the class
+                CK((launch_filter<12, 8, false>(ctx, S, F, C, 0, sink, n_sm, pac_words)));
+                CK((launch_filter<13, 4, false>(ctx, S, F, C, 1, sink, n_sm, pac_words)));
+                CK((launch_filter<14, 2, false>(ctx, S, F, C, 2, sink, n_sm, pac_words)));
+                CK((launch_filter<15, 1, false>(ctx, S, F, C, 3, sink, n_sm, pac_words)));
+                CK((launch_filter<16, 1, false>(ctx, S, F, C, 4, sink, n_sm, pac_words)));
+                CK((launch_filter<17, 1, false>(ctx, S, F, C, 5, sink, n_sm, pac_words)));
+            }
         }
         CK((launch_vote<10, 2>(ctx, S, C, 0, sink, n_sm)));
         CK((launch_vote<11, 1>(ctx, S, C, 1, sink, n_sm)));

@@ -452,7 +452,13 @@ __device__ int gmx_round_diag0(const DevIndex &ix, int ns, int mer, int kmin, co
     return -1;
 }
 
-template <int F_LOG2, int WARPS>
+// BITS: kmin == 2 only needs "was this diagonal hit before": a blocked Bloom filter over BITS (one 32-bit word per
+// diagonal, two bits inside it) -- half the filter bytes of the byte counters at a fifth of their false positives,
+// and three shared-memory operations per hit instead of four.  Lanes that set bits of one word in the same step can
+// lose each other's bits; every lane re-reads its word after a __syncwarp and repeats the store until its own bits
+// are there (bits already in the word are never lost: each store is a superset of what the lane read after the
+// previous step's barrier).
+template <int F_LOG2, int WARPS, bool BITS>
 __global__ void __launch_bounds__(WARPS * 32, 1) k_vote_filter(DevIndex ix, uint32_t pac_words, SeedStore S, ClassLists F, ClassLists E,
                                                             int cls, int kmin, int mer, CandSink sink)
 {
@@ -565,20 +571,53 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_vote_filter(DevIndex ix, uint
                 for (int u = 0; u < U; ++u)
                     if (valid[u] && sa[u] <= off) { valid[u] = (u == first_u && lane == first_lane); inc[u] = total; }
             }
-            uint32_t h1[U], h2[U], c1[U], c2[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                h1[u] = (diag[u] * 0x9E3779B1u) >> (32 - F_LOG2); h2[u] = (diag[u] * 0x85EBCA77u + 0x27D4EB2Fu) >> (32 - F_LOG2);
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) { c1[u] = valid[u] ? filt[h1[u]] : 0u; c2[u] = valid[u] ? filt[h2[u]] : 0u; }
             bool flag[U];
+            if (BITS) {
+                // blocked Bloom filter: one word per diagonal, two bits inside it -> one load, one store, one re-read
+                uint32_t *fw = reinterpret_cast<uint32_t *>(filt);
+                uint32_t w[U], b[U], o[U];
+                bool pd[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                flag[u] = valid[u] && (int)(min(c1[u], c2[u]) + inc[u]) > need;
-                if (valid[u]) {
-                    filt[h1[u]] = (uint8_t)min(c1[u] + inc[u], 255u);
-                    filt[h2[u]] = (uint8_t)min(c2[u] + inc[u], 255u);
+                for (int u = 0; u < U; ++u) {
+                    const uint32_t g1 = diag[u] * 0x9E3779B1u, g2 = diag[u] * 0x85EBCA77u + 0x27D4EB2Fu;
+                    w[u] = g1 >> (32 - (F_LOG2 - 2));
+                    b[u] = (1u << (g2 >> 27)) | (1u << ((g2 >> 22) & 31u));
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) o[u] = valid[u] ? fw[w[u]] : 0xffffffffu;
+                bool pend = false;
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    pd[u] = (o[u] & b[u]) != b[u];
+                    flag[u] = valid[u] && (!pd[u] || inc[u] >= 2u);
+                    pend |= pd[u];
+                }
+                while (__any_sync(0xffffffffu, pend)) {
+#pragma unroll
+                    for (int u = 0; u < U; ++u) if (pd[u]) fw[w[u]] = o[u] | b[u];
+                    __syncwarp();
+                    pend = false;
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        if (pd[u]) { o[u] = fw[w[u]]; pd[u] = (o[u] & b[u]) != b[u]; }
+                        pend |= pd[u];
+                    }
+                }
+            } else {
+                uint32_t h1[U], h2[U], c1[U], c2[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    h1[u] = (diag[u] * 0x9E3779B1u) >> (32 - F_LOG2); h2[u] = (diag[u] * 0x85EBCA77u + 0x27D4EB2Fu) >> (32 - F_LOG2);
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) { c1[u] = valid[u] ? filt[h1[u]] : 0u; c2[u] = valid[u] ? filt[h2[u]] : 0u; }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    flag[u] = valid[u] && (int)(min(c1[u], c2[u]) + inc[u]) > need;
+                    if (valid[u]) {
+                        filt[h1[u]] = (uint8_t)min(c1[u] + inc[u], 255u);
+                        filt[h2[u]] = (uint8_t)min(c2[u] + inc[u], 255u);
+                    }
                 }
             }
 #pragma unroll
