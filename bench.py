@@ -295,6 +295,8 @@ def own_arm(a):
     m.synchronize()
     log(f"[bench] context created (index upload + SA de-sampling) in {time.time() - t:.1f}s")
     m.set_option(api.OPT_COLLECT_HITS, 0)
+    if os.environ.get("GMX_FILTER_SHIFT"):
+        m.set_option(api.OPT_FILTER_SHIFT, int(os.environ["GMX_FILTER_SHIFT"]))
     stream = torch.cuda.Stream(device=dev)
     m.set_stream(stream.cuda_stream)
 

@@ -35,7 +35,7 @@ EXPORTS = [
     "gmx_get_stage_stats", "gmx_set_option",
 ]
 
-OPT_COLLECT_HITS, OPT_CHUNK_READS, OPT_VOTE_FILTER = 1, 2, 3
+OPT_COLLECT_HITS, OPT_CHUNK_READS, OPT_VOTE_FILTER, OPT_FILTER_SHIFT = 1, 2, 3, 4
 
 
 class GmxError(RuntimeError):

@@ -113,6 +113,7 @@ struct gmx_ctx {
     size_t chunk_reads = 1 << 18;
     bool collect_hits = true;
     bool use_filter = true;                    // GMX_OPT_VOTE_FILTER
+    int filter_shift = 0;                      // GMX_OPT_FILTER_SHIFT
     int n_sm = 148;
     DevBuf d_best_cigar;
     // input of the last multi-chunk gmx_map_batch (gmx_score_batch re-runs the batch from it)
@@ -828,13 +829,20 @@ static int phase_a(gmx_ctx *ctx, const gmx_reads *reads, int32_t lo, int32_t hi,
         CandSink sink; sink.keys = ctx->d_keys.as<unsigned long long>(); sink.count = &dc->n_cand; sink.overflow = &dc->cand_overflow; sink.cap = (uint32_t)ctx->cand_cap;
         stage_begin(ctx, ST_VOTE);
         if (use_filter) {
-            if (P.kmin == 2) {       // Bloom filter over bits: 4 bytes of filter per SA hit of the class
-                CK((launch_filter<11, 8, true>(ctx, S, F, C, 0, sink, n_sm, pac_words)));
-                CK((launch_filter<12, 8, true>(ctx, S, F, C, 1, sink, n_sm, pac_words)));
-                CK((launch_filter<13, 4, true>(ctx, S, F, C, 2, sink, n_sm, pac_words)));
-                CK((launch_filter<14, 2, true>(ctx, S, F, C, 3, sink, n_sm, pac_words)));
-                CK((launch_filter<15, 1, true>(ctx, S, F, C, 4, sink, n_sm, pac_words)));
-                CK((launch_filter<16, 1, true>(ctx, S, F, C, 5, sink, n_sm, pac_words)));
+            if (P.kmin == 2) {       // blocked Bloom filter over bits: (4 << filter_shift) bytes of filter per SA hit of the class
+                for (int c = 0; c < GMX_N_CLASSES; ++c) {
+                    cudaError_t e = cudaSuccess;
+                    switch (std::min(std::max(11 + c + ctx->filter_shift, 10), 16)) {
+                        case 10: e = launch_filter<10, 8, true>(ctx, S, F, C, c, sink, n_sm, pac_words); break;
+                        case 11: e = launch_filter<11, 8, true>(ctx, S, F, C, c, sink, n_sm, pac_words); break;
+                        case 12: e = launch_filter<12, 8, true>(ctx, S, F, C, c, sink, n_sm, pac_words); break;
+                        case 13: e = launch_filter<13, 4, true>(ctx, S, F, C, c, sink, n_sm, pac_words); break;
+                        case 14: e = launch_filter<14, 2, true>(ctx, S, F, C, c, sink, n_sm, pac_words); break;
+                        case 15: e = launch_filter<15, 1, true>(ctx, S, F, C, c, sink, n_sm, pac_words); break;
+                        default: e = launch_filter<16, 1, true>(ctx, S, F, C, c, sink, n_sm, pac_words); break;
+                    }
+                    CK(e);
+                }
             } else {                  // byte counters: 8 bytes of filter per SA hit of the class
                 CK((launch_filter<12, 8, false>(ctx, S, F, C, 0, sink, n_sm, pac_words)));
                 CK((launch_filter<13, 4, false>(ctx, S, F, C, 1, sink, n_sm, pac_words)));
@@ -1172,6 +1180,9 @@ extern "C" int gmx_set_option(gmx_ctx *ctx, int option, int64_t value)
             if (value < 1 || value > (1 << 22)) { ctx->err = "chunk_reads must be in 1..4194304"; return GMX_ERR_INVALID; }
             ctx->chunk_reads = (size_t)value; return GMX_OK;
         case GMX_OPT_VOTE_FILTER: ctx->use_filter = value != 0; return GMX_OK;
+        case GMX_OPT_FILTER_SHIFT:
+            if (value < -2 || value > 2) { ctx->err = "filter_shift must be in -2..2"; return GMX_ERR_INVALID; }
+            ctx->filter_shift = (int)value; return GMX_OK;
         default: ctx->err = "unknown option"; return GMX_ERR_INVALID;
     }
 }

@@ -246,6 +246,7 @@ int gmx_finish(gmx_ctx *ctx, float *amount_genome, float *const planes[5]);
 #define GMX_OPT_CHUNK_READS  2   /* reads processed per internal chunk (default 262144)                     */
 #define GMX_OPT_VOTE_FILTER  3   /* 1 (default): counting-filter + exact-verification vote kernel with the exact
                                     hash-table kernels as its overflow path; 0: exact hash tables for every task  */
+#define GMX_OPT_FILTER_SHIFT 4   /* tuning: log2 scale of the kmin == 2 vote filter (default 0 = 4 bytes per SA hit)     */
 int gmx_set_option(gmx_ctx *ctx, int option, int64_t value);
 
 /* ---- instrumentation ---------------------------------------------------------------------- */
