@@ -455,8 +455,8 @@ __device__ int gmx_round_diag0(const DevIndex &ix, int ns, int mer, int kmin, co
 // BITS: kmin == 2 only needs "was this diagonal hit before": a blocked Bloom filter over BITS (one 32-bit word per
 // diagonal, two bits inside it) -- half the filter bytes of the byte counters at a fifth of their false positives,
 // and three shared-memory operations per hit instead of four.  Lanes that set bits of one word in the same step can
-// lose each other's bits; every lane re-reads its word after a __syncwarp and repeats the store until its own bits
-// are there (bits already in the word are never lost: each store is a superset of what the lane read after the
+// lose each other's bits; every lane re-reads its word after a __syncwarp and repairs a loss with an atomic OR
+// (bits already in the word are never lost: each plain store is a superset of what the lane read after the
 // previous step's barrier).
 template <int F_LOG2, int WARPS, bool BITS>
 __global__ void __launch_bounds__(WARPS * 32, 1) k_vote_filter(DevIndex ix, uint32_t pac_words, SeedStore S, ClassLists F, ClassLists E,
@@ -585,23 +585,20 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_vote_filter(DevIndex ix, uint
                 }
 #pragma unroll
                 for (int u = 0; u < U; ++u) o[u] = valid[u] ? fw[w[u]] : 0xffffffffu;
-                bool pend = false;
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    pd[u] = (o[u] & b[u]) != b[u];
+                    pd[u] = (o[u] & b[u]) != b[u];                       // invalid lanes read all-ones: never pending
                     flag[u] = valid[u] && (!pd[u] || inc[u] >= 2u);
-                    pend |= pd[u];
                 }
-                while (__any_sync(0xffffffffu, pend)) {
+                // plain stores; a lane whose bits were overwritten by a neighbour's store to the same word (a few
+                // lanes per step) repairs them with an atomic OR, which is safe once every plain store has landed
 #pragma unroll
-                    for (int u = 0; u < U; ++u) if (pd[u]) fw[w[u]] = o[u] | b[u];
-                    __syncwarp();
-                    pend = false;
+                for (int u = 0; u < U; ++u) if (pd[u]) fw[w[u]] = o[u] | b[u];
+                __syncwarp();
 #pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        if (pd[u]) { o[u] = fw[w[u]]; pd[u] = (o[u] & b[u]) != b[u]; }
-                        pend |= pd[u];
-                    }
+                for (int u = 0; u < U; ++u) {
+                    const uint32_t now = pd[u] ? fw[w[u]] : 0xffffffffu;
+                    if ((now & b[u]) != b[u]) atomicOr(&fw[w[u]], b[u]);
                 }
             } else {
                 uint32_t h1[U], h2[U], c1[U], c2[U];
