@@ -693,7 +693,7 @@ extern "C" int gmx_pair_hmm(gmx_ctx *ctx, const gmx_reads *reads, int64_t n_task
     CK(out.ensure((size_t)n_tasks * win_stride * 5 * 4));
     CK(cudaMemsetAsync(out.p, 0, (size_t)n_tasks * win_stride * 5 * 4, ctx->stream));
     size_t per_task = gmx_phmm_scratch_doubles(max_len);
-    int64_t wave = std::min<int64_t>(n_tasks, 148 * 8);
+    int64_t wave = std::min<int64_t>(n_tasks, 148 * 16);
     CK(scratch.ensure((size_t)wave * per_task * 8));
     for (int64_t t0 = 0; t0 < n_tasks; t0 += wave) {
         int64_t cnt = std::min<int64_t>(wave, n_tasks - t0);
@@ -962,7 +962,7 @@ static int phase_b(gmx_ctx *ctx)
         CK(ctx->d_hmm.ensure((size_t)n_leaders * max_len * 5 * 4));
         L.hmm = ctx->d_hmm.as<float>();
         size_t per_task = gmx_phmm_scratch_doubles(max_len);
-        uint32_t wave = std::min<uint32_t>(n_leaders, (uint32_t)ctx->n_sm * 8);
+        uint32_t wave = std::min<uint32_t>(n_leaders, (uint32_t)ctx->n_sm * 16);     // resident warps: register-bound
         CK(ctx->d_phmm_scratch.ensure((size_t)wave * per_task * 8));
         stage_begin(ctx, ST_PHMM);
         int launches = 0;

@@ -19,7 +19,8 @@
 #define GMX_PHMM_THREADS 32
 #define GMX_PHMM_MAXC 8                       // columns per lane -> read length <= 256 in SNP mode
 
-__host__ __device__ inline size_t gmx_phmm_scratch_doubles(int max_len) { return (size_t)max_len * max_len * 3; }
+// forward matrix parked in global memory: (fM, fY) per cell -- the X state never enters the posterior
+__host__ __device__ inline size_t gmx_phmm_scratch_doubles(int max_len) { return (size_t)max_len * max_len * 2; }
 
 struct PhmmConst {
     double Tmm, Tgm, Tmg, Tgg, q, t;          // floats promoted to double
@@ -58,6 +59,8 @@ __device__ __forceinline__ float gmx_phmm_emit(const ReadView &rd, const DevTabl
 }
 
 // One warp: posteriors of read `rd` against window `win` (m == n).  post: float[m][5], zeroed by the caller.
+// MAXC = columns per lane the register arrays are sized for (5: reads <= 160 bp, 8: <= 256 bp).
+template <int MAXC>
 __device__ void gmx_pair_hmm_warp(const ReadView &rd, const WindowView &win, const DevTables &T, double *F, float *post)
 {
     const int lane = threadIdx.x & 31;
@@ -65,36 +68,39 @@ __device__ void gmx_pair_hmm_warp(const ReadView &rd, const WindowView &win, con
     const int C = (m + 31) >> 5;
     const PhmmConst K = gmx_phmm_const();
     const int j0 = lane * C;                                   // first 0-based genome column of the strip
-    int gb[GMX_PHMM_MAXC], gbn[GMX_PHMM_MAXC];                  // genome base of column j, and of column j+1
+    int gb[MAXC], gbn[MAXC];                  // genome base of column j, and of column j+1
 #pragma unroll
-    for (int c = 0; c < GMX_PHMM_MAXC; ++c) {
+    for (int c = 0; c < MAXC; ++c) {
         int j = j0 + c;
         gb[c] = (c < C && j < m) ? win.base(j) : 0;
         gbn[c] = (c < C && j + 1 < m) ? win.base(j + 1) : 0;
     }
 
     // ---------------- forward (reference :141-157); f index (i, j) 1-based, strip column c <-> j = j0 + c + 1
-    double pM[GMX_PHMM_MAXC], pX[GMX_PHMM_MAXC], pY[GMX_PHMM_MAXC];     // row i-1 of the strip
+    double pM[MAXC], pX[MAXC], pY[MAXC];     // row i-1 of the strip
 #pragma unroll
-    for (int c = 0; c < GMX_PHMM_MAXC; ++c) { pM[c] = 0; pX[c] = 0; pY[c] = 0; }
+    for (int c = 0; c < MAXC; ++c) { pM[c] = 0; pX[c] = 0; pY[c] = 0; }
     // boundary cells on the left of the strip: (i-1, j0) "diag" and (i, j0) "left"
     double dM = 0, dX = 0, dY = 0, lM = 0, lY = 0;
     double outM = 0, outX = 0, outY = 0;                         // last column of the row just computed
     double fE_M = 0, fE_X = 0, fE_Y = 0;
+    float4 row_nxt = (1 - lane >= 1 && 1 - lane <= n) ? rd.phmm_row(T, 0 - lane) : make_float4(0, 0, 0, 0);
     for (int s = 1; s <= n + 31; ++s) {
         // receive the left neighbour's last column of the row it computed in the previous step (= my row i)
         double rM = gmx_shfl_d(outM, lane - 1), rX = gmx_shfl_d(outX, lane - 1), rY = gmx_shfl_d(outY, lane - 1);
         int i = s - lane;                                      // 1-based read row
+        const float4 row_cur = row_nxt;
+        row_nxt = (i + 1 >= 1 && i + 1 <= n) ? rd.phmm_row(T, i) : make_float4(0, 0, 0, 0);   // emission row of the next step
         if (lane == 0) { rM = 0; rX = 0; rY = 0; }             // column 0: f[i][0] = 0 for i >= 1
         // previous step's received row is now the diagonal row (i-1); for lane 0, (i-1, 0) is (0,0) when i == 1
         if (i >= 1 && i <= n) {
             if (lane == 0) { dM = (i == 1) ? 1.0 : 0.0; dX = 0; dY = 0; }
             lM = rM; lY = rY;
-            float4 row = rd.phmm_row(T, i - 1);
+            const float4 row = row_cur;
             double cM_prev = dM, cX_prev = dX, cY_prev = dY;   // (i-1, j-1) for the first column
             double leftM = lM, leftY = lY;                     // (i, j-1)
 #pragma unroll
-            for (int c = 0; c < GMX_PHMM_MAXC; ++c) {
+            for (int c = 0; c < MAXC; ++c) {
                 int j = j0 + c;                                // 0-based genome column
                 if (c < C && j < m) {
                     float e = gmx_phmm_emit(rd, T, row, i - 1, gb[c]);
@@ -105,8 +111,7 @@ __device__ void gmx_pair_hmm_warp(const ReadView &rd, const WindowView &win, con
                     cM_prev = pM[c]; cX_prev = pX[c]; cY_prev = pY[c];      // becomes (i-1, j) = diag of the next column
                     pM[c] = fM; pX[c] = fX; pY[c] = fY;
                     leftM = fM; leftY = fY;
-                    double *f = F + ((size_t)(i - 1) * m + j) * 3;
-                    f[0] = fM; f[1] = fX; f[2] = fY;
+                    reinterpret_cast<double2 *>(F)[(size_t)(i - 1) * m + j] = make_double2(fM, fY);
                     if (i == n && j == m - 1) { fE_M = fM; fE_X = fX; fE_Y = fY; }
                     outM = fM; outX = fX; outY = fY;
                 }
@@ -121,10 +126,10 @@ __device__ void gmx_pair_hmm_warp(const ReadView &rd, const WindowView &win, con
     const double fE = __dmul_rn(K.t, __dadd_rn(__dadd_rn(fE_M, fE_X), fE_Y));                  // reference :160
 
     // ---------------- backward (reference :164-204) + posterior (:206-241); b index (i, j) 0-based
-    double qM[GMX_PHMM_MAXC], qX[GMX_PHMM_MAXC];               // row i+1 of the strip (bM, bX)
-    float acc[GMX_PHMM_MAXC][5];
+    double qM[MAXC], qX[MAXC];               // row i+1 of the strip (bM, bX)
+    float acc[MAXC][5];
 #pragma unroll
-    for (int c = 0; c < GMX_PHMM_MAXC; ++c) { qM[c] = 0; qX[c] = 0;
+    for (int c = 0; c < MAXC; ++c) { qM[c] = 0; qX[c] = 0;
 #pragma unroll
         for (int b = 0; b < 5; ++b) acc[c][b] = 0.f; }
     double eM = 0;                                             // bM of (i+1, strip_end+1): diagonal boundary on the right
@@ -142,8 +147,14 @@ __device__ void gmx_pair_hmm_warp(const ReadView &rd, const WindowView &win, con
             double rightM_next = eM;                           // bM (i+1, j+1) for the last column of the strip
             double rightY = rY;                                // bY (i, j+1)
             double firstM = 0, firstY = 0;
+            double2 fv[MAXC];                                  // f[i+1][j+1] of the strip, all loads in flight before the chain
 #pragma unroll
-            for (int c = GMX_PHMM_MAXC - 1; c >= 0; --c) {
+            for (int c = 0; c < MAXC; ++c) {
+                int j = j0 + c;
+                fv[c] = (c < C && j < m) ? reinterpret_cast<const double2 *>(F)[(size_t)i * m + j] : make_double2(0, 0);
+            }
+#pragma unroll
+            for (int c = MAXC - 1; c >= 0; --c) {
                 int j = j0 + c;
                 if (c < C && j < m) {
                     double bM, bX, bY;
@@ -166,9 +177,8 @@ __device__ void gmx_pair_hmm_warp(const ReadView &rd, const WindowView &win, con
                         bY = __dadd_rn(__dmul_rn((double)eTgm, diagM), __dmul_rn((double)K.qTgg, rightY));
                     }
                     // posterior of (read i, genome j): f[i+1][j+1] * b[i][j] / fE, M and Y states
-                    const double *f = F + ((size_t)i * m + j) * 3;
-                    double pMv = __ddiv_rn(__dmul_rn(f[0], bM), fE);
-                    double pYv = __ddiv_rn(__dmul_rn(f[2], bY), fE);
+                    double pMv = __ddiv_rn(__dmul_rn(fv[c].x, bM), fE);
+                    double pYv = __ddiv_rn(__dmul_rn(fv[c].y, bY), fE);
                     double add = __dadd_rn(pYv, pMv);
 #pragma unroll
                     for (int b = 0; b < 5; ++b) if (b == code) acc[c][b] = (float)__dadd_rn((double)acc[c][b], add);
@@ -183,7 +193,7 @@ __device__ void gmx_pair_hmm_warp(const ReadView &rd, const WindowView &win, con
         }
     }
 #pragma unroll
-    for (int c = 0; c < GMX_PHMM_MAXC; ++c) {
+    for (int c = 0; c < MAXC; ++c) {
         int j = j0 + c;
         if (c < C && j < m) {
 #pragma unroll
@@ -201,7 +211,8 @@ __global__ void __launch_bounds__(GMX_PHMM_THREADS) k_pair_hmm_tasks(DevReads R,
     if ((int64_t)blockIdx.x >= cnt) return;
     ReadView rd = gmx_read_view(R, read_idx[t], strand ? strand[t] : 0);
     WindowView win; win.pac = nullptr; win.pos = 0; win.chars = windows + t * win_stride;
-    gmx_pair_hmm_warp(rd, win, T, scratch + (size_t)blockIdx.x * per_task, post + (size_t)t * win_stride * 5);
+    if (rd.n <= 160) gmx_pair_hmm_warp<5>(rd, win, T, scratch + (size_t)blockIdx.x * per_task, post + (size_t)t * win_stride * 5);
+    else gmx_pair_hmm_warp<GMX_PHMM_MAXC>(rd, win, T, scratch + (size_t)blockIdx.x * per_task, post + (size_t)t * win_stride * 5);
 }
 
 // one group leader per warp (SNPScoredSeq::score, reference src/SNPScoredSeq.cpp:44-67)
@@ -214,5 +225,6 @@ __global__ void __launch_bounds__(GMX_PHMM_THREADS) k_pair_hmm_leaders(DevIndex 
     gmx_decode_key(keys[L.lead_cand[s]], task, round, diag);
     ReadView rd = gmx_read_view(R, (int)(task >> 1), (int)(task & 1));
     WindowView win; win.pac = ix.pac; win.pos = diag; win.chars = nullptr;
-    gmx_pair_hmm_warp(rd, win, T, scratch + (size_t)blockIdx.x * per_task, L.hmm + (size_t)s * L.max_len * 5);
+    if (rd.n <= 160) gmx_pair_hmm_warp<5>(rd, win, T, scratch + (size_t)blockIdx.x * per_task, L.hmm + (size_t)s * L.max_len * 5);
+    else gmx_pair_hmm_warp<GMX_PHMM_MAXC>(rd, win, T, scratch + (size_t)blockIdx.x * per_task, L.hmm + (size_t)s * L.max_len * 5);
 }
