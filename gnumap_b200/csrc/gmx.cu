@@ -962,14 +962,24 @@ static int phase_b(gmx_ctx *ctx)
         CK(ctx->d_hmm.ensure((size_t)n_leaders * max_len * 5 * 4));
         L.hmm = ctx->d_hmm.as<float>();
         size_t per_task = gmx_phmm_scratch_doubles(max_len);
-        uint32_t wave = std::min<uint32_t>(n_leaders, (uint32_t)ctx->n_sm * 16);     // resident warps: register-bound
+        uint32_t wave = std::min<uint32_t>(n_leaders, (uint32_t)ctx->n_sm * 24);     // resident warps: register-bound
         CK(ctx->d_phmm_scratch.ensure((size_t)wave * per_task * 8));
         stage_begin(ctx, ST_PHMM);
         int launches = 0;
+        const int C = (max_len + 31) / 32;
         for (uint32_t s0 = 0; s0 < n_leaders; s0 += wave) {
             uint32_t cnt = std::min<uint32_t>(wave, n_leaders - s0);
-            k_pair_hmm_leaders<<<cnt, GMX_PHMM_THREADS, 0, ctx->stream>>>(ctx->ix, ctx->dreads, ctx->tab, cs.keys, L, s0, cnt,
-                                                                         ctx->d_phmm_scratch.as<double>(), per_task);
+            double *scr = ctx->d_phmm_scratch.as<double>();
+#define GMX_PHMM_LAUNCH(CT) k_pair_hmm_leaders<CT><<<cnt, GMX_PHMM_THREADS, 0, ctx->stream>>>(ctx->ix, ctx->dreads, ctx->tab, cs.keys, L, s0, cnt, scr, per_task)
+            switch (C) {
+                case 1: GMX_PHMM_LAUNCH(1); break;
+                case 2: GMX_PHMM_LAUNCH(2); break;
+                case 3: GMX_PHMM_LAUNCH(3); break;
+                case 4: GMX_PHMM_LAUNCH(4); break;
+                case 5: GMX_PHMM_LAUNCH(5); break;
+                default: GMX_PHMM_LAUNCH(0); break;
+            }
+#undef GMX_PHMM_LAUNCH
             CK(cudaGetLastError());
             launches++;
         }

@@ -20,7 +20,7 @@
 #define GMX_PHMM_MAXC 8                       // columns per lane -> read length <= 256 in SNP mode
 
 // forward matrix parked in global memory: (fM, fY) per cell -- the X state never enters the posterior
-__host__ __device__ inline size_t gmx_phmm_scratch_doubles(int max_len) { return (size_t)max_len * max_len * 2; }
+__host__ __device__ inline size_t gmx_phmm_scratch_doubles(int max_len) { return (size_t)max_len * (size_t)(((max_len + 31) / 32) * 32) * 2; }
 
 struct PhmmConst {
     double Tmm, Tgm, Tmg, Tgg, q, t;          // floats promoted to double
@@ -202,6 +202,154 @@ __device__ void gmx_pair_hmm_warp(const ReadView &rd, const WindowView &win, con
     }
 }
 
+// ---- fast path: packed-genome windows, C columns per lane known at compile time -------------------------
+// Same recurrences, but the strip loops carry no per-cell range checks: the matrix is padded to 32*C columns.
+// Padding is inert: forward values flow left->right / top->bottom (padded columns never feed real ones), and in the
+// backward sweep a padded cell only ever combines zeros, so real cells of the last column see exactly the
+// reference's special-cased formulas (x + 0.0 is exact).  Row n-1 of the backward sweep (reference :164-183) is
+// peeled.  Posteriors are accumulated in shared memory ([column slot][code][lane]: conflict-free) and the two
+// divisions by fE become multiplications by its reciprocal (K2c is a tolerance kernel: 1e-5 relative).
+#define GMX_PHMM_FAST_MAXC 5
+
+template <int C>
+__device__ void gmx_pair_hmm_warp_fast(const ReadView &rd, const uint8_t *pac, int64_t pos, const DevTables &T, double2 *F, float *post,
+                                       float *acc_s /* [C][5][32] */, float4 *erow_s /* [32*C] */, uint8_t *code_s /* [32*C] */)
+{
+    const int lane = threadIdx.x & 31;
+    const int n = rd.n, m = rd.n;
+    constexpr int MP = 32 * C;                                   // padded row length
+    // per-row operands of the read, staged once: emission row p_seq(pwm[i], g) for g = a,c,g,t and the consensus code
+    for (int i = lane; i < n; i += 32) {
+        erow_s[i] = rd.phmm_row(T, i);
+        const char ch = gmx_max_char(rd.pwm_row(T, i));
+        code_s[i] = (uint8_t)(ch == 'a' ? 0 : ch == 'c' ? 1 : ch == 'g' ? 2 : ch == 't' ? 3 : 4);
+    }
+    __syncwarp();
+    const PhmmConst K = gmx_phmm_const();
+    const int j0 = lane * C;
+    int gb[C], gbn[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        const int j = j0 + c;
+        gb[c] = j < m ? gmx_pac_base(pac, pos + j) : 0;
+        gbn[c] = j + 1 < m ? gmx_pac_base(pac, pos + j + 1) : 0;
+    }
+#pragma unroll
+    for (int x = 0; x < C * 5; ++x) acc_s[x * 32 + lane] = 0.f;
+
+    // ---------------- forward
+    double pM[C], pX[C], pY[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) { pM[c] = 0; pX[c] = 0; pY[c] = 0; }
+    double dM = 0, dX = 0, dY = 0;
+    double outM = 0, outX = 0, outY = 0;
+    for (int s = 1; s <= n + 31; ++s) {
+        double rM = gmx_shfl_d(outM, lane - 1), rX = gmx_shfl_d(outX, lane - 1), rY = gmx_shfl_d(outY, lane - 1);
+        const int i = s - lane;                                  // 1-based read row
+        if (lane == 0) { rM = 0; rX = 0; rY = 0; }
+        if (i >= 1 && i <= n) {
+            const float4 row = erow_s[i - 1];
+            if (lane == 0) { dM = (i == 1) ? 1.0 : 0.0; dX = 0; dY = 0; }
+            double cM = dM, cX = dX, cY = dY;                    // (i-1, j-1)
+            double leftM = rM, leftY = rY;                       // (i, j-1)
+            double2 *frow = F + (size_t)(i - 1) * MP + j0;
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const float e = gmx_sel4(row, gb[c], 0.f);
+                const double sum = __dadd_rn(__dadd_rn(__dmul_rn(K.Tmm, cM), __dmul_rn(K.Tgm, cX)), __dmul_rn(K.Tgm, cY));
+                const double fM = __dmul_rn((double)e, sum);
+                const double fX = __dmul_rn(K.q, __dadd_rn(__dmul_rn(K.Tmg, pM[c]), __dmul_rn(K.Tgg, pX[c])));
+                const double fY = __dmul_rn(K.q, __dadd_rn(__dmul_rn(K.Tmg, leftM), __dmul_rn(K.Tgg, leftY)));
+                cM = pM[c]; cX = pX[c]; cY = pY[c];
+                pM[c] = fM; pX[c] = fX; pY[c] = fY;
+                leftM = fM; leftY = fY;
+                frow[c] = make_double2(fM, fY);
+            }
+            outM = pM[C - 1]; outX = pX[C - 1]; outY = pY[C - 1];
+            dM = rM; dX = rX; dY = rY;
+        }
+    }
+    // fE from row n, column m-1: held by lane `owner`, strip slot `c_last`
+    const int owner = (m - 1) / C, c_last = (m - 1) - owner * C;
+    double eMv = pM[0], eXv = pX[0], eYv = pY[0];
+#pragma unroll
+    for (int c = 1; c < C; ++c) if (c == c_last) { eMv = pM[c]; eXv = pX[c]; eYv = pY[c]; }
+    eMv = gmx_shfl_d(eMv, owner); eXv = gmx_shfl_d(eXv, owner); eYv = gmx_shfl_d(eYv, owner);
+    const double fE = __dmul_rn(K.t, __dadd_rn(__dadd_rn(eMv, eXv), eYv));
+    const double inv_fE = 1.0 / fE;
+
+    // ---------------- backward + posterior
+    double qM[C], qX[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) { qM[c] = 0; qX[c] = 0; }
+    double eM = 0, sndM = 0, sndY = 0;
+    const double dqTmg = (double)K.qTmg, dqTgg = (double)K.qTgg;
+    double2 fv_nxt[C];                                           // forward values of the row handled in the next step
+#pragma unroll
+    for (int c = 0; c < C; ++c) fv_nxt[c] = make_double2(0, 0);
+    if (lane == 31) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) fv_nxt[c] = F[(size_t)(n - 1) * MP + j0 + c];
+    }
+    for (int s = 0; s <= n - 1 + 31; ++s) {
+        double rM = gmx_shfl_d(sndM, lane + 1), rY = gmx_shfl_d(sndY, lane + 1);
+        if (lane == 31) { rM = 0; rY = 0; }
+        const int i = (n - 1) - (s - (31 - lane));               // 0-based read row
+        double2 fv[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) fv[c] = fv_nxt[c];
+        if (i - 1 >= 0 && i - 1 <= n - 1) {                      // request the next step's row before this one's chain
+            const double2 *fnext = F + (size_t)(i - 1) * MP + j0;
+#pragma unroll
+            for (int c = 0; c < C; ++c) fv_nxt[c] = fnext[c];
+        }
+        if (i >= 0 && i <= n - 1) {
+            const float4 row = (i + 1 <= n - 1) ? erow_s[i + 1] : make_float4(0, 0, 0, 0);
+            const int code = code_s[i];
+            float *acc = acc_s + code * 32 + lane;
+            double diagM = eM, rightY = rY;
+            if (i == n - 1) {                                    // last read row (reference :164-183)
+#pragma unroll
+                for (int c = C - 1; c >= 0; --c) {
+                    const int j = j0 + c;
+                    double bM = __dmul_rn(dqTmg, rightY), bX = 0, bY = __dmul_rn(dqTgg, rightY);
+                    if (j == m - 1) { bM = K.t; bX = K.t; bY = K.t; }
+                    if (j > m - 1) { bM = 0; bX = 0; bY = 0; }
+                    const double add = __dadd_rn(__dmul_rn(__dmul_rn(fv[c].y, bY), inv_fE), __dmul_rn(__dmul_rn(fv[c].x, bM), inv_fE));
+                    if (j <= m - 1) acc[c * 160] = (float)__dadd_rn((double)acc[c * 160], add);
+                    qM[c] = bM; qX[c] = bX; rightY = bY;
+                }
+            } else {
+#pragma unroll
+                for (int c = C - 1; c >= 0; --c) {
+                    const float e = gmx_sel4(row, gbn[c], 0.f);
+                    const double eTmm = (double)__fmul_rn(e, K.fTmm), eTgm = (double)__fmul_rn(e, K.fTgm);
+                    const double tX = __dmul_rn(dqTmg, qX[c]), tY = __dmul_rn(dqTmg, rightY);
+                    const double bM = __dadd_rn(__dadd_rn(__dmul_rn(eTmm, diagM), tX), tY);
+                    const double gd = __dmul_rn(eTgm, diagM);
+                    const double bX = __dadd_rn(gd, __dmul_rn(dqTgg, qX[c]));
+                    const double bY = __dadd_rn(gd, __dmul_rn(dqTgg, rightY));
+                    const double add = __dadd_rn(__dmul_rn(__dmul_rn(fv[c].y, bY), inv_fE), __dmul_rn(__dmul_rn(fv[c].x, bM), inv_fE));
+                    acc[c * 160] = (float)__dadd_rn((double)acc[c * 160], add);
+                    diagM = qM[c];
+                    qM[c] = bM; qX[c] = bX; rightY = bY;
+                }
+            }
+            eM = rM;
+            sndM = qM[0]; sndY = rightY;
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        const int j = j0 + c;
+        if (j < m) {
+#pragma unroll
+            for (int b = 0; b < 5; ++b) post[(size_t)j * 5 + b] = acc_s[(c * 5 + b) * 32 + lane];
+        }
+    }
+}
+
 // explicit-window tasks (kernel-level entry point gmx_pair_hmm)
 __global__ void __launch_bounds__(GMX_PHMM_THREADS) k_pair_hmm_tasks(DevReads R, DevTables T, int64_t t0, int64_t cnt, const int32_t *read_idx,
                                                                      const uint8_t *strand, const uint8_t *windows, int win_stride,
@@ -215,16 +363,27 @@ __global__ void __launch_bounds__(GMX_PHMM_THREADS) k_pair_hmm_tasks(DevReads R,
     else gmx_pair_hmm_warp<GMX_PHMM_MAXC>(rd, win, T, scratch + (size_t)blockIdx.x * per_task, post + (size_t)t * win_stride * 5);
 }
 
-// one group leader per warp (SNPScoredSeq::score, reference src/SNPScoredSeq.cpp:44-67)
+// one group leader per warp (SNPScoredSeq::score, reference src/SNPScoredSeq.cpp:44-67).  C_T > 0: every read of the
+// chunk fits 32 * C_T columns (fast path, padded); C_T == 0: generic path.
+template <int C_T>
 __global__ void __launch_bounds__(GMX_PHMM_THREADS) k_pair_hmm_leaders(DevIndex ix, DevReads R, DevTables T, const unsigned long long *keys,
                                                                        LeaderStore L, uint32_t s0, uint32_t cnt, double *scratch, size_t per_task)
 {
+    constexpr int CS = C_T > 0 ? C_T : 1;
+    __shared__ float acc_s[CS * 5 * 32];
+    __shared__ float4 erow_s[CS * 32];
+    __shared__ uint8_t code_s[CS * 32];
     if (blockIdx.x >= cnt) return;
     uint32_t s = s0 + blockIdx.x;
     uint32_t task, round, diag;
     gmx_decode_key(keys[L.lead_cand[s]], task, round, diag);
     ReadView rd = gmx_read_view(R, (int)(task >> 1), (int)(task & 1));
-    WindowView win; win.pac = ix.pac; win.pos = diag; win.chars = nullptr;
-    if (rd.n <= 160) gmx_pair_hmm_warp<5>(rd, win, T, scratch + (size_t)blockIdx.x * per_task, L.hmm + (size_t)s * L.max_len * 5);
-    else gmx_pair_hmm_warp<GMX_PHMM_MAXC>(rd, win, T, scratch + (size_t)blockIdx.x * per_task, L.hmm + (size_t)s * L.max_len * 5);
+    double *my = scratch + (size_t)blockIdx.x * per_task;
+    float *out = L.hmm + (size_t)s * L.max_len * 5;
+    if (C_T > 0) {
+        gmx_pair_hmm_warp_fast<CS>(rd, ix.pac, diag, T, reinterpret_cast<double2 *>(my), out, acc_s, erow_s, code_s);
+    } else {
+        WindowView win; win.pac = ix.pac; win.pos = diag; win.chars = nullptr;
+        gmx_pair_hmm_warp<GMX_PHMM_MAXC>(rd, win, T, my, out);
+    }
 }
