@@ -832,7 +832,9 @@ static int phase_a(gmx_ctx *ctx, const gmx_reads *reads, int32_t lo, int32_t hi,
             if (P.kmin == 2) {       // blocked Bloom filter over bits: (4 << filter_shift) bytes of filter per SA hit of the class
                 for (int c = 0; c < GMX_N_CLASSES; ++c) {
                     cudaError_t e = cudaSuccess;
-                    switch (std::min(std::max(11 + c + ctx->filter_shift, 10), 16)) {
+                    // measured on B200: occupancy beats a sparse filter -- 8 KB (20 warps/SM) up to 8k hits per task
+                    static const int kBitsLog2[GMX_N_CLASSES] = {11, 12, 13, 13, 13, 15};
+                    switch (std::min(std::max(kBitsLog2[c] + ctx->filter_shift, 10), 16)) {
                         case 10: e = launch_filter<10, 8, true>(ctx, S, F, C, c, sink, n_sm, pac_words); break;
                         case 11: e = launch_filter<11, 8, true>(ctx, S, F, C, c, sink, n_sm, pac_words); break;
                         case 12: e = launch_filter<12, 8, true>(ctx, S, F, C, c, sink, n_sm, pac_words); break;
