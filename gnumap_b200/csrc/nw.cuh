@@ -197,8 +197,102 @@ __device__ float gmx_nw_band_score_any(const ReadView &rd, const WindowView &win
     return prev[G + 1];
 }
 
+// ---- K2a fast path: G == 3, FASTQ read (LUT rows), window in the packed genome ---------------------
+// Same cell arithmetic (one __fadd_rn for the substitution, one per gap, max of three), restructured so that no
+// register array is shifted and no branch sits in the interior rows: the value of column j lives in slot j & 7
+// (7 live columns + the one entering), the 8 row phases are unrolled so every slot index is a compile-time
+// constant, and the 4-way choice of the substitution value by the genome base is three byte-permutes with
+// selectors kept per slot.
+struct NwFastState {
+    float S[8];            // nm[i+1][j] of the live columns, slot j & 7
+    uint32_t A[8], B[8];   // PRMT selectors of the slot's genome base: bit 0 / bit 1
+};
+
+__device__ __forceinline__ float gmx_nw_pick(const float4 &sub, uint32_t selA, uint32_t selB)
+{
+    const uint32_t lo = __byte_perm(__float_as_uint(sub.x), __float_as_uint(sub.y), selA);
+    const uint32_t hi = __byte_perm(__float_as_uint(sub.z), __float_as_uint(sub.w), selA);
+    return __uint_as_float(__byte_perm(lo, hi, selB));
+}
+
+// one row i with i & 7 == P.  INTERIOR: 3 <= i <= n - 5 (every band column inside [0, n-1], right guard outside)
+template <int P, bool INTERIOR>
+__device__ __forceinline__ void gmx_nw_fast_row(NwFastState &st, int i, int n, const float4 &sub, const uint8_t *pac, int64_t pos, float gap)
+{
+    // the column entering the band on the left: j = i - 3, slot (P + 5) & 7
+    {
+        constexpr int sn = (P + 5) & 7;
+        const int jn = i - 3;
+        int g = 0;
+        if (INTERIOR || jn >= 0) g = gmx_pac_base(pac, pos + jn);
+        st.A[sn] = (g & 1) ? 0x7654u : 0x3210u;
+        st.B[sn] = (g & 2) ? 0x7654u : 0x3210u;
+        st.S[sn] = (!INTERIOR && i == n - 1) ? __fmul_rn(gap, 4.f) : GMX_NEG_INF;       // nm[n][n-4] is a border cell
+    }
+    float right = (!INTERIOR && i + 4 == n) ? __fmul_rn(gap, (float)(n - i)) : GMX_NEG_INF;   // nm[i][i+4]
+    float diag = st.S[(P + 4) & 7];                                                      // nm[i+1][i+4]
+#pragma unroll
+    for (int d = 3; d >= -3; --d) {
+        constexpr int dummy = 0; (void)dummy;
+        const int s = (P + d + 8) & 7;
+        const float up = st.S[s];
+        float v = gmx_max3(__fadd_rn(diag, gmx_nw_pick(sub, st.A[s], st.B[s])), __fadd_rn(up, gap), __fadd_rn(right, gap));
+        if (!INTERIOR) {
+            const int j = i + d;
+            if (j >= n) v = (j == n) ? __fmul_rn(gap, (float)(n - i)) : GMX_NEG_INF;
+            else if (j < 0) v = GMX_NEG_INF;
+        }
+        diag = up; st.S[s] = v; right = v;
+    }
+}
+
+__device__ float gmx_nw_band_score_fast3(const ReadView &rd, const uint8_t *pac, int64_t pos, const DevTables &T, float gap)
+{
+    const int n = rd.n;
+    NwFastState st;
+    // row n: nm[n][j] = gap * (n - j) for j <= n, NEG_INF beyond (reference src/bin_seq.cpp:805-807); columns n-3 .. n+3
+#pragma unroll
+    for (int s = 0; s < 8; ++s) { st.S[s] = GMX_NEG_INF; st.A[s] = 0x3210u; st.B[s] = 0x3210u; }
+    for (int j = n - 3; j <= n + 3; ++j) {
+        const float v = j <= n ? __fmul_rn(gap, (float)(n - j)) : GMX_NEG_INF;
+        const int g = (j >= 0 && j < n) ? gmx_pac_base(pac, pos + j) : 0;
+        const uint32_t a = (g & 1) ? 0x7654u : 0x3210u, b = (g & 2) ? 0x7654u : 0x3210u;
+#pragma unroll
+        for (int s = 0; s < 8; ++s) if (s == (j & 7)) { st.S[s] = v; st.A[s] = a; st.B[s] = b; }
+    }
+    int i = n - 1;
+    while (i >= 0) {
+        if ((i & 7) == 7 && i <= n - 5 && i - 7 >= 3) {
+            gmx_nw_fast_row<7, true>(st, i, n, rd.sub_row(T, i), pac, pos, gap);
+            gmx_nw_fast_row<6, true>(st, i - 1, n, rd.sub_row(T, i - 1), pac, pos, gap);
+            gmx_nw_fast_row<5, true>(st, i - 2, n, rd.sub_row(T, i - 2), pac, pos, gap);
+            gmx_nw_fast_row<4, true>(st, i - 3, n, rd.sub_row(T, i - 3), pac, pos, gap);
+            gmx_nw_fast_row<3, true>(st, i - 4, n, rd.sub_row(T, i - 4), pac, pos, gap);
+            gmx_nw_fast_row<2, true>(st, i - 5, n, rd.sub_row(T, i - 5), pac, pos, gap);
+            gmx_nw_fast_row<1, true>(st, i - 6, n, rd.sub_row(T, i - 6), pac, pos, gap);
+            gmx_nw_fast_row<0, true>(st, i - 7, n, rd.sub_row(T, i - 7), pac, pos, gap);
+            i -= 8;
+            continue;
+        }
+        const float4 sub = rd.sub_row(T, i);
+        switch (i & 7) {
+            case 7: gmx_nw_fast_row<7, false>(st, i, n, sub, pac, pos, gap); break;
+            case 6: gmx_nw_fast_row<6, false>(st, i, n, sub, pac, pos, gap); break;
+            case 5: gmx_nw_fast_row<5, false>(st, i, n, sub, pac, pos, gap); break;
+            case 4: gmx_nw_fast_row<4, false>(st, i, n, sub, pac, pos, gap); break;
+            case 3: gmx_nw_fast_row<3, false>(st, i, n, sub, pac, pos, gap); break;
+            case 2: gmx_nw_fast_row<2, false>(st, i, n, sub, pac, pos, gap); break;
+            case 1: gmx_nw_fast_row<1, false>(st, i, n, sub, pac, pos, gap); break;
+            default: gmx_nw_fast_row<0, false>(st, i, n, sub, pac, pos, gap); break;
+        }
+        --i;
+    }
+    return st.S[0];                                           // nm[0][0]
+}
+
 __device__ __forceinline__ float gmx_nw_score_dispatch(const ReadView &rd, const WindowView &win, const DevTables &T, float gap, int G)
 {
+    if (G == 3 && win.pac && !rd.pwm && rd.n >= 8) return gmx_nw_band_score_fast3(rd, win.pac, win.pos, T, gap);
     if (G == 3) return gmx_nw_band_score<3>(rd, win, T, gap);
     return gmx_nw_band_score_any(rd, win, T, gap, G);
 }
