@@ -75,6 +75,7 @@ struct gmx_ctx {
     DevBuf d_offsets[2], d_seq[2], d_qual[2], d_pwm[2];     // double-buffered: chunk i+1 uploads while chunk i computes
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t up_ev[2] = {nullptr, nullptr};
+    cudaEvent_t done_ev[2] = {nullptr, nullptr};          // last kernel that reads buffer set [slot] has been issued
     DevReads up_view[2];
     int32_t up_max_len[2] = {0, 0};
     DevReads dreads;
@@ -115,7 +116,10 @@ struct gmx_ctx {
     bool use_filter = true;                    // GMX_OPT_VOTE_FILTER
     int filter_shift = 0;                      // GMX_OPT_FILTER_SHIFT
     int n_sm = 148;
-    DevBuf d_best_cigar;
+    DevBuf d_best_cigar[2], d_out_results[2];  // staging of the fast download path, double-buffered
+    cudaStream_t d2h_stream = nullptr;
+    cudaEvent_t gather_ev[2] = {nullptr, nullptr}, dl_ev[2] = {nullptr, nullptr};
+    int dl_slot = 0;
     // input of the last multi-chunk gmx_map_batch (gmx_score_batch re-runs the batch from it)
     gmx_reads keep; bool keep_valid = false;
     std::vector<int64_t> keep_offsets; std::vector<uint8_t> keep_seq, keep_qual; std::vector<float> keep_pwm;
@@ -304,7 +308,9 @@ extern "C" int gmx_create(gmx_ctx **out, const gmx_index *index, const gmx_param
     CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     ctx->own_stream = true;
     CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-    for (int b = 0; b < 2; ++b) CK(cudaEventCreateWithFlags(&ctx->up_ev[b], cudaEventDisableTiming));
+    for (int b = 0; b < 2; ++b) { CK(cudaEventCreateWithFlags(&ctx->up_ev[b], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&ctx->done_ev[b], cudaEventDisableTiming)); }
+    CK(cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
+    for (int b = 0; b < 2; ++b) { CK(cudaEventCreateWithFlags(&ctx->gather_ev[b], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&ctx->dl_ev[b], cudaEventDisableTiming)); }
     for (int s = 0; s < ST_COUNT; ++s) { CK(cudaEventCreate(&ctx->ev[s][0])); CK(cudaEventCreate(&ctx->ev[s][1])); }
     stage_reset(ctx);
     cudaDeviceGetAttribute(&ctx->n_sm, cudaDevAttrMultiProcessorCount, device);
@@ -386,12 +392,13 @@ extern "C" void gmx_destroy(gmx_ctx *ctx)
                       &ctx->d_seed_count, &ctx->d_seed_off, &ctx->d_seed_n, &ctx->d_seed_hits, &ctx->d_cls_list, &ctx->d_cls_meta,
                       &ctx->d_keys, &ctx->d_keys_alt, &ctx->d_sort_tmp, &ctx->d_score, &ctx->d_leader, &ctx->d_slot, &ctx->d_lead_cand,
                       &ctx->d_hashes, &ctx->d_expv, &ctx->d_counters, &ctx->d_results, &ctx->d_alen, &ctx->d_aligned, &ctx->d_cigar,
-                      &ctx->d_hmm, &ctx->d_moves, &ctx->d_arena, &ctx->d_phmm_scratch, &ctx->d_best_cigar, &ctx->d_seed_code, &ctx->d_kmer_tab};
+                      &ctx->d_hmm, &ctx->d_moves, &ctx->d_arena, &ctx->d_phmm_scratch, &ctx->d_best_cigar[0], &ctx->d_best_cigar[1], &ctx->d_out_results[0], &ctx->d_out_results[1], &ctx->d_seed_code, &ctx->d_kmer_tab};
     for (DevBuf *b : bufs) b->release();
     ctx->h_best_cigar.release();
     if (ctx->ev[0][0]) for (int s = 0; s < ST_COUNT; ++s) { cudaEventDestroy(ctx->ev[s][0]); cudaEventDestroy(ctx->ev[s][1]); }
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
-    for (int b = 0; b < 2; ++b) if (ctx->up_ev[b]) cudaEventDestroy(ctx->up_ev[b]);
+    if (ctx->d2h_stream) { cudaStreamSynchronize(ctx->d2h_stream); cudaStreamDestroy(ctx->d2h_stream); }
+    for (int b = 0; b < 2; ++b) { if (ctx->done_ev[b]) cudaEventDestroy(ctx->done_ev[b]); if (ctx->up_ev[b]) cudaEventDestroy(ctx->up_ev[b]); if (ctx->gather_ev[b]) cudaEventDestroy(ctx->gather_ev[b]); if (ctx->dl_ev[b]) cudaEventDestroy(ctx->dl_ev[b]); }
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -1009,19 +1016,24 @@ static int download_chunk(gmx_ctx *ctx, bool scored, gmx_read_result *results_ou
     LeaderStore &L = cs.L;
     stage_begin(ctx, ST_DOWNLOAD);
     if (!ctx->collect_hits) {
-        // fast path: fixed-size records only
-        CK(ctx->d_best_cigar.ensure((size_t)std::max(n, 1) * GMX_CIGAR_STRIDE));
-        k_gather_best<<<nblk(n, 128), 128, 0, ctx->stream>>>(ctx->d_results.as<gmx_read_result>(), n, ctx->d_slot.as<int32_t>(), L,
-                                                           ctx->d_best_cigar.as<char>(), GMX_CIGAR_STRIDE, scored && n_leaders ? 1 : 0, scored ? 1 : 0);
+        // fast path: fixed-size records only, staged and copied out on a second stream while the next chunk computes
+        const int sl = ctx->dl_slot; ctx->dl_slot ^= 1;
+        CK(ctx->d_best_cigar[sl].ensure((size_t)std::max(n, 1) * GMX_CIGAR_STRIDE));
+        CK(ctx->d_out_results[sl].ensure((size_t)std::max(n, 1) * sizeof(gmx_read_result)));
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->dl_ev[sl], 0));            // the staging slot's previous copy has left
+        k_gather_best<<<nblk(n, 128), 128, 0, ctx->stream>>>(ctx->d_results.as<gmx_read_result>(), ctx->d_out_results[sl].as<gmx_read_result>(), n,
+                                                           ctx->d_slot.as<int32_t>(), L, ctx->d_best_cigar[sl].as<char>(), GMX_CIGAR_STRIDE,
+                                                           scored && n_leaders ? 1 : 0);
         CK(cudaGetLastError());
+        CK(cudaEventRecord(ctx->gather_ev[sl], ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->d2h_stream, ctx->gather_ev[sl], 0));
         gmx_read_result *dst = results_out ? results_out + lo : ctx->h_results.data() + lo;
-        CK(cudaMemcpyAsync(dst, ctx->d_results.p, (size_t)n * sizeof(gmx_read_result), cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaMemcpyAsync(ctx->h_best_cigar.as<char>() + (size_t)lo * GMX_CIGAR_STRIDE, ctx->d_best_cigar.p, (size_t)n * GMX_CIGAR_STRIDE,
-                           cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(dst, ctx->d_out_results[sl].p, (size_t)n * sizeof(gmx_read_result), cudaMemcpyDeviceToHost, ctx->d2h_stream));
+        CK(cudaMemcpyAsync(ctx->h_best_cigar.as<char>() + (size_t)lo * GMX_CIGAR_STRIDE, ctx->d_best_cigar[sl].p, (size_t)n * GMX_CIGAR_STRIDE,
+                           cudaMemcpyDeviceToHost, ctx->d2h_stream));
+        CK(cudaEventRecord(ctx->dl_ev[sl], ctx->d2h_stream));
         stage_end(ctx, ST_DOWNLOAD, (uint64_t)n, (uint64_t)n * (sizeof(gmx_read_result) + GMX_CIGAR_STRIDE), 1);
-        CK(cudaStreamSynchronize(ctx->stream));
-        stage_collect(ctx);
-        return GMX_OK;
+        return GMX_OK;                                                      // run_batch / gmx_score_batch drain d2h_stream
     }
     gmx_read_result *hres = ctx->h_results.data() + lo;
     CK(cudaMemcpyAsync(hres, ctx->d_results.p, (size_t)n * sizeof(gmx_read_result), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1119,7 +1131,8 @@ static int run_batch(gmx_ctx *ctx, const gmx_reads *reads, gmx_read_result *resu
     int slot = 0;
     for (int32_t lo = 0; lo < n; lo += step, slot ^= 1) {
         int32_t hi = (int32_t)std::min<int64_t>(n, (int64_t)lo + (int64_t)step);
-        if (hi < n) {   // buffer set slot^1 was last read by chunk i-1, which has been synchronised
+        if (hi < n) {   // buffer set slot^1 was last read by chunk i-1: its kernels must have drained first
+            CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->done_ev[slot ^ 1], 0));
             int r = issue_upload(ctx, reads, hi, (int32_t)std::min<int64_t>(n, (int64_t)hi + (int64_t)step), slot ^ 1, ctx->copy_stream);
             if (r != GMX_OK) return r;
         }
@@ -1129,9 +1142,13 @@ static int run_batch(gmx_ctx *ctx, const gmx_reads *reads, gmx_read_result *resu
         if (do_score) { r = phase_b(ctx); if (r != GMX_OK) return r; }
         r = download_chunk(ctx, do_score, results);
         if (r != GMX_OK) return r;
+        CK(cudaEventRecord(ctx->done_ev[slot], ctx->stream));
         if (!last_and_split && !do_score) ctx->cs.valid = false;
     }
     if (do_score) ctx->cs.valid = false;
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaStreamSynchronize(ctx->d2h_stream));
+    stage_collect(ctx);
     ctx->mapped = true; ctx->scored = do_score;
     return GMX_OK;
 }
@@ -1174,6 +1191,9 @@ extern "C" int gmx_score_batch(gmx_ctx *ctx, gmx_read_result *results)
         if (r != GMX_OK) return r;
         r = download_chunk(ctx, true, results);
         if (r != GMX_OK) return r;
+        CK(cudaStreamSynchronize(ctx->stream));
+        CK(cudaStreamSynchronize(ctx->d2h_stream));
+        stage_collect(ctx);
         ctx->cs.valid = false; ctx->scored = true;
         return GMX_OK;
     }

@@ -1089,8 +1089,8 @@ __global__ void __launch_bounds__(128) k_scatter(DevIndex ix, DevReads R, DevPar
 // ---- best alignment per read (fast download path) ------------------------------------------------
 // One thread per read: copies the CIGAR of the best group next to the per-read result so that only
 // [n_reads] fixed-size records leave the device when the caller does not ask for the hit list.
-__global__ void __launch_bounds__(128) k_gather_best(gmx_read_result *results, int n_reads, const int32_t *slot, LeaderStore L,
-                                                     char *best_cigar, int stride, int have_traceback, int final_pass)
+__global__ void __launch_bounds__(128) k_gather_best(const gmx_read_result *results, gmx_read_result *out, int n_reads, const int32_t *slot,
+                                                     LeaderStore L, char *best_cigar, int stride, int have_traceback)
 {
     int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_reads) return;
@@ -1099,12 +1099,13 @@ __global__ void __launch_bounds__(128) k_gather_best(gmx_read_result *results, i
     const bool has = have_traceback && res.status == GMX_READ_MAPPED && res.best_group >= 0;
     if (has) {
         int s = slot[res.hit_begin + res.best_group];
-        results[r].best_aligned_len = L.alen[s];
+        res.best_aligned_len = L.alen[s];
         const uint4 *src = reinterpret_cast<const uint4 *>(L.cigar + (size_t)s * L.c_stride);
         for (int k = 0; k < stride / 16; ++k) dst[k] = src[k];
     } else {
         for (int k = 0; k < stride / 16; ++k) dst[k] = make_uint4(0, 0, 0, 0);
     }
-    // the candidate range / leader index are device-internal; a later PHASE B pass still needs them
-    if (final_pass) { results[r].hit_begin = 0; results[r].hit_end = 0; results[r].best_group = -1; }
+    // the candidate range / leader index are device-internal (and stay intact in `results` for a later PHASE B)
+    res.hit_begin = 0; res.hit_end = 0; res.best_group = -1;
+    out[r] = res;
 }
