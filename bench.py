@@ -383,10 +383,20 @@ def own_arm(a):
         top = max(kstages, key=lambda k: st["ms"][k])
         launches = st["launches"][top]
         achieved = st["bytes"][top] / (st["ms"][top] * 1e-3) / 1e9 if st["ms"][top] > 0 else 0.0
+        traffic = None
+        try:   # DRAM bytes per SA hit of the vote kernel from the committed ncu --set full capture, scaled to this launch
+            tj = json.load(open(os.path.join(ROOT, "profiles", "vote_kernel_traffic.json")))
+            if top == "locate_vote":
+                traffic = tj["dram_bytes_per_sa_hit"] * st["units"][top] / max(st["launches"][top] / 12, 1)
+        except (OSError, KeyError, ValueError):
+            pass
         roofline = {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None, "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback",
+                    "traffic": traffic, "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback",
                     "algorithmic_bytes_per_step": st["bytes"][top] / a.steps, "ms_per_step": st["ms"][top] / a.steps,
                     "launches_per_step": launches / a.steps,
+                    "note": "stage = 12 launches per chunk of 262144 reads (6 filter + 6 exact classes); one of them (k_vote_filter<13,4,true> on this "
+                            "workload) carries ~all tasks, the rest find empty lists (~5 us each); achieved/traffic are per loaded launch; "
+                            "the kernel is ALU/LSU-bound (profiles/r01_ncu_raw_k_vote_filter_v7.txt), not HBM-bound",
                     "stages_ms_per_step": {k: round(v / a.steps, 3) for k, v in st["ms"].items()},
                     "stages_units_per_step": {k: v // a.steps for k, v in st["units"].items()}}
         nw_cells = st["units"].get("nw_score", 0)
