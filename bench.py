@@ -394,6 +394,7 @@ def own_arm(a):
                     "traffic": traffic, "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback",
                     "algorithmic_bytes_per_step": st["bytes"][top] / a.steps, "ms_per_step": st["ms"][top] / a.steps,
                     "launches_per_step": launches / a.steps,
+                    "algorithmic_bytes_per_loaded_launch": st["bytes"][top] / max(launches / 12, 1) if top == "locate_vote" else st["bytes"][top] / max(launches, 1),
                     "note": "stage = 12 launches per chunk of 262144 reads (6 filter + 6 exact classes); one of them (k_vote_filter<13,4,true> on this "
                             "workload) carries ~all tasks, the rest find empty lists (~5 us each); achieved/traffic are per loaded launch; "
                             "the kernel is ALU/LSU-bound (profiles/r01_ncu_raw_k_vote_filter_v7.txt), not HBM-bound",
