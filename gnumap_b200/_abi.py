@@ -7,7 +7,7 @@ import numpy as np
 
 GMX_OK = 0
 GMX_ERR_INVALID, GMX_ERR_CUDA, GMX_ERR_NOMEM, GMX_ERR_UNSUPPORTED = -1, -2, -3, -4
-GMX_ERR_OVERFLOW, GMX_ERR_NO_DEVICE, GMX_ERR_STATE = -5, -6, -7
+GMX_ERR_OVERFLOW, GMX_ERR_NO_DEVICE, GMX_ERR_STATE, GMX_ERR_FORMAT = -5, -6, -7, -8
 
 READ_MAPPED, READ_UNMATCHED, READ_TOO_SHORT, READ_TOO_POOR, READ_TOO_MANY = 0, 1, 2, 3, 4
 POS_STRAND, NEG_STRAND = 0, 1
@@ -39,7 +39,8 @@ class GmxParams(C.Structure):
 
 class GmxReads(C.Structure):
     _fields_ = [("n_reads", C.c_int32), ("offsets", C.c_void_p), ("seq", C.c_void_p),
-                ("qual", C.c_void_p), ("pwm", C.c_void_p), ("on_device", C.c_int32), ("max_len", C.c_int32)]
+                ("qual", C.c_void_p), ("pwm", C.c_void_p), ("on_device", C.c_int32), ("max_len", C.c_int32),
+                ("qual_offsets", C.c_void_p), ("lens", C.c_void_p)]
 
 
 class GmxStageStats(C.Structure):
@@ -55,6 +56,9 @@ READ_RESULT_DTYPE = np.dtype([
     ("best_n_positions", "<i4"), ("best_first_strand", "<i4"), ("best_first_pos", "<u8"),
     ("hit_begin", "<i4"), ("hit_end", "<i4"), ("best_group", "<i4"), ("best_aligned_len", "<i4"),
 ], align=True)
+
+FASTQ_REC_DTYPE = np.dtype([("name_off", "<i8"), ("seq_off", "<i8"), ("qual_off", "<i8"), ("name_len", "<i4"),
+                            ("seq_len", "<i4"), ("qual_len", "<i4"), ("pad", "<i4")], align=True)
 
 HIT_DTYPE = np.dtype([
     ("pos", "<u8"), ("score", "<f4"), ("read", "<i4"), ("group", "<i2"), ("strand", "u1"),

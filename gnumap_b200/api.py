@@ -32,7 +32,7 @@ EXPORTS = [
     "gmx_set_stream", "gmx_synchronize", "gmx_fm_search", "gmx_sa_locate", "gmx_get_windows", "gmx_self_score",
     "gmx_nw_score", "gmx_nw_traceback", "gmx_pair_hmm", "gmx_map_batch", "gmx_score_batch", "gmx_process_batch",
     "gmx_get_hits", "gmx_get_best_alignments", "gmx_accumulators_device", "gmx_reset_accumulators", "gmx_finish",
-    "gmx_get_stage_stats", "gmx_set_option",
+    "gmx_get_stage_stats", "gmx_set_option", "gmx_fastq_scan_host", "gmx_fastq_scan", "gmx_process_fastq",
 ]
 
 OPT_COLLECT_HITS, OPT_CHUNK_READS, OPT_VOTE_FILTER, OPT_FILTER_SHIFT = 1, 2, 3, 4
@@ -78,6 +78,9 @@ def load_library():
         L.gmx_finish.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.gmx_get_stage_stats.argtypes = [C.c_void_p, C.c_void_p]
         L.gmx_set_option.argtypes = [C.c_void_p, C.c_int, C.c_int64]
+        L.gmx_fastq_scan_host.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
+        L.gmx_fastq_scan.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
+        L.gmx_process_fastq.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.c_void_p]
         _lib = L
     return _lib
 
@@ -86,6 +89,27 @@ def default_params() -> GmxParams:
     p = GmxParams()
     load_library().gmx_default_params(C.byref(p))
     return p
+
+
+def fastq_scan_host(text: bytes, illumina: int = 0) -> np.ndarray:
+    """SeqReader::get_more_fastq record index of `text` (reference semantics incl. recovery); needs no GPU."""
+    L = load_library()
+    buf = np.frombuffer(text, dtype=np.uint8)
+    n = C.c_int64(0)
+    cap = max(text.count(b"\n") // 4 + 2, 4)
+    recs = np.zeros(cap, dtype=_abi.FASTQ_REC_DTYPE)
+    rc = L.gmx_fastq_scan_host(buf.ctypes.data if len(buf) else recs.ctypes.data, len(buf), illumina, recs.ctypes.data, cap, C.byref(n))
+    if rc != 0:
+        raise GmxError(rc, "gmx_fastq_scan_host", L.gmx_strerror(rc).decode())
+    return recs[: n.value]
+
+
+def batch_from_fastq(text: bytes, recs: np.ndarray):
+    """(names, ReadBatch) of a record index: Read::name / seq / fq with the quality cut to the sequence length."""
+    names = [text[int(r["name_off"]): int(r["name_off"]) + int(r["name_len"])].decode() for r in recs]
+    seqs = [text[int(r["seq_off"]): int(r["seq_off"]) + int(r["seq_len"])] for r in recs]
+    quals = [text[int(r["qual_off"]): int(r["qual_off"]) + int(r["seq_len"])] for r in recs]
+    return names, ReadBatch(seqs, quals)
 
 
 class Mapper:
@@ -224,6 +248,33 @@ class Mapper:
         self._ck(self.L.gmx_score_batch(self._ctx, C.c_void_p(results.ctypes.data)), "gmx_score_batch")
         out = dict(results=results)
         return self._fetch(batch, out, True) if fetch else out
+
+    def fastq_scan(self, text: bytes) -> np.ndarray:
+        """Device FASTQ indexer (well-formed text only: GmxError(GMX_ERR_FORMAT) otherwise)."""
+        buf = np.frombuffer(text, dtype=np.uint8)
+        cap = max(text.count(b"\n") // 4 + 2, 4)
+        recs = np.zeros(cap, dtype=_abi.FASTQ_REC_DTYPE)
+        n = C.c_int64(0)
+        self._ck(self.L.gmx_fastq_scan(self._ctx, buf.ctypes.data, len(buf), 0, recs.ctypes.data, cap, C.byref(n)), "gmx_fastq_scan")
+        return recs[: n.value]
+
+    def process_fastq(self, text: bytes, fetch: bool = True):
+        """FASTQ text -> PHASE A + B with the reads used in place on the device; falls back to the host scan (the
+        reference's recovery path) when the text is not well-formed.  Returns (names, dict as process_batch)."""
+        buf = np.frombuffer(text, dtype=np.uint8)
+        cap = max(text.count(b"\n") // 4 + 2, 4)
+        results = np.zeros(cap, dtype=READ_RESULT_DTYPE); recs = np.zeros(cap, dtype=_abi.FASTQ_REC_DTYPE)
+        n = C.c_int64(0)
+        rc = self.L.gmx_process_fastq(self._ctx, buf.ctypes.data if len(buf) else recs.ctypes.data, len(buf), 0, results.ctypes.data, cap, C.byref(n), recs.ctypes.data)
+        if rc == _abi.GMX_ERR_FORMAT:
+            recs = fastq_scan_host(text, self.params.illumina)
+            names, batch = batch_from_fastq(text, recs)
+            return names, self.process_batch(batch, fetch=fetch)
+        self._ck(rc, "gmx_process_fastq")
+        recs = recs[: n.value]
+        names, batch = batch_from_fastq(text, recs)
+        out = dict(results=results[: n.value])
+        return names, (self._fetch(batch, out, True) if fetch else out)
 
     def best_cigars(self, n_reads: int, stride: int = 64) -> np.ndarray:
         cig = np.zeros((n_reads, stride), dtype=np.uint8)

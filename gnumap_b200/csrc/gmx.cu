@@ -13,6 +13,7 @@
 
 #include "pipeline.cuh"
 #include "pair_hmm.cuh"
+#include "fastq.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // small utilities
@@ -82,6 +83,7 @@ struct gmx_ctx {
     std::vector<int64_t> h_offsets;            // offsets of the last batch (for gmx_get_hits)
     // pipeline buffers
     DevBuf d_seed_code;
+    DevBuf d_fq_text, d_fq_nl, d_fq_tmp, d_fq_seq_off, d_fq_qual_off, d_fq_len, d_fq_recs, d_fq_flags, d_fq_count;   // FASTQ indexer
     DevBuf d_prep, d_seed_rank, d_seed_count, d_seed_off, d_seed_n, d_seed_hits, d_cls_list, d_cls_meta;
     DevBuf d_keys, d_keys_alt, d_sort_tmp, d_score, d_leader, d_slot, d_lead_cand, d_hashes, d_expv, d_counters;
     DevBuf d_results, d_alen, d_aligned, d_cigar, d_hmm, d_moves, d_arena, d_phmm_scratch;
@@ -268,6 +270,7 @@ extern "C" const char *gmx_strerror(int code)
         case GMX_ERR_OVERFLOW: return "device work list overflow";
         case GMX_ERR_NO_DEVICE: return "no CUDA device (there is no CPU fallback)";
         case GMX_ERR_STATE: return "invalid call sequence";
+        case GMX_ERR_FORMAT: return "malformed FASTQ text";
         default: return "unknown error";
     }
 }
@@ -392,7 +395,7 @@ extern "C" void gmx_destroy(gmx_ctx *ctx)
                       &ctx->d_seed_count, &ctx->d_seed_off, &ctx->d_seed_n, &ctx->d_seed_hits, &ctx->d_cls_list, &ctx->d_cls_meta,
                       &ctx->d_keys, &ctx->d_keys_alt, &ctx->d_sort_tmp, &ctx->d_score, &ctx->d_leader, &ctx->d_slot, &ctx->d_lead_cand,
                       &ctx->d_hashes, &ctx->d_expv, &ctx->d_counters, &ctx->d_results, &ctx->d_alen, &ctx->d_aligned, &ctx->d_cigar,
-                      &ctx->d_hmm, &ctx->d_moves, &ctx->d_arena, &ctx->d_phmm_scratch, &ctx->d_best_cigar[0], &ctx->d_best_cigar[1], &ctx->d_out_results[0], &ctx->d_out_results[1], &ctx->d_seed_code, &ctx->d_kmer_tab};
+                      &ctx->d_hmm, &ctx->d_moves, &ctx->d_arena, &ctx->d_phmm_scratch, &ctx->d_best_cigar[0], &ctx->d_best_cigar[1], &ctx->d_out_results[0], &ctx->d_out_results[1], &ctx->d_seed_code, &ctx->d_kmer_tab, &ctx->d_fq_text, &ctx->d_fq_nl, &ctx->d_fq_tmp, &ctx->d_fq_seq_off, &ctx->d_fq_qual_off, &ctx->d_fq_len, &ctx->d_fq_recs, &ctx->d_fq_flags, &ctx->d_fq_count};
     for (DevBuf *b : bufs) b->release();
     ctx->h_best_cigar.release();
     if (ctx->ev[0][0]) for (int s = 0; s < ST_COUNT; ++s) { cudaEventDestroy(ctx->ev[s][0]); cudaEventDestroy(ctx->ev[s][1]); }
@@ -481,10 +484,12 @@ static int issue_upload(gmx_ctx *ctx, const gmx_reads *reads, int32_t lo, int32_
     if (r != GMX_OK) return r;
     DevReads &v = ctx->up_view[slot];
     v.n_reads = n; v.qbase = ctx->params.illumina ? 64 : 33;
-    v.qual = nullptr; v.pwm = nullptr;
+    v.qual = nullptr; v.pwm = nullptr; v.qoffsets = nullptr; v.lens = nullptr;
     if (reads->on_device) {
         v.offsets = reads->offsets + lo;
         v.seq = reads->seq; v.qual = reads->qual; v.pwm = reads->pwm;
+        v.qoffsets = reads->qual_offsets ? reads->qual_offsets + lo : nullptr;
+        v.lens = reads->lens ? reads->lens + lo : nullptr;
     } else {
         int64_t base = reads->offsets[lo], total = reads->offsets[hi] - base;
         CK(ctx->d_offsets[slot].ensure(((size_t)n + 1) * 8));
@@ -1260,4 +1265,161 @@ extern "C" int gmx_get_stage_stats(gmx_ctx *ctx, gmx_stage_stats *out)
         out->bytes[s] = ctx->stage_bytes[s]; out->launches[s] = ctx->stage_launches[s];
     }
     return GMX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// next row: FASTQ text -> reads
+// ------------------------------------------------------------------------------------------------
+// SeqReader::get_more_fastq, reference src/SeqReader.cpp:1023-1292, line by line (READ_BUFFER batching, adaptor
+// trimming and PWM construction aside: the PWM is built on the device from (base, quality char)).
+extern "C" int gmx_fastq_scan_host(const char *text, int64_t len, int illumina, gmx_fastq_rec *recs, int64_t capacity, int64_t *n_recs)
+{
+    if (!text || len < 0 || !n_recs || (capacity > 0 && !recs)) return GMX_ERR_INVALID;
+    FastqLines in{text, len, 0, false};
+    int64_t n = 0;
+    int rc = GMX_OK;
+    int qbase = illumina ? 64 : 33;
+    while (true) {
+        if (in.eof) break;                                         // :1060
+        int64_t no, nn, so, sn, po, pn, qo, qn;
+        in.getline(no, nn);                                        // :1070
+        while (nn == 0 && !in.eof) in.getline(no, nn);             // :1073-1076 blank lines
+        if (in.eof) break;                                         // :1079
+        in.getline(so, sn); in.getline(po, pn); in.getline(qo, qn);                      // :1086-1088
+        bool ended = false;
+        while (in.first(no, nn) != '@' || in.first(po, pn) != '+' || sn > qn) {           // :1091
+            if (in.first(no, nn) != '@' || in.first(po, pn) != '+') {                      // :1095
+                while ((in.first(no, nn) != '@' || in.first(po, pn) != '+') && !in.eof) {
+                    no = so; nn = sn; so = po; sn = pn; po = qo; pn = qn;               // shift the four lines up
+                    in.getline(qo, qn);
+                    if (in.eof) { ended = true; break; }                                  // :1106
+                }
+                if (ended || in.eof) { ended = true; break; }                             // :1114
+            }
+            if (sn > qn) {                                                                // :1125
+                in.getline(no, nn); in.getline(so, sn); in.getline(po, pn); in.getline(qo, qn);
+                if (in.eof) { ended = true; break; }                                      // :1135
+            }
+        }
+        if (ended) break;
+        // quality characters below the offset give max_prb < 0: with --illumina the reference turns the flag off and
+        // restarts the read at offset 33 (:1180-1188), otherwise it throws (:1189-1196)
+        for (int64_t i = 0; i < sn; ++i) {
+            int Q = (int)(unsigned char)text[qo + i] - qbase;
+            if (Q < 0) {
+                if (qbase == 64) { qbase = 33; i = -1; continue; }
+                rc = GMX_ERR_FORMAT;
+                break;
+            }
+        }
+        if (rc != GMX_OK) break;
+        if (n < capacity) {
+            gmx_fastq_rec &r = recs[n];
+            r.name_off = no + 1; r.name_len = (int32_t)(nn - 1); r.seq_off = so; r.seq_len = (int32_t)sn;
+            r.qual_off = qo; r.qual_len = (int32_t)qn; r.pad = 0;
+        }
+        ++n;
+    }
+    *n_recs = n;
+    if (rc != GMX_OK) return rc;
+    return n > capacity ? GMX_ERR_OVERFLOW : GMX_OK;
+}
+
+// device indexer; leaves seq_off / qual_off / seq_len / recs in ctx buffers and the text on the device
+static int fastq_scan_device(gmx_ctx *ctx, const char *text, int64_t len, int text_on_device, int64_t *n_recs, int32_t *max_len, const char **d_text_out)
+{
+    if (len >= 0x7fffffffll) { ctx->err = "FASTQ text of 2 GiB or more per call: split it at a record boundary"; return GMX_ERR_UNSUPPORTED; }
+    const char *d_text = text;
+    if (!text_on_device) {
+        CK(ctx->d_fq_text.ensure((size_t)len + 16));
+        CK(cudaMemcpyAsync(ctx->d_fq_text.p, text, (size_t)len, cudaMemcpyHostToDevice, ctx->stream));
+        d_text = ctx->d_fq_text.as<char>();
+    }
+    *d_text_out = d_text;
+    *n_recs = 0; *max_len = 0;
+    if (len == 0) return GMX_OK;
+    // newline positions, in order: count them first so that the position list is sized exactly
+    CK(ctx->d_fq_count.ensure(16));
+    thrust::counting_iterator<uint32_t> idx(0);
+    IsNewline pred{d_text};
+    CK(cudaMemsetAsync(ctx->d_fq_count.p, 0, 16, ctx->stream));
+    k_count_newlines<<<ctx->n_sm * 8, 256, 0, ctx->stream>>>(d_text, len, ctx->d_fq_count.as<unsigned long long>() + 1);
+    uint32_t n_expect = 0;
+    {
+        unsigned long long h = 0;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(&h, ctx->d_fq_count.as<unsigned long long>() + 1, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        n_expect = (uint32_t)h;
+    }
+    CK(ctx->d_fq_nl.ensure(((size_t)n_expect + 16) * 4));
+    size_t tmp_bytes = 0;
+    CK(cub::DeviceSelect::If(nullptr, tmp_bytes, idx, ctx->d_fq_nl.as<uint32_t>(), ctx->d_fq_count.as<uint32_t>(), (int)len, pred, ctx->stream));
+    CK(ctx->d_fq_tmp.ensure(tmp_bytes));
+    CK(cub::DeviceSelect::If(ctx->d_fq_tmp.p, tmp_bytes, idx, ctx->d_fq_nl.as<uint32_t>(), ctx->d_fq_count.as<uint32_t>(), (int)len, pred, ctx->stream));
+    uint32_t n_nl = 0;
+    char last = 0;
+    CK(cudaMemcpyAsync(&n_nl, ctx->d_fq_count.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(&last, d_text + len - 1, 1, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const uint64_t n_lines = (uint64_t)n_nl + (last != '\n' ? 1 : 0);
+    if (n_lines % 4 != 0) { ctx->err = "FASTQ text is not a whole number of 4-line records (blank or missing lines): use gmx_fastq_scan_host"; return GMX_ERR_FORMAT; }
+    const uint32_t n = (uint32_t)(n_lines / 4);
+    if (n == 0) return GMX_OK;
+    CK(ctx->d_fq_seq_off.ensure((size_t)n * 8)); CK(ctx->d_fq_qual_off.ensure((size_t)n * 8)); CK(ctx->d_fq_len.ensure((size_t)n * 4));
+    CK(ctx->d_fq_recs.ensure((size_t)n * sizeof(gmx_fastq_rec))); CK(ctx->d_fq_flags.ensure(16));
+    const uint32_t init[4] = {0u, 0u, 0xffffffffu, 0u};
+    CK(cudaMemcpyAsync(ctx->d_fq_flags.p, init, 16, cudaMemcpyHostToDevice, ctx->stream));
+    FastqDev out;
+    out.seq_off = ctx->d_fq_seq_off.as<int64_t>(); out.qual_off = ctx->d_fq_qual_off.as<int64_t>(); out.seq_len = ctx->d_fq_len.as<int32_t>();
+    out.recs = ctx->d_fq_recs.as<gmx_fastq_rec>(); out.flags = ctx->d_fq_flags.as<uint32_t>();
+    k_fastq_records<<<nblk(n, 256), 256, 0, ctx->stream>>>(d_text, len, ctx->d_fq_nl.as<uint32_t>(), n_nl, n, ctx->params.illumina ? 64 : 33, out);
+    CK(cudaGetLastError());
+    uint32_t flags[4];
+    CK(cudaMemcpyAsync(flags, ctx->d_fq_flags.p, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (flags[0]) {
+        char b[160];
+        snprintf(b, sizeof(b), "%u malformed FASTQ record(s), first at record %u: use gmx_fastq_scan_host", flags[0], flags[2]);
+        ctx->err = b;
+        return GMX_ERR_FORMAT;
+    }
+    *n_recs = n; *max_len = (int32_t)flags[1];
+    return GMX_OK;
+}
+
+extern "C" int gmx_fastq_scan(gmx_ctx *ctx, const char *text, int64_t len, int text_on_device, gmx_fastq_rec *recs, int64_t capacity, int64_t *n_recs)
+{
+    if (!ctx || !text || len < 0 || !n_recs) return GMX_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    int32_t max_len = 0; const char *d_text = nullptr;
+    int r = fastq_scan_device(ctx, text, len, text_on_device, n_recs, &max_len, &d_text);
+    if (r != GMX_OK) return r;
+    if (recs) {
+        if (capacity < *n_recs) return GMX_ERR_OVERFLOW;
+        CK(cudaMemcpyAsync(recs, ctx->d_fq_recs.p, (size_t)*n_recs * sizeof(gmx_fastq_rec), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return GMX_OK;
+}
+
+extern "C" int gmx_process_fastq(gmx_ctx *ctx, const char *text, int64_t len, int text_on_device, gmx_read_result *results, int64_t capacity,
+                                 int64_t *n_reads, gmx_fastq_rec *recs)
+{
+    if (!ctx || !text || len < 0 || !n_reads) return GMX_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    int32_t max_len = 0; const char *d_text = nullptr;
+    int r = fastq_scan_device(ctx, text, len, text_on_device, n_reads, &max_len, &d_text);
+    if (r != GMX_OK) return r;
+    if ((results || recs) && capacity < *n_reads) return GMX_ERR_OVERFLOW;
+    if (*n_reads > 0x7fffffffll) return GMX_ERR_UNSUPPORTED;
+    if (recs && *n_reads) CK(cudaMemcpyAsync(recs, ctx->d_fq_recs.p, (size_t)*n_reads * sizeof(gmx_fastq_rec), cudaMemcpyDeviceToHost, ctx->d2h_stream));
+    gmx_reads in;
+    memset(&in, 0, sizeof(in));
+    in.n_reads = (int32_t)*n_reads;
+    in.offsets = ctx->d_fq_seq_off.as<int64_t>();
+    in.seq = reinterpret_cast<const uint8_t *>(d_text); in.qual = reinterpret_cast<const uint8_t *>(d_text);
+    in.qual_offsets = ctx->d_fq_qual_off.as<int64_t>(); in.lens = ctx->d_fq_len.as<int32_t>();
+    in.on_device = 1; in.max_len = std::max(max_len, 1);
+    return run_batch(ctx, &in, results, true);
 }

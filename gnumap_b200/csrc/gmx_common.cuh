@@ -49,9 +49,16 @@ struct DevReads {
     const uint8_t *seq;      // raw ASCII
     const uint8_t *qual;     // raw ASCII (may be null when pwm is given)
     const float   *pwm;      // optional [total][4]
+    const int64_t *qoffsets; // optional: quality string of read r starts at qual[qoffsets[r]] (FASTQ text used in place)
+    const int32_t *lens;     // optional: explicit read lengths (reads not contiguous in `seq`)
     int32_t n_reads;
     int32_t qbase;           // 33, or 64 with --illumina
 };
+
+__device__ __forceinline__ int gmx_read_len(const DevReads &R, int r)
+{
+    return R.lens ? R.lens[r] : (int)(R.offsets[r + 1] - R.offsets[r]);
+}
 
 __device__ __forceinline__ int gmx_nt4(uint8_t c)
 {   // reference src/bntseq.c:47-64 nst_nt4_table, folded to 0..3 / 4

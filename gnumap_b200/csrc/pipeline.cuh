@@ -31,9 +31,9 @@ __device__ __forceinline__ ReadView gmx_read_view(const DevReads &R, int r, int 
 {
     ReadView v;
     int64_t off = R.offsets[r];
-    v.n = (int)(R.offsets[r + 1] - off);
+    v.n = gmx_read_len(R, r);
     v.seq = R.seq + off;
-    v.qual = R.qual ? R.qual + off : nullptr;
+    v.qual = R.qual ? R.qual + (R.qoffsets ? R.qoffsets[r] : off) : nullptr;
     v.pwm = R.pwm ? R.pwm + 4 * off : nullptr;
     v.neg = neg;
     return v;
@@ -90,7 +90,7 @@ __global__ void k_seed_walk(DevIndex ix, DevReads R, DevParams P, const ReadPrep
     if (active && !R.seq) active = false;
     if (active) {
         int64_t off = R.offsets[r];
-        int n = (int)(R.offsets[r + 1] - off);
+        int n = gmx_read_len(R, r);
         const uint8_t *seq = R.seq + off;
         // oriented consensus symbol: POS = nt4(seq[x]); NEG = complement of seq[n-1-x]
         // (reverse_comp maps every non-acgt character to 'n', which never matches)
@@ -828,7 +828,7 @@ __global__ void __launch_bounds__(128) k_finalize_reads(DevIndex ix, DevReads R,
     res.best_first_strand = 0; res.best_first_pos = 0; res.hit_begin = 0; res.hit_end = 0; res.best_group = -1; res.best_aligned_len = 0;
     if (pr.status == GMX_READ_TOO_SHORT) { res.top_score = -2; if (lane == 0) O.results[r] = res; return; }
     if (pr.status == GMX_READ_TOO_POOR) { res.top_score = -3; if (lane == 0) O.results[r] = res; return; }
-    const int n = (int)(R.offsets[r + 1] - R.offsets[r]);
+    const int n = gmx_read_len(R, r);
     uint32_t lo = gmx_lower_bound(keys, n_cand, (unsigned long long)(2 * (uint32_t)r) << 40);
     uint32_t hi = gmx_lower_bound(keys, n_cand, (unsigned long long)(2 * (uint32_t)r + 2) << 40);
 
@@ -1049,7 +1049,7 @@ __global__ void __launch_bounds__(128) k_scatter(DevIndex ix, DevReads R, DevPar
     float total = (float)(exp((double)score[ld]) / denom);
     int same = ((task & 1) == (tl & 1));                 // strand == firstStrand of the group
     if (P.mode == GMX_MODE_SNP) {
-        int n = (int)(R.offsets[r + 1] - R.offsets[r]);
+        int n = gmx_read_len(R, r);
         const float *hmm = L.hmm + (size_t)s * L.max_len * 5;
         for (int i = lane; i < n; i += 32) {
             int64_t p = (int64_t)diag + i;

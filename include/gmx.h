@@ -35,6 +35,7 @@ extern "C" {
 #define GMX_ERR_OVERFLOW    -5   /* an internal device work list overflowed even after regrowth */
 #define GMX_ERR_NO_DEVICE   -6   /* no CUDA device: there is no CPU fallback */
 #define GMX_ERR_STATE       -7   /* call sequence violated (e.g. score_batch without map_batch) */
+#define GMX_ERR_FORMAT      -8   /* malformed FASTQ text (device indexer: use gmx_fastq_scan_host; host: invalid quality) */
 
 /* ---- per-read status (mirrors the sentinels the reference stores in gTopReadScore,
  *      reference inc/const_include.h:184-188 and src/Driver.cpp:446-611) ----------------------- */
@@ -117,6 +118,11 @@ typedef struct gmx_reads {
     int32_t        on_device; /* 0: the four arrays are host memory (copied to the GPU inside the call);
                                  1: they already live in the memory of the context's GPU             */
     int32_t        max_len;   /* longest read of the batch; 0 = let the library scan offsets (host only) */
+    /* Reads used in place inside a larger text (FASTQ): device-resident batches only.  When `lens` is given, read r
+     * is seq[offsets[r] .. +lens[r]) and offsets has n_reads entries; when `qual_offsets` is given its quality string
+     * starts at qual[qual_offsets[r]].  NULL for packed batches. */
+    const int64_t *qual_offsets;
+    const int32_t *lens;
 } gmx_reads;
 
 /* Per-read outcome of PHASE A + PHASE B  (== gTopReadScore / gReadDenominator / the best
@@ -239,6 +245,29 @@ int gmx_reset_accumulators(gmx_ctx *ctx);
  * the host arrays GetGenomeAmtPtr() / GetGenome{A,C,G,T,N}Ptr() (GenomeBwt.h:199-209).
  * planes may be NULL in Normal mode. */
 int gmx_finish(gmx_ctx *ctx, float *amount_genome, float *const planes[5]);
+
+/* ---- next row: FASTQ text -> reads -------------------------------------------
+ * SeqReader::get_more_fastq (reference src/SeqReader.cpp:1023-1292).  One record per read, offsets into the text. */
+typedef struct gmx_fastq_rec {
+    int64_t name_off;          /* read name without the '@' (Read::name, SeqReader.cpp:1263)          */
+    int64_t seq_off;           /* Read::seq                                                           */
+    int64_t qual_off;          /* Read::fq (may be longer than the sequence; the PWM uses seq_len of it) */
+    int32_t name_len, seq_len, qual_len, pad;
+} gmx_fastq_rec;
+
+/* Host restatement with the reference's recovery from malformed records.  Returns GMX_ERR_FORMAT when a quality
+ * character maps to Q < 0 (the reference throws "Invalid Fastq Character"), GMX_ERR_OVERFLOW when capacity is short
+ * (*n_recs then holds the count).  Needs no GPU. */
+int gmx_fastq_scan_host(const char *text, int64_t len, int illumina, gmx_fastq_rec *recs, int64_t capacity, int64_t *n_recs);
+
+/* The same index on the GPU for well-formed text (4 lines per record, '@' / '+' in place, len(qual) >= len(seq)):
+ * newline compaction + one thread per record.  text may be host (copied in) or device memory.  Any record that would
+ * need the reference's recovery path gives GMX_ERR_FORMAT: fall back to gmx_fastq_scan_host.  recs may be NULL. */
+int gmx_fastq_scan(gmx_ctx *ctx, const char *text, int64_t len, int text_on_device, gmx_fastq_rec *recs, int64_t capacity, int64_t *n_recs);
+
+/* gmx_fastq_scan + gmx_process_batch with the reads used in place inside the (device copy of the) text. */
+int gmx_process_fastq(gmx_ctx *ctx, const char *text, int64_t len, int text_on_device, gmx_read_result *results, int64_t capacity,
+                      int64_t *n_reads, gmx_fastq_rec *recs);
 
 /* ---- options ----------------------------------------------------------------------------- */
 #define GMX_OPT_COLLECT_HITS 1   /* 1 (default): keep every accepted (pos,strand) for gmx_get_hits; 0: only the

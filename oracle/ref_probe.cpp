@@ -26,6 +26,7 @@
 #include "BSScoredSeq.h"
 #include "SNPScoredSeq.h"
 #include "SequenceOperations.h"
+#include "SeqReader.h"
 
 const char *pos_matrix = NULL;      /* src/Driver.cpp:72, read by a_matrices.c */
 #include "a_matrices.c"
@@ -194,6 +195,28 @@ int refp_score_once(int kind, const float *pwm, int n, const char *gen_string, d
     delete ss;
     free_rows(rows, n);
     return 0;
+}
+
+/* SeqReader on a FASTQ file: one line "name\tseq\tfq\n" per Read, in order (reference src/SeqReader.cpp:1023-1292).
+ * Returns the number of reads, or -1 when the reader threw (invalid quality character). */
+int refp_read_fastq(const char *fn, char *out, int cap)
+{
+    refp_init();
+    int n = 0, used = 0;
+    try {
+        SeqReader sr;
+        sr.use(fn);
+        Read *r;
+        while ((r = sr.GetNextSequence()) != 0) {
+            std::string line = std::string(r->name ? r->name : "") + "\t" + r->seq + "\t" + r->fq + "\n";
+            if (used + (int)line.size() < cap) { memcpy(out + used, line.data(), line.size()); used += (int)line.size(); }
+            ++n;
+        }
+    } catch (...) {
+        return -1;
+    }
+    out[used] = 0;
+    return n;
 }
 
 } /* extern "C" */

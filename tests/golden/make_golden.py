@@ -13,6 +13,8 @@ Outputs (committed; the GPU box has no /root/reference and only reads these file
                         ScoredSeq::score() accumulator footprints for the three modes;
   ref_index.npz         the index files the reference's bwa_index wrote for a small two-contig FASTA (bytes), next
                         to the FASTA's bases -- pins gnumap_b200/index.py byte for byte;
+  ref_fastq.json        FASTQ texts (well-formed and malformed) with what the reference's SeqReader returns for them
+                        (name, sequence, quality string per Read) -- pins gmx_fastq_scan_host incl. its recovery paths;
   ref_program_<mode>.json.gz   whole-program runs of oracle/_ref/gnumap (`-c 1`, zero-initialised accumulators):
                         the reads, the sorted SAM body and the .sgr / .gmp rows.
 
@@ -193,12 +195,57 @@ def make_program(tmp):
         print(f"ref_program_{mode}.json.gz: {len(sam)} SAM records, matched {rec['matched']}")
 
 
+def fastq_cases():
+    """FASTQ texts that exercise SeqReader::get_more_fastq incl. its recovery paths."""
+    rng = np.random.default_rng(77)
+    def rec(name, n, qn=None, plus=b"+"):
+        seq = bytes(b"ACGTN"[int(c)] for c in rng.integers(0, 5, size=n))
+        q = bytes(int(x) + 33 for x in rng.integers(0, 41, size=n if qn is None else qn))
+        return b"@" + name + b"\n" + seq + b"\n" + plus + b"\n" + q + b"\n"
+    good = b"".join(rec(b"g%d" % i, int(rng.integers(1, 120))) for i in range(40))
+    cases = {
+        "well_formed": good,
+        "no_final_newline": good[:-1],
+        "plus_repeats_name": b"".join(rec(b"p%d" % i, 30, plus=b"+p%d" % i) for i in range(5)),
+        "blank_lines_between": rec(b"a", 10) + b"\n\n" + rec(b"b", 12) + b"\n" + rec(b"c", 9),
+        "quality_longer": rec(b"a", 10, qn=15) + rec(b"b", 8),
+        "quality_shorter_then_recover": rec(b"a", 10, qn=6) + rec(b"b", 8) + rec(b"c", 7),
+        "garbage_line": rec(b"a", 10) + b"GARBAGE\n" + rec(b"b", 8) + rec(b"c", 5),
+        "missing_plus": b"@a\nACGT\nIIII\n" + rec(b"b", 8) + rec(b"c", 6),
+        "truncated_last_record": rec(b"a", 10) + b"@b\nACGT\n+\n",
+        "crlf": rec(b"a", 10).replace(b"\n", b"\r\n") + rec(b"b", 6).replace(b"\n", b"\r\n"),
+        "empty_sequence": b"@e\n\n+\n\n" + rec(b"b", 6),
+        "lowercase_and_other_letters": b"@x\nacgtRYKM\n+\nIIIIIIII\n",
+        "bad_quality_char": b"@x\nACGT\n+\nII I\n",
+        "empty_file": b"",
+    }
+    return cases
+
+
+def make_fastq(tmp):
+    import ctypes as C
+    L = C.CDLL(O.REF_PROBE)
+    out = {}
+    for name, text in fastq_cases().items():
+        fn = os.path.join(tmp, name + ".fq")
+        with open(fn, "wb") as f:
+            f.write(text)
+        buf = C.create_string_buffer(1 << 20)
+        n = L.refp_read_fastq(fn.encode(), buf, 1 << 20)
+        reads = [ln.split("\t") for ln in buf.value.decode("latin-1").split("\n")[:-1]] if n > 0 else []
+        out[name] = {"text": text.decode("latin-1"), "n": n, "reads": reads}
+    with open(os.path.join(HERE, "ref_fastq.json"), "w") as f:
+        json.dump(out, f, indent=0)
+    print("ref_fastq.json:", {k: v["n"] for k, v in out.items()})
+
+
 def main():
     O.build()
     if not (O.have_ref_binary() and os.path.exists(O.REF_PROBE)):
         raise SystemExit("oracle/_ref is missing: run `make -C oracle ref` where /root/reference exists")
     tmp = tempfile.mkdtemp(prefix="gmx_golden_")
     try:
+        make_fastq(tmp)
         make_functions(tmp)
         make_index(tmp)
         make_program(tmp)

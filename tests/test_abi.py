@@ -41,6 +41,7 @@ int main(void) {
   printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(gmx_index), sizeof(gmx_params), sizeof(gmx_reads), sizeof(gmx_read_result), sizeof(gmx_hit), sizeof(gmx_stage_stats));
   printf("%zu %zu %zu %zu %zu\\n", offsetof(gmx_read_result, best_first_pos), offsetof(gmx_read_result, hit_begin), offsetof(gmx_read_result, best_aligned_len), offsetof(gmx_hit, group), offsetof(gmx_params, gap));
   printf("%zu %zu\\n", offsetof(gmx_reads, on_device), offsetof(gmx_index, seq_offset));
+  printf("%zu %zu %zu\\n", sizeof(gmx_fastq_rec), offsetof(gmx_fastq_rec, seq_len), offsetof(gmx_reads, lens));
   return 0; }
 ''')
     exe = tmp_path / "layout"
@@ -60,6 +61,9 @@ int main(void) {
     assert sizes[10] == _abi.GmxParams.gap.offset
     assert sizes[11] == _abi.GmxReads.on_device.offset
     assert sizes[12] == _abi.GmxIndex.seq_offset.offset
+    assert sizes[13] == _abi.FASTQ_REC_DTYPE.itemsize
+    assert sizes[14] == _abi.FASTQ_REC_DTYPE.fields["seq_len"][1]
+    assert sizes[15] == _abi.GmxReads.lens.offset
 
 
 def test_default_params_are_the_reference_defaults():

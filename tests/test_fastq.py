@@ -1,0 +1,96 @@
+"""SURVEY.md §8(f) rank 1 -- FASTQ text -> reads.
+
+CPU: gmx_fastq_scan_host (C++ restatement of SeqReader::get_more_fastq incl. its recovery from malformed records)
+against what the reference's own SeqReader returned for the same texts (tests/golden/ref_fastq.json).
+GPU: the device indexer equals the host scan on well-formed text and refuses malformed text; gmx_process_fastq
+(reads used in place inside the text) equals gmx_process_batch on the packed reads."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from gnumap_b200 import _abi, api, index, synth
+from tests import common
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "ref_fastq.json")
+
+
+def fields(text, recs):
+    return [[text[int(r["name_off"]): int(r["name_off"]) + int(r["name_len"])].decode("latin-1"),
+             text[int(r["seq_off"]): int(r["seq_off"]) + int(r["seq_len"])].decode("latin-1"),
+             text[int(r["qual_off"]): int(r["qual_off"]) + int(r["qual_len"])].decode("latin-1")] for r in recs]
+
+
+def test_host_scan_matches_the_reference_reader():
+    cases = json.load(open(GOLD))
+    assert len(cases) >= 14
+    for name, c in cases.items():
+        text = c["text"].encode("latin-1")
+        if c["n"] < 0:                                    # the reference threw "Invalid Fastq Character"
+            with pytest.raises(api.GmxError) as e:
+                api.fastq_scan_host(text)
+            assert e.value.code == _abi.GMX_ERR_FORMAT, name
+            continue
+        got = fields(text, api.fastq_scan_host(text))
+        assert got == c["reads"], f"{name}: {got[:3]} vs {c['reads'][:3]}"
+
+
+def test_illumina_offset_falls_back_like_the_reference():
+    # quality chars below 64 with --illumina: the reference turns the flag off and re-reads at offset 33 (SeqReader.cpp:1180-1188)
+    text = b"@a\nACGT\n+\n5555\n"
+    assert len(api.fastq_scan_host(text, illumina=1)) == 1
+
+
+def make_fastq_text(reads):
+    lut = np.frombuffer(b"ACGTN", dtype=np.uint8)
+    out = []
+    for k in range(reads["bases"].shape[0]):
+        out.append(b"@r%d\n" % k + lut[reads["bases"][k]].tobytes() + b"\n+\n" + (reads["quals"][k] + 33).astype(np.uint8).tobytes() + b"\n")
+    return b"".join(out)
+
+
+@pytest.mark.gpu
+def test_device_indexer_equals_host_scan():
+    cases = json.load(open(GOLD))
+    contigs = synth.make_genome(5000, 3)
+    m = api.Mapper(index.build_index(contigs))
+    well = ("well_formed", "no_final_newline", "plus_repeats_name", "quality_longer", "empty_sequence", "lowercase_and_other_letters", "empty_file")
+    for name, c in cases.items():
+        text = c["text"].encode("latin-1")
+        if name in well:
+            assert fields(text, m.fastq_scan(text)) == c["reads"], name
+        else:                                             # needs the recovery path (or is invalid): the device refuses
+            with pytest.raises(api.GmxError) as e:
+                m.fastq_scan(text)
+            assert e.value.code == _abi.GMX_ERR_FORMAT, name
+    m.close()
+
+
+@pytest.mark.gpu
+def test_process_fastq_equals_process_batch():
+    contigs, batch, reads = common.world_plain(seed=31, length=200_000, n_reads=3000, read_len=80)
+    ix = index.build_index(contigs)
+    text = make_fastq_text(reads)
+    m = api.Mapper(ix)
+    want = m.process_batch(batch)
+    amount_want, _ = m.finish()
+    m.reset_accumulators()
+    names, got = m.process_fastq(text)
+    assert names == [f"r{k}" for k in range(batch.n_reads)]
+    common.compare_batches(got, want)
+    assert np.allclose(m.finish()[0], amount_want, rtol=1e-5, atol=1e-6)
+    # malformed text: same answer through the host-scan fallback (one garbage line and one blank line inserted)
+    lines = text.split(b"\n")
+    messy = b"\n".join(lines[:400] + [b"GARBAGE"] + lines[400:800] + [b""] + lines[800:])
+    m.reset_accumulators()
+    names2, got2 = m.process_fastq(messy)
+    assert names2 == names
+    common.compare_batches(got2, want)
+    # chunked + fast download path
+    m.set_option(api.OPT_CHUNK_READS, 700); m.set_option(api.OPT_COLLECT_HITS, 0)
+    m.reset_accumulators()
+    _, got3 = m.process_fastq(text, fetch=False)
+    for f in ("status", "best_first_pos", "best_score", "n_groups"):
+        assert np.array_equal(got3["results"][f], want["results"][f]), f
+    m.close()
