@@ -371,6 +371,49 @@ def own_arm(a):
     ms_e2e, wall_e2e, _ = timed(host_batch, a.steps)
     mapped = int((res_np["status"] == 0).sum())
 
+    # next row: the same step fed with FASTQ TEXT (pinned host buffer): H2D of the raw text, device record
+    # indexer, reads used in place, D2H of the results and of the record index
+    fastq = None
+    if not a.no_fastq:
+        name_w = 9
+        rec_len = 1 + name_w + 1 + L + 3 + L + 1
+        txt = np.empty((n, rec_len), dtype=np.uint8)
+        txt[:, 0] = ord("@")
+        ids = np.arange(n, dtype=np.int64)
+        for d in range(name_w):
+            txt[:, name_w - d] = ord("0") + (ids // 10 ** d) % 10
+        txt[:, 1 + name_w] = 10
+        txt[:, 2 + name_w: 2 + name_w + L] = np.frombuffer(b"ACGTN", dtype=np.uint8)[reads["bases"]]
+        txt[:, 2 + name_w + L: 5 + name_w + L] = np.frombuffer(b"\n+\n", dtype=np.uint8)
+        txt[:, 5 + name_w + L: 5 + name_w + 2 * L] = reads["quals"].astype(np.uint8) + 33
+        txt[:, -1] = 10
+        text_h = torch.from_numpy(txt.reshape(-1)).pin_memory()
+        recs_h = torch.zeros(n * _abi.FASTQ_REC_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+        n_out = C.c_int64(0)
+
+        def fq_step():
+            rc = m.L.gmx_process_fastq(m._ctx, text_h.data_ptr(), text_h.numel(), 0, res_h.data_ptr(), n, C.byref(n_out), recs_h.data_ptr())
+            if rc != 0:
+                raise RuntimeError(f"gmx_process_fastq: {rc} {m.L.gmx_last_error(m._ctx).decode()}")
+
+        fq_step()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.time()
+        for _ in range(a.steps):
+            fq_step()
+        torch.cuda.synchronize()
+        fq_ms = (time.time() - t0) * 1e3
+        if world > 1:
+            tt = torch.tensor([fq_ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            fq_ms = float(tt.item())
+        assert n_out.value == n and int((res_np["status"] == 0).sum()) == mapped
+        fastq = {"value": n * world * a.steps / (fq_ms * 1e-3), "unit": "reads/s", "h2d_bytes_per_step": int(text_h.numel()),
+                 "d2h_bytes_per_step": int(n * (_abi.READ_RESULT_DTYPE.itemsize + 64 + _abi.FASTQ_REC_DTYPE.itemsize)),
+                 "what": "gmx_process_fastq: FASTQ text in pinned host memory -> device record indexer -> reads used in place -> results (wall clock)"}
+
     if rank == 0:
         peaks = {}
         try:
@@ -418,6 +461,23 @@ def own_arm(a):
                     rr.close()
             except Exception as e:  # the baseline is reported, never required
                 cpu = {"value": None, "unit": "reads/s", "cores": 0, "kind": "reference", "sample": f"unavailable: {e}"}
+        if fastq is not None and not a.no_cpu:
+            try:      # the reference's own FASTQ reader (SeqReader, one thread) on a sample of the same text
+                from oracle import oracle as O
+                Lp = C.CDLL(O.REF_PROBE)
+                ns = min(n, 200_000)
+                fn = os.path.join(CACHE, f"sample_{os.getpid()}.fq")
+                with open(fn, "wb") as f:
+                    f.write(txt[:ns].tobytes())
+                buf = C.create_string_buffer(ns * (2 * L + 32))
+                t0 = time.time()
+                got = Lp.refp_read_fastq(fn.encode(), buf, len(buf))
+                dt = time.time() - t0
+                os.unlink(fn)
+                fastq["cpu_reader"] = {"value": got / dt, "unit": "reads/s", "cores": 1, "kind": "reference",
+                                       "sample": f"{ns} reads of the same text through the reference's SeqReader::get_more_fastq (PWM construction included)"}
+            except Exception as e:
+                fastq["cpu_reader"] = {"value": None, "sample": f"unavailable: {e}"}
         total_reads = n * world * a.steps
         line = {
             "metric": "reads/sec (probabilistic-NW mapping)", "value": total_reads / (ms_dev * 1e-3), "unit": "reads/s",
@@ -432,6 +492,7 @@ def own_arm(a):
             "gpu_launches": int(sum(st["launches"].values())),
             "roofline": roofline,
             "cpu_baseline": cpu,
+            "fastq_row": fastq,
         }
         emit(line)
     m.close()
@@ -452,6 +513,7 @@ def main():
     ap.add_argument("--genome-seed", type=int, default=100)
     ap.add_argument("--reads-seed", type=int, default=101)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-fastq", action="store_true", help="skip the FASTQ-text leg")
     ap.add_argument("--wall", action="store_true", help="use max(event, wall) time")
     a = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
