@@ -32,7 +32,7 @@ EXPORTS = [
     "gmx_set_stream", "gmx_synchronize", "gmx_fm_search", "gmx_sa_locate", "gmx_get_windows", "gmx_self_score",
     "gmx_nw_score", "gmx_nw_traceback", "gmx_pair_hmm", "gmx_map_batch", "gmx_score_batch", "gmx_process_batch",
     "gmx_get_hits", "gmx_get_best_alignments", "gmx_accumulators_device", "gmx_reset_accumulators", "gmx_finish",
-    "gmx_get_stage_stats", "gmx_set_option", "gmx_fastq_scan_host", "gmx_fastq_scan", "gmx_process_fastq",
+    "gmx_get_stage_stats", "gmx_set_option", "gmx_fastq_scan_host", "gmx_fastq_scan", "gmx_process_fastq", "gmx_format_sam",
 ]
 
 OPT_COLLECT_HITS, OPT_CHUNK_READS, OPT_VOTE_FILTER, OPT_FILTER_SHIFT = 1, 2, 3, 4
@@ -80,6 +80,7 @@ def load_library():
         L.gmx_set_option.argtypes = [C.c_void_p, C.c_int, C.c_int64]
         L.gmx_fastq_scan_host.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
         L.gmx_fastq_scan.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
+        L.gmx_format_sam.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
         L.gmx_process_fastq.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.c_void_p]
         _lib = L
     return _lib
@@ -275,6 +276,22 @@ class Mapper:
         names, batch = batch_from_fastq(text, recs)
         out = dict(results=results[: n.value])
         return names, (self._fetch(batch, out, True) if fetch else out)
+
+    def format_sam(self, text: bytes, recs: np.ndarray, results: np.ndarray) -> bytes:
+        """SAM body of the batch last scored (ScoredSeq::get_SAM + the reference's writer), as bytes."""
+        buf = np.frombuffer(text, dtype=np.uint8)
+        recs = np.ascontiguousarray(recs); results = np.ascontiguousarray(results)
+        names = (C.c_char_p * len(self.index.names))(*[nm.encode() for nm in self.index.names])
+        n = C.c_int64(0)
+        cap = int(len(results)) * 64 + int(recs["seq_len"].sum() + recs["qual_len"].sum() + recs["name_len"].sum()) * 2 + 4096
+        while True:
+            out = np.zeros(cap, dtype=np.uint8)
+            rc = self.L.gmx_format_sam(self._ctx, buf.ctypes.data, recs.ctypes.data, results.ctypes.data, len(results), names, out.ctypes.data, cap, C.byref(n))
+            if rc == _abi.GMX_ERR_OVERFLOW:
+                cap = n.value + 16
+                continue
+            self._ck(rc, "gmx_format_sam")
+            return out[: n.value].tobytes()
 
     def best_cigars(self, n_reads: int, stride: int = 64) -> np.ndarray:
         cig = np.zeros((n_reads, stride), dtype=np.uint8)

@@ -4,6 +4,7 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include <algorithm>
+#include <thread>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -118,6 +119,9 @@ struct gmx_ctx {
     bool use_filter = true;                    // GMX_OPT_VOTE_FILTER
     int filter_shift = 0;                      // GMX_OPT_FILTER_SHIFT
     int n_sm = 148;
+    DevBuf d_multi, d_multi_count;             // (read, pos, strand) of multi-position best groups (fast path)
+    std::vector<MultiPos> h_multi;
+    std::vector<int64_t> h_seq_offset;         // host copy of the sequence offsets (+ l_pac) for pos -> chromosome
     DevBuf d_best_cigar[2], d_out_results[2];  // staging of the fast download path, double-buffered
     cudaStream_t d2h_stream = nullptr;
     cudaEvent_t gather_ev[2] = {nullptr, nullptr}, dl_ev[2] = {nullptr, nullptr};
@@ -338,6 +342,7 @@ extern "C" int gmx_create(gmx_ctx **out, const gmx_index *index, const gmx_param
     std::vector<int64_t> offs(index->n_seqs + 1);
     for (int i = 0; i < index->n_seqs; ++i) offs[i] = index->seq_offset[i];
     offs[index->n_seqs] = index->l_pac;
+    ctx->h_seq_offset = offs;
     CK(ctx->d_seq_offset.ensure(offs.size() * 8));
     CK(cudaMemcpyAsync(ctx->d_seq_offset.p, offs.data(), offs.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
     CK(ctx->d_sa_full.ensure((index->seq_len + 1) * 4));
@@ -395,7 +400,7 @@ extern "C" void gmx_destroy(gmx_ctx *ctx)
                       &ctx->d_seed_count, &ctx->d_seed_off, &ctx->d_seed_n, &ctx->d_seed_hits, &ctx->d_cls_list, &ctx->d_cls_meta,
                       &ctx->d_keys, &ctx->d_keys_alt, &ctx->d_sort_tmp, &ctx->d_score, &ctx->d_leader, &ctx->d_slot, &ctx->d_lead_cand,
                       &ctx->d_hashes, &ctx->d_expv, &ctx->d_counters, &ctx->d_results, &ctx->d_alen, &ctx->d_aligned, &ctx->d_cigar,
-                      &ctx->d_hmm, &ctx->d_moves, &ctx->d_arena, &ctx->d_phmm_scratch, &ctx->d_best_cigar[0], &ctx->d_best_cigar[1], &ctx->d_out_results[0], &ctx->d_out_results[1], &ctx->d_seed_code, &ctx->d_kmer_tab, &ctx->d_fq_text, &ctx->d_fq_nl, &ctx->d_fq_tmp, &ctx->d_fq_seq_off, &ctx->d_fq_qual_off, &ctx->d_fq_len, &ctx->d_fq_recs, &ctx->d_fq_flags, &ctx->d_fq_count};
+                      &ctx->d_hmm, &ctx->d_moves, &ctx->d_arena, &ctx->d_phmm_scratch, &ctx->d_best_cigar[0], &ctx->d_best_cigar[1], &ctx->d_out_results[0], &ctx->d_out_results[1], &ctx->d_seed_code, &ctx->d_kmer_tab, &ctx->d_multi, &ctx->d_multi_count, &ctx->d_fq_text, &ctx->d_fq_nl, &ctx->d_fq_tmp, &ctx->d_fq_seq_off, &ctx->d_fq_qual_off, &ctx->d_fq_len, &ctx->d_fq_recs, &ctx->d_fq_flags, &ctx->d_fq_count};
     for (DevBuf *b : bufs) b->release();
     ctx->h_best_cigar.release();
     if (ctx->ev[0][0]) for (int s = 0; s < ST_COUNT; ++s) { cudaEventDestroy(ctx->ev[s][0]); cudaEventDestroy(ctx->ev[s][1]); }
@@ -1026,6 +1031,22 @@ static int download_chunk(gmx_ctx *ctx, bool scored, gmx_read_result *results_ou
         CK(ctx->d_best_cigar[sl].ensure((size_t)std::max(n, 1) * GMX_CIGAR_STRIDE));
         CK(ctx->d_out_results[sl].ensure((size_t)std::max(n, 1) * sizeof(gmx_read_result)));
         CK(cudaStreamWaitEvent(ctx->stream, ctx->dl_ev[sl], 0));            // the staging slot's previous copy has left
+        if (scored && n_cand) {                                             // positions of multi-position best groups (SAM row)
+            CK(ctx->d_multi.ensure((size_t)n_cand * sizeof(MultiPos))); CK(ctx->d_multi_count.ensure(16));
+            CK(cudaMemsetAsync(ctx->d_multi_count.p, 0, 4, ctx->stream));
+            k_gather_multi<<<nblk(n_cand, 256), 256, 0, ctx->stream>>>(cs.keys, ctx->d_leader.as<int32_t>(), n_cand, ctx->d_results.as<gmx_read_result>(),
+                                                                      lo, ctx->d_multi.as<MultiPos>(), ctx->d_multi_count.as<uint32_t>(), n_cand);
+            CK(cudaGetLastError());
+            uint32_t nm = 0;
+            CK(cudaMemcpyAsync(&nm, ctx->d_multi_count.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            if (nm) {
+                size_t at = ctx->h_multi.size();
+                ctx->h_multi.resize(at + nm);
+                CK(cudaMemcpyAsync(ctx->h_multi.data() + at, ctx->d_multi.p, (size_t)nm * sizeof(MultiPos), cudaMemcpyDeviceToHost, ctx->stream));
+                CK(cudaStreamSynchronize(ctx->stream));
+            }
+        }
         k_gather_best<<<nblk(n, 128), 128, 0, ctx->stream>>>(ctx->d_results.as<gmx_read_result>(), ctx->d_out_results[sl].as<gmx_read_result>(), n,
                                                            ctx->d_slot.as<int32_t>(), L, ctx->d_best_cigar[sl].as<char>(), GMX_CIGAR_STRIDE,
                                                            scored && n_leaders ? 1 : 0);
@@ -1119,6 +1140,7 @@ static int run_batch(gmx_ctx *ctx, const gmx_reads *reads, gmx_read_result *resu
     if (n > 0) { int r = batch_max_len(ctx, reads, &max_len); if (r != GMX_OK) return r; }
     ctx->h_results.assign(ctx->collect_hits || !results ? (size_t)n : 0, gmx_read_result());
     ctx->h_hits.clear();
+    ctx->h_multi.clear();
     ctx->h_a_stride = max_len + 2 * ctx->params.max_gap + 8;
     CK(ctx->h_best_cigar.ensure((size_t)std::max(n, 1) * GMX_CIGAR_STRIDE));
     if (ctx->collect_hits) {
@@ -1422,4 +1444,137 @@ extern "C" int gmx_process_fastq(gmx_ctx *ctx, const char *text, int64_t len, in
     in.qual_offsets = ctx->d_fq_qual_off.as<int64_t>(); in.lens = ctx->d_fq_len.as<int32_t>();
     in.on_device = 1; in.max_len = std::max(max_len, 1);
     return run_batch(ctx, &in, results, true);
+}
+
+// ------------------------------------------------------------------------------------------------
+// next row: SAM emission
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct SamPos { uint64_t pos; int strand; };
+
+inline char sam_rc(char c)
+{   // reverse_comp, reference inc/SequenceOperations.h:56-96: anything that is not acgtACGT- becomes 'n'
+    switch (c) {
+        case 'a': return 't'; case 'c': return 'g'; case 'g': return 'c'; case 't': return 'a';
+        case 'A': return 'T'; case 'C': return 'G'; case 'G': return 'C'; case 'T': return 'A';
+        case '-': return '-'; default: return 'n';
+    }
+}
+
+// reverse_CIGAR, reference inc/SequenceOperations.h:109-123 (its digit test is 48..58)
+inline void sam_reverse_cigar(const char *c, std::string &out)
+{
+    out.clear();
+    std::string num, rev;
+    for (; *c; ++c) {
+        if (*c >= 48 && *c <= 58) num += *c;
+        else { rev = num + *c + rev; num.clear(); }
+    }
+    out = rev;
+}
+
+inline int sam_mapq(double total)
+{   // reference inc/ScoredSeq.h:302-309
+    int q;
+    if (total == 1) q = 30;
+    else {
+        double v = 1 - total;
+        q = v <= 0 ? 30 : (int)round(-10 * log(v) / log(10.0));
+    }
+    return q > 30 ? 30 : q;
+}
+
+void sam_format_range(const gmx_ctx *ctx, const char *text, const gmx_fastq_rec *recs, const gmx_read_result *results, int64_t lo, int64_t hi,
+                      const char *const *chrom_names, const std::vector<std::vector<SamPos>> *multi_of, const std::vector<int64_t> &multi_index,
+                      std::string &out)
+{
+    const std::vector<int64_t> &off = ctx->h_seq_offset;
+    const char *best_cigar = ctx->h_best_cigar.as<char>();
+    char num[64];
+    std::string rcig, seq_rc, qual_rv;
+    for (int64_t r = lo; r < hi; ++r) {
+        const gmx_read_result &res = results[r];
+        if (res.status != GMX_READ_MAPPED) continue;                        // unmapped reads print nothing (Driver.cpp:620-629)
+        const gmx_fastq_rec &rec = recs[r];
+        const char *cigar = best_cigar + (size_t)r * GMX_CIGAR_STRIDE;
+        const double total = exp((double)res.best_score) / res.denominator;
+        const int q = sam_mapq(total);
+        const double xa = (double)res.best_score * (1.0 / (double)ctx->params.adjust);     // XA prints score / gADJUST (Driver.cpp:2202)
+        // positions of the best group, ascending (pos, strand) as std::set iterates them
+        SamPos one{res.best_first_pos, res.best_first_strand};
+        const SamPos *ps = &one; size_t np = 1;
+        if (res.best_n_positions > 1) {
+            const int64_t mi = multi_index[r];
+            if (mi >= 0) { ps = (*multi_of)[mi].data(); np = (*multi_of)[mi].size(); }
+        }
+        bool have_rc = false;
+        for (size_t k = 0; k < np; ++k) {
+            const uint64_t pos = ps[k].pos; const bool neg = ps[k].strand == GMX_NEG_STRAND;
+            size_t rid = std::upper_bound(off.begin(), off.end() - 1, (int64_t)pos) - off.begin() - 1;
+            out.append(text + rec.name_off, (size_t)rec.name_len);
+            out += neg ? "\t16\t" : "\t0\t";
+            out += chrom_names[rid];
+            snprintf(num, sizeof(num), "\t%lld\t%d\t", (long long)((int64_t)pos - off[rid] + 1), q);
+            out += num;
+            if (neg) { sam_reverse_cigar(cigar, rcig); out += rcig; } else out += cigar;
+            out += "\t*\t0\t0\t";
+            if (neg) {
+                if (!have_rc) {
+                    seq_rc.assign((size_t)rec.seq_len, 'n'); qual_rv.assign((size_t)rec.qual_len, '!');
+                    for (int i = 0; i < rec.seq_len; ++i) seq_rc[i] = sam_rc(text[rec.seq_off + rec.seq_len - 1 - i]);
+                    for (int i = 0; i < rec.qual_len; ++i) qual_rv[i] = text[rec.qual_off + rec.qual_len - 1 - i];
+                    have_rc = true;
+                }
+                out += seq_rc; out += '\t'; out += qual_rv;
+            } else {
+                out.append(text + rec.seq_off, (size_t)rec.seq_len); out += '\t'; out.append(text + rec.qual_off, (size_t)rec.qual_len);
+            }
+            snprintf(num, sizeof(num), "\tXA:f:%g\tXP:f:%g\tX0:i:%d\n", xa, (double)res.best_posterior, res.best_n_positions);
+            out += num;
+        }
+    }
+}
+}  // namespace
+
+extern "C" int gmx_format_sam(gmx_ctx *ctx, const char *text, const gmx_fastq_rec *recs, const gmx_read_result *results, int64_t n_reads,
+                              const char *const *chrom_names, char *out, int64_t cap, int64_t *len)
+{
+    if (!ctx || !text || !recs || !results || !chrom_names || !len || n_reads < 0 || (cap > 0 && !out)) return GMX_ERR_INVALID;
+    if (!ctx->scored || n_reads != ctx->last_n_reads) { ctx->err = "gmx_format_sam formats the batch last scored"; return GMX_ERR_STATE; }
+    // positions of the multi-position best groups: from the hit list (collect mode) or from the device list (fast path)
+    std::vector<int64_t> multi_index((size_t)n_reads, -1);
+    std::vector<std::vector<SamPos>> multi_of;
+    auto add = [&](int64_t r, uint64_t pos, int strand) {
+        if (multi_index[r] < 0) { multi_index[r] = (int64_t)multi_of.size(); multi_of.emplace_back(); }
+        multi_of[multi_index[r]].push_back(SamPos{pos, strand});
+    };
+    if (ctx->collect_hits) {
+        for (int64_t r = 0; r < n_reads; ++r) {
+            const gmx_read_result &res = results[r];
+            if (res.status != GMX_READ_MAPPED || res.best_n_positions <= 1) continue;
+            for (int32_t h = res.hit_begin; h < res.hit_end; ++h)
+                if (ctx->h_hits[h].group == res.best_group) add(r, ctx->h_hits[h].pos, ctx->h_hits[h].strand);
+        }
+    } else {
+        for (const MultiPos &m : ctx->h_multi) if (m.read >= 0 && m.read < n_reads) add(m.read, m.pos, m.strand);
+    }
+    for (auto &v : multi_of) std::sort(v.begin(), v.end(), [](const SamPos &a, const SamPos &b) { return a.pos != b.pos ? a.pos < b.pos : a.strand < b.strand; });
+    // format in parallel slices, concatenate in read order
+    unsigned nt = std::max(1u, std::min(std::thread::hardware_concurrency(), 16u));
+    if (n_reads < 4096) nt = 1;
+    std::vector<std::string> parts(nt);
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; ++t) {
+        const int64_t a = n_reads * t / nt, b = n_reads * (t + 1) / nt;
+        if (nt == 1) sam_format_range(ctx, text, recs, results, a, b, chrom_names, &multi_of, multi_index, parts[t]);
+        else th.emplace_back([=, &parts, &multi_of, &multi_index]() { sam_format_range(ctx, text, recs, results, a, b, chrom_names, &multi_of, multi_index, parts[t]); });
+    }
+    for (auto &x : th) x.join();
+    int64_t total = 0;
+    for (auto &p : parts) total += (int64_t)p.size();
+    *len = total;
+    if (total > cap) return GMX_ERR_OVERFLOW;
+    int64_t at = 0;
+    for (auto &p : parts) { memcpy(out + at, p.data(), p.size()); at += (int64_t)p.size(); }
+    return GMX_OK;
 }

@@ -1109,3 +1109,26 @@ __global__ void __launch_bounds__(128) k_gather_best(const gmx_read_result *resu
     res.hit_begin = 0; res.hit_end = 0; res.best_group = -1;
     out[r] = res;
 }
+
+// ---- SAM row: every (position, strand) of the best group ------------------------------
+// get_SAM prints one record per element of the best ScoredSeq's position set (reference inc/ScoredSeq.h:293-404,
+// src/Driver.cpp:700-716).  The per-read record already carries the smallest one; groups with more than one
+// position (repeats) append all of theirs here -- a short list, so the fast download path stays fixed-size.
+struct MultiPos { uint64_t pos; int32_t read; int32_t strand; };
+
+__global__ void __launch_bounds__(256) k_gather_multi(const unsigned long long *keys, const int32_t *leader, uint32_t n_cand,
+                                                      const gmx_read_result *results, int32_t read_base, MultiPos *out, uint32_t *count, uint32_t cap)
+{
+    uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_cand) return;
+    const int32_t ld = leader[c];
+    if (ld < 0) return;
+    uint32_t task, round, diag;
+    gmx_decode_key(keys[c], task, round, diag);
+    const int r = (int)(task >> 1);
+    const gmx_read_result &res = results[r];
+    if (res.status != GMX_READ_MAPPED || res.best_n_positions <= 1 || res.best_group < 0) return;
+    if (ld != res.hit_begin + res.best_group) return;
+    const uint32_t at = atomicAdd(count, 1u);
+    if (at < cap) { MultiPos m; m.pos = diag; m.read = read_base + r; m.strand = (int32_t)(task & 1); out[at] = m; }
+}

@@ -269,6 +269,15 @@ int gmx_fastq_scan(gmx_ctx *ctx, const char *text, int64_t len, int text_on_devi
 int gmx_process_fastq(gmx_ctx *ctx, const char *text, int64_t len, int text_on_device, gmx_read_result *results, int64_t capacity,
                       int64_t *n_reads, gmx_fastq_rec *recs);
 
+/* ---- next row: SAM emission ------------------------------------------------------
+ * ScoredSeq::get_SAM (reference inc/ScoredSeq.h:293-404) + the SAM writer (src/Driver.cpp:2146-2217): the body
+ * lines of the last scored batch, in read order, one per (position, strand) of each read's best group, byte for
+ * byte as the reference prints them.  Works with GMX_OPT_COLLECT_HITS 0 or 1.  names / seq / qual come from
+ * `recs` into `text` (gmx_fastq_rec: name_off/len, seq_off/len, qual_off/qual_len); chrom_names[i] is the name of
+ * sequence i of the index.  Returns GMX_ERR_OVERFLOW with *len = bytes needed when `cap` is short. */
+int gmx_format_sam(gmx_ctx *ctx, const char *text, const gmx_fastq_rec *recs, const gmx_read_result *results, int64_t n_reads,
+                   const char *const *chrom_names, char *out, int64_t cap, int64_t *len);
+
 /* ---- options ----------------------------------------------------------------------------- */
 #define GMX_OPT_COLLECT_HITS 1   /* 1 (default): keep every accepted (pos,strand) for gmx_get_hits; 0: only the
                                     per-read results and the best group's CIGAR leave the device           */

@@ -94,3 +94,24 @@ def test_process_fastq_equals_process_batch():
     for f in ("status", "best_first_pos", "best_score", "n_groups"):
         assert np.array_equal(got3["results"][f], want["results"][f]), f
     m.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("collect", [1, 0])
+def test_native_sam_equals_the_reference_binary(collect):
+    """gmx_format_sam against the SAM body the unmodified reference binary wrote (whole-program
+    fixture with a planted repeat: multi-position best groups, both strands, indels)."""
+    from tests import test_oracle_golden as G
+    rec = G.load_program("normal")
+    lut = {c: i for i, c in enumerate("ACGT")}
+    contigs = [(n, np.array([lut[c] for c in s], dtype=np.uint8)) for n, s in rec["contigs"]]
+    ix = index.build_index(contigs)
+    text = "".join(f"@{nm}\n{s}\n+\n{q}\n" for nm, s, q in rec["reads"]).encode()
+    m = api.Mapper(ix)
+    m.set_option(api.OPT_COLLECT_HITS, collect)
+    names, got = m.process_fastq(text, fetch=False)
+    recs = api.fastq_scan_host(text)
+    sam = m.format_sam(text, recs, got["results"]).decode().split("\n")[:-1]
+    assert sorted(sam) == sorted(rec["sam"])
+    assert max(int(ln.split("X0:i:")[1]) for ln in sam) > 1, "fixture must contain multi-position groups"
+    m.close()
