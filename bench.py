@@ -410,9 +410,21 @@ def own_arm(a):
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             fq_ms = float(tt.item())
         assert n_out.value == n and int((res_np["status"] == 0).sum()) == mapped
+        # SAM row: native formatting of the batch just scored
+        sam_cap = n * (2 * L + 96)
+        sam_buf = np.empty(sam_cap, dtype=np.uint8)
+        names_c = (C.c_char_p * len(ix.names))(*[nm.encode() for nm in ix.names])
+        sam_len = C.c_int64(0)
+        t0 = time.time()
+        rc = m.L.gmx_format_sam(m._ctx, text_h.data_ptr(), recs_h.data_ptr(), res_h.data_ptr(), n, names_c, sam_buf.ctypes.data, sam_cap, C.byref(sam_len))
+        sam_s = time.time() - t0
+        if rc != 0:
+            raise RuntimeError(f"gmx_format_sam: {rc} {m.L.gmx_last_error(m._ctx).decode()}")
         fastq = {"value": n * world * a.steps / (fq_ms * 1e-3), "unit": "reads/s", "h2d_bytes_per_step": int(text_h.numel()),
                  "d2h_bytes_per_step": int(n * (_abi.READ_RESULT_DTYPE.itemsize + 64 + _abi.FASTQ_REC_DTYPE.itemsize)),
-                 "what": "gmx_process_fastq: FASTQ text in pinned host memory -> device record indexer -> reads used in place -> results (wall clock)"}
+                 "what": "gmx_process_fastq: FASTQ text in pinned host memory -> device record indexer -> reads used in place -> results (wall clock)",
+                 "sam": {"value": n / sam_s, "unit": "reads/s", "bytes": int(sam_len.value), "host_threads": min(os.cpu_count() or 1, 16),
+                         "what": "gmx_format_sam: SAM body of the batch (ScoredSeq::get_SAM + writer), host C++"}}
 
     if rank == 0:
         peaks = {}
