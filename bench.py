@@ -358,6 +358,9 @@ def own_arm(a):
             ms = float(tt.item())
         return ms, wall_ms, dict(ms=stage_ms, units=stage_units, bytes=stage_bytes, launches=stage_launch)
 
+    # nvidia-smi needs a few hundred ms to deliver its first sample: start it before the warm-up (same kernels, same
+    # load) and keep it running through the timed region
+    sampler = ClockSampler(local) if rank == 0 else None
     for _ in range(a.warmup):
         step(dev_batch)
     for _ in range(max(a.warmup // 2, 1)):
@@ -365,7 +368,6 @@ def own_arm(a):
     final_reduce()                      # warm NCCL up too
     m.reset_accumulators()
 
-    sampler = ClockSampler(local) if rank == 0 else None
     ms_dev, wall_dev, st = timed(dev_batch, a.steps)
     clocks = sampler.stop() if sampler else None
     ms_e2e, wall_e2e, _ = timed(host_batch, a.steps)

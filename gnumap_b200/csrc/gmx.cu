@@ -1473,6 +1473,15 @@ inline void sam_reverse_cigar(const char *c, std::string &out)
     out = rev;
 }
 
+inline void sam_put_int(std::string &out, int64_t v)
+{
+    char b[24]; int n = 0;
+    const bool neg = v < 0; uint64_t u = neg ? (uint64_t)(-v) : (uint64_t)v;
+    do { b[n++] = (char)('0' + u % 10); u /= 10; } while (u);
+    if (neg) out += '-';
+    while (n) out += b[--n];
+}
+
 inline int sam_mapq(double total)
 {   // reference inc/ScoredSeq.h:302-309
     int q;
@@ -1514,8 +1523,7 @@ void sam_format_range(const gmx_ctx *ctx, const char *text, const gmx_fastq_rec 
             out.append(text + rec.name_off, (size_t)rec.name_len);
             out += neg ? "\t16\t" : "\t0\t";
             out += chrom_names[rid];
-            snprintf(num, sizeof(num), "\t%lld\t%d\t", (long long)((int64_t)pos - off[rid] + 1), q);
-            out += num;
+            out += '\t'; sam_put_int(out, (int64_t)pos - off[rid] + 1); out += '\t'; sam_put_int(out, q); out += '\t';
             if (neg) { sam_reverse_cigar(cigar, rcig); out += rcig; } else out += cigar;
             out += "\t*\t0\t0\t";
             if (neg) {
@@ -1529,7 +1537,7 @@ void sam_format_range(const gmx_ctx *ctx, const char *text, const gmx_fastq_rec 
             } else {
                 out.append(text + rec.seq_off, (size_t)rec.seq_len); out += '\t'; out.append(text + rec.qual_off, (size_t)rec.qual_len);
             }
-            snprintf(num, sizeof(num), "\tXA:f:%g\tXP:f:%g\tX0:i:%d\n", xa, (double)res.best_posterior, res.best_n_positions);
+            if (k == 0) snprintf(num, sizeof(num), "\tXA:f:%g\tXP:f:%g\tX0:i:%d\n", xa, (double)res.best_posterior, res.best_n_positions);
             out += num;
         }
     }
@@ -1559,22 +1567,28 @@ extern "C" int gmx_format_sam(gmx_ctx *ctx, const char *text, const gmx_fastq_re
         for (const MultiPos &m : ctx->h_multi) if (m.read >= 0 && m.read < n_reads) add(m.read, m.pos, m.strand);
     }
     for (auto &v : multi_of) std::sort(v.begin(), v.end(), [](const SamPos &a, const SamPos &b) { return a.pos != b.pos ? a.pos < b.pos : a.strand < b.strand; });
-    // format in parallel slices, concatenate in read order
-    unsigned nt = std::max(1u, std::min(std::thread::hardware_concurrency(), 16u));
+    // format in parallel slices into pre-sized buffers, then copy them into place in parallel (read order is kept)
+    unsigned nt = std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
     if (n_reads < 4096) nt = 1;
     std::vector<std::string> parts(nt);
-    std::vector<std::thread> th;
-    for (unsigned t = 0; t < nt; ++t) {
+    auto run = [&](auto &&fn) {
+        if (nt == 1) { fn(0u); return; }
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < nt; ++t) th.emplace_back(fn, t);
+        for (auto &x : th) x.join();
+    };
+    run([&](unsigned t) {
         const int64_t a = n_reads * t / nt, b = n_reads * (t + 1) / nt;
-        if (nt == 1) sam_format_range(ctx, text, recs, results, a, b, chrom_names, &multi_of, multi_index, parts[t]);
-        else th.emplace_back([=, &parts, &multi_of, &multi_index]() { sam_format_range(ctx, text, recs, results, a, b, chrom_names, &multi_of, multi_index, parts[t]); });
-    }
-    for (auto &x : th) x.join();
-    int64_t total = 0;
-    for (auto &p : parts) total += (int64_t)p.size();
-    *len = total;
-    if (total > cap) return GMX_ERR_OVERFLOW;
-    int64_t at = 0;
-    for (auto &p : parts) { memcpy(out + at, p.data(), p.size()); at += (int64_t)p.size(); }
+        size_t est = 0;
+        for (int64_t r = a; r < b; ++r)
+            if (results[r].status == GMX_READ_MAPPED) est += (size_t)(recs[r].name_len + recs[r].seq_len + recs[r].qual_len + 96) * (size_t)std::max(results[r].best_n_positions, 1);
+        parts[t].reserve(est);
+        sam_format_range(ctx, text, recs, results, a, b, chrom_names, &multi_of, multi_index, parts[t]);
+    });
+    std::vector<int64_t> at(nt + 1, 0);
+    for (unsigned t = 0; t < nt; ++t) at[t + 1] = at[t] + (int64_t)parts[t].size();
+    *len = at[nt];
+    if (at[nt] > cap) return GMX_ERR_OVERFLOW;
+    run([&](unsigned t) { memcpy(out + at[t], parts[t].data(), parts[t].size()); });
     return GMX_OK;
 }

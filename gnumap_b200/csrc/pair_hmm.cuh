@@ -20,7 +20,7 @@
 #define GMX_PHMM_MAXC 8                       // columns per lane -> read length <= 256 in SNP mode
 
 // forward matrix parked in global memory: (fM, fY) per cell -- the X state never enters the posterior
-__host__ __device__ inline size_t gmx_phmm_scratch_doubles(int max_len) { return (size_t)max_len * (size_t)(((max_len + 31) / 32) * 32) * 2; }
+__host__ __device__ inline size_t gmx_phmm_scratch_doubles(int max_len) { return (size_t)(max_len + 33) * (size_t)(((max_len + 31) / 32) * 32) * 2; }
 
 struct PhmmConst {
     double Tmm, Tgm, Tmg, Tgg, q, t;          // floats promoted to double
@@ -252,7 +252,9 @@ __device__ void gmx_pair_hmm_warp_fast(const ReadView &rd, const uint8_t *pac, i
             if (lane == 0) { dM = (i == 1) ? 1.0 : 0.0; dX = 0; dY = 0; }
             double cM = dM, cX = dX, cY = dY;                    // (i-1, j-1)
             double leftM = rM, leftY = rY;                       // (i, j-1)
-            double2 *frow = F + (size_t)(i - 1) * MP + j0;
+            // parked by STEP, slot-major: at any step the 32 lanes write 32 adjacent double2 (the backward sweep reads
+            // the block of forward step n + 31 - s_b at its step s_b: the skew cancels, both sides are coalesced)
+            double2 *frow = F + (size_t)s * MP + lane;
 #pragma unroll
             for (int c = 0; c < C; ++c) {
                 const float e = gmx_sel4(row, gb[c], 0.f);
@@ -263,7 +265,7 @@ __device__ void gmx_pair_hmm_warp_fast(const ReadView &rd, const uint8_t *pac, i
                 cM = pM[c]; cX = pX[c]; cY = pY[c];
                 pM[c] = fM; pX[c] = fX; pY[c] = fY;
                 leftM = fM; leftY = fY;
-                frow[c] = make_double2(fM, fY);
+                frow[c * 32] = make_double2(fM, fY);
             }
             outM = pM[C - 1]; outX = pX[C - 1]; outY = pY[C - 1];
             dM = rM; dX = rX; dY = rY;
@@ -287,9 +289,9 @@ __device__ void gmx_pair_hmm_warp_fast(const ReadView &rd, const uint8_t *pac, i
     double2 fv_nxt[C];                                           // forward values of the row handled in the next step
 #pragma unroll
     for (int c = 0; c < C; ++c) fv_nxt[c] = make_double2(0, 0);
-    if (lane == 31) {
+    if (lane == 31) {                                            // row n-1 of lane 31 was written at forward step n + 31
 #pragma unroll
-        for (int c = 0; c < C; ++c) fv_nxt[c] = F[(size_t)(n - 1) * MP + j0 + c];
+        for (int c = 0; c < C; ++c) fv_nxt[c] = F[(size_t)(n + 31) * MP + c * 32 + lane];
     }
     for (int s = 0; s <= n - 1 + 31; ++s) {
         double rM = gmx_shfl_d(sndM, lane + 1), rY = gmx_shfl_d(sndY, lane + 1);
@@ -299,9 +301,9 @@ __device__ void gmx_pair_hmm_warp_fast(const ReadView &rd, const uint8_t *pac, i
 #pragma unroll
         for (int c = 0; c < C; ++c) fv[c] = fv_nxt[c];
         if (i - 1 >= 0 && i - 1 <= n - 1) {                      // request the next step's row before this one's chain
-            const double2 *fnext = F + (size_t)(i - 1) * MP + j0;
+            const double2 *fnext = F + (size_t)(n + 31 - (s + 1)) * MP + lane;
 #pragma unroll
-            for (int c = 0; c < C; ++c) fv_nxt[c] = fnext[c];
+            for (int c = 0; c < C; ++c) fv_nxt[c] = fnext[c * 32];
         }
         if (i >= 0 && i <= n - 1) {
             const float4 row = (i + 1 <= n - 1) ? erow_s[i + 1] : make_float4(0, 0, 0, 0);
