@@ -281,3 +281,54 @@ def test_fast_path_split_phases_chunking_and_device_input(api, O, plain):
 
 def api_mod(api):
     return api
+
+
+def test_full_size_properties(api):
+    """BASELINE configs[1] at its full size (100 Mb genome, 1 M x 100 bp reads) through properties that do not need
+    the oracle: truth recovery, conservation of posterior mass in the accumulators, run-to-run determinism of the
+    per-read results, and equality of the FASTQ-text path with the packed path."""
+    import torch
+    from gnumap_b200 import synth
+    contigs = synth.make_genome(100_000_000, 100)
+    ix = index.build_index(contigs, device="cuda")
+    codes = contigs[0][1]
+    n, L = 1_000_000, 100
+    reads = synth.simulate_reads(codes, n, L, 101, sub_rate=0.01, qlo=15, qhi=40)
+    batch = _abi.ReadBatch.from_arrays(reads["bases"], reads["quals"])
+    m = api.Mapper(ix)
+    m.set_option(api_mod(api).OPT_COLLECT_HITS, 0)
+    a = m.process_batch(batch, fetch=False)["results"].copy()
+    amount, _ = m.finish()
+    # (1) truth: a read without indels maps to its source position and strand
+    mapped = a["status"] == _abi.READ_MAPPED
+    assert mapped.mean() > 0.995
+    ok = (a["best_first_pos"] == reads["pos"].astype(np.uint64)) & (a["best_first_strand"] == reads["strand"])
+    assert ok[mapped].mean() > 0.999, ok[mapped].mean()
+    # (2) every accepted (position, strand) adds posterior x aligned length; posteriors of one read sum to 1 over its
+    # positions, so the accumulators hold one unit of mass per aligned base of every mapped read
+    mass = float(amount.sum(dtype=np.float64))
+    want = float(a["best_aligned_len"][mapped].sum())
+    assert abs(mass - want) <= 2e-3 * want, (mass, want)
+    # (3) a second pass gives bit-identical per-read records (atomics only reorder the accumulator sums)
+    m.reset_accumulators()
+    b = m.process_batch(batch, fetch=False)["results"]
+    for f in a.dtype.names:
+        assert np.array_equal(a[f], b[f]), f
+    # (4) the same reads as FASTQ text, used in place on the device
+    lut = np.frombuffer(b"ACGTN", dtype=np.uint8)
+    rec_len = 1 + 7 + 1 + L + 3 + L + 1
+    txt = np.empty((n, rec_len), dtype=np.uint8)
+    txt[:, 0] = ord("@")
+    ids = np.arange(n)
+    for d in range(7):
+        txt[:, 7 - d] = ord("0") + (ids // 10 ** d) % 10
+    txt[:, 8] = 10
+    txt[:, 9:9 + L] = lut[reads["bases"]]
+    txt[:, 9 + L:12 + L] = np.frombuffer(b"\n+\n", dtype=np.uint8)
+    txt[:, 12 + L:12 + 2 * L] = reads["quals"].astype(np.uint8) + 33
+    txt[:, -1] = 10
+    m.reset_accumulators()
+    _, c = m.process_fastq(txt.tobytes(), fetch=False)
+    for f in ("status", "best_first_pos", "best_first_strand", "best_score", "n_groups", "best_n_positions", "best_aligned_len"):
+        assert np.array_equal(a[f], c["results"][f]), f
+    m.close()
