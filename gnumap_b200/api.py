@@ -32,7 +32,7 @@ EXPORTS = [
     "gmx_set_stream", "gmx_synchronize", "gmx_fm_search", "gmx_sa_locate", "gmx_get_windows", "gmx_self_score",
     "gmx_nw_score", "gmx_nw_traceback", "gmx_pair_hmm", "gmx_map_batch", "gmx_score_batch", "gmx_process_batch",
     "gmx_get_hits", "gmx_get_best_alignments", "gmx_accumulators_device", "gmx_reset_accumulators", "gmx_finish",
-    "gmx_get_stage_stats", "gmx_set_option", "gmx_fastq_scan_host", "gmx_fastq_scan", "gmx_process_fastq", "gmx_format_sam",
+    "gmx_get_stage_stats", "gmx_set_option", "gmx_fastq_scan_host", "gmx_fastq_scan", "gmx_process_fastq", "gmx_format_sam", "gmx_format_sgr",
 ]
 
 OPT_COLLECT_HITS, OPT_CHUNK_READS, OPT_VOTE_FILTER, OPT_FILTER_SHIFT = 1, 2, 3, 4
@@ -81,6 +81,7 @@ def load_library():
         L.gmx_fastq_scan_host.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
         L.gmx_fastq_scan.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
         L.gmx_format_sam.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
+        L.gmx_format_sgr.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
         L.gmx_process_fastq.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.c_void_p]
         _lib = L
     return _lib
@@ -291,6 +292,20 @@ class Mapper:
                 cap = n.value + 16
                 continue
             self._ck(rc, "gmx_format_sam")
+            return out[: n.value].tobytes()
+
+    def format_sgr(self, min_print: float = 0.001) -> bytes:
+        """The .sgr text of the accumulators as they stand on the device (GenomeBwt::PrintFinalSGR)."""
+        names = (C.c_char_p * len(self.index.names))(*[nm.encode() for nm in self.index.names])
+        n = C.c_int64(0)
+        cap = 1 << 16
+        while True:
+            out = np.zeros(cap, dtype=np.uint8)
+            rc = self.L.gmx_format_sgr(self._ctx, names, min_print, out.ctypes.data, cap, C.byref(n))
+            if rc == _abi.GMX_ERR_OVERFLOW:
+                cap = n.value + 16
+                continue
+            self._ck(rc, "gmx_format_sgr")
             return out[: n.value].tobytes()
 
     def best_cigars(self, n_reads: int, stride: int = 64) -> np.ndarray:

@@ -43,6 +43,17 @@ __global__ void k_count_newlines(const char *text, int64_t len, unsigned long lo
     if ((threadIdx.x & 31) == 0 && n) atomicAdd(count, n);
 }
 
+struct AboveThreshold {
+    const float *v; float t;
+    __host__ __device__ bool operator()(uint32_t i) const { return v[i] > t; }
+};
+
+__global__ void k_gather_f32(const float *v, const uint32_t *idx, uint32_t n, float *out)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = v[idx[i]];
+}
+
 struct FastqDev {
     int64_t *seq_off;      // [n]
     int64_t *qual_off;     // [n]

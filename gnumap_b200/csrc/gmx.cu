@@ -1592,3 +1592,69 @@ extern "C" int gmx_format_sam(gmx_ctx *ctx, const char *text, const gmx_fastq_re
     run([&](unsigned t) { memcpy(out + at[t], parts[t].data(), parts[t].size()); });
     return GMX_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// next row: .sgr output
+// ------------------------------------------------------------------------------------------------
+extern "C" int gmx_format_sgr(gmx_ctx *ctx, const char *const *chrom_names, float min_print, char *out, int64_t cap, int64_t *len)
+{
+    if (!ctx || !chrom_names || !len || (cap > 0 && !out)) return GMX_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    const uint64_t nb = ctx->acc.n_amount;
+    if (nb >= 0x7fffffffull) { ctx->err = "more than 2^31 accumulator bins"; return GMX_ERR_UNSUPPORTED; }
+    // printable bins, in order, selected on the device
+    DevBuf d_idx, d_val, d_cnt, d_tmp;
+    CK(d_idx.ensure((size_t)nb * 4 + 16)); CK(d_cnt.ensure(16));
+    thrust::counting_iterator<uint32_t> it(0);
+    AboveThreshold pred{ctx->acc.amount, min_print};
+    size_t tmp_bytes = 0;
+    CK(cub::DeviceSelect::If(nullptr, tmp_bytes, it, d_idx.as<uint32_t>(), d_cnt.as<uint32_t>(), (int)nb, pred, ctx->stream));
+    CK(d_tmp.ensure(tmp_bytes));
+    CK(cub::DeviceSelect::If(d_tmp.p, tmp_bytes, it, d_idx.as<uint32_t>(), d_cnt.as<uint32_t>(), (int)nb, pred, ctx->stream));
+    uint32_t n = 0;
+    CK(cudaMemcpyAsync(&n, d_cnt.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    std::vector<uint32_t> idx(n); std::vector<float> val(n);
+    if (n) {
+        CK(d_val.ensure((size_t)n * 4));
+        k_gather_f32<<<nblk(n, 256), 256, 0, ctx->stream>>>(ctx->acc.amount, d_idx.as<uint32_t>(), n, d_val.as<float>());
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(idx.data(), d_idx.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(val.data(), d_val.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    d_idx.release(); d_val.release(); d_cnt.release(); d_tmp.release();
+    // the reference's loop counter walks the genome in steps of gen_size from 0 and prints bin count / gen_size under the
+    // sequence that contains `count`
+    const std::vector<int64_t> &off = ctx->h_seq_offset;
+    const uint64_t gs = ctx->params.gen_size;
+    unsigned nt = std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
+    if (n < 65536) nt = 1;
+    std::vector<std::string> parts(nt);
+    auto run = [&](auto &&fn) {
+        if (nt == 1) { fn(0u); return; }
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < nt; ++t) th.emplace_back(fn, t);
+        for (auto &x : th) x.join();
+    };
+    run([&](unsigned t) {
+        const size_t a = (size_t)n * t / nt, b = (size_t)n * (t + 1) / nt;
+        std::string &o = parts[t];
+        o.reserve((b - a) * 32);
+        char num[48];
+        for (size_t k = a; k < b; ++k) {
+            const int64_t count = (int64_t)((uint64_t)idx[k] * gs);
+            if (count >= off.back()) continue;
+            const size_t rid = std::upper_bound(off.begin(), off.end() - 1, count) - off.begin() - 1;
+            o += chrom_names[rid];
+            int w = snprintf(num, sizeof(num), "\t%lld\t%.5f\n", (long long)(count - off[rid] + 1), (double)val[k]);
+            o.append(num, (size_t)w);
+        }
+    });
+    std::vector<int64_t> at(nt + 1, 0);
+    for (unsigned t = 0; t < nt; ++t) at[t + 1] = at[t] + (int64_t)parts[t].size();
+    *len = at[nt];
+    if (at[nt] > cap) return GMX_ERR_OVERFLOW;
+    run([&](unsigned t) { memcpy(out + at[t], parts[t].data(), parts[t].size()); });
+    return GMX_OK;
+}

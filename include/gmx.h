@@ -278,6 +278,13 @@ int gmx_process_fastq(gmx_ctx *ctx, const char *text, int64_t len, int text_on_d
 int gmx_format_sam(gmx_ctx *ctx, const char *text, const gmx_fastq_rec *recs, const gmx_read_result *results, int64_t n_reads,
                    const char *const *chrom_names, char *out, int64_t cap, int64_t *len);
 
+/* ---- next row: .sgr output (Normal-mode part) ----------------------------------
+ * GenomeBwt::PrintFinalSGR (reference src/GenomeBwt.cpp:1212-1273): one line "chrom\tpos\t%.5f" per accumulator bin
+ * whose value exceeds min_print (the reference's MIN_PRINT is 0.001), in genome order, from the accumulators as they
+ * stand on the device (after the caller's NCCL reduce, if any).  The printable bins are selected on the device.
+ * Returns GMX_ERR_OVERFLOW with *len = bytes needed when `cap` is short. */
+int gmx_format_sgr(gmx_ctx *ctx, const char *const *chrom_names, float min_print, char *out, int64_t cap, int64_t *len);
+
 /* ---- options ----------------------------------------------------------------------------- */
 #define GMX_OPT_COLLECT_HITS 1   /* 1 (default): keep every accepted (pos,strand) for gmx_get_hits; 0: only the
                                     per-read results and the best group's CIGAR leave the device           */

@@ -115,3 +115,30 @@ def test_native_sam_equals_the_reference_binary(collect):
     assert sorted(sam) == sorted(rec["sam"])
     assert max(int(ln.split("X0:i:")[1]) for ln in sam) > 1, "fixture must contain multi-position groups"
     m.close()
+
+
+@pytest.mark.gpu
+def test_native_sgr_equals_the_reference_binary():
+    """SURVEY.md §8(f) rank 3 (Normal-mode part): gmx_format_sgr against the .sgr the unmodified reference binary wrote.
+    FP32 atomics reorder the sums, so values are compared numerically at the file's five decimals; the set of printed
+    bins may differ only where the value sits on the MIN_PRINT threshold."""
+    from tests import test_oracle_golden as G
+    from gnumap_b200 import output
+    rec = G.load_program("normal")
+    lut = {c: i for i, c in enumerate("ACGT")}
+    contigs = [(n, np.array([lut[c] for c in s], dtype=np.uint8)) for n, s in rec["contigs"]]
+    ix = index.build_index(contigs)
+    text = "".join(f"@{nm}\n{s}\n+\n{q}\n" for nm, s, q in rec["reads"]).encode()
+    m = api.Mapper(ix)
+    m.process_fastq(text, fetch=False)
+    got = m.format_sgr().decode().split("\n")[:-1]
+    amount, _ = m.finish()
+    assert got == list(output.sgr_lines(ix, amount, 8)), "native formatter differs from the restated printer on the same accumulators"
+    def table(lines):
+        return {(c, int(p)): float(v) for c, p, v in (ln.split("\t") for ln in lines)}
+    g, w = table(got), table(rec["sgr"])
+    for k in set(g) | set(w):
+        a, b = g.get(k, 0.0), w.get(k, 0.0)
+        assert abs(a - b) <= 1e-5 * abs(b) + 1.1e-5 or max(a, b) < 0.00102, (k, a, b)
+    assert len(w) > 1000
+    m.close()
