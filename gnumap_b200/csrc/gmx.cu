@@ -119,6 +119,7 @@ struct gmx_ctx {
     bool use_filter = true;                    // GMX_OPT_VOTE_FILTER
     int filter_shift = 0;                      // GMX_OPT_FILTER_SHIFT
     int n_sm = 148;
+    DevBuf d_ranges;                           // candidate range per read
     DevBuf d_multi, d_multi_count;             // (read, pos, strand) of multi-position best groups (fast path)
     std::vector<MultiPos> h_multi;
     std::vector<int64_t> h_seq_offset;         // host copy of the sequence offsets (+ l_pac) for pos -> chromosome
@@ -400,7 +401,7 @@ extern "C" void gmx_destroy(gmx_ctx *ctx)
                       &ctx->d_seed_count, &ctx->d_seed_off, &ctx->d_seed_n, &ctx->d_seed_hits, &ctx->d_cls_list, &ctx->d_cls_meta,
                       &ctx->d_keys, &ctx->d_keys_alt, &ctx->d_sort_tmp, &ctx->d_score, &ctx->d_leader, &ctx->d_slot, &ctx->d_lead_cand,
                       &ctx->d_hashes, &ctx->d_expv, &ctx->d_counters, &ctx->d_results, &ctx->d_alen, &ctx->d_aligned, &ctx->d_cigar,
-                      &ctx->d_hmm, &ctx->d_moves, &ctx->d_arena, &ctx->d_phmm_scratch, &ctx->d_best_cigar[0], &ctx->d_best_cigar[1], &ctx->d_out_results[0], &ctx->d_out_results[1], &ctx->d_seed_code, &ctx->d_kmer_tab, &ctx->d_multi, &ctx->d_multi_count, &ctx->d_fq_text, &ctx->d_fq_nl, &ctx->d_fq_tmp, &ctx->d_fq_seq_off, &ctx->d_fq_qual_off, &ctx->d_fq_len, &ctx->d_fq_recs, &ctx->d_fq_flags, &ctx->d_fq_count};
+                      &ctx->d_hmm, &ctx->d_moves, &ctx->d_arena, &ctx->d_phmm_scratch, &ctx->d_best_cigar[0], &ctx->d_best_cigar[1], &ctx->d_out_results[0], &ctx->d_out_results[1], &ctx->d_seed_code, &ctx->d_kmer_tab, &ctx->d_multi, &ctx->d_multi_count, &ctx->d_ranges, &ctx->d_fq_text, &ctx->d_fq_nl, &ctx->d_fq_tmp, &ctx->d_fq_seq_off, &ctx->d_fq_qual_off, &ctx->d_fq_len, &ctx->d_fq_recs, &ctx->d_fq_flags, &ctx->d_fq_count};
     for (DevBuf *b : bufs) b->release();
     ctx->h_best_cigar.release();
     if (ctx->ev[0][0]) for (int s = 0; s < ST_COUNT; ++s) { cudaEventDestroy(ctx->ev[s][0]); cudaEventDestroy(ctx->ev[s][1]); }
@@ -937,10 +938,14 @@ static int phase_a(gmx_ctx *ctx, const gmx_reads *reads, int32_t lo, int32_t hi,
     O.results = ctx->d_results.as<gmx_read_result>(); O.leader = ctx->d_leader.as<int32_t>(); O.slot = ctx->d_slot.as<int32_t>();
     O.lead_cand = ctx->d_lead_cand.as<uint32_t>(); O.n_leaders = &dc->n_leaders; O.n_accepted = &dc->n_accepted;
     O.hashes = ctx->d_hashes.as<uint64_t>(); O.expv = ctx->d_expv.as<double>();
+    CK(ctx->d_ranges.ensure((size_t)n * 8));
+    O.range = ctx->d_ranges.as<uint32_t>();
     stage_begin(ctx, ST_FINALIZE);
+    CK(cudaMemsetAsync(ctx->d_ranges.p, 0, (size_t)n * 8, ctx->stream));
+    if (n_cand) { k_cand_ranges<<<nblk(n_cand, 256), 256, 0, ctx->stream>>>(keys, n_cand, ctx->d_ranges.as<uint32_t>()); CK(cudaGetLastError()); }
     k_finalize_reads<<<nblk((int64_t)n * 32, 128), 128, 0, ctx->stream>>>(ctx->ix, ctx->dreads, P, ctx->d_prep.as<ReadPrep>(), keys, ctx->d_score.as<float>(), n_cand, O);
     CK(cudaGetLastError());
-    stage_end(ctx, ST_FINALIZE, (uint64_t)n, 0, 1);
+    stage_end(ctx, ST_FINALIZE, (uint64_t)n, 0, 2);
 
     CK(cudaMemcpyAsync(&hc.c, dc, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));

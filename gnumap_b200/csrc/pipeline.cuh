@@ -801,6 +801,17 @@ __device__ int gmx_key_compare(const DevIndex &ix, uint32_t da, int na, uint32_t
     return 0;
 }
 
+// candidate range of every read in the sorted key list (replaces two binary searches per read): range[2r], range[2r+1];
+// the array is zeroed first, so reads without candidates keep the empty range [0, 0)
+__global__ void k_cand_ranges(const unsigned long long *keys, uint32_t n_cand, uint32_t *range)
+{
+    uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_cand) return;
+    const uint32_t r = (uint32_t)(keys[c] >> 41);                     // task >> 1
+    if (c == 0 || (uint32_t)(keys[c - 1] >> 41) != r) range[2 * r] = c;
+    if (c + 1 == n_cand || (uint32_t)(keys[c + 1] >> 41) != r) range[2 * r + 1] = c + 1;
+}
+
 struct FinalizeOut {
     gmx_read_result *results;   // [n_reads]
     int32_t *leader;            // [n_cand] candidate index of the group leader, or -1 (not accepted)
@@ -810,6 +821,7 @@ struct FinalizeOut {
     uint32_t *n_accepted;
     uint64_t *hashes;           // [n_cand] scratch: key hash of accepted candidates
     double   *expv;             // [n_cand] scratch: exp(score) of accepted candidates
+    const uint32_t *range;      // [2 * n_reads] candidate range of every read (k_cand_ranges)
 };
 
 // One warp per read.  Candidates of the read are contiguous in the sorted list: POS strand then
@@ -829,8 +841,7 @@ __global__ void __launch_bounds__(128) k_finalize_reads(DevIndex ix, DevReads R,
     if (pr.status == GMX_READ_TOO_SHORT) { res.top_score = -2; if (lane == 0) O.results[r] = res; return; }
     if (pr.status == GMX_READ_TOO_POOR) { res.top_score = -3; if (lane == 0) O.results[r] = res; return; }
     const int n = gmx_read_len(R, r);
-    uint32_t lo = gmx_lower_bound(keys, n_cand, (unsigned long long)(2 * (uint32_t)r) << 40);
-    uint32_t hi = gmx_lower_bound(keys, n_cand, (unsigned long long)(2 * (uint32_t)r + 2) << 40);
+    const uint32_t lo = O.range[2 * r], hi = O.range[2 * r + 1];
 
     // pass 1: validity, top score, acceptance, exp(score), key hash
     int n_valid = 0, n_acc = 0;
