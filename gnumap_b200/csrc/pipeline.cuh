@@ -579,9 +579,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_vote_filter(DevIndex ix, uint
                 bool pd[U];
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    const uint32_t g1 = diag[u] * 0x9E3779B1u, g2 = diag[u] * 0x85EBCA77u + 0x27D4EB2Fu;
+                    // one multiply: the word index from the top bits of the product, the two bit positions from the
+                    // ten bits below them (all depend on at least the low 17 bits of the diagonal)
+                    const uint32_t g1 = diag[u] * 0x9E3779B1u;
                     w[u] = g1 >> (32 - (F_LOG2 - 2));
-                    b[u] = (1u << (g2 >> 27)) | (1u << ((g2 >> 22) & 31u));
+                    b[u] = (1u << ((g1 >> (27 - (F_LOG2 - 2))) & 31u)) | (1u << ((g1 >> (22 - (F_LOG2 - 2))) & 31u));
                 }
 #pragma unroll
                 for (int u = 0; u < U; ++u) o[u] = valid[u] ? fw[w[u]] : 0xffffffffu;
@@ -617,10 +619,13 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_vote_filter(DevIndex ix, uint
                     }
                 }
             }
+            bool any_flag = false;
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const uint32_t fm = __ballot_sync(0xffffffffu, flag[u]);
-                if (fm) {
+            for (int u = 0; u < U; ++u) any_flag |= flag[u];
+            if (__any_sync(0xffffffffu, any_flag)) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const uint32_t fm = __ballot_sync(0xffffffffu, flag[u]);
                     if (flag[u]) {
                         const uint32_t at = qn + (uint32_t)__popc(fm & lt);
                         if (at < GMX_FQ_CAP) fs->queue[at] = diag[u];
