@@ -208,7 +208,8 @@ __device__ void gmx_pair_hmm_warp(const ReadView &rd, const WindowView &win, con
 // backward sweep a padded cell only ever combines zeros, so real cells of the last column see exactly the
 // reference's special-cased formulas (x + 0.0 is exact).  Row n-1 of the backward sweep (reference :164-183) is
 // peeled.  Posteriors are accumulated in shared memory ([column slot][code][lane]: conflict-free) and the two
-// divisions by fE become multiplications by its reciprocal (K2c is a tolerance kernel: 1e-5 relative).
+// divisions by fE become multiplications by its reciprocal and the recurrences use fused multiply-adds (K2c is a
+// tolerance kernel: 1e-5 relative; the generic path below keeps the reference's operation order).
 #define GMX_PHMM_FAST_MAXC 5
 
 template <int C>
@@ -238,6 +239,7 @@ __device__ void gmx_pair_hmm_warp_fast(const ReadView &rd, const uint8_t *pac, i
     for (int x = 0; x < C * 5; ++x) acc_s[x * 32 + lane] = 0.f;
 
     // ---------------- forward
+    const double dqTmg = (double)K.qTmg, dqTgg = (double)K.qTgg;
     double pM[C], pX[C], pY[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) { pM[c] = 0; pX[c] = 0; pY[c] = 0; }
@@ -258,10 +260,11 @@ __device__ void gmx_pair_hmm_warp_fast(const ReadView &rd, const uint8_t *pac, i
 #pragma unroll
             for (int c = 0; c < C; ++c) {
                 const float e = gmx_sel4(row, gb[c], 0.f);
-                const double sum = __dadd_rn(__dadd_rn(__dmul_rn(K.Tmm, cM), __dmul_rn(K.Tgm, cX)), __dmul_rn(K.Tgm, cY));
-                const double fM = __dmul_rn((double)e, sum);
-                const double fX = __dmul_rn(K.q, __dadd_rn(__dmul_rn(K.Tmg, pM[c]), __dmul_rn(K.Tgg, pX[c])));
-                const double fY = __dmul_rn(K.q, __dadd_rn(__dmul_rn(K.Tmg, leftM), __dmul_rn(K.Tgg, leftY)));
+                // fused multiply-adds: this is the tolerance kernel (posteriors within 1e-5), and FMA only removes roundings
+                const double sum = fma(K.Tmm, cM, fma(K.Tgm, cX, K.Tgm * cY));
+                const double fM = (double)e * sum;
+                const double fX = fma(dqTmg, pM[c], dqTgg * pX[c]);
+                const double fY = fma(dqTmg, leftM, dqTgg * leftY);
                 cM = pM[c]; cX = pX[c]; cY = pY[c];
                 pM[c] = fM; pX[c] = fX; pY[c] = fY;
                 leftM = fM; leftY = fY;
@@ -285,7 +288,6 @@ __device__ void gmx_pair_hmm_warp_fast(const ReadView &rd, const uint8_t *pac, i
 #pragma unroll
     for (int c = 0; c < C; ++c) { qM[c] = 0; qX[c] = 0; }
     double eM = 0, sndM = 0, sndY = 0;
-    const double dqTmg = (double)K.qTmg, dqTgg = (double)K.qTgg;
     double2 fv_nxt[C];                                           // forward values of the row handled in the next step
 #pragma unroll
     for (int c = 0; c < C; ++c) fv_nxt[c] = make_double2(0, 0);
@@ -326,12 +328,11 @@ __device__ void gmx_pair_hmm_warp_fast(const ReadView &rd, const uint8_t *pac, i
                 for (int c = C - 1; c >= 0; --c) {
                     const float e = gmx_sel4(row, gbn[c], 0.f);
                     const double eTmm = (double)__fmul_rn(e, K.fTmm), eTgm = (double)__fmul_rn(e, K.fTgm);
-                    const double tX = __dmul_rn(dqTmg, qX[c]), tY = __dmul_rn(dqTmg, rightY);
-                    const double bM = __dadd_rn(__dadd_rn(__dmul_rn(eTmm, diagM), tX), tY);
-                    const double gd = __dmul_rn(eTgm, diagM);
-                    const double bX = __dadd_rn(gd, __dmul_rn(dqTgg, qX[c]));
-                    const double bY = __dadd_rn(gd, __dmul_rn(dqTgg, rightY));
-                    const double add = __dadd_rn(__dmul_rn(__dmul_rn(fv[c].y, bY), inv_fE), __dmul_rn(__dmul_rn(fv[c].x, bM), inv_fE));
+                    const double bM = fma(eTmm, diagM, fma(dqTmg, qX[c], dqTmg * rightY));
+                    const double gd = eTgm * diagM;
+                    const double bX = fma(dqTgg, qX[c], gd);
+                    const double bY = fma(dqTgg, rightY, gd);
+                    const double add = fma(fv[c].y, bY, fv[c].x * bM) * inv_fE;
                     acc[c * 160] = (float)__dadd_rn((double)acc[c * 160], add);
                     diagM = qM[c];
                     qM[c] = bM; qX[c] = bX; rightY = bY;
