@@ -541,8 +541,7 @@ def main():
                "--master-port", "29517", os.path.abspath(__file__), *sys.argv[1:]]
         raise SystemExit(subprocess.call(cmd))
     import __graft_entry__ as g
-    if int(os.environ.get("LOCAL_RANK", "0")) == 0:
-        g.build()
+    g.build()                       # serialised by a file lock: a no-op on every rank but the first when something is stale
     own_arm(a)
 
 
