@@ -332,3 +332,25 @@ def test_full_size_properties(api):
     for f in ("status", "best_first_pos", "best_first_strand", "best_score", "n_groups", "best_n_positions", "best_aligned_len"):
         assert np.array_equal(a[f], c["results"][f]), f
     m.close()
+
+
+def test_raw_pwm_reads_match_fastq_reads(api, O, plain):
+    """PRB / INT inputs reach the path as raw float PWMs (reference src/SeqReader.cpp:541-571,901-978).  A batch whose PWM
+    rows are the FASTQ rows must give the same per-read results through the raw-PWM code paths of every kernel."""
+    ix, batch, _ = plain
+    sub = batch.slice(0, 400)
+    pwm = np.concatenate([O.fastq_pwm(sub.seq[sub.offsets[r]:sub.offsets[r + 1]].tobytes(), sub.qual[sub.offsets[r]:sub.offsets[r + 1]].tobytes())
+                          for r in range(sub.n_reads)])
+    seqs = [sub.seq[sub.offsets[r]:sub.offsets[r + 1]].tobytes() for r in range(sub.n_reads)]
+    raw = _abi.ReadBatch(seqs, None, pwm=pwm)
+    for mode in (_abi.MODE_NORMAL, _abi.MODE_SNP):
+        pg = common.set_mode(api.default_params(), mode); po = common.set_mode(O.default_params(), mode)
+        m = api.Mapper(ix, pg)
+        got = m.process_batch(raw)
+        amount, planes = m.finish()
+        want = O.process_batch(O.OracleIndex(ix), po, sub)
+        common.compare_batches(got, want)
+        assert np.allclose(amount, want["amount"], rtol=1e-5, atol=1e-6)
+        if planes is not None:
+            assert np.allclose(planes, want["planes"], rtol=1e-5, atol=1e-6)
+        m.close()
