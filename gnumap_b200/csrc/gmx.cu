@@ -708,6 +708,7 @@ extern "C" int gmx_pair_hmm(gmx_ctx *ctx, const gmx_reads *reads, int64_t n_task
     int32_t max_len = 0;
     int r = upload_tasks(ctx, u, reads, n_tasks, read_idx, strand, windows, win_stride, nullptr, &max_len);
     if (r != GMX_OK) return r;
+    if (max_len > 32 * GMX_PHMM_MAXC) { ctx->err = "reads longer than 256 bp are not supported by the pair-HMM kernel"; return GMX_ERR_UNSUPPORTED; }
     CK(out.ensure((size_t)n_tasks * win_stride * 5 * 4));
     CK(cudaMemsetAsync(out.p, 0, (size_t)n_tasks * win_stride * 5 * 4, ctx->stream));
     size_t per_task = gmx_phmm_scratch_doubles(max_len);
@@ -983,6 +984,7 @@ static int phase_b(gmx_ctx *ctx)
     CK(cudaGetLastError());
     stage_end(ctx, ST_TRACEBACK, (uint64_t)n_leaders * (uint64_t)std::max(7 * max_len - 12, 0), 0, 1);
     if (P.mode == GMX_MODE_SNP) {
+        if (max_len > 32 * GMX_PHMM_MAXC) { ctx->err = "SNP mode: reads longer than 256 bp are not supported by the pair-HMM kernel"; return GMX_ERR_UNSUPPORTED; }
         CK(ctx->d_hmm.ensure((size_t)n_leaders * max_len * 5 * 4));
         L.hmm = ctx->d_hmm.as<float>();
         size_t per_task = gmx_phmm_scratch_doubles(max_len);

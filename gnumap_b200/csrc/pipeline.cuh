@@ -944,8 +944,10 @@ __global__ void __launch_bounds__(128) k_finalize_reads(DevIndex ix, DevReads R,
         bool lead = (c < hi) && O.leader[c] == (int32_t)c;
         float sc = lead ? score[c] : -1.0f;
         if (lead && exp((double)sc) > exp(-1.0)) {
-            bool better = (best_c < 0) || sc > best_sc;
-            if (!better && sc == best_sc) {
+            // the reference compares exp(score) (a double that saturates at +inf for scores above ~709.78: very long
+            // reads), so scores are compared through it; equal values fall back to the key order
+            bool better = (best_c < 0) || exp((double)sc) > exp((double)best_sc);
+            if (!better && exp((double)sc) == exp((double)best_sc)) {
                 uint32_t ta, ra, da, tb, rb, db; gmx_decode_key(keys[c], ta, ra, da); gmx_decode_key(keys[best_c], tb, rb, db);
                 better = gmx_key_compare(ix, da, (int)(ta & 1), db, (int)(tb & 1), n) < 0;
             }
@@ -958,8 +960,8 @@ __global__ void __launch_bounds__(128) k_finalize_reads(DevIndex ix, DevReads R,
         int oc = __shfl_xor_sync(0xffffffffu, best_c, o);
         bool better = false;
         if (oc >= 0) {
-            if (best_c < 0 || osc > best_sc) better = true;
-            else if (osc == best_sc && oc != best_c) {
+            if (best_c < 0 || exp((double)osc) > exp((double)best_sc)) better = true;
+            else if (exp((double)osc) == exp((double)best_sc) && oc != best_c) {
                 uint32_t ta, ra, da, tb, rb, db; gmx_decode_key(keys[oc], ta, ra, da); gmx_decode_key(keys[best_c], tb, rb, db);
                 int cmp = gmx_key_compare(ix, da, (int)(ta & 1), db, (int)(tb & 1), n);
                 better = cmp < 0;

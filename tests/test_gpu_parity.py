@@ -354,3 +354,39 @@ def test_raw_pwm_reads_match_fastq_reads(api, O, plain):
         if planes is not None:
             assert np.allclose(planes, want["planes"], rtol=1e-5, atol=1e-6)
         m.close()
+
+
+def test_long_reads_take_the_exact_vote_path(api, O):
+    """Reads beyond the filter kernel's span (k-mer offset + mer > 448) fall back to the exact hash-table kernels; the
+    generic band / traceback paths handle lengths up to GMX_MAX_READ_LEN; SNP mode refuses reads over 256 bp loudly."""
+    from gnumap_b200 import synth
+    contigs = synth.make_genome(400_000, 41, n_contigs=2)
+    codes = np.concatenate([c for _, c in contigs])
+    ix = index.build_index(contigs)
+    seqs, quals = [], []
+    lut = np.frombuffer(b"ACGTN", dtype=np.uint8)
+    for k, L in enumerate((300, 449, 470, 600, 900, 120, 200, 256)):     # exp(score) stays finite up to ~940 bp
+        r = synth.simulate_reads(codes, 12, L, 900 + k, indel_rate=0.3)
+        for i in range(12):
+            seqs.append(lut[r["bases"][i]].tobytes()); quals.append((r["quals"][i] + 33).astype(np.uint8).tobytes())
+    batch = _abi.ReadBatch(seqs, quals)
+    m = api.Mapper(ix)
+    got = m.process_batch(batch)
+    amount, _ = m.finish()
+    want = O.process_batch(O.OracleIndex(ix), O.default_params(), batch)
+    common.compare_batches(got, want)
+    assert np.allclose(amount, want["amount"], rtol=1e-5, atol=1e-6)
+    assert (want["results"]["status"] == _abi.READ_MAPPED).sum() > 80
+    m.close()
+    ps = common.set_mode(api.default_params(), _abi.MODE_SNP)
+    m = api.Mapper(ix, ps)
+    with pytest.raises(api_mod(api).GmxError) as e:
+        m.process_batch(batch)
+    assert e.value.code == _abi.GMX_ERR_UNSUPPORTED
+    short = _abi.ReadBatch(seqs[60:], quals[60:])                 # 120, 200 and 256 bp: generic pair-HMM path above 160 bp
+    got = m.process_batch(short)
+    amount, planes = m.finish()
+    want = O.process_batch(O.OracleIndex(ix), common.set_mode(O.default_params(), _abi.MODE_SNP), short)
+    common.compare_batches(got, want)
+    assert np.allclose(planes, want["planes"], rtol=1e-5, atol=1e-6)
+    m.close()
