@@ -457,6 +457,21 @@ def own_arm(a):
                             "the kernel is ALU/LSU-bound (profiles/r01_ncu_raw_k_vote_filter_v7.txt), not HBM-bound",
                     "stages_ms_per_step": {k: round(v / a.steps, 3) for k, v in st["ms"].items()},
                     "stages_units_per_step": {k: v // a.steps for k, v in st["units"].items()}}
+        # per-kernel table: algorithmic bytes (or cell updates) / CUDA-event time, against the measured HBM peak or the
+        # nominal no-FMA FP32 issue rate (148 SMs x 128 lanes x 1.965 GHz = 37.2 TFLOP/s; 12 flops per NW cell)
+        kernels = {}
+        for k in ("seed_walk", "locate_vote", "scatter", "prep_reads"):
+            if st["ms"].get(k, 0) > 0 and st["bytes"].get(k, 0) > 0:
+                gbs = st["bytes"][k] / (st["ms"][k] * 1e-3) / 1e9
+                kernels[k] = {"bound": "hbm", "ms_per_step": st["ms"][k] / a.steps, "algorithmic_GB_per_step": st["bytes"][k] / a.steps / 1e9,
+                              "achieved_GBs": gbs, "frac_of_hbm_peak": gbs / peak}
+        for k in ("nw_score", "nw_traceback", "pair_hmm"):
+            if st["ms"].get(k, 0) > 0 and st["units"].get(k, 0) > 0:
+                gc = st["units"][k] / (st["ms"][k] * 1e-3) / 1e9
+                kernels[k] = {"bound": "fp64 pipe" if k == "pair_hmm" else "fp32 alu (no fma)", "ms_per_step": st["ms"][k] / a.steps, "GCUPS": gc}
+                if k != "pair_hmm":
+                    kernels[k]["frac_of_fp32_nofma_peak"] = gc * 12 / 37200.0
+        roofline["kernels"] = kernels
         nw_cells = st["units"].get("nw_score", 0)
         gcups = nw_cells / (st["ms"]["nw_score"] * 1e-3) / 1e9 if st["ms"].get("nw_score", 0) > 0 else None
         cpu = None
