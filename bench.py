@@ -295,6 +295,8 @@ def own_arm(a):
     m.synchronize()
     log(f"[bench] context created (index upload + SA de-sampling) in {time.time() - t:.1f}s")
     m.set_option(api.OPT_COLLECT_HITS, 0)
+    if os.environ.get("GMX_CHUNK_READS"):
+        m.set_option(api.OPT_CHUNK_READS, int(os.environ["GMX_CHUNK_READS"]))
     if os.environ.get("GMX_FILTER_SHIFT"):
         m.set_option(api.OPT_FILTER_SHIFT, int(os.environ["GMX_FILTER_SHIFT"]))
     stream = torch.cuda.Stream(device=dev)
@@ -452,7 +454,7 @@ def own_arm(a):
                     "algorithmic_bytes_per_step": st["bytes"][top] / a.steps, "ms_per_step": st["ms"][top] / a.steps,
                     "launches_per_step": launches / a.steps,
                     "algorithmic_bytes_per_loaded_launch": st["bytes"][top] / max(launches / 12, 1) if top == "locate_vote" else st["bytes"][top] / max(launches, 1),
-                    "note": "stage = 12 launches per chunk of 262144 reads (6 filter + 6 exact classes); one of them (k_vote_filter<13,4,true> on this "
+                    "note": "stage = 12 launches per chunk of 524288 reads (6 filter + 6 exact classes); one of them (k_vote_filter<13,4,true> on this "
                             "workload) carries ~all tasks, the rest find empty lists (~5 us each); achieved/traffic are per loaded launch; "
                             "the kernel is ALU/LSU-bound (profiles/r01_ncu_raw_k_vote_filter_v7.txt), not HBM-bound",
                     "stages_ms_per_step": {k: round(v / a.steps, 3) for k, v in st["ms"].items()},

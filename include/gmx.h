@@ -288,7 +288,7 @@ int gmx_format_sgr(gmx_ctx *ctx, const char *const *chrom_names, float min_print
 /* ---- options ----------------------------------------------------------------------------- */
 #define GMX_OPT_COLLECT_HITS 1   /* 1 (default): keep every accepted (pos,strand) for gmx_get_hits; 0: only the
                                     per-read results and the best group's CIGAR leave the device           */
-#define GMX_OPT_CHUNK_READS  2   /* reads processed per internal chunk (default 262144)                     */
+#define GMX_OPT_CHUNK_READS  2   /* reads processed per internal chunk (default 524288)                     */
 #define GMX_OPT_VOTE_FILTER  3   /* 1 (default): counting-filter + exact-verification vote kernel with the exact
                                     hash-table kernels as its overflow path; 0: exact hash tables for every task  */
 #define GMX_OPT_FILTER_SHIFT 4   /* tuning: log2 scale of the kmin == 2 vote filter (default 0 = 4 bytes per SA hit)     */

@@ -249,10 +249,10 @@ def test_fast_path_split_phases_chunking_and_device_input(api, O, plain):
     assert [bytes(r).split(b"\0")[0].decode() for r in m.best_cigars(batch.n_reads)] == want["cigars"]
     amount_chunked, _ = m.finish()
     assert np.allclose(amount_chunked, amount_fast, rtol=1e-5, atol=1e-6)
-    m.set_option(api_mod(api).OPT_CHUNK_READS, 1 << 18)
+    m.set_option(api_mod(api).OPT_CHUNK_READS, 1 << 19)
     m.set_option(api_mod(api).OPT_COLLECT_HITS, 1)
     # (3) gmx_map_batch + gmx_score_batch (resident single chunk) and (4) multi-chunk split (re-run from the kept copy)
-    for chunk in (1 << 18, 300):
+    for chunk in (1 << 19, 300):
         m.reset_accumulators()
         m.set_option(api_mod(api).OPT_CHUNK_READS, chunk)
         a = m.process_batch(batch, score=False)
@@ -262,7 +262,7 @@ def test_fast_path_split_phases_chunking_and_device_input(api, O, plain):
         b = m.score_batch(batch)
         common.compare_batches(b, want)
         assert np.allclose(m.finish()[0], want["amount"], rtol=1e-5, atol=1e-6)
-    m.set_option(api_mod(api).OPT_CHUNK_READS, 1 << 18)
+    m.set_option(api_mod(api).OPT_CHUNK_READS, 1 << 19)
     # (5) device-resident reads
     m.reset_accumulators()
     dev = torch.device("cuda", 0)
