@@ -379,7 +379,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_vote_smem(DevIndex ix, SeedStore
 // mask over all k-mers, hence the exact count and the exact round at which the reference's counter reaches
 // kmin (inc/align_seq2_raw.cpp:28-35,262-274).  The entry queued by that very round's hit emits the candidate,
 // which also de-duplicates without any exact table.
-#define GMX_FQ_CAP 256           // vote-queue entries per task; overflow -> exact path
+#define GMX_FQ_CAP 256           // vote-queue entries per task; drained whenever another step might not fit
 #define GMX_FILTER_MAX_SEEDS 64
 #define GMX_FILTER_MAX_SPAN 448  // max k-mer offset + mer: the window words must fit the 32 lanes ((15 + span) / 16 + 2 < 32)
 
@@ -527,7 +527,80 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_vote_filter(DevIndex ix, uint
         // pass 1: count votes approximately, queue the hits that may complete kmin votes.  The hits of ONE k-mer
         // are distinct diagonals, so up to 32 * U of them are handled as one step: all loads, then all stores.
         // The suffix-array words of the next step are requested before the current one is processed.
+        // queue -> candidates: distinct queued diagonals, exact votes from the genome, emission.  Runs whenever the queue
+        // may not hold another step (repeat-rich reads) and once at the end; a diagonal drained twice is emitted twice
+        // with the same key and dropped after the sort (k_cand_score).
         uint32_t qn = 0;
+        uint32_t ne = 0;
+        auto drain = [&]() {
+            // distinct queued diagonals, compacted in place (a diagonal is queued once per k-mer that hits it)
+            uint32_t n2 = 0;
+            for (uint32_t q0 = 0; q0 < qn; q0 += 32) {
+                const uint32_t q = q0 + lane;
+                const bool in = q < qn;
+                const uint32_t d = in ? fs->queue[q] : (GMX_EMPTY_KEY - (uint32_t)lane);      // padding lanes never match
+                const uint32_t peers = __match_any_sync(0xffffffffu, d);
+                bool first = in && (__ffs(peers) - 1 == lane);
+                for (uint32_t j = 0; j < n2; ++j) first = first && fs->queue[j] != d;
+                __syncwarp();
+                const uint32_t fm = __ballot_sync(0xffffffffu, first);
+                if (first) fs->queue[n2 + (uint32_t)__popc(fm & lt)] = d;   // n2 + rank <= q: never overtakes unread entries
+                n2 += (uint32_t)__popc(fm);
+                __syncwarp();
+            }
+
+            // pass 2: exact votes of each distinct diagonal from its genome window, four windows in flight
+            uint32_t limit[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) limit[h] = (uint32_t)ix.seq_len - cur.off[h] - (uint32_t)mer;
+            auto flush = [&]() {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(sink.count, ne);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                __syncwarp();
+                if ((uint32_t)lane < ne) {
+                    if (base + lane < sink.cap) sink.keys[base + lane] = fs->outb[lane];
+                    else *sink.overflow = 1u;
+                }
+                __syncwarp();
+                ne = 0;
+            };
+            const uint32_t *pac32 = reinterpret_cast<const uint32_t *>(ix.pac);
+            for (uint32_t q0 = 0; q0 < n2; q0 += 4) {
+                uint32_t d[4], raw[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) d[i] = q0 + i < n2 ? fs->queue[q0 + i] : GMX_EMPTY_KEY;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const uint32_t idx = min((d[i] >> 4) + (uint32_t)lane, pac_words - 1u);   // the pad words are zero
+                    raw[i] = __ldg(pac32 + idx);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if (d[i] == GMX_EMPTY_KEY) continue;
+                    int round = -1;
+                    if (d[i] != 0u) {
+                        const uint32_t ww = __byte_perm(raw[i], 0, 0x0123);   // bases are packed most significant first
+                        const unsigned long long m = mer <= 16 ? gmx_exact_mask<true>(ww, d[i], ns, mer, cur.off, cur.code, limit, lane)
+                                                               : gmx_exact_mask<false>(ww, d[i], ns, mer, cur.off, cur.code, limit, lane);
+                        if (__popcll(m) >= kmin) {
+                            const uint32_t lo = (uint32_t)m, hi = (uint32_t)(m >> 32);
+                            const int pl = __popc(lo);
+                            round = kmin <= pl ? (int)__fns(lo, 0, kmin) : 32 + (int)__fns(hi, 0, kmin - pl);
+                        }
+                    } else {
+                        round = gmx_round_diag0(ix, ns, mer, kmin, fs, lane);
+                    }
+                    if (round >= 0) {
+                        if (lane == 0) fs->outb[ne] = ((unsigned long long)task << 40) | ((unsigned long long)round << 32) | d[i];
+                        ne++;
+                        if (ne == 32) flush();
+                    }
+                }
+            }
+            if (ne) flush();
+            qn = 0;
+        };
         int s_cur = 0; uint32_t t_cur = 0;
         uint32_t sa_nxt[U];
         auto issue = [&](int s, uint32_t t0, uint32_t (&dst)[U]) {
@@ -538,7 +611,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_vote_filter(DevIndex ix, uint
             for (int u = 0; u < U; ++u) dst[u] = t + 32u * u < cnt ? __ldg(p + 32 * u) : GMX_SA_INVALID;
         };
         if (ns > 0) issue(0, 0, sa_nxt);
-        while (s_cur < ns) {
+        do {                                                           // pass-1 segments separated by queue drains (one drain site)
+        while (s_cur < ns && qn <= GMX_FQ_CAP - 32u * U) {        // room for one more step of flagged hits
             uint32_t sa[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) sa[u] = sa_nxt[u];
@@ -636,79 +710,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_vote_filter(DevIndex ix, uint
             __syncwarp();
             s_cur = s_n; t_cur = t_n;
         }
-        if (qn > GMX_FQ_CAP) {                                         // repeat-rich read: exact tables take over
-            if (lane == 0) gmx_class_append(E, gmx_exact_class(S.hits[task]), task);
-            cur = nxt;
-            continue;
-        }
-
-        // distinct queued diagonals, compacted in place (a diagonal is queued once per k-mer that hits it)
-        uint32_t n2 = 0;
-        for (uint32_t q0 = 0; q0 < qn; q0 += 32) {
-            const uint32_t q = q0 + lane;
-            const bool in = q < qn;
-            const uint32_t d = in ? fs->queue[q] : (GMX_EMPTY_KEY - (uint32_t)lane);      // padding lanes never match
-            const uint32_t peers = __match_any_sync(0xffffffffu, d);
-            bool first = in && (__ffs(peers) - 1 == lane);
-            for (uint32_t j = 0; j < n2; ++j) first = first && fs->queue[j] != d;
-            __syncwarp();
-            const uint32_t fm = __ballot_sync(0xffffffffu, first);
-            if (first) fs->queue[n2 + (uint32_t)__popc(fm & lt)] = d;   // n2 + rank <= q: never overtakes unread entries
-            n2 += (uint32_t)__popc(fm);
-            __syncwarp();
-        }
-
-        // pass 2: exact votes of each distinct diagonal from its genome window, four windows in flight
-        uint32_t limit[2];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) limit[h] = (uint32_t)ix.seq_len - cur.off[h] - (uint32_t)mer;
-        uint32_t ne = 0;
-        auto flush = [&]() {
-            uint32_t base = 0;
-            if (lane == 0) base = atomicAdd(sink.count, ne);
-            base = __shfl_sync(0xffffffffu, base, 0);
-            __syncwarp();
-            if ((uint32_t)lane < ne) {
-                if (base + lane < sink.cap) sink.keys[base + lane] = fs->outb[lane];
-                else *sink.overflow = 1u;
-            }
-            __syncwarp();
-            ne = 0;
-        };
-        const uint32_t *pac32 = reinterpret_cast<const uint32_t *>(ix.pac);
-        for (uint32_t q0 = 0; q0 < n2; q0 += 4) {
-            uint32_t d[4], raw[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) d[i] = q0 + i < n2 ? fs->queue[q0 + i] : GMX_EMPTY_KEY;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const uint32_t idx = min((d[i] >> 4) + (uint32_t)lane, pac_words - 1u);   // the pad words are zero
-                raw[i] = __ldg(pac32 + idx);
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                if (d[i] == GMX_EMPTY_KEY) continue;
-                int round = -1;
-                if (d[i] != 0u) {
-                    const uint32_t ww = __byte_perm(raw[i], 0, 0x0123);   // bases are packed most significant first
-                    const unsigned long long m = mer <= 16 ? gmx_exact_mask<true>(ww, d[i], ns, mer, cur.off, cur.code, limit, lane)
-                                                           : gmx_exact_mask<false>(ww, d[i], ns, mer, cur.off, cur.code, limit, lane);
-                    if (__popcll(m) >= kmin) {
-                        const uint32_t lo = (uint32_t)m, hi = (uint32_t)(m >> 32);
-                        const int pl = __popc(lo);
-                        round = kmin <= pl ? (int)__fns(lo, 0, kmin) : 32 + (int)__fns(hi, 0, kmin - pl);
-                    }
-                } else {
-                    round = gmx_round_diag0(ix, ns, mer, kmin, fs, lane);
-                }
-                if (round >= 0) {
-                    if (lane == 0) fs->outb[ne] = ((unsigned long long)task << 40) | ((unsigned long long)round << 32) | d[i];
-                    ne++;
-                    if (ne == 32) flush();
-                }
-            }
-        }
-        if (ne) flush();
+        drain();
+        } while (s_cur < ns);
         __syncwarp();
         cur = nxt;
     }
@@ -766,7 +769,9 @@ __global__ void __launch_bounds__(128) k_cand_score(DevIndex ix, DevReads R, Dev
     gmx_decode_key(keys[c], task, round, diag);
     ReadView rd = gmx_read_view(R, (int)(task >> 1), (int)(task & 1));
     float sc = __int_as_float(0x7fc00000);                       // NaN: window is "" (chromosome boundary)
-    if (gmx_window_valid(ix, diag, rd.n)) {
+    // a diagonal drained from the vote queue twice arrives twice with the same key: keep the first copy only
+    const bool dup = c > 0 && keys[c - 1] == keys[c];
+    if (!dup && gmx_window_valid(ix, diag, rd.n)) {
         WindowView win; win.pac = ix.pac; win.pos = diag; win.chars = nullptr;
         sc = gmx_nw_score_dispatch(rd, win, T, P.gap, P.max_gap);
     }
