@@ -1,50 +1,3 @@
-# INTEGRATION — wiring `libgmx.so` into the unchanged GNUMAP driver
-
-The reference (byucsl/gnumap 4.0.0 BETA, C++03) has **no plugin, operator or FFI layer**: its hot path is reached
-through the abstract class `Genome` (`inc/Genome.h:88-141`), stack-allocated `bin_seq` objects and
-`virtual ScoredSeq::score` (`inc/ScoredSeq.h:259`), all driven by the two per-batch loops of the worker threads
-(`src/Driver.cpp:2344-2373`).  The drop-in boundary is therefore the C ABI in [`include/gmx.h`](include/gmx.h):
-plain C, pointers and sizes, error codes, no C++/torch types.  The reference is compiled code and its toolchain
-(g++) is what a maintainer uses, so the binding below is C++ calling that C ABI — four patch points in otherwise
-unchanged code (SURVEY.md §8b).  Options, SAM/SGR/GMP writers, read parsing and `PrintFinal*` are untouched.
-
-## Entry point ↔ reference interface
-
-| `include/gmx.h` | replaces (reference file:line) |
-|---|---|
-| `gmx_default_params`, `gmx_params` | the globals the path reads, snapshotted after `main` has finished editing them: `inc/const_define.h:43-107`, `setup_alignment_matrices` `inc/a_matrices.c:25-126`, BS / A→G / `-S` edits `src/Driver.cpp:1083-1315` |
-| `gmx_create(index, params, device)` | the in-memory index after `gGen.LoadGenome()` (`src/Driver.cpp:1428-1429`, `bwaidx_t` `inc/GenomeBwt.h:64-72`); also de-samples the SA and allocates zeroed accumulators (`src/GenomeBwt.cpp:323`, `src/Genome.cpp:198-288`) |
-| `gmx_fm_search` | `GenomeBwt::get_sa_int` `src/GenomeBwt.cpp:438-474` → `bwt_match_exact` `src/bwt.c:222-239` |
-| `gmx_sa_locate` | `GenomeBwt::get_sa_coord` `src/GenomeBwt.cpp:431-436` → `bwt_sa` `src/bwt.c:86-97` |
-| `gmx_get_windows` | `GenomeBwt::GetString` `src/GenomeBwt.cpp:384-415` |
-| `gmx_self_score` | `bin_seq::get_align_score(read, consensus, 0, n-1)` `src/bin_seq.cpp:739-759,860-893` |
-| `gmx_nw_score` | `bin_seq::get_align_score(read, gen)` `src/bin_seq.cpp:761-850` |
-| `gmx_nw_traceback` | `bin_seq::get_align_score_w_traceback` `src/bin_seq.cpp:445-718` |
-| `gmx_pair_hmm` | `bin_seq::pairHMM` `src/bin_seq.cpp:60-244` |
-| `gmx_map_batch` | PHASE A loop: `set_top_matches` `src/Driver.cpp:432-612` → `align_sequence` / `process_hits` `inc/align_seq2_raw.cpp:22-328` |
-| `gmx_score_batch` | PHASE B loop: `create_match_output` `src/Driver.cpp:614-753` → `{Normal,BS,SNP}ScoredSeq::score` |
-| `gmx_process_batch` | both loops of one worker iteration `src/Driver.cpp:2344-2373` |
-| `gmx_get_hits`, `gmx_get_best_alignments` | `ScoredSeq::positions` / the traceback `get_SAM` re-runs for the CIGAR (`inc/ScoredSeq.h:293-404`) |
-| `gmx_fastq_scan_host`, `gmx_fastq_scan`, `gmx_process_fastq` (next row) | `SeqReader::get_more_fastq` `src/SeqReader.cpp:1023-1292` (FASTQ text → `Read::name/seq/fq`; the PWM is built on the device from (base, quality char)) |
-| `gmx_format_sam` (next row) | `ScoredSeq::get_SAM` `inc/ScoredSeq.h:293-404` + the SAM writer `src/Driver.cpp:2146-2217` |
-| `gmx_accumulators_device`, `gmx_finish` | the MPI block `src/Driver.cpp:1615-1811` and the host arrays `GetGenomeAmtPtr()` / `GetGenome{A,C,G,T,N}Ptr()` `inc/GenomeBwt.h:199-209` read by `PrintFinal*` |
-
-Per-read outcomes are data (`gmx_read_result.status`, `top_score` carries the reference's sentinels
-`READ_TOO_SHORT -2`, `READ_TOO_POOR -3`, `READ_TOO_MANY 999999`, `inc/const_include.h:184-188`); CUDA errors are
-return codes plus `gmx_last_error`, nothing is thrown across the boundary.  The caller owns every host buffer, the
-library owns all device memory.  One context drives one GPU; calls on one context are serialised by the caller
-(one worker thread per context — the reference's `-c N` becomes N contexts on N GPUs, or N streams on one).
-
-## The binding a maintainer adds: `integration/gnumap_gmx_bridge.cpp`
-
-The reference-side stub is a real translation unit, not pseudo-code: it includes the reference's own headers
-(`const_include.h`, `GenomeBwt.h`, `ScoredSeq.h`), uses its globals and types (`Read`, `TopReadOutput`, `bwaidx_t`,
-`GenomeBwt::GetPosPair`) and reaches `libgmx.so` only through `include/gmx.h`.  `tests/test_abi.py::
-test_reference_side_binding_compiles` compiles it against `/root/reference/inc` (where the reference is present), so
-the binding is known to match the reference's real declarations.  Link the patched driver with
-`-L<repo>/gnumap_b200 -lgmx -lcudart`.
-
-```cpp
 // gnumap_gmx_bridge.cpp -- the reference-side binding of INTEGRATION.md as a compilable translation unit.
 //
 // This file is what a GNUMAP maintainer adds next to src/Driver.cpp: it sees the reference's own headers and globals
@@ -200,19 +153,3 @@ void gmx_collect(GenomeBwt &gen)
     gmx_destroy(gGmx);
     gGmx = 0;
 }
-```
-
-`gmx_map_batch` + `gmx_score_batch` exist for a driver that wants to keep the reference's two-loop shape (PHASE A for
-the whole slice, then PHASE B); `gmx_process_batch` is the same work with one download.  A driver that also hands over
-its input and output formatting uses `gmx_process_fastq` (FASTQ text in) and `gmx_format_sam` / `gmx_format_sgr`
-(SAM body and `.sgr` text out).
-
-## The host-side mirror used by the tests
-
-`gnumap_b200/api.py` is a thin ctypes mirror of the same ABI with the reference's names (`Mapper.get_sa_int`,
-`get_sa_coord`, `GetString`, `get_align_score`, `get_align_score_w_traceback`, `pairHMM`, `process_batch`,
-`finish`), so that the parity tests read like the reference's own call sites; `gnumap_b200/output.py` restates the
-reference's SAM / SGR / GMP formatters so whole-program output can be diffed against the reference binary;
-`gnumap_b200/index.py` reads and writes the reference's `.gnumap.{bwt,sa,pac,ann,amb}` files byte for byte;
-`gnumap_b200/sharding.py` holds the read-sharding + accumulator-reduce scheme for N GPUs.  PyTorch appears only as
-plumbing (device tensors for resident inputs, streams/events for timing, `torch.distributed` for NCCL).

@@ -110,3 +110,22 @@ def test_product_never_touches_the_oracle():
                     txt = open(os.path.join(dirpath, f), errors="ignore").read()
                     assert "liboracle" not in txt and "gnumap_oracle" not in txt and "from oracle" not in txt and "import oracle" not in txt, \
                         f"{base}/{f} references the oracle"
+
+
+def test_reference_side_binding_compiles(tmp_path):
+    """integration/gnumap_gmx_bridge.cpp (the stub shown in INTEGRATION.md) must compile against the reference's own
+    headers: the binding uses the reference's real types (Read, TopReadOutput, bwaidx_t, GenomeBwt)."""
+    ref_inc = "/root/reference/inc"
+    if not os.path.isdir(ref_inc):
+        pytest.skip("the reference checkout is not present on this machine")
+    src = os.path.join(ROOT, "integration", "gnumap_gmx_bridge.cpp")
+    obj = tmp_path / "bridge.o"
+    subprocess.check_call(["g++", "-std=c++0x", "-w", "-I", ref_inc, "-I", os.path.join(ROOT, "oracle", "gsl_stub"),
+                           "-I", os.path.join(ROOT, "include"), "-DGMX_BRIDGE_TEST_ACCESS", "-c", src, "-o", str(obj)])
+    syms = subprocess.check_output(["nm", "-C", str(obj)], text=True)
+    for fn in ("gmx_attach(GenomeBwt&, int)", "gmx_run_slice(GenomeBwt&", "gmx_collect(GenomeBwt&)"):
+        assert fn in syms
+    for dep in ("gmx_create", "gmx_process_batch", "gmx_get_hits", "gmx_get_best_alignments", "gmx_finish", "gmx_destroy"):
+        assert f"U {dep}" in syms, f"the binding should call {dep} through the C ABI"
+    # the stub in INTEGRATION.md is this file, verbatim
+    assert open(src).read() in open(os.path.join(ROOT, "INTEGRATION.md")).read()
