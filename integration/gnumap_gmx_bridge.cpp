@@ -121,7 +121,9 @@ void gmx_run_slice(GenomeBwt &gen, unsigned read_begin, unsigned read_end, unsig
         good_seqs++;
         // what ScoredSeq::get_SAM fills (inc/ScoredSeq.h:293-404): one TopReadOutput per (position, strand) of the best group
         const double total = exp((double)res[i].best_score) / res[i].denominator;
-        int mapq = total == 1 ? 30 : (int)round(-10 * log(1 - total) / log(10.0));
+        // the denominator was summed from the device's exp(): the host's exp() may differ in the last place, so a
+        // sole hit can give a ratio one ulp above 1
+        int mapq = (total >= 1) ? 30 : (int)round(-10 * log(1 - total) / log(10.0));
         if (mapq > 30) mapq = 30;
         for (int32_t h = res[i].hit_begin; h < res[i].hit_end; ++h) {
             if (hits[h].group != res[i].best_group) continue;
@@ -148,8 +150,14 @@ void gmx_run_slice(GenomeBwt &gen, unsigned read_begin, unsigned read_end, unsig
 void gmx_collect(GenomeBwt &gen)
 {
     float *planes[5] = {gen.GetGenomeAPtr(), gen.GetGenomeCPtr(), gen.GetGenomeGPtr(), gen.GetGenomeTPtr(), gen.GetGenomeNPtr()};
-    // several GPUs: one process per GPU, ncclAllReduce(sum, f32) on gmx_accumulators_device() first
-    if (gmx_finish(gGmx, gen.GetGenomeAmtPtr(), planes) != GMX_OK) gmx_die("gmx_finish");
+    // several GPUs: one process per GPU, ncclAllReduce(sum, f32) on gmx_accumulators_device() first.
+    // The library keeps ceil(l_pac / gGEN_SIZE) bins; the reference allocates l_pac / gGEN_SIZE floats (src/GenomeBwt.cpp:323).
+    uint64_t n_amount = 0, n_plane = 0;
+    if (gmx_accumulators_device(gGmx, 0, &n_amount, 0, &n_plane) != GMX_OK) gmx_die("gmx_accumulators_device");
+    std::vector<float> amount((size_t)n_amount);
+    if (gmx_finish(gGmx, n_amount ? &amount[0] : 0, planes) != GMX_OK) gmx_die("gmx_finish");
+    const uint64_t ref_bins = (uint64_t)GMX_GENOME_INDEX(gen)->bns->l_pac / gGEN_SIZE;
+    memcpy(gen.GetGenomeAmtPtr(), amount.data(), sizeof(float) * (size_t)(ref_bins < n_amount ? ref_bins : n_amount));
     gmx_destroy(gGmx);
     gGmx = 0;
 }
