@@ -81,7 +81,6 @@ struct gmx_ctx {
     DevReads up_view[2];
     int32_t up_max_len[2] = {0, 0};
     DevReads dreads;
-    std::vector<int64_t> h_offsets;            // offsets of the last batch (for gmx_get_hits)
     // pipeline buffers
     DevBuf d_seed_code;
     DevBuf d_fq_text, d_fq_nl, d_fq_tmp, d_fq_seq_off, d_fq_qual_off, d_fq_len, d_fq_recs, d_fq_flags, d_fq_count;   // FASTQ indexer
@@ -257,7 +256,7 @@ static int build_tables(gmx_ctx *ctx)
     float *d = ctx->d_tables.as<float>();
     ctx->tab.sub_pos = d; ctx->tab.sub_neg = d + kLutFloats; ctx->tab.pwm_lut = d + 2 * kLutFloats;
     ctx->tab.phmm_pos = d + 3 * kLutFloats; ctx->tab.phmm_neg = d + 4 * kLutFloats;
-    ctx->tab.S = d + 5 * kLutFloats; ctx->tab.P = d + 5 * kLutFloats + 1024; ctx->tab.self_lut = nullptr;
+    ctx->tab.S = d + 5 * kLutFloats; ctx->tab.P = d + 5 * kLutFloats + 1024;
     return GMX_OK;
 }
 

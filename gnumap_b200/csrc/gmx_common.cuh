@@ -36,7 +36,6 @@ struct DevTables {
     const float *sub_pos;    // [5][GMX_NQ][4]  get_val(pwm(base,q), genome g) for the read as given
     const float *sub_neg;    // [5][GMX_NQ][4]  same for the reverse-complemented PWM row
     const float *pwm_lut;    // [5][GMX_NQ][4]  FASTQ -> PWM row
-    const float *self_lut;   // [5][GMX_NQ]     get_align_score_mid term for base codes 0..3 (4: see kernel)
     const float *phmm_pos;   // [5][GMX_NQ][4]  p_seq(pwm(base,q), genome g) (pair HMM emission)
     const float *phmm_neg;   // [5][GMX_NQ][4]
     const float *S;          // [256][4] gALIGN_SCORES

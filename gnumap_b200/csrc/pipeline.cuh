@@ -3,12 +3,17 @@
 //
 //   k_prep_reads      set_top_matches prologue           reference src/Driver.cpp:446-497
 //   k_seed_walk       align_sequence k-mer walk + K1     reference inc/align_seq2_raw.cpp:192-243
-//   k_vote_smem/_gmem K1b locate + K1c diagonal vote     reference inc/align_seq2_raw.cpp:262-274,28-35
+//   k_classify        tasks by SA-hit count -> filter / exact class lists
+//   k_vote_filter     K1b locate + K1c diagonal vote     reference inc/align_seq2_raw.cpp:262-274,28-35
+//                     (Bloom / counting filter + exact verification against the packed genome: the fast path)
+//   k_vote_smem/_gmem same, exact hash tables (kmin == 1, very long reads, > 16 k hits per task)
 //   k_cand_score      GetString + K2a                    reference inc/align_seq2_raw.cpp:43-64
+//   k_cand_ranges     candidate range of every read in the sorted key list
 //   k_finalize_reads  acceptance, grouping, denominator  reference inc/align_seq2_raw.cpp:95-165,
 //                     best group                          reference src/Driver.cpp:593-611,640-680
 //   k_traceback       K2b per group                      reference src/NormalScoredSeq.cpp:40-62
 //   k_scatter         K3                                 reference src/NormalScoredSeq.cpp:68-75 etc.
+//   k_gather_best / k_gather_multi   fixed-size per-read records, positions of multi-position best groups
 #pragma once
 
 #include "fm_index.cuh"
@@ -216,7 +221,7 @@ struct CandSink {
 
 __device__ __forceinline__ uint32_t gmx_hash32(uint32_t x) { return (x * 0x9E3779B1u) ^ (x >> 15); }
 
-template <bool GLOBAL_TABLE>
+// exact vote of one task with atomics on a table in global memory (k_vote_gmem: tasks beyond the shared-memory classes)
 __device__ __forceinline__ void gmx_vote_task(const DevIndex &ix, const SeedStore &S, uint32_t task, int kmin,
                                               uint32_t *keys, uint32_t *cnts, uint32_t mask, CandSink sink, int lane)
 {
@@ -748,7 +753,7 @@ __global__ void __launch_bounds__(128) k_vote_gmem(DevIndex ix, SeedStore S, Cla
         for (uint32_t x = lane; x < slots; x += 32) keys[x] = GMX_EMPTY_KEY;
         for (uint32_t x = lane; x < slots / 4; x += 32) cnts[x] = 0;
         __syncwarp();
-        gmx_vote_task<true>(ix, S, task, kmin, keys, cnts, slots - 1, sink, lane);
+        gmx_vote_task(ix, S, task, kmin, keys, cnts, slots - 1, sink, lane);
         __syncwarp();
     }
 }
@@ -779,13 +784,6 @@ __global__ void __launch_bounds__(128) k_cand_score(DevIndex ix, DevReads R, Dev
 }
 
 // ---- per-read finalisation ---------------------------------------------------------------------
-__device__ __forceinline__ uint32_t gmx_lower_bound(const unsigned long long *keys, uint32_t n, unsigned long long v)
-{
-    uint32_t lo = 0, hi = n;
-    while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (keys[mid] < v) lo = mid + 1; else hi = mid; }
-    return lo;
-}
-
 // base j of the read-orientation key string of candidate (diag, neg): POS = window[j];
 // NEG = complement(window[n-1-j])  (reference inc/align_seq2_raw.cpp:125-128)
 __device__ __forceinline__ int gmx_key_base(const DevIndex &ix, uint32_t diag, int neg, int n, int j)
