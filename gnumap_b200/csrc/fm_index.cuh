@@ -117,6 +117,33 @@ __device__ __forceinline__ bool gmx_match_exact_tab(const DevIndex &ix, int len,
     return true;
 }
 
+// The same search for a k-mer already packed 2 bits per base (first base most significant) with a mask of its
+// non-ACGT positions (bit t set <=> base t is not ACGT): the seed walk keeps both in a rolling window.
+__device__ __forceinline__ bool gmx_match_exact_packed(const DevIndex &ix, int len, unsigned long long code, unsigned long long bad,
+                                                       uint64_t &k_out, uint64_t &l_out, uint32_t &n_steps)
+{
+    if (bad) return false;                       // the reference stops at the first non-ACGT symbol: absent
+    const int T = ix.tab_len;
+    uint64_t k, l;
+    int i;
+    if (T > 0 && len >= T) {
+        const uint2 kl = __ldg(ix.kmer_tab + (uint32_t)(code & ((1ull << (2 * T)) - 1ull)));
+        if (kl.x > kl.y) return false;
+        k = kl.x; l = kl.y; i = len - T - 1;
+    } else { k = 0; l = ix.seq_len; i = len - 1; }
+    for (; i >= 0; --i) {
+        const uint32_t c = (uint32_t)(code >> (2 * (len - 1 - i))) & 3u;
+        n_steps++;
+        const uint64_t ok = gmx_bwt_occ(ix, k - 1, c);
+        const uint64_t ol = gmx_bwt_occ(ix, l, c);
+        k = ix.L2[c] + ok + 1;
+        l = ix.L2[c] + ol;
+        if (k > l) return false;
+    }
+    k_out = k; l_out = l;
+    return true;
+}
+
 // ---- kernels ---------------------------------------------------------------------------------
 
 // fill the memoised table: entry `code` = interval of the T-mer whose symbols are the base-4 digits of `code`

@@ -103,14 +103,31 @@ __global__ void k_seed_walk(DevIndex ix, DevReads R, DevParams P, const ReadPrep
             int c = gmx_nt4(seq[neg ? n - 1 - x : x]);
             return (uint32_t)((neg && c < 4) ? 3 - c : c);
         };
+        // rolling window: the k-mer at `wbase`, 2 bits per base (first base most significant), and its non-ACGT mask.
+        // The walk moves by one base after a miss and by `jump` after a hit, so a lookup usually adds <= jump bases.
+        const int mer = P.mer;
+        const unsigned long long wmask = mer < 32 ? ((1ull << (2 * mer)) - 1ull) : ~0ull, bmask = (1ull << mer) - 1ull;
+        unsigned long long wcode = 0, wbad = 0;
+        int wbase = -(1 << 20);                                   // nothing loaded
+        auto window_at = [&](int base) {
+            int d = base - wbase;
+            if (d < 0 || d >= mer) { d = mer; wcode = 0; wbad = 0; }
+            for (int t = mer - d; t < mer; ++t) {
+                const uint32_t c = sym_at(base + t);
+                wcode = (wcode << 2) | (unsigned long long)(c & 3u);
+                wbad = (wbad << 1) | (unsigned long long)(c > 3u);
+            }
+            wcode &= wmask; wbad &= bmask;
+            wbase = base;
+        };
         unsigned last = (unsigned)n - (unsigned)P.mer;
         for (unsigned i = 0; i < last; i += (unsigned)P.jump) {
             unsigned j;
             bool found = false;
             uint64_t k = 0, l = 0;
             for (j = 0; j + i < last; j++) {
-                unsigned base = i + j;
-                bool hit = gmx_match_exact_tab(ix, P.mer, [&](int t) { return sym_at((int)base + t); }, k, l, n_steps);
+                window_at((int)(i + j));
+                bool hit = gmx_match_exact_packed(ix, mer, wcode, wbad, k, l, n_steps);
                 n_lookups++;
                 if (!hit) continue;
                 if (P.max_kmer_hits > 0 && l - k + 1 > (uint64_t)P.max_kmer_hits) continue;
@@ -123,9 +140,7 @@ __global__ void k_seed_walk(DevIndex ix, DevReads R, DevParams P, const ReadPrep
                 S.rank[S.at(task, ns)] = (uint32_t)k;
                 S.count[S.at(task, ns)] = (uint32_t)(l - k + 1);
                 S.offset[S.at(task, ns)] = (uint16_t)i;
-                unsigned long long code = 0;
-                for (int t = 0; t < P.mer; ++t) code = (code << 2) | (unsigned long long)(sym_at((int)i + t) & 3u);
-                S.code[S.at(task, ns)] = code;
+                S.code[S.at(task, ns)] = wcode;                   // the window is at i: the k-mer just found
                 total += (uint32_t)(l - k + 1);
                 ns++;
             }
