@@ -2,6 +2,7 @@
 // and the batched PHASE A / PHASE B pipeline.  sm_100a only; there is no CPU fallback -- without a
 // CUDA device every entry point returns GMX_ERR_NO_DEVICE.
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include <algorithm>
 #include <thread>
@@ -119,6 +120,7 @@ struct gmx_ctx {
     int filter_shift = 0;                      // GMX_OPT_FILTER_SHIFT
     int n_sm = 148;
     DevBuf d_ranges;                           // candidate range per read
+    DevBuf d_groups, d_read_base;              // groups per read and their exclusive scan (leader slots)
     DevBuf d_multi, d_multi_count;             // (read, pos, strand) of multi-position best groups (fast path)
     std::vector<MultiPos> h_multi;
     std::vector<int64_t> h_seq_offset;         // host copy of the sequence offsets (+ l_pac) for pos -> chromosome
@@ -400,7 +402,7 @@ extern "C" void gmx_destroy(gmx_ctx *ctx)
                       &ctx->d_seed_count, &ctx->d_seed_off, &ctx->d_seed_n, &ctx->d_seed_hits, &ctx->d_cls_list, &ctx->d_cls_meta,
                       &ctx->d_keys, &ctx->d_keys_alt, &ctx->d_sort_tmp, &ctx->d_score, &ctx->d_leader, &ctx->d_slot, &ctx->d_lead_cand,
                       &ctx->d_hashes, &ctx->d_expv, &ctx->d_counters, &ctx->d_results, &ctx->d_alen, &ctx->d_aligned, &ctx->d_cigar,
-                      &ctx->d_hmm, &ctx->d_moves, &ctx->d_arena, &ctx->d_phmm_scratch, &ctx->d_best_cigar[0], &ctx->d_best_cigar[1], &ctx->d_out_results[0], &ctx->d_out_results[1], &ctx->d_seed_code, &ctx->d_kmer_tab, &ctx->d_multi, &ctx->d_multi_count, &ctx->d_ranges, &ctx->d_fq_text, &ctx->d_fq_nl, &ctx->d_fq_tmp, &ctx->d_fq_seq_off, &ctx->d_fq_qual_off, &ctx->d_fq_len, &ctx->d_fq_recs, &ctx->d_fq_flags, &ctx->d_fq_count};
+                      &ctx->d_hmm, &ctx->d_moves, &ctx->d_arena, &ctx->d_phmm_scratch, &ctx->d_best_cigar[0], &ctx->d_best_cigar[1], &ctx->d_out_results[0], &ctx->d_out_results[1], &ctx->d_seed_code, &ctx->d_kmer_tab, &ctx->d_multi, &ctx->d_multi_count, &ctx->d_ranges, &ctx->d_groups, &ctx->d_read_base, &ctx->d_fq_text, &ctx->d_fq_nl, &ctx->d_fq_tmp, &ctx->d_fq_seq_off, &ctx->d_fq_qual_off, &ctx->d_fq_len, &ctx->d_fq_recs, &ctx->d_fq_flags, &ctx->d_fq_count};
     for (DevBuf *b : bufs) b->release();
     ctx->h_best_cigar.release();
     if (ctx->ev[0][0]) for (int s = 0; s < ST_COUNT; ++s) { cudaEventDestroy(ctx->ev[s][0]); cudaEventDestroy(ctx->ev[s][1]); }
@@ -940,12 +942,24 @@ static int phase_a(gmx_ctx *ctx, const gmx_reads *reads, int32_t lo, int32_t hi,
     O.hashes = ctx->d_hashes.as<uint64_t>(); O.expv = ctx->d_expv.as<double>();
     CK(ctx->d_ranges.ensure((size_t)n * 8));
     O.range = ctx->d_ranges.as<uint32_t>();
+    CK(ctx->d_groups.ensure((size_t)n * 4 + 16)); CK(ctx->d_read_base.ensure((size_t)n * 4 + 16));
+    O.groups_per_read = ctx->d_groups.as<uint32_t>();
     stage_begin(ctx, ST_FINALIZE);
+    CK(cudaMemsetAsync(ctx->d_groups.p, 0, (size_t)n * 4, ctx->stream));
     CK(cudaMemsetAsync(ctx->d_ranges.p, 0, (size_t)n * 8, ctx->stream));
     if (n_cand) { k_cand_ranges<<<nblk(n_cand, 256), 256, 0, ctx->stream>>>(keys, n_cand, ctx->d_ranges.as<uint32_t>()); CK(cudaGetLastError()); }
     k_finalize_reads<<<nblk((int64_t)n * 32, 128), 128, 0, ctx->stream>>>(ctx->ix, ctx->dreads, P, ctx->d_prep.as<ReadPrep>(), keys, ctx->d_score.as<float>(), n_cand, O);
     CK(cudaGetLastError());
-    stage_end(ctx, ST_FINALIZE, (uint64_t)n, 0, 2);
+    if (n_cand) {
+        size_t scan_bytes = 0;
+        CK(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, ctx->d_groups.as<uint32_t>(), ctx->d_read_base.as<uint32_t>(), (int)n, ctx->stream));
+        CK(ctx->d_sort_tmp.ensure(scan_bytes));
+        CK(cub::DeviceScan::ExclusiveSum(ctx->d_sort_tmp.p, scan_bytes, ctx->d_groups.as<uint32_t>(), ctx->d_read_base.as<uint32_t>(), (int)n, ctx->stream));
+        k_assign_slots<<<nblk(n_cand, 256), 256, 0, ctx->stream>>>(keys, ctx->d_leader.as<int32_t>(), ctx->d_slot.as<int32_t>(), ctx->d_read_base.as<uint32_t>(),
+                                                                  ctx->d_lead_cand.as<uint32_t>(), n_cand, &dc->n_leaders, &dc->n_accepted);
+        CK(cudaGetLastError());
+    }
+    stage_end(ctx, ST_FINALIZE, (uint64_t)n, 0, 4);
 
     CK(cudaMemcpyAsync(&hc.c, dc, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));

@@ -835,6 +835,41 @@ __global__ void k_cand_ranges(const unsigned long long *keys, uint32_t n_cand, u
     if (c + 1 == n_cand || (uint32_t)(keys[c + 1] >> 41) != r) range[2 * r + 1] = c + 1;
 }
 
+__device__ __forceinline__ double gmx_shfl_f64(double v, int src)
+{
+    int lo = __double2loint(v), hi = __double2hiint(v);
+    lo = __shfl_sync(0xffffffffu, lo, src); hi = __shfl_sync(0xffffffffu, hi, src);
+    return __hiloint2double(hi, lo);
+}
+__device__ __forceinline__ double gmx_shfl_xor_f64(double v, int mask)
+{
+    int lo = __double2loint(v), hi = __double2hiint(v);
+    lo = __shfl_xor_sync(0xffffffffu, lo, mask); hi = __shfl_xor_sync(0xffffffffu, hi, mask);
+    return __hiloint2double(hi, lo);
+}
+
+// leader rank within the read -> leader slot: slot = read_base[read] + rank (read_base = exclusive scan of the reads'
+// group counts); also counts the leaders and the accepted candidates of the chunk
+__global__ void __launch_bounds__(256) k_assign_slots(const unsigned long long *keys, const int32_t *leader, int32_t *slot, const uint32_t *read_base,
+                                                      uint32_t *lead_cand, uint32_t n_cand, uint32_t *n_leaders, uint32_t *n_accepted)
+{
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool in = c < n_cand;
+    const bool acc = in && leader[c] >= 0;
+    const bool lead = acc && slot[c] >= 0;
+    if (lead) {
+        const uint32_t r = (uint32_t)(keys[c] >> 41);
+        const uint32_t s = read_base[r] + (uint32_t)slot[c];
+        slot[c] = (int32_t)s;
+        lead_cand[s] = c;
+    }
+    const uint32_t am = __ballot_sync(0xffffffffu, acc), lm = __ballot_sync(0xffffffffu, lead);
+    if ((threadIdx.x & 31) == 0) {
+        if (am) atomicAdd(n_accepted, (uint32_t)__popc(am));
+        if (lm) atomicAdd(n_leaders, (uint32_t)__popc(lm));
+    }
+}
+
 struct FinalizeOut {
     gmx_read_result *results;   // [n_reads]
     int32_t *leader;            // [n_cand] candidate index of the group leader, or -1 (not accepted)
@@ -842,6 +877,7 @@ struct FinalizeOut {
     uint32_t *lead_cand;        // [lead_cap] candidate index per leader slot
     uint32_t *n_leaders;
     uint32_t *n_accepted;
+    uint32_t *groups_per_read;  // [n_reads] distinct accepted genome strings of the read (0 when not mapped)
     uint64_t *hashes;           // [n_cand] scratch: key hash of accepted candidates
     double   *expv;             // [n_cand] scratch: exp(score) of accepted candidates
     const uint32_t *range;      // [2 * n_reads] candidate range of every read (k_cand_ranges)
@@ -865,6 +901,104 @@ __global__ void __launch_bounds__(128) k_finalize_reads(DevIndex ix, DevReads R,
     if (pr.status == GMX_READ_TOO_POOR) { res.top_score = -3; if (lane == 0) O.results[r] = res; return; }
     const int n = gmx_read_len(R, r);
     const uint32_t lo = O.range[2 * r], hi = O.range[2 * r + 1];
+
+    if (hi - lo <= 32u) {
+        // ---- common case: at most one candidate per lane, everything stays in registers (no round trips through the
+        // scratch arrays between the passes) -- same decisions, same order of the FP64 sums
+        const uint32_t cnt = hi - lo;
+        const uint32_t c = lo + (uint32_t)lane;
+        const bool in = (uint32_t)lane < cnt;
+        const float sc = in ? score[c] : 0.f;
+        uint32_t task = 0, round = 0, diag = 0;
+        if (in) gmx_decode_key(keys[c], task, round, diag);
+        const bool valid = in && !isnan(sc);
+        const bool acc = valid && ((double)sc >= pr.min_align);
+        const uint32_t accm = __ballot_sync(0xffffffffu, acc);
+        const int n_acc = __popc(accm);
+        res.n_candidates = __popc(__ballot_sync(0xffffffffu, valid));
+        double top = (valid && (double)sc > 0.0) ? (double)sc : 0.0;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) { double t = __shfl_xor_sync(0xffffffffu, top, o); if (t > top) top = t; }
+        if (n_acc == 0) {
+            res.status = GMX_READ_UNMATCHED;
+            if (in) { O.leader[c] = -1; O.slot[c] = -1; }
+            if (lane == 0) O.results[r] = res;
+            return;
+        }
+        // group leaders: first accepted candidate (processing order) with the same key string
+        int lead_lane = lane;
+        if (n_acc > 1) {
+            const uint64_t h = acc ? gmx_key_hash(ix, diag, (int)(task & 1), n) : 0ull;
+            bool open = acc;
+            for (uint32_t m = accm; m; m &= m - 1) {
+                const int p = __ffs(m) - 1;
+                const uint64_t hp = __shfl_sync(0xffffffffu, h, p);
+                const uint32_t dp = __shfl_sync(0xffffffffu, diag, p), tp = __shfl_sync(0xffffffffu, task, p);
+                if (open && p < lane && hp == h && gmx_key_compare(ix, diag, (int)(task & 1), dp, (int)(tp & 1), n) == 0) { lead_lane = p; open = false; }
+            }
+        }
+        const bool lead = acc && lead_lane == lane;
+        const uint32_t leadm = __ballot_sync(0xffffffffu, lead);
+        const int n_groups = __popc(leadm), joined = n_acc - n_groups;
+        if ((P.unique_only && joined > 0) || (uint32_t)n_groups > P.max_matches) {
+            res.status = GMX_READ_TOO_MANY; res.top_score = 999999; res.denominator = 0; res.n_groups = 0;
+            if (in) { O.leader[c] = -1; O.slot[c] = -1; }
+            if (lane == 0) O.results[r] = res;
+            return;
+        }
+        // denominator: exp(score) of every accepted candidate, added in processing order (one FP64 exp per lane: the
+        // same value serves the denominator, the best-group comparison and the posterior)
+        const double ev = acc ? exp((double)sc) : 0.0;
+        double denom = 0.0;
+        for (uint32_t m = accm; m; m &= m - 1) denom = __dadd_rn(denom, gmx_shfl_f64(ev, __ffs(m) - 1));
+        // best group: largest exp(score), strict >, groups visited in key order, starting from exp(-1)
+        const double e_floor = exp(-1.0);
+        const bool cand = lead && ev > e_floor;
+        double best_e = cand ? ev : 0.0;
+        float best_sc = cand ? sc : -1.0f;
+        int best_lane = cand ? lane : -1;
+        uint32_t best_diag = diag, best_task = task;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            const double oe = gmx_shfl_xor_f64(best_e, o);
+            const float osc = __shfl_xor_sync(0xffffffffu, best_sc, o);
+            const int ol = __shfl_xor_sync(0xffffffffu, best_lane, o);
+            const uint32_t od = __shfl_xor_sync(0xffffffffu, best_diag, o), ot = __shfl_xor_sync(0xffffffffu, best_task, o);
+            bool better = false;
+            if (ol >= 0) {
+                if (best_lane < 0 || oe > best_e) better = true;
+                else if (oe == best_e && ol != best_lane)
+                    better = gmx_key_compare(ix, od, (int)(ot & 1), best_diag, (int)(best_task & 1), n) < 0;
+            }
+            if (better) { best_e = oe; best_sc = osc; best_lane = ol; best_diag = od; best_task = ot; }
+        }
+        // leader slots + per-candidate outputs for PHASE B
+        // slot[] holds the leader's rank within its read here; k_assign_slots adds the read's base (an exclusive scan
+        // of groups_per_read) -- no same-address atomic per read
+        if (in) {
+            O.leader[c] = acc ? (int32_t)(lo + (uint32_t)lead_lane) : -1;
+            O.slot[c] = lead ? (int32_t)__popc(leadm & ((1u << lane) - 1u)) : -1;
+        }
+        if (lane == 0) O.groups_per_read[r] = (uint32_t)n_groups;
+        res.status = GMX_READ_MAPPED;
+        res.top_score = top; res.denominator = denom; res.n_groups = n_groups;
+        res.hit_begin = (int32_t)lo; res.hit_end = (int32_t)hi;
+        if (best_lane >= 0) {
+            const bool mem = acc && lead_lane == best_lane;
+            const int members = __popc(__ballot_sync(0xffffffffu, mem));
+            uint64_t first = mem ? (((uint64_t)diag << 1) | (task & 1)) : ~0ull;
+#pragma unroll
+            for (int o = 16; o; o >>= 1) { uint64_t t = __shfl_xor_sync(0xffffffffu, first, o); if (t < first) first = t; }
+            res.best_group = best_lane;
+            res.best_score = best_sc;
+            res.best_posterior = (float)(best_e / denom);
+            res.best_n_positions = members;
+            res.best_first_strand = (int)(best_task & 1);
+            res.best_first_pos = first >> 1;
+        }
+        if (lane == 0) O.results[r] = res;
+        return;
+    }
 
     // pass 1: validity, top score, acceptance, exp(score), key hash
     int n_valid = 0, n_acc = 0;
@@ -988,19 +1122,16 @@ __global__ void __launch_bounds__(128) k_finalize_reads(DevIndex ix, DevReads R,
         if (better) { best_sc = osc; best_c = oc; }
     }
 
-    // leader slots (any order) + counts
+    // leader ranks within the read (k_assign_slots turns them into slots)
+    uint32_t rank_base = 0;
     for (uint32_t c0 = lo; c0 < hi; c0 += 32) {
         uint32_t c = c0 + lane;
         bool lead = (c < hi) && O.leader[c] == (int32_t)c;
         uint32_t m = __ballot_sync(0xffffffffu, lead);
-        if (m) {
-            uint32_t base = 0;
-            if (lane == 0) base = atomicAdd(O.n_leaders, (uint32_t)__popc(m));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (lead) { uint32_t s = base + (uint32_t)__popc(m & ((1u << lane) - 1u)); O.slot[c] = (int32_t)s; O.lead_cand[s] = c; }
-        }
+        if (lead) O.slot[c] = (int32_t)(rank_base + (uint32_t)__popc(m & ((1u << lane) - 1u)));
+        rank_base += (uint32_t)__popc(m);
     }
-    if (lane == 0) atomicAdd(O.n_accepted, (uint32_t)n_acc);
+    if (lane == 0) O.groups_per_read[r] = (uint32_t)n_groups;
 
     res.status = GMX_READ_MAPPED;
     res.top_score = top; res.denominator = denom; res.n_groups = n_groups;
