@@ -495,10 +495,15 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_vote_filter(DevIndex ix, uint
 
     // seeds of a task in registers: seed `lane` and seed `lane + 32`; fetched one task ahead
     struct Meta { uint32_t task; int ns; uint32_t rank[2], cnt[2], off[2]; unsigned long long code[2]; };
+    // tasks are taken GRAB at a time: one same-address atomic per task would serialise 2 M returning atomics per step
+    constexpr uint32_t GRAB = 4;
+    uint32_t w_pos = 0, w_end = 0;
     auto next_work = [&]() -> uint32_t {
+        if (w_pos + 1 < w_end) return ++w_pos;
         uint32_t w = 0;
-        if (lane == 0) w = atomicAdd(&F.cursor[cls], 1u);
-        return __shfl_sync(0xffffffffu, w, 0);
+        if (lane == 0) w = atomicAdd(&F.cursor[cls], GRAB);
+        w_pos = __shfl_sync(0xffffffffu, w, 0); w_end = w_pos + GRAB;
+        return w_pos;
     };
     auto fetch = [&](uint32_t w, Meta &m) {
         m.task = list[w];
@@ -513,6 +518,19 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_vote_filter(DevIndex ix, uint
         }
     };
 
+    uint32_t ne = 0;                                             // emitted keys waiting in fs->outb (kept across tasks)
+    auto flush = [&]() {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(sink.count, ne);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        __syncwarp();
+        if ((uint32_t)lane < ne) {
+            if (base + lane < sink.cap) sink.keys[base + lane] = fs->outb[lane];
+            else *sink.overflow = 1u;
+        }
+        __syncwarp();
+        ne = 0;
+    };
     Meta cur, nxt;
     uint32_t w = next_work();
     if (w < n_list) fetch(w, cur);
@@ -551,7 +569,6 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_vote_filter(DevIndex ix, uint
         // may not hold another step (repeat-rich reads) and once at the end; a diagonal drained twice is emitted twice
         // with the same key and dropped after the sort (k_cand_score).
         uint32_t qn = 0;
-        uint32_t ne = 0;
         auto drain = [&]() {
             // distinct queued diagonals, compacted in place (a diagonal is queued once per k-mer that hits it)
             uint32_t n2 = 0;
@@ -573,18 +590,6 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_vote_filter(DevIndex ix, uint
             uint32_t limit[2];
 #pragma unroll
             for (int h = 0; h < 2; ++h) limit[h] = (uint32_t)ix.seq_len - cur.off[h] - (uint32_t)mer;
-            auto flush = [&]() {
-                uint32_t base = 0;
-                if (lane == 0) base = atomicAdd(sink.count, ne);
-                base = __shfl_sync(0xffffffffu, base, 0);
-                __syncwarp();
-                if ((uint32_t)lane < ne) {
-                    if (base + lane < sink.cap) sink.keys[base + lane] = fs->outb[lane];
-                    else *sink.overflow = 1u;
-                }
-                __syncwarp();
-                ne = 0;
-            };
             const uint32_t *pac32 = reinterpret_cast<const uint32_t *>(ix.pac);
             for (uint32_t q0 = 0; q0 < n2; q0 += 4) {
                 uint32_t d[4], raw[4];
@@ -618,7 +623,6 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_vote_filter(DevIndex ix, uint
                     }
                 }
             }
-            if (ne) flush();
             qn = 0;
         };
         int s_cur = 0; uint32_t t_cur = 0;
@@ -735,6 +739,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_vote_filter(DevIndex ix, uint
         __syncwarp();
         cur = nxt;
     }
+    if (ne) flush();
 }
 
 // Tasks whose hit count exceeds the largest shared-memory table (repeat-rich reads): same insert
