@@ -1025,7 +1025,7 @@ static int phase_b(gmx_ctx *ctx)
         stage_end(ctx, ST_PHMM, (uint64_t)n_leaders * (uint64_t)max_len * (uint64_t)max_len, 0, launches);
     }
     stage_begin(ctx, ST_SCATTER);
-    k_scatter<<<nblk((int64_t)n_cand * 32, 128), 128, 0, ctx->stream>>>(ctx->ix, ctx->dreads, P, cs.keys, ctx->d_score.as<float>(), ctx->d_leader.as<int32_t>(),
+    k_scatter<<<nblk(n_cand, 128), 128, 0, ctx->stream>>>(ctx->ix, ctx->dreads, P, cs.keys, ctx->d_score.as<float>(), ctx->d_leader.as<int32_t>(),
                                                                         ctx->d_slot.as<int32_t>(), n_cand, ctx->d_results.as<gmx_read_result>(), L, ctx->acc);
     CK(cudaGetLastError());
     // per accepted (position, strand): one float RMW per aligned base and plane, Normal mode

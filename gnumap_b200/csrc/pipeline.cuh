@@ -1207,11 +1207,15 @@ __global__ void __launch_bounds__(128) k_scatter(DevIndex ix, DevReads R, DevPar
                                                  const float *score, const int32_t *leader, const int32_t *slot, uint32_t n_cand,
                                                  const gmx_read_result *results, LeaderStore L, Accum A)
 {
-    uint32_t c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    int lane = threadIdx.x & 31;
-    if (c >= n_cand) return;
-    int32_t ld = leader[c];
-    if (ld < 0) return;
+    // a warp owns 32 consecutive candidates and scatters the accepted ones in turn with all its lanes (most
+    // candidates are not accepted: a warp per candidate would launch four idle warps for every working one)
+    const uint32_t c_lane = (blockIdx.x * blockDim.x + threadIdx.x);
+    const int lane = threadIdx.x & 31;
+    const int32_t ld_lane = c_lane < n_cand ? leader[c_lane] : -1;
+    for (uint32_t todo = __ballot_sync(0xffffffffu, ld_lane >= 0); todo; todo &= todo - 1) {
+    const int src = __ffs(todo) - 1;
+    const uint32_t c = (c_lane & ~31u) + (uint32_t)src;
+    const int32_t ld = __shfl_sync(0xffffffffu, ld_lane, src);
     uint32_t task, round, diag, tl, rl, dl;
     gmx_decode_key(keys[c], task, round, diag);
     gmx_decode_key(keys[ld], tl, rl, dl);
@@ -1235,7 +1239,7 @@ __global__ void __launch_bounds__(128) k_scatter(DevIndex ix, DevReads R, DevPar
                 atomicAdd(&A.planes[b][p / P.gen_size], __fmul_rn(v, total));
             }
         }
-        return;
+        continue;
     }
     int alen = L.alen[s];
     const uint8_t *al = L.aligned + (size_t)s * L.a_stride;
@@ -1255,6 +1259,7 @@ __global__ void __launch_bounds__(128) k_scatter(DevIndex ix, DevReads R, DevPar
             if (!same && code < 4) code = 3 - code;
             if (code < 5) atomicAdd(&A.planes[code][bin], total);
         }
+    }
     }
 }
 
