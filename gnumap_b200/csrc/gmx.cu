@@ -96,6 +96,7 @@ struct gmx_ctx {
     std::vector<gmx_read_result> h_results;
     std::vector<gmx_hit> h_hits;
     HostBuf h_best_cigar;                      // pinned [n_reads][GMX_CIGAR_STRIDE]
+    HostBuf h_counters;                        // pinned staging of the per-chunk device counters
     std::vector<uint8_t> h_best_aligned;       // [n_reads][a_stride]  (collect_hits only)
     int h_a_stride = 0;
     // state of the chunk whose PHASE A results are resident on the device
@@ -121,7 +122,8 @@ struct gmx_ctx {
     int n_sm = 148;
     DevBuf d_ranges;                           // candidate range per read
     DevBuf d_groups, d_read_base;              // groups per read and their exclusive scan (leader slots)
-    DevBuf d_multi, d_multi_count;             // (read, pos, strand) of multi-position best groups (fast path)
+    DevBuf d_multi, d_multi_count;             // (read, pos, strand) of multi-position best groups (fast path), whole batch
+    uint32_t multi_cap = 0; bool multi_overflow = false;
     std::vector<MultiPos> h_multi;
     std::vector<int64_t> h_seq_offset;         // host copy of the sequence offsets (+ l_pac) for pos -> chromosome
     DevBuf d_best_cigar[2], d_out_results[2];  // staging of the fast download path, double-buffered
@@ -405,6 +407,7 @@ extern "C" void gmx_destroy(gmx_ctx *ctx)
                       &ctx->d_hmm, &ctx->d_moves, &ctx->d_arena, &ctx->d_phmm_scratch, &ctx->d_best_cigar[0], &ctx->d_best_cigar[1], &ctx->d_out_results[0], &ctx->d_out_results[1], &ctx->d_seed_code, &ctx->d_kmer_tab, &ctx->d_multi, &ctx->d_multi_count, &ctx->d_ranges, &ctx->d_groups, &ctx->d_read_base, &ctx->d_fq_text, &ctx->d_fq_nl, &ctx->d_fq_tmp, &ctx->d_fq_seq_off, &ctx->d_fq_qual_off, &ctx->d_fq_len, &ctx->d_fq_recs, &ctx->d_fq_flags, &ctx->d_fq_count};
     for (DevBuf *b : bufs) b->release();
     ctx->h_best_cigar.release();
+    ctx->h_counters.release();
     if (ctx->ev[0][0]) for (int s = 0; s < ST_COUNT; ++s) { cudaEventDestroy(ctx->ev[s][0]); cudaEventDestroy(ctx->ev[s][1]); }
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
     if (ctx->d2h_stream) { cudaStreamSynchronize(ctx->d2h_stream); cudaStreamDestroy(ctx->d2h_stream); }
@@ -834,7 +837,9 @@ static int phase_a(gmx_ctx *ctx, const gmx_reads *reads, int32_t lo, int32_t hi,
     CK(cudaGetLastError());
     stage_end(ctx, ST_SEED, 0, 0, 1);
 
-    struct { Counters c; ChunkStats s; } hc;
+    struct HostCounters { Counters c; ChunkStats s; };
+    CK(ctx->h_counters.ensure(sizeof(HostCounters)));
+    HostCounters &hc = *ctx->h_counters.as<HostCounters>();          // pinned: the two small D2H copies per chunk stay asynchronous
     uint32_t n_cand = 0;
     for (int attempt = 0;; ++attempt) {
         CK(cudaMemsetAsync(dc, 0, sizeof(Counters), ctx->stream));
@@ -1051,21 +1056,10 @@ static int download_chunk(gmx_ctx *ctx, bool scored, gmx_read_result *results_ou
         CK(ctx->d_best_cigar[sl].ensure((size_t)std::max(n, 1) * GMX_CIGAR_STRIDE));
         CK(ctx->d_out_results[sl].ensure((size_t)std::max(n, 1) * sizeof(gmx_read_result)));
         CK(cudaStreamWaitEvent(ctx->stream, ctx->dl_ev[sl], 0));            // the staging slot's previous copy has left
-        if (scored && n_cand) {                                             // positions of multi-position best groups (SAM row)
-            CK(ctx->d_multi.ensure((size_t)n_cand * sizeof(MultiPos))); CK(ctx->d_multi_count.ensure(16));
-            CK(cudaMemsetAsync(ctx->d_multi_count.p, 0, 4, ctx->stream));
+        if (scored && n_cand && ctx->multi_cap) {                           // positions of multi-position best groups (SAM row)
             k_gather_multi<<<nblk(n_cand, 256), 256, 0, ctx->stream>>>(cs.keys, ctx->d_leader.as<int32_t>(), n_cand, ctx->d_results.as<gmx_read_result>(),
-                                                                      lo, ctx->d_multi.as<MultiPos>(), ctx->d_multi_count.as<uint32_t>(), n_cand);
+                                                                      lo, ctx->d_multi.as<MultiPos>(), ctx->d_multi_count.as<uint32_t>(), ctx->multi_cap);
             CK(cudaGetLastError());
-            uint32_t nm = 0;
-            CK(cudaMemcpyAsync(&nm, ctx->d_multi_count.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
-            CK(cudaStreamSynchronize(ctx->stream));
-            if (nm) {
-                size_t at = ctx->h_multi.size();
-                ctx->h_multi.resize(at + nm);
-                CK(cudaMemcpyAsync(ctx->h_multi.data() + at, ctx->d_multi.p, (size_t)nm * sizeof(MultiPos), cudaMemcpyDeviceToHost, ctx->stream));
-                CK(cudaStreamSynchronize(ctx->stream));
-            }
         }
         k_gather_best<<<nblk(n, 128), 128, 0, ctx->stream>>>(ctx->d_results.as<gmx_read_result>(), ctx->d_out_results[sl].as<gmx_read_result>(), n,
                                                            ctx->d_slot.as<int32_t>(), L, ctx->d_best_cigar[sl].as<char>(), GMX_CIGAR_STRIDE,
@@ -1161,6 +1155,12 @@ static int run_batch(gmx_ctx *ctx, const gmx_reads *reads, gmx_read_result *resu
     ctx->h_results.assign(ctx->collect_hits || !results ? (size_t)n : 0, gmx_read_result());
     ctx->h_hits.clear();
     ctx->h_multi.clear();
+    ctx->multi_overflow = false; ctx->multi_cap = 0;
+    if (!ctx->collect_hits && do_score && n > 0) {
+        ctx->multi_cap = (uint32_t)std::min<int64_t>(4ll * n + 65536, 0x7fffffffll);
+        CK(ctx->d_multi.ensure((size_t)ctx->multi_cap * sizeof(MultiPos))); CK(ctx->d_multi_count.ensure(16));
+        CK(cudaMemsetAsync(ctx->d_multi_count.p, 0, 4, ctx->stream));
+    }
     ctx->h_a_stride = max_len + 2 * ctx->params.max_gap + 8;
     CK(ctx->h_best_cigar.ensure((size_t)std::max(n, 1) * GMX_CIGAR_STRIDE));
     if (ctx->collect_hits) {
@@ -1196,6 +1196,13 @@ static int run_batch(gmx_ctx *ctx, const gmx_reads *reads, gmx_read_result *resu
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaStreamSynchronize(ctx->d2h_stream));
     stage_collect(ctx);
+    if (ctx->multi_cap) {                                                   // the batch's multi-position list: one small copy
+        uint32_t nm = 0;
+        CK(cudaMemcpy(&nm, ctx->d_multi_count.p, 4, cudaMemcpyDeviceToHost));
+        if (nm > ctx->multi_cap) { ctx->multi_overflow = true; nm = ctx->multi_cap; }
+        ctx->h_multi.resize(nm);
+        if (nm) CK(cudaMemcpy(ctx->h_multi.data(), ctx->d_multi.p, (size_t)nm * sizeof(MultiPos), cudaMemcpyDeviceToHost));
+    }
     ctx->mapped = true; ctx->scored = do_score;
     return GMX_OK;
 }
@@ -1234,6 +1241,12 @@ extern "C" int gmx_score_batch(gmx_ctx *ctx, gmx_read_result *results)
     if (ctx->last_n_reads == 0) { ctx->scored = true; return GMX_OK; }
     if (ctx->cs.valid) {
         ctx->h_hits.clear();
+        ctx->h_multi.clear(); ctx->multi_overflow = false; ctx->multi_cap = 0;
+        if (!ctx->collect_hits) {
+            ctx->multi_cap = (uint32_t)std::min<int64_t>(4ll * ctx->last_n_reads + 65536, 0x7fffffffll);
+            CK(ctx->d_multi.ensure((size_t)ctx->multi_cap * sizeof(MultiPos))); CK(ctx->d_multi_count.ensure(16));
+            CK(cudaMemsetAsync(ctx->d_multi_count.p, 0, 4, ctx->stream));
+        }
         int r = phase_b(ctx);
         if (r != GMX_OK) return r;
         r = download_chunk(ctx, true, results);
@@ -1241,6 +1254,13 @@ extern "C" int gmx_score_batch(gmx_ctx *ctx, gmx_read_result *results)
         CK(cudaStreamSynchronize(ctx->stream));
         CK(cudaStreamSynchronize(ctx->d2h_stream));
         stage_collect(ctx);
+        if (ctx->multi_cap) {
+            uint32_t nm = 0;
+            CK(cudaMemcpy(&nm, ctx->d_multi_count.p, 4, cudaMemcpyDeviceToHost));
+            if (nm > ctx->multi_cap) { ctx->multi_overflow = true; nm = ctx->multi_cap; }
+            ctx->h_multi.resize(nm);
+            if (nm) CK(cudaMemcpy(ctx->h_multi.data(), ctx->d_multi.p, (size_t)nm * sizeof(MultiPos), cudaMemcpyDeviceToHost));
+        }
         ctx->cs.valid = false; ctx->scored = true;
         return GMX_OK;
     }
@@ -1569,6 +1589,7 @@ extern "C" int gmx_format_sam(gmx_ctx *ctx, const char *text, const gmx_fastq_re
 {
     if (!ctx || !text || !recs || !results || !chrom_names || !len || n_reads < 0 || (cap > 0 && !out)) return GMX_ERR_INVALID;
     if (!ctx->scored || n_reads != ctx->last_n_reads) { ctx->err = "gmx_format_sam formats the batch last scored"; return GMX_ERR_STATE; }
+    if (!ctx->collect_hits && ctx->multi_overflow) { ctx->err = "more multi-position hits than the fast path keeps (4 per read): set GMX_OPT_COLLECT_HITS"; return GMX_ERR_OVERFLOW; }
     // positions of the multi-position best groups: from the hit list (collect mode) or from the device list (fast path)
     std::vector<int64_t> multi_index((size_t)n_reads, -1);
     std::vector<std::vector<SamPos>> multi_of;
