@@ -568,7 +568,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_vote_filter(DevIndex ix, uint
         // queue -> candidates: distinct queued diagonals, exact votes from the genome, emission.  Runs whenever the queue
         // may not hold another step (repeat-rich reads) and once at the end; a diagonal drained twice is emitted twice
         // with the same key and dropped after the sort (k_cand_score).
-        uint32_t qn = 0;
+        uint32_t qn = 0, d0_hits = 0;
         auto drain = [&]() {
             // distinct queued diagonals, compacted in place (a diagonal is queued once per k-mer that hits it)
             uint32_t n2 = 0;
@@ -636,7 +636,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_vote_filter(DevIndex ix, uint
         };
         if (ns > 0) issue(0, 0, sa_nxt);
         do {                                                           // pass-1 segments separated by queue drains (one drain site)
-        while (s_cur < ns && qn <= GMX_FQ_CAP - 32u * U) {        // room for one more step of flagged hits
+        while (s_cur < ns && qn < GMX_FQ_CAP - 32u * U) {         // room for one more step of flagged hits and diagonal 0
             uint32_t sa[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) sa[u] = sa_nxt[u];
@@ -646,28 +646,24 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_vote_filter(DevIndex ix, uint
             if (t_n >= fs->cnt[s_cur]) { s_n = s_cur + 1; t_n = 0; }
             if (s_n < ns) issue(s_n, t_n, sa_nxt);
 
-            uint32_t diag[U], inc[U];
+            uint32_t diag[U];
             bool valid[U];
-            bool any_clamp = false;
+            uint32_t lowest = sa[0];                                // invalid lanes hold 0xffffffff
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 valid[u] = sa[u] != GMX_SA_INVALID;
-                const bool clamp = valid[u] && sa[u] <= off;
-                any_clamp |= clamp;
-                diag[u] = clamp ? 0u : sa[u] - off;
-                inc[u] = 1;
+                diag[u] = sa[u] - off;
+                if (u) lowest = min(lowest, sa[u]);
             }
-            if (__any_sync(0xffffffffu, any_clamp)) {              // hits on diagonal 0: one lane votes for all of them
-                uint32_t total = 0; int first_u = -1, first_lane = -1;
+            // hits clamped to diagonal 0 (sa <= off: only at the very start of the genome) bypass the filter: they are
+            // counted per task and diagonal 0 is verified exactly from the genome once, at the task's last drain
+            if (__any_sync(0xffffffffu, lowest <= off)) {
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    const uint32_t cm = __ballot_sync(0xffffffffu, valid[u] && sa[u] <= off);
-                    if (cm && first_u < 0) { first_u = u; first_lane = __ffs(cm) - 1; }
-                    total += (uint32_t)__popc(cm);
+                    const bool clamp = valid[u] && sa[u] <= off;
+                    d0_hits += (uint32_t)__popc(__ballot_sync(0xffffffffu, clamp));
+                    valid[u] = valid[u] && !clamp;
                 }
-#pragma unroll
-                for (int u = 0; u < U; ++u)
-                    if (valid[u] && sa[u] <= off) { valid[u] = (u == first_u && lane == first_lane); inc[u] = total; }
             }
             bool flag[U];
             if (BITS) {
@@ -688,17 +684,23 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_vote_filter(DevIndex ix, uint
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     pd[u] = (o[u] & b[u]) != b[u];                       // invalid lanes read all-ones: never pending
-                    flag[u] = valid[u] && (!pd[u] || inc[u] >= 2u);
+                    flag[u] = valid[u] && !pd[u];
                 }
                 // plain stores; a lane whose bits were overwritten by a neighbour's store to the same word (a few
                 // lanes per step) repairs them with an atomic OR, which is safe once every plain store has landed
 #pragma unroll
                 for (int u = 0; u < U; ++u) if (pd[u]) fw[w[u]] = o[u] | b[u];
                 __syncwarp();
+                bool lost[U], any_lost = false;
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     const uint32_t now = pd[u] ? fw[w[u]] : 0xffffffffu;
-                    if ((now & b[u]) != b[u]) atomicOr(&fw[w[u]], b[u]);
+                    lost[u] = (now & b[u]) != b[u];
+                    any_lost |= lost[u];
+                }
+                if (any_lost) {
+#pragma unroll
+                    for (int u = 0; u < U; ++u) if (lost[u]) atomicOr(&fw[w[u]], b[u]);
                 }
             } else {
                 uint32_t h1[U], h2[U], c1[U], c2[U];
@@ -710,10 +712,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_vote_filter(DevIndex ix, uint
                 for (int u = 0; u < U; ++u) { c1[u] = valid[u] ? filt[h1[u]] : 0u; c2[u] = valid[u] ? filt[h2[u]] : 0u; }
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    flag[u] = valid[u] && (int)(min(c1[u], c2[u]) + inc[u]) > need;
+                    flag[u] = valid[u] && (int)(min(c1[u], c2[u]) + 1u) > need;
                     if (valid[u]) {
-                        filt[h1[u]] = (uint8_t)min(c1[u] + inc[u], 255u);
-                        filt[h2[u]] = (uint8_t)min(c2[u] + inc[u], 255u);
+                        filt[h1[u]] = (uint8_t)min(c1[u] + 1u, 255u);
+                        filt[h2[u]] = (uint8_t)min(c2[u] + 1u, 255u);
                     }
                 }
             }
@@ -733,6 +735,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_vote_filter(DevIndex ix, uint
             }
             __syncwarp();
             s_cur = s_n; t_cur = t_n;
+        }
+        if (s_cur >= ns && d0_hits) {                                  // diagonal 0 joins the last drain
+            if (lane == 0) fs->queue[qn] = 0u;
+            qn++;
+            __syncwarp();
         }
         drain();
         } while (s_cur < ns);

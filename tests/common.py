@@ -39,6 +39,32 @@ def world_repeats(seed=5, n_reads=600, read_len=100):
     return contigs, _abi.ReadBatch.from_arrays(reads["bases"], reads["quals"]), reads
 
 
+def world_genome_start(seed=21, n_reads=240, read_len=100):
+    """Reads whose k-mers hit the first bases of the genome, so that `sa <= offset` and the reference clamps the
+    diagonal to 0 (inc/align_seq2_raw.cpp:270): reads starting at 0..6, reads with 1..12 extra leading bases in front
+    of genome[0:], a short tandem repeat at the genome start (several clamped hits per k-mer), plus ordinary reads."""
+    rng = np.random.default_rng(seed)
+    unit = rng.integers(0, 4, size=23, dtype=np.uint8)
+    head = np.concatenate([unit, unit, unit, rng.integers(0, 4, size=40, dtype=np.uint8)])
+    body = rng.integers(0, 4, size=80_000, dtype=np.uint8)
+    codes = np.concatenate([head, body]).astype(np.uint8)
+    contigs = [("s1", codes[:50_000]), ("s2", codes[50_000:])]
+    reads = synth.simulate_reads(codes, n_reads, read_len, seed + 1, sub_rate=0.005, indel_rate=0.05)
+    k = 0
+    for start in range(0, 7):
+        reads["bases"][k] = codes[start:start + read_len]; k += 1
+    for lead in range(1, 13):
+        for rep in range(3):
+            pre = rng.integers(0, 4, size=lead, dtype=np.uint8)
+            r = np.concatenate([pre, codes[: read_len - lead]])
+            if rep == 2:
+                r = COMP[r[::-1]]
+            reads["bases"][k] = r; k += 1
+    for start in (0, 23, 46):                       # inside the tandem repeat
+        reads["bases"][k] = codes[start:start + read_len]; k += 1
+    return contigs, _abi.ReadBatch.from_arrays(reads["bases"], reads["quals"]), reads
+
+
 def world_ragged(seed=9):
     """Variable read lengths in one batch incl. too-short, all-N and lowest-quality reads."""
     contigs = synth.make_genome(150_000, seed, n_contigs=3)

@@ -126,7 +126,7 @@ def test_reference_kats(api, O):
 
 
 @pytest.mark.parametrize("mode", [_abi.MODE_NORMAL, _abi.MODE_BS, _abi.MODE_SNP])
-@pytest.mark.parametrize("world", ["plain", "repeats", "ragged"])
+@pytest.mark.parametrize("world", ["plain", "repeats", "ragged", "genome_start"])
 def test_pipeline_matches_oracle(api, O, world, mode):
     contigs, batch, _ = getattr(common, "world_" + world)()
     ix = index.build_index(contigs)
