@@ -32,7 +32,7 @@ EXPORTS = [
     "gmx_set_stream", "gmx_synchronize", "gmx_fm_search", "gmx_sa_locate", "gmx_get_windows", "gmx_self_score",
     "gmx_nw_score", "gmx_nw_traceback", "gmx_pair_hmm", "gmx_map_batch", "gmx_score_batch", "gmx_process_batch",
     "gmx_get_hits", "gmx_get_best_alignments", "gmx_accumulators_device", "gmx_reset_accumulators", "gmx_finish",
-    "gmx_get_stage_stats", "gmx_set_option", "gmx_fastq_scan_host", "gmx_fastq_scan", "gmx_process_fastq", "gmx_format_sam", "gmx_format_sgr",
+    "gmx_get_stage_stats", "gmx_set_option", "gmx_fastq_scan_host", "gmx_fastq_scan", "gmx_process_fastq", "gmx_format_sam", "gmx_format_sgr", "gmx_format_gmp", "gmx_snp_call",
 ]
 
 OPT_COLLECT_HITS, OPT_CHUNK_READS, OPT_VOTE_FILTER, OPT_FILTER_SHIFT = 1, 2, 3, 4
@@ -81,7 +81,9 @@ def load_library():
         L.gmx_fastq_scan_host.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
         L.gmx_fastq_scan.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
         L.gmx_format_sam.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
-        L.gmx_format_sgr.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
+        L.gmx_format_sgr.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
+        L.gmx_snp_call.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double), C.c_char_p, C.c_int]
+        L.gmx_format_gmp.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_float, C.c_int, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
         L.gmx_process_fastq.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.c_void_p]
         _lib = L
     return _lib
@@ -104,6 +106,19 @@ def fastq_scan_host(text: bytes, illumina: int = 0) -> np.ndarray:
     if rc != 0:
         raise GmxError(rc, "gmx_fastq_scan_host", L.gmx_strerror(rc).decode())
     return recs[: n.value]
+
+
+def snp_call(counts, genome_base: int, monoploid: bool = False, snp_pval: float = 0.001):
+    """GenomeBwt::is_snp + the PrintSNPCall column for one position's read counts (A,C,G,T,N); needs no GPU.
+    Returns (first, second, diploid, pval, text)."""
+    L = load_library()
+    c = np.ascontiguousarray(counts, dtype=np.float32)
+    first, second, dip, pv = C.c_int(0), C.c_int(0), C.c_int(0), C.c_double(0.0)
+    text = C.create_string_buffer(96)
+    rc = L.gmx_snp_call(c.ctypes.data, genome_base, int(monoploid), snp_pval, C.byref(first), C.byref(second), C.byref(dip), C.byref(pv), text, 96)
+    if rc != 0:
+        raise GmxError(rc, "gmx_snp_call", L.gmx_strerror(rc).decode())
+    return first.value, second.value, bool(dip.value), pv.value, text.value
 
 
 def batch_from_fastq(text: bytes, recs: np.ndarray):
@@ -306,6 +321,22 @@ class Mapper:
                 cap = n.value + 16
                 continue
             self._ck(rc, "gmx_format_sgr")
+            return out[: n.value].tobytes()
+
+    def format_gmp(self, target_base: int = -1, min_print: float = 0.001, snp_pval: float = 0.001, monoploid: bool = False) -> bytes:
+        """The .gmp text of the accumulators as they stand on the device: GenomeBwt::PrintFinalSNP with the
+        likelihood-ratio SNP call in SNP mode, GenomeBwt::PrintFinalBisulfite (rows at genome base `target_base`,
+        0..3 = a,c,g,t) in bisulfite / A->G mode."""
+        names = (C.c_char_p * len(self.index.names))(*[nm.encode() for nm in self.index.names])
+        n = C.c_int64(0)
+        cap = 1 << 16
+        while True:
+            out = np.zeros(cap, dtype=np.uint8)
+            rc = self.L.gmx_format_gmp(self._ctx, names, target_base, min_print, snp_pval, int(monoploid), out.ctypes.data, cap, C.byref(n))
+            if rc == _abi.GMX_ERR_OVERFLOW:
+                cap = n.value + 16
+                continue
+            self._ck(rc, "gmx_format_gmp")
             return out[: n.value].tobytes()
 
     def best_cigars(self, n_reads: int, stride: int = 64) -> np.ndarray:

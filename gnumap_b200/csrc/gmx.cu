@@ -16,6 +16,7 @@
 #include "pipeline.cuh"
 #include "pair_hmm.cuh"
 #include "fastq.cuh"
+#include "gmp_out.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // small utilities
@@ -1637,7 +1638,7 @@ extern "C" int gmx_format_sam(gmx_ctx *ctx, const char *text, const gmx_fastq_re
 // ------------------------------------------------------------------------------------------------
 // next row: .sgr output
 // ------------------------------------------------------------------------------------------------
-extern "C" int gmx_format_sgr(gmx_ctx *ctx, const char *const *chrom_names, float min_print, char *out, int64_t cap, int64_t *len)
+extern "C" int gmx_format_sgr(gmx_ctx *ctx, const char *const *chrom_names, double min_print, char *out, int64_t cap, int64_t *len)
 {
     if (!ctx || !chrom_names || !len || (cap > 0 && !out)) return GMX_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
@@ -1647,7 +1648,7 @@ extern "C" int gmx_format_sgr(gmx_ctx *ctx, const char *const *chrom_names, floa
     DevBuf d_idx, d_val, d_cnt, d_tmp;
     CK(d_idx.ensure((size_t)nb * 4 + 16)); CK(d_cnt.ensure(16));
     thrust::counting_iterator<uint32_t> it(0);
-    AboveThreshold pred{ctx->acc.amount, min_print};
+    SgrRowSelect pred{ctx->acc.amount, min_print};            // float > double literal, compared in double as the reference does
     size_t tmp_bytes = 0;
     CK(cub::DeviceSelect::If(nullptr, tmp_bytes, it, d_idx.as<uint32_t>(), d_cnt.as<uint32_t>(), (int)nb, pred, ctx->stream));
     CK(d_tmp.ensure(tmp_bytes));
@@ -1682,14 +1683,16 @@ extern "C" int gmx_format_sgr(gmx_ctx *ctx, const char *const *chrom_names, floa
         const size_t a = (size_t)n * t / nt, b = (size_t)n * (t + 1) / nt;
         std::string &o = parts[t];
         o.reserve((b - a) * 32);
-        char num[48];
+        char num[96];
         for (size_t k = a; k < b; ++k) {
             const int64_t count = (int64_t)((uint64_t)idx[k] * gs);
             if (count >= off.back()) continue;
             const size_t rid = std::upper_bound(off.begin(), off.end() - 1, count) - off.begin() - 1;
             o += chrom_names[rid];
-            int w = snprintf(num, sizeof(num), "\t%lld\t%.5f\n", (long long)(count - off[rid] + 1), (double)val[k]);
-            o.append(num, (size_t)w);
+            char *e = num; *e++ = '\t';
+            e = gmx_put_int(e, (long long)(count - off[rid] + 1)); *e++ = '\t';
+            e = gmx_put_fixed(e, val[k], 5); *e++ = '\n';
+            o.append(num, (size_t)(e - num));
         }
     });
     std::vector<int64_t> at(nt + 1, 0);
@@ -1697,5 +1700,102 @@ extern "C" int gmx_format_sgr(gmx_ctx *ctx, const char *const *chrom_names, floa
     *len = at[nt];
     if (at[nt] > cap) return GMX_ERR_OVERFLOW;
     run([&](unsigned t) { memcpy(out + at[t], parts[t].data(), parts[t].size()); });
+    return GMX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// next row: .gmp output with the SNP call (SNP / bisulfite / A->G part)
+// ------------------------------------------------------------------------------------------------
+extern "C" int gmx_format_gmp(gmx_ctx *ctx, const char *const *chrom_names, int target_base, double min_print, float snp_pval, int snp_monoploid,
+                              char *out, int64_t cap, int64_t *len)
+{
+    if (!ctx || !chrom_names || !len || (cap > 0 && !out)) return GMX_ERR_INVALID;
+    const bool snp = ctx->params.mode == GMX_MODE_SNP;
+    if (ctx->params.mode == GMX_MODE_NORMAL || !ctx->acc.planes[0]) { ctx->err = "the .gmp file exists in SNP / bisulfite / A->G mode only (gmx_format_sgr prints Normal mode)"; return GMX_ERR_STATE; }
+    if (!snp && (target_base < 0 || target_base > 3)) { ctx->err = "bisulfite / A->G rows need the genome base to report (0..3 = a,c,g,t)"; return GMX_ERR_INVALID; }
+    CK(cudaSetDevice(ctx->device));
+    const uint64_t nb = ctx->acc.n_amount;
+    if (nb >= 0x7fffffffull) { ctx->err = "more than 2^31 accumulator bins"; return GMX_ERR_UNSUPPORTED; }
+    const uint64_t gs = ctx->params.gen_size;
+    const uint64_t l_pac = (uint64_t)ctx->h_seq_offset.back();
+    // printable rows, in genome order, selected and gathered on the device
+    DevBuf d_idx, d_rows, d_base, d_cnt, d_tmp;
+    CK(d_idx.ensure((size_t)nb * 4 + 16)); CK(d_cnt.ensure(16));
+    thrust::counting_iterator<uint32_t> it(0);
+    GmpRowSelect pred{ctx->acc.amount, ctx->ix.pac, gs, l_pac, min_print, snp ? -1 : target_base};
+    size_t tmp_bytes = 0;
+    CK(cub::DeviceSelect::If(nullptr, tmp_bytes, it, d_idx.as<uint32_t>(), d_cnt.as<uint32_t>(), (int)nb, pred, ctx->stream));
+    CK(d_tmp.ensure(tmp_bytes));
+    CK(cub::DeviceSelect::If(d_tmp.p, tmp_bytes, it, d_idx.as<uint32_t>(), d_cnt.as<uint32_t>(), (int)nb, pred, ctx->stream));
+    uint32_t n = 0;
+    CK(cudaMemcpyAsync(&n, d_cnt.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    std::vector<uint32_t> idx(n); std::vector<float> rows((size_t)n * 6); std::vector<uint8_t> base(n);
+    if (n) {
+        CK(d_rows.ensure((size_t)n * 24)); CK(d_base.ensure(n));
+        k_gmp_gather<<<nblk(n, 256), 256, 0, ctx->stream>>>(ctx->acc.amount, ctx->acc.planes[0], ctx->acc.planes[1], ctx->acc.planes[2], ctx->acc.planes[3],
+                                                            ctx->acc.planes[4], ctx->ix.pac, gs, l_pac, d_idx.as<uint32_t>(), n, d_rows.as<float>(), d_base.as<uint8_t>());
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(idx.data(), d_idx.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(rows.data(), d_rows.p, (size_t)n * 24, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(base.data(), d_base.p, n, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    d_idx.release(); d_rows.release(); d_base.release(); d_cnt.release(); d_tmp.release();
+    const std::vector<int64_t> &off = ctx->h_seq_offset;
+    unsigned nt = std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
+    if (n < 16384) nt = 1;
+    std::vector<std::string> parts(nt);
+    auto run = [&](auto &&fn) {
+        if (nt == 1) { fn(0u); return; }
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < nt; ++t) th.emplace_back(fn, t);
+        for (auto &x : th) x.join();
+    };
+    run([&](unsigned t) {
+        const size_t a = (size_t)n * t / nt, b = (size_t)n * (t + 1) / nt;
+        std::string &o = parts[t];
+        o.reserve((b - a) * 80);
+        char line[256];
+        for (size_t k = a; k < b; ++k) {
+            const int64_t count = (int64_t)((uint64_t)idx[k] * gs);
+            if (count >= off.back()) continue;
+            const size_t rid = std::upper_bound(off.begin(), off.end() - 1, count) - off.begin() - 1;
+            o += chrom_names[rid];
+            char *e = line; *e++ = '\t';
+            e = gmx_put_int(e, (long long)(count - off[rid] + 1)); *e++ = '\t';
+            e = gmx_put_fixed(e, rows[k], snp ? 5 : 6);                        // "%.5f" in PrintFinalSNP, "%f" in PrintFinalBisulfite
+            float counts[5];
+            for (int c = 0; c < 5; ++c) { counts[c] = rows[(size_t)(c + 1) * n + k]; *e++ = '\t'; e = gmx_put_fixed(e, counts[c], 5); }
+            if (snp) e = gmx_put_snp_call(e, counts, base[k], snp_monoploid != 0, snp_pval);
+            *e++ = '\n';
+            o.append(line, (size_t)(e - line));
+        }
+    });
+    std::vector<int64_t> at(nt + 1, 0);
+    for (unsigned t = 0; t < nt; ++t) at[t + 1] = at[t] + (int64_t)parts[t].size();
+    *len = at[nt];
+    if (at[nt] > cap) return GMX_ERR_OVERFLOW;
+    run([&](unsigned t) { memcpy(out + at[t], parts[t].data(), parts[t].size()); });
+    return GMX_OK;
+}
+
+// GenomeBwt::is_snp + the call column of PrintSNPCall for one position; host arithmetic only (no context, no device)
+extern "C" int gmx_snp_call(const float counts[5], int genome_base, int snp_monoploid, float snp_pval, int *first, int *second, int *diploid,
+                            double *pval, char *text, int text_cap)
+{
+    if (!counts || genome_base < 0 || genome_base > 4) return GMX_ERR_INVALID;
+    const GmpCall c = gmx_snp_call(counts, snp_monoploid != 0);
+    if (first) *first = c.first;
+    if (second) *second = c.second;
+    if (diploid) *diploid = c.diploid ? 1 : 0;
+    if (pval) *pval = c.pval;
+    if (text) {
+        char buf[96];
+        char *e = gmx_put_snp_call(buf, counts, genome_base, snp_monoploid != 0, snp_pval);
+        const int n = (int)(e - buf);
+        if (n + 1 > text_cap) return GMX_ERR_OVERFLOW;
+        memcpy(text, buf, (size_t)n); text[n] = 0;
+    }
     return GMX_OK;
 }

@@ -104,7 +104,7 @@ def sgr_lines(index, amount: np.ndarray, gen_size: int, min_print: float = 0.001
             ok = bins < len(amount)
             vals = np.zeros(len(idx), dtype=np.float32)
             vals[ok] = amount[bins[ok]]
-            sel = np.nonzero(vals > np.float32(min_print))[0]
+            sel = np.nonzero(vals.astype(np.float64) > min_print)[0]      # float against the double literal MIN_PRINT
             for k in sel:
                 yield "%s\t%d\t%.5f" % (name, int(idx[k]) - start + 1, float(vals[k]))
             count = int(idx[-1]) + gen_size
@@ -118,7 +118,7 @@ def gmp_rows(index, amount: np.ndarray, planes: np.ndarray, mode: int, min_print
     genome base is 'c' and amount > 0.  gen_size is 1 in both modes."""
     codes = index.codes()
     if mode == _abi.MODE_SNP:
-        sel = np.nonzero(amount[: index.l_pac] > np.float32(min_print))[0]
+        sel = np.nonzero(amount[: index.l_pac].astype(np.float64) > min_print)[0]
     else:
         sel = np.nonzero((amount[: index.l_pac] > 0) & (codes == 1))[0]
     rid = np.searchsorted(index.seq_offset, sel, side="right") - 1

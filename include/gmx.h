@@ -280,10 +280,36 @@ int gmx_format_sam(gmx_ctx *ctx, const char *text, const gmx_fastq_rec *recs, co
 
 /* ---- next row: .sgr output (Normal-mode part) ----------------------------------
  * GenomeBwt::PrintFinalSGR (reference src/GenomeBwt.cpp:1212-1273): one line "chrom\tpos\t%.5f" per accumulator bin
- * whose value exceeds min_print (the reference's MIN_PRINT is 0.001), in genome order, from the accumulators as they
+ * whose value exceeds min_print (the reference's MIN_PRINT is the double 0.001; the float is compared in double as
+ * there), in genome order, from the accumulators as they
  * stand on the device (after the caller's NCCL reduce, if any).  The printable bins are selected on the device.
  * Returns GMX_ERR_OVERFLOW with *len = bytes needed when `cap` is short. */
-int gmx_format_sgr(gmx_ctx *ctx, const char *const *chrom_names, float min_print, char *out, int64_t cap, int64_t *len);
+int gmx_format_sgr(gmx_ctx *ctx, const char *const *chrom_names, double min_print, char *out, int64_t cap, int64_t *len);
+
+/* ---- next row: .gmp output with the SNP call (SNP / bisulfite / A->G part) -------
+ * GenomeBwt::PrintFinalSNP (reference src/GenomeBwt.cpp:930-1005) in GMX_MODE_SNP: one row
+ * "chrom\tpos\t%.5f" + the five read planes as "\t%.5f" + the call column of PrintSNPCall (:1011-1092) for every
+ * position whose amount exceeds min_print (MIN_PRINT 0.001 there).  The call is the reference's likelihood-ratio
+ * test -- dipLRT (:760-873), or LRT (:739-755) when snp_monoploid (--snp_monop) -- against snp_pval (--snp_pval,
+ * gSNP_PVAL, default 0.001); the chi-square CDF the reference takes from GSL is computed by the library.
+ * GenomeBwt::PrintFinalBisulfite (:1094-1205) in GMX_MODE_BS: "chrom\tpos\t%f" + five "\t%.5f" for every position
+ * with amount > 0 whose genome base is target_base (0..3 = a,c,g,t; the reference reports 'c' for -b on the + strand,
+ * 'g' for --b2 / - strand only, 'a' / 't' for A->G on the + / - strand, :1136-1160); min_print, snp_pval and
+ * snp_monoploid are ignored there and target_base is ignored in SNP mode.
+ * Rows are selected and gathered on the device from the accumulators as they stand (after the caller's NCCL reduce, if
+ * any); the host formats them on many threads.  GMX_ERR_STATE in Normal mode; GMX_ERR_OVERFLOW with *len = bytes
+ * needed when `cap` is short. */
+int gmx_format_gmp(gmx_ctx *ctx, const char *const *chrom_names, int target_base, double min_print, float snp_pval, int snp_monoploid,
+                   char *out, int64_t cap, int64_t *len);
+
+/* GenomeBwt::is_snp (reference src/GenomeBwt.cpp:874-898: LRT :739-755 when snp_monoploid, else dipLRT :760-873) for
+ * the read counts (A,C,G,T,N) of one position, and the call column PrintSNPCall (:1011-1092) prints for it when the
+ * genome holds base `genome_base` (0..4 = a,c,g,t,n) there: "\tN", "\t[YN]:g->x p_val=%.2e" or
+ * "\t[YN]:g->x/y p_val=%.2e".  Pure host arithmetic (no context, no device): it is what gmx_format_gmp runs per row.
+ * first / second = most and second most supported base (second = -1 when the test was monoploid-only), any output
+ * pointer may be NULL; text needs 48 bytes. */
+int gmx_snp_call(const float counts[5], int genome_base, int snp_monoploid, float snp_pval, int *first, int *second, int *diploid,
+                 double *pval, char *text, int text_cap);
 
 /* ---- options ----------------------------------------------------------------------------- */
 #define GMX_OPT_COLLECT_HITS 1   /* 1 (default): keep every accepted (pos,strand) for gmx_get_hits; 0: only the

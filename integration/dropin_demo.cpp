@@ -10,7 +10,7 @@
 //   restated here (10 lines)  : the SAM record printer of single_write_cond_wait (reference src/Driver.cpp:2166-2205),
 //                               with the same ostream operations so that numbers print identically
 //
-//   gnumap_gmx_demo <genome.fa> <reads.fq> <out_prefix> [normal|snp|bs]
+//   gnumap_gmx_demo <genome.fa> <reads.fq> <out_prefix> [normal|snp|snp_monop|bs]
 #include <pthread.h>
 #include <cstdio>
 #include <cstring>
@@ -39,6 +39,7 @@ double *gTopReadScore;
 void gmx_attach(GenomeBwt &gen, int device);
 void gmx_run_slice(GenomeBwt &gen, unsigned read_begin, unsigned read_end, unsigned &good_seqs, unsigned &bad_seqs, std::vector<TopReadOutput> &sam_out);
 void gmx_collect(GenomeBwt &gen);
+void gmx_print_final(GenomeBwt &gen, const char *fn);
 
 static void write_sam(std::ofstream &of, std::vector<TopReadOutput> &v)
 {   // reference src/Driver.cpp:2166-2205
@@ -59,7 +60,7 @@ static void write_sam(std::ofstream &of, std::vector<TopReadOutput> &v)
 
 int main(int argc, char **argv)
 {
-    if (argc < 4) { fprintf(stderr, "usage: %s genome.fa reads.fq out_prefix [normal|snp|bs]\n", argv[0]); return 2; }
+    if (argc < 4) { fprintf(stderr, "usage: %s genome.fa reads.fq out_prefix [normal|snp|snp_monop|bs]\n", argv[0]); return 2; }
     const std::string mode = argc > 4 ? argv[4] : "normal";
     InitProg();                                   // const_define.h:127-164
     gINT2BASE[5] = 'I'; gINT2BASE[6] = 'D';
@@ -67,7 +68,7 @@ int main(int argc, char **argv)
     gMER_SIZE = DEF_MER_SIZE;                      // src/Driver.cpp:1162-1207 defaults
     gJUMP_SIZE = gMER_SIZE / 2;
     gVERBOSE = 0;
-    if (mode == "snp") { gSNP = true; gGEN_SIZE = 1; }                                   // src/Driver.cpp:3203-3211
+    if (mode == "snp" || mode == "snp_monop") { gSNP = true; gGEN_SIZE = 1; gSNP_MONOP = mode == "snp_monop"; }                                   // src/Driver.cpp:3203-3211
     if (mode == "bs") { gBISULFITE = true; gGEN_SIZE = 1; gALIGN_SCORES[(int)'c'][3] = gMATCH; }   // :2805-2810, :1260-1268
 
     GenomeBwt gen;
@@ -100,6 +101,7 @@ int main(int argc, char **argv)
         for (unsigned k = 0; k < n; ++k) { delete_read(gReadArray[k]); gReadArray[k] = 0; }
     }
     of.close();
+    gmx_print_final(gen, (std::string(argv[3]) + ".native").c_str());   // the library's printers on the same accumulators
     gmx_collect(gen);
     gen.PrintFinal(argv[3]);                      // the reference's own .sgr / .gmp printers on the GPU's accumulators
     fprintf(stdout, "#\tSequences matched: %u\n#\tSequences not matched: %u\n", good, bad);

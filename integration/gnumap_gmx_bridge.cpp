@@ -146,6 +146,34 @@ void gmx_run_slice(GenomeBwt &gen, unsigned read_begin, unsigned read_end, unsig
     }
 }
 
+// optional, before patch point 4: the library's own printers in place of gGen.PrintFinal (src/Driver.cpp:1820-1823).
+// GenomeBwt::PrintFinal picks the file by mode (src/GenomeBwt.cpp:911-923); rows are selected on the GPU from the
+// accumulators where they are, so the 4-24 B per genome position never cross to the host.
+void gmx_print_final(GenomeBwt &gen, const char *fn)
+{
+    const bntseq_t *bns = GMX_GENOME_INDEX(gen)->bns;
+    std::vector<const char *> names((size_t)bns->n_seqs);
+    for (int i = 0; i < bns->n_seqs; ++i) names[(size_t)i] = bns->anns[i].name;
+    const bool gmp = gSNP || gBISULFITE || gATOG;
+    int target = -1;                                  // genome base PrintFinalBisulfite reports (src/GenomeBwt.cpp:1136-1160)
+    if (!gSNP && gBISULFITE) target = (gMATCH_POS_STRAND && !gBISULFITE2) ? 1 : 2;
+    else if (!gSNP && gATOG) target = gMATCH_POS_STRAND ? 0 : 3;
+    std::vector<char> text;
+    int64_t len = 0;
+    for (int pass = 0; pass < 2; ++pass) {            // first pass sizes the buffer
+        const int rc = gmp ? gmx_format_gmp(gGmx, &names[0], target, 0.001, gSNP_PVAL, gSNP_MONOP ? 1 : 0, text.empty() ? 0 : &text[0], (int64_t)text.size(), &len)
+                           : gmx_format_sgr(gGmx, &names[0], 0.001, text.empty() ? 0 : &text[0], (int64_t)text.size(), &len);
+        if (rc == GMX_OK) break;
+        if (rc != GMX_ERR_OVERFLOW || pass) gmx_die(gmp ? "gmx_format_gmp" : "gmx_format_sgr");
+        text.resize((size_t)len);
+    }
+    const std::string path = std::string(fn) + (gmp ? ".gmp" : ".sgr");
+    FILE *f = fopen(path.c_str(), "w");
+    if (!f) { perror(path.c_str()); exit(1); }
+    if (len) fwrite(&text[0], 1, (size_t)len, f);
+    fclose(f);
+}
+
 // patch point 4 ---------------------------------------------------------------------------------------------------
 void gmx_collect(GenomeBwt &gen)
 {

@@ -280,6 +280,18 @@ class RefProbe:
         n = self.L.refp_get_string(begin, size, ptr(out))
         return out[:n].tobytes()
 
+    def snp_call(self, count: int, counts, monop: bool = False, pval: float = 0.001) -> bytes:
+        """Call column GenomeBwt::PrintSNPCall prints for read counts (A,C,G,T,N) at genome position `count`
+        (set_mode(2) before load_genome)."""
+        c = np.ascontiguousarray(counts, dtype=np.float32)
+        out = C.create_string_buffer(128)
+        f = self.L.refp_snp_call
+        f.argtypes = [C.c_uint64, C.c_void_p, C.c_int, C.c_float, C.c_char_p, C.c_int]
+        n = f(count, ptr(c), int(monop), pval, out, 128)
+        if n < 0:
+            raise RuntimeError("refp_snp_call: no SNP-mode genome loaded")
+        return out.value
+
     def score_once(self, kind, pwm, gen_string: bytes, align_score: float, positions, denom: float, cap: int):
         pwm = np.ascontiguousarray(pwm, dtype=np.float32)
         pos = np.asarray([p for p, _ in positions], dtype=np.uint64)

@@ -197,6 +197,28 @@ int refp_score_once(int kind, const float *pwm, int n, const char *gen_string, d
     return 0;
 }
 
+/* The call column GenomeBwt::PrintSNPCall (src/GenomeBwt.cpp:1011-1092) prints for the read counts `counts`
+ * (A,C,G,T,N) placed at genome position `count`.  Needs refp_set_mode(2) before refp_load_genome (the five
+ * read planes only exist in SNP / bisulfite mode). */
+int refp_snp_call(uint64_t count, const float *counts, int monop, float pval, char *out, int cap)
+{
+    if (!g_gen || !g_gen->GetGenomeAPtr()) return -1;
+    float *planes[5] = {g_gen->GetGenomeAPtr(), g_gen->GetGenomeCPtr(), g_gen->GetGenomeGPtr(), g_gen->GetGenomeTPtr(), g_gen->GetGenomeNPtr()};
+    float total = 0;
+    for (int b = 0; b < 5; ++b) { planes[b][count] = counts[b]; total += counts[b]; }
+    g_gen->GetGenomeAmtPtr()[count] = total;
+    gSNP_MONOP = monop != 0; gSNP_PVAL = pval;
+    char *buf = 0; size_t len = 0;
+    FILE *f = open_memstream(&buf, &len);
+    g_gen->PrintSNPCall(count, f);
+    fclose(f);
+    int n = (int)len < cap - 1 ? (int)len : cap - 1;
+    memcpy(out, buf, n); out[n] = 0;
+    free(buf);
+    return n;
+}
+
+
 /* SeqReader on a FASTQ file: one line "name\tseq\tfq\n" per Read, in order (reference src/SeqReader.cpp:1023-1292).
  * Returns the number of reads, or -1 when the reader threw (invalid quality character). */
 int refp_read_fastq(const char *fn, char *out, int cap)

@@ -195,6 +195,42 @@ def make_program(tmp):
         print(f"ref_program_{mode}.json.gz: {len(sam)} SAM records, matched {rec['matched']}")
 
 
+def make_snp_calls(tmp):
+    """Call columns of GenomeBwt::PrintSNPCall (reference src/GenomeBwt.cpp:1011-1092 over is_snp / LRT / dipLRT
+    :739-898) for random read-count vectors, through the unmodified reference objects.  gsl_cdf_chisq_P comes from
+    oracle/gsl_stub (the reference build's GSL differs from it only in the last digits of 1 - P)."""
+    R = O.RefProbe()
+    R.set_mode(2)
+    contigs = synth.make_genome(2000, 5, n_contigs=1)
+    fa = os.path.join(tmp, "lrt.fa")
+    synth.write_fasta(fa, contigs)
+    R.load_genome(fa)
+    codes = contigs[0][1]
+    rng = np.random.default_rng(2024)
+    cases = []
+    for t in range(3000):
+        cov = float(rng.choice([1, 2, 3, 5, 8, 15, 30, 60, 200, 1000]))
+        c = (rng.dirichlet(np.ones(5) * rng.choice([0.05, 0.3, 1.0])) * cov).astype(np.float32)
+        if t % 5 == 1:
+            c = np.round(c).astype(np.float32)
+        if t % 5 == 2:
+            c = np.zeros(5, np.float32); c[rng.integers(0, 5)] = cov; c[rng.integers(0, 5)] += np.float32(cov * rng.choice([0.0, 0.3, 0.34, 0.5, 1.0]))
+        if t % 150 == 3:
+            c = np.zeros(5, np.float32)
+        pos = int(rng.integers(0, 2000))
+        monop = bool(t % 3 == 0)
+        pval = float(rng.choice([0.001, 0.05]))
+        cases.append({"counts": [float(x) for x in c], "base": int(codes[pos]), "monop": monop, "pval": pval,
+                      "call": R.snp_call(pos, c, monop, pval).decode()})
+    R.set_mode(0)
+    with gzip.GzipFile(os.path.join(HERE, "ref_snp_calls.json.gz"), "wb", mtime=0) as f:
+        f.write(json.dumps(cases).encode())
+    kinds = {}
+    for c in cases:
+        kinds[c["call"][:3]] = kinds.get(c["call"][:3], 0) + 1
+    print("ref_snp_calls.json.gz:", kinds)
+
+
 def fastq_cases():
     """FASTQ texts that exercise SeqReader::get_more_fastq incl. its recovery paths."""
     rng = np.random.default_rng(77)
@@ -249,6 +285,7 @@ def main():
         make_functions(tmp)
         make_index(tmp)
         make_program(tmp)
+        make_snp_calls(tmp)
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
 

@@ -142,3 +142,49 @@ def test_native_sgr_equals_the_reference_binary():
         assert abs(a - b) <= 1e-5 * abs(b) + 1.1e-5 or max(a, b) < 0.00102, (k, a, b)
     assert len(w) > 1000
     m.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["snp", "bs"])
+def test_native_gmp_rows_and_calls(mode):
+    """SURVEY.md §8(f) rank 3 (SNP / bisulfite part): gmx_format_gmp -- rows selected and gathered on the device --
+    against the restated row printer on the same accumulators (text equality; the call column through gmx_snp_call,
+    itself pinned to the reference's PrintSNPCall by tests/test_host_logic.py), and against the .gmp the unmodified
+    reference binary wrote (numbers at the file's decimals: FP32 atomics reorder the sums)."""
+    from tests import test_oracle_golden as G, common
+    from gnumap_b200 import output
+    rec = G.load_program(mode)
+    lut = {c: i for i, c in enumerate("ACGT")}
+    contigs = [(n, np.array([lut[c] for c in s], dtype=np.uint8)) for n, s in rec["contigs"]]
+    ix = index.build_index(contigs)
+    p = common.set_mode(api.default_params(), _abi.MODE_SNP if mode == "snp" else _abi.MODE_BS)
+    text = "".join(f"@{nm}\n{s}\n+\n{q}\n" for nm, s, q in rec["reads"]).encode()
+    m = api.Mapper(ix, p)
+    m.process_fastq(text, fetch=False)
+    got = m.format_gmp(target_base=-1 if mode == "snp" else 1).decode().split("\n")
+    assert got[-1] == "" and len(got) > 1000
+    got = got[:-1]
+    amount, planes = m.finish()
+    codes = ix.codes()
+    want = []
+    for r in output.gmp_rows(ix, amount, planes, p.mode):
+        line = ("%s\t%d\t%.5f" if mode == "snp" else "%s\t%d\t%f") % r[:3] + "".join("\t%.5f" % x for x in r[3:8])
+        if mode == "snp":
+            pos = int(ix.seq_offset[ix.names.index(r[0])]) + r[1] - 1
+            line += api.snp_call(np.array(r[3:8], dtype=np.float32), int(codes[pos]))[4].decode()
+        want.append(line)
+    assert got == want
+    ref = {tuple(ln.split("\t")[:2]): ln.split("\t") for ln in rec["gmp"]}
+    mine = {tuple(ln.split("\t")[:2]): ln.split("\t") for ln in got}
+    both = set(ref) & set(mine)
+    assert len(both) >= 0.999 * len(ref) and len(mine) <= 1.001 * len(ref) + 2
+    same = 0
+    for k in both:
+        assert np.allclose([float(x) for x in mine[k][2:8]], [float(x) for x in ref[k][2:8]], rtol=1e-5, atol=1.1e-5), (mine[k], ref[k])
+        same += mine[k][8:] == ref[k][8:]
+    assert same >= 0.995 * len(both)
+    m.close()
+    m0 = api.Mapper(ix)
+    with pytest.raises(api.GmxError):
+        m0.format_gmp()                      # Normal mode has no .gmp
+    m0.close()

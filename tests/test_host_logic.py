@@ -74,3 +74,19 @@ def test_simulated_reads_are_reproducible_and_true():
         src = codes[a["pos"][r]:a["pos"][r] + 80]
         want = comp[src[::-1]] if a["strand"][r] else src
         assert np.array_equal(a["bases"][r], want)
+
+
+def test_snp_call_matches_reference_printer():
+    """the library's likelihood-ratio SNP call (gmx_snp_call, host arithmetic, what gmx_format_gmp
+    runs per row) against the call column the UNMODIFIED reference's GenomeBwt::PrintSNPCall printed for 3000 read-count
+    vectors (tests/golden/ref_snp_calls.json.gz, made by tests/golden/make_golden.py:make_snp_calls): byte for byte,
+    p-values included."""
+    import gzip, json, os
+    from gnumap_b200 import api
+    cases = json.loads(gzip.open(os.path.join(os.path.dirname(__file__), "golden", "ref_snp_calls.json.gz")).read())
+    kinds = set()
+    for c in cases:
+        first, second, dip, pval, text = api.snp_call(c["counts"], c["base"], c["monop"], c["pval"])
+        assert text.decode() == c["call"], (c, text)
+        kinds.add(c["call"][:3] + ("/" if "/" in c["call"] else ""))
+    assert {"\tN", "\tN:", "\tY:", "\tN:/", "\tY:/"} <= kinds
