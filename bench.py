@@ -424,11 +424,27 @@ def own_arm(a):
         sam_s = time.time() - t0
         if rc != 0:
             raise RuntimeError(f"gmx_format_sam: {rc} {m.L.gmx_last_error(m._ctx).decode()}")
+        # accumulator output row: .sgr text of the accumulators as they stand (device row selection + host text)
+        sgr_cap = 64 << 20
+        sgr_buf = np.empty(sgr_cap, dtype=np.uint8)
+        sgr_len = C.c_int64(0)
+        t0 = time.time()
+        rc = m.L.gmx_format_sgr(m._ctx, names_c, 0.001, sgr_buf.ctypes.data, sgr_cap, C.byref(sgr_len))
+        if rc == _abi.GMX_ERR_OVERFLOW:
+            sgr_cap = int(sgr_len.value) + 16; sgr_buf = np.empty(sgr_cap, dtype=np.uint8)
+            t0 = time.time()
+            rc = m.L.gmx_format_sgr(m._ctx, names_c, 0.001, sgr_buf.ctypes.data, sgr_cap, C.byref(sgr_len))
+        sgr_s = time.time() - t0
+        if rc != 0:
+            raise RuntimeError(f"gmx_format_sgr: {rc} {m.L.gmx_last_error(m._ctx).decode()}")
+        sgr_rows = int((sgr_buf[: sgr_len.value] == 10).sum())
         fastq = {"value": n * world * a.steps / (fq_ms * 1e-3), "unit": "reads/s", "h2d_bytes_per_step": int(text_h.numel()),
                  "d2h_bytes_per_step": int(n * (_abi.READ_RESULT_DTYPE.itemsize + 64 + _abi.FASTQ_REC_DTYPE.itemsize)),
                  "what": "gmx_process_fastq: FASTQ text in pinned host memory -> device record indexer -> reads used in place -> results (wall clock)",
                  "sam": {"value": n / sam_s, "unit": "reads/s", "bytes": int(sam_len.value), "host_threads": min(os.cpu_count() or 1, 16),
-                         "what": "gmx_format_sam: SAM body of the batch (ScoredSeq::get_SAM + writer), host C++"}}
+                         "what": "gmx_format_sam: SAM body of the batch (ScoredSeq::get_SAM + writer), host C++"},
+                 "sgr": {"seconds": sgr_s, "rows": sgr_rows, "bytes": int(sgr_len.value), "bins_scanned": int(acc[0].numel()) if isinstance(acc, (list, tuple)) else None,
+                         "what": "gmx_format_sgr: GenomeBwt::PrintFinalSGR of the accumulators (device scan + select, host text)"}}
 
     if rank == 0:
         peaks = {}
