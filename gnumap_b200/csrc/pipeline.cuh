@@ -499,26 +499,28 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_vote_filter(DevIndex ix, uint
 
     // seeds of a task in registers: seed `lane` and seed `lane + 32`; fetched one task ahead
     struct Meta { uint32_t task; int ns; uint32_t rank[2], cnt[2], off[2]; unsigned long long code[2]; };
-    // tasks are taken GRAB at a time: one same-address atomic per task would serialise 2 M returning atomics per step
+    // Work items are taken GRAB at a time (one same-address atomic per task would serialise 2 M returning atomics
+    // per step), and nothing on the way to a task's k-mers waits for a load it has just issued: the cursor of the
+    // next grab is requested one grab ahead, its task ids (lanes 0..GRAB-1) one task later, and a task's k-mers --
+    // whose addresses follow from the task id alone -- while the task before it is processed.
     constexpr uint32_t GRAB = 4;
-    uint32_t w_pos = 0, w_end = 0;
-    auto next_work = [&]() -> uint32_t {
-        if (w_pos + 1 < w_end) return ++w_pos;
+    auto grab = [&]() -> uint32_t {
         uint32_t w = 0;
         if (lane == 0) w = atomicAdd(&F.cursor[cls], GRAB);
-        w_pos = __shfl_sync(0xffffffffu, w, 0); w_end = w_pos + GRAB;
-        return w_pos;
+        return __shfl_sync(0xffffffffu, w, 0);
     };
-    auto fetch = [&](uint32_t w, Meta &m) {
-        m.task = list[w];
-        m.ns = S.n_seeds[m.task];
+    auto load_ids = [&](uint32_t base) -> uint32_t { return ((uint32_t)lane < GRAB && base + lane < n_list) ? list[base + lane] : 0xffffffffu; };
+    const int64_t last_seed = S.n_tasks * S.max_seeds - 1;
+    const bool two_halves = S.max_seeds > 32;
+    auto fetch = [&](uint32_t task, Meta &m) {                  // unmasked: lanes beyond the task's k-mers are cleared when used
+        m.task = task;
+        m.ns = S.n_seeds[task];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            const int s = lane + 32 * h;
-            const bool in = s < m.ns && s < GMX_FILTER_MAX_SEEDS;
-            const int64_t at = S.at(m.task, in ? s : 0);
-            m.rank[h] = in ? S.rank[at] : 0u; m.cnt[h] = in ? S.count[at] : 0u; m.off[h] = in ? S.offset[at] : 0u;
-            m.code[h] = in ? S.code[at] : 0ull;
+            m.rank[h] = 0u; m.cnt[h] = 0u; m.off[h] = 0u; m.code[h] = 0ull;
+            if (h == 1 && !two_halves) break;
+            const int64_t at = min(S.at(task, lane + 32 * h), last_seed);
+            m.rank[h] = S.rank[at]; m.cnt[h] = S.count[at]; m.off[h] = S.offset[at]; m.code[h] = S.code[at];
         }
     };
 
@@ -536,25 +538,35 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_vote_filter(DevIndex ix, uint
         ne = 0;
     };
     Meta cur, nxt;
-    uint32_t w = next_work();
-    if (w < n_list) fetch(w, cur);
-    while (w < n_list) {
+    uint32_t g_base = grab();
+    uint32_t g_ids = load_ids(g_base);
+    uint32_t n_base = grab(), n_ids = 0xffffffffu;
+    bool n_ids_pending = true;
+    uint32_t slot = 0;
+    bool has_cur = g_base < n_list;
+    if (has_cur) fetch(__shfl_sync(0xffffffffu, g_ids, 0), cur);
+    while (has_cur) {
+        // step the cursor to the next work item and start loading its k-mers
+        if (n_ids_pending && slot >= 1) { n_ids = load_ids(n_base); n_ids_pending = false; }
+        if (++slot == GRAB) { g_base = n_base; g_ids = n_ids; slot = 0; n_base = grab(); n_ids_pending = true; }
+        const bool has_next = g_base + slot < n_list;
+        const uint32_t next_task = __shfl_sync(0xffffffffu, g_ids, (int)slot);
+        if (has_next) fetch(next_task, nxt);
+
         const uint32_t task = cur.task;
         const int ns = cur.ns;
         bool unsupported = ns > GMX_FILTER_MAX_SEEDS;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int s = lane + 32 * h;
+            if (!(s < ns && s < GMX_FILTER_MAX_SEEDS)) { cur.rank[h] = 0u; cur.cnt[h] = 0u; cur.off[h] = 0u; cur.code[h] = 0ull; }
             if (s < GMX_FILTER_MAX_SEEDS) { fs->rank[s] = cur.rank[h]; fs->cnt[s] = cur.cnt[h]; fs->offs[s] = (uint16_t)cur.off[h]; fs->codes[s] = cur.code[h]; }
             if (s < ns && cur.off[h] + (uint32_t)mer > GMX_FILTER_MAX_SPAN) unsupported = true;
         }
         unsupported = __any_sync(0xffffffffu, unsupported);
-        // the next task's seeds travel while this one is processed
-        w = next_work();
-        if (w < n_list) fetch(w, nxt);
         if (unsupported) {
             if (lane == 0) gmx_class_append(E, gmx_exact_class(S.hits[task]), task);
-            cur = nxt;
+            cur = nxt; has_cur = has_next;
             continue;
         }
         // pull every suffix-array line this task will read into L2 while the filter is being cleared
@@ -734,7 +746,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_vote_filter(DevIndex ix, uint
         drain();
         } while (s_cur < ns);
         __syncwarp();
-        cur = nxt;
+        cur = nxt; has_cur = has_next;
     }
     if (ne) flush();
 }
