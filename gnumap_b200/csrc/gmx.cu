@@ -234,8 +234,8 @@ static const size_t kLutFloats = 5 * GMX_NQ * 4;
 static int build_tables(gmx_ctx *ctx)
 {
     const gmx_params &p = ctx->params;
-    // layout: sub_pos | sub_neg | pwm_lut | phmm_pos | phmm_neg | S | P | self(unused)
-    std::vector<float> h(5 * kLutFloats + 2 * 1024);
+    // layout: sub_pos | sub_neg | pwm_lut | phmm_pos | phmm_neg | S | P | self
+    std::vector<float> h(5 * kLutFloats + 2 * 1024 + 256 * GMX_NQ);
     float *sub_pos = h.data(), *sub_neg = sub_pos + kLutFloats, *pwm_lut = sub_neg + kLutFloats;
     float *phmm_pos = pwm_lut + kLutFloats, *phmm_neg = phmm_pos + kLutFloats, *S = phmm_neg + kLutFloats, *P = S + 1024;
     for (int code = 0; code < 5; ++code)
@@ -255,13 +255,19 @@ static int build_tables(gmx_ctx *ctx)
         }
     memcpy(S, p.align_scores, sizeof(float) * 1024);
     memcpy(P, p.phmm_scores, sizeof(float) * 1024);
+    float *self = P + 1024;
+    for (int ch = 0; ch < 256; ++ch) {
+        int code = 4;
+        switch (ch) { case 'A': case 'a': code = 0; break; case 'C': case 'c': code = 1; break; case 'G': case 'g': code = 2; break; case 'T': case 't': code = 3; break; }
+        for (int q = 0; q < GMX_NQ; ++q) self[ch * GMX_NQ + q] = get_val_host(pwm_lut + ((size_t)code * GMX_NQ + q) * 4, p.align_scores[ch]);
+    }
     CK(ctx->d_tables.ensure(h.size() * sizeof(float)));
     CK(cudaMemcpyAsync(ctx->d_tables.p, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     float *d = ctx->d_tables.as<float>();
     ctx->tab.sub_pos = d; ctx->tab.sub_neg = d + kLutFloats; ctx->tab.pwm_lut = d + 2 * kLutFloats;
     ctx->tab.phmm_pos = d + 3 * kLutFloats; ctx->tab.phmm_neg = d + 4 * kLutFloats;
-    ctx->tab.S = d + 5 * kLutFloats; ctx->tab.P = d + 5 * kLutFloats + 1024;
+    ctx->tab.S = d + 5 * kLutFloats; ctx->tab.P = d + 5 * kLutFloats + 1024; ctx->tab.self = d + 5 * kLutFloats + 2048;
     return GMX_OK;
 }
 
@@ -490,9 +496,6 @@ static int issue_upload(gmx_ctx *ctx, const gmx_reads *reads, int32_t lo, int32_
     int32_t n = hi - lo;
     if (!reads->seq) { ctx->err = "gmx_reads.seq is required (the consensus string for raw-PWM reads)"; return GMX_ERR_INVALID; }
     if (!reads->qual && !reads->pwm) { ctx->err = "gmx_reads needs qual or pwm"; return GMX_ERR_INVALID; }
-    int32_t max_len = 0;
-    int r = scan_max_len(ctx, reads, lo, hi, &max_len);
-    if (r != GMX_OK) return r;
     DevReads &v = ctx->up_view[slot];
     v.n_reads = n; v.qbase = ctx->params.illumina ? 64 : 33;
     v.qual = nullptr; v.pwm = nullptr; v.qoffsets = nullptr; v.lens = nullptr;
@@ -520,8 +523,12 @@ static int issue_upload(gmx_ctx *ctx, const gmx_reads *reads, int32_t lo, int32_
             v.pwm = ctx->d_pwm[slot].as<float>() - 4 * base;
         }
     }
-    ctx->up_max_len[slot] = max_len;
     CK(cudaEventRecord(ctx->up_ev[slot], stream));
+    // the chunk's longest read is found on the host while the copies run
+    int32_t max_len = 0;
+    int r = scan_max_len(ctx, reads, lo, hi, &max_len);
+    if (r != GMX_OK) return r;
+    ctx->up_max_len[slot] = max_len;
     return GMX_OK;
 }
 
@@ -600,7 +607,7 @@ extern "C" int gmx_self_score(gmx_ctx *ctx, const gmx_reads *reads, float *score
     CK(ctx->d_prep.ensure((size_t)n * sizeof(ReadPrep)));
     DevParams dp = ctx->dparams; dp.mer = 0;             // score every read regardless of length
     dp.cutoff = -INFINITY;
-    k_prep_reads<<<nblk(n, 128), 128, 0, ctx->stream>>>(ctx->dreads, ctx->tab, dp, ctx->d_prep.as<ReadPrep>());
+    k_prep_reads<<<nblk(n, GMX_PREP_THREADS), GMX_PREP_THREADS, 0, ctx->stream>>>(ctx->dreads, ctx->tab, dp, ctx->d_prep.as<ReadPrep>());
     CK(cudaGetLastError());
     std::vector<ReadPrep> h(n);
     CK(cudaMemcpyAsync(h.data(), ctx->d_prep.p, (size_t)n * sizeof(ReadPrep), cudaMemcpyDeviceToHost, ctx->stream));
@@ -828,7 +835,7 @@ static int phase_a(gmx_ctx *ctx, const gmx_reads *reads, int32_t lo, int32_t hi,
     // a3 + status
     stage_begin(ctx, ST_PREP);
     CK(cudaMemsetAsync(ds, 0, sizeof(ChunkStats), ctx->stream));
-    k_prep_reads<<<nblk(n, 128), 128, 0, ctx->stream>>>(ctx->dreads, ctx->tab, P, ctx->d_prep.as<ReadPrep>());
+    k_prep_reads<<<nblk(n, GMX_PREP_THREADS), GMX_PREP_THREADS, 0, ctx->stream>>>(ctx->dreads, ctx->tab, P, ctx->d_prep.as<ReadPrep>());
     CK(cudaGetLastError());
     stage_end(ctx, ST_PREP, (uint64_t)n, (uint64_t)total_bases * 2, 1);
 
@@ -1151,8 +1158,8 @@ static int run_batch(gmx_ctx *ctx, const gmx_reads *reads, gmx_read_result *resu
     if (!ctx || !reads || reads->n_reads < 0 || (reads->n_reads > 0 && !reads->offsets)) return GMX_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
     const int32_t n = reads->n_reads;
-    int32_t max_len = 0;
-    if (n > 0) { int r = batch_max_len(ctx, reads, &max_len); if (r != GMX_OK) return r; }
+    int32_t max_len = 0;       // of the whole batch: only the hit-collecting download needs it before the first chunk runs
+    if (n > 0 && (ctx->collect_hits || reads->on_device)) { int r = batch_max_len(ctx, reads, &max_len); if (r != GMX_OK) return r; }
     ctx->h_results.assign(ctx->collect_hits || !results ? (size_t)n : 0, gmx_read_result());
     ctx->h_hits.clear();
     ctx->h_multi.clear();
@@ -1171,17 +1178,35 @@ static int run_batch(gmx_ctx *ctx, const gmx_reads *reads, gmx_read_result *resu
     ctx->last_n_reads = n; ctx->last_max_len = 0;
     ctx->mapped = false; ctx->scored = false; ctx->cs.valid = false;
     stage_reset(ctx);
+    // Chunk schedule.  A chunk's upload rides under its predecessor's kernels and its download under its successor's,
+    // so what a batch exposes is the first upload, the last download, and any upload longer than the kernels it hides
+    // under.  When PHASE A and B run together, a host batch therefore starts with a short chunk (1/16 of the regular
+    // size) and triples it until the regular size is reached (a read's kernels take ~4x its PCIe time), and every
+    // batch ends with a chunk of 1/8.
     const int32_t step = (int32_t)ctx->chunk_reads;
+    const int32_t edge = std::max<int32_t>(step / 8, 1);
+    std::vector<int32_t> cuts(1, 0);
+    if (do_score && n > 4 * edge) {
+        int32_t at = 0;
+        if (!reads->on_device)
+            for (int32_t c = std::max<int32_t>(step / 16, 1); c < step && at + c < (n - edge) / 2; c *= 3) { at += c; cuts.push_back(at); }
+        const int32_t body = n - at - edge;
+        const int32_t parts = std::max<int32_t>(1, (int32_t)(((int64_t)body - edge + step - 1) / step));     // a part may exceed the regular size by 1/8
+        for (int32_t k = 1; k <= parts; ++k) cuts.push_back(at + (int32_t)((int64_t)body * k / parts));
+        cuts.push_back(n);
+    } else {
+        for (int32_t lo = 0; lo < n; lo += step) cuts.push_back((int32_t)std::min<int64_t>(n, (int64_t)lo + step));
+    }
     if (n > 0) {   // first chunk's upload; every later one is issued while its predecessor computes
-        int r = issue_upload(ctx, reads, 0, std::min<int32_t>(n, step), 0, ctx->copy_stream);
+        int r = issue_upload(ctx, reads, 0, cuts[1], 0, ctx->copy_stream);
         if (r != GMX_OK) return r;
     }
     int slot = 0;
-    for (int32_t lo = 0; lo < n; lo += step, slot ^= 1) {
-        int32_t hi = (int32_t)std::min<int64_t>(n, (int64_t)lo + (int64_t)step);
+    for (size_t c = 0; c + 1 < cuts.size(); ++c, slot ^= 1) {
+        const int32_t lo = cuts[c], hi = cuts[c + 1];
         if (hi < n) {   // buffer set slot^1 was last read by chunk i-1: its kernels must have drained first
             CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->done_ev[slot ^ 1], 0));
-            int r = issue_upload(ctx, reads, hi, (int32_t)std::min<int64_t>(n, (int64_t)hi + (int64_t)step), slot ^ 1, ctx->copy_stream);
+            int r = issue_upload(ctx, reads, hi, cuts[c + 2], slot ^ 1, ctx->copy_stream);
             if (r != GMX_OK) return r;
         }
         int r = phase_a(ctx, reads, lo, hi, slot);

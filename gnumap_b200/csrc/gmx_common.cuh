@@ -40,6 +40,7 @@ struct DevTables {
     const float *phmm_neg;   // [5][GMX_NQ][4]
     const float *S;          // [256][4] gALIGN_SCORES
     const float *P;          // [256][4] gPHMM_ALIGN_SCORES
+    const float *self;       // [256][GMX_NQ]  get_val(pwm(nt4(ch), q), ch): one base's term of the read's self score
 };
 
 // Device view of one batch of reads.

@@ -45,21 +45,55 @@ __device__ __forceinline__ ReadView gmx_read_view(const DevReads &R, int r, int 
 }
 
 // ---- a3 + status ------------------------------------------------------------------------------
-__global__ void k_prep_reads(DevReads R, DevTables T, DevParams P, ReadPrep *prep)
+// One thread per read; the score is a left-to-right FP32 sum over the bases, so the read is walked sequentially.
+// Byte loads with a stride of one read length between lanes would cost 32 L1 wavefronts each, so the block first
+// stages its (contiguous) reads in shared memory with coalesced word loads; the per-base term
+// get_val(pwm(base, Q), seq[i]) is a pure function of the two characters and comes from a 96 KB table.
+#define GMX_PREP_THREADS 128
+#define GMX_PREP_STAGE_BYTES (GMX_PREP_THREADS * 176)        // reads of up to 176 bases on average per block
+__global__ void __launch_bounds__(GMX_PREP_THREADS) k_prep_reads(DevReads R, DevTables T, DevParams P, ReadPrep *prep)
 {
-    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ __align__(16) uint8_t s_seq[GMX_PREP_STAGE_BYTES + 8], s_qual[GMX_PREP_STAGE_BYTES + 8];
+    const int r0 = blockIdx.x * blockDim.x;
+    const int r = r0 + threadIdx.x;
+    const int r1 = min(r0 + (int)blockDim.x, R.n_reads);
+    // contiguous layout (no raw PWM, no in-place FASTQ offsets): the block's reads are one byte range
+    bool staged = false;
+    int64_t lead = 0;
+    if (!R.pwm && !R.qoffsets && !R.lens && R.qual) {
+        const int64_t b0 = R.offsets[r0], b1 = R.offsets[r1];
+        const uintptr_t a_seq = (uintptr_t)(R.seq + b0), a_qual = (uintptr_t)(R.qual + b0);
+        lead = (int64_t)(a_seq & 3u);
+        if ((a_qual & 3u) == (uintptr_t)lead && b1 - b0 + lead <= GMX_PREP_STAGE_BYTES) {
+            staged = true;
+            const uint32_t *g_seq = reinterpret_cast<const uint32_t *>(a_seq - lead), *g_qual = reinterpret_cast<const uint32_t *>(a_qual - lead);
+            const int words = (int)((b1 - b0 + lead + 3) >> 2);
+            for (int w = threadIdx.x; w < words; w += blockDim.x) {
+                reinterpret_cast<uint32_t *>(s_seq)[w] = g_seq[w];
+                reinterpret_cast<uint32_t *>(s_qual)[w] = g_qual[w];
+            }
+        }
+        lead -= b0;                                        // shared index of genome-order byte x is x + lead
+    }
+    __syncthreads();
     if (r >= R.n_reads) return;
     ReadView rd = gmx_read_view(R, r, 0);
     ReadPrep out; out.min_align = 0; out.max_align = 0; out.status = GMX_READ_MAPPED;
     if ((unsigned)rd.n < (unsigned)P.mer) { out.status = GMX_READ_TOO_SHORT; prep[r] = out; return; }
     // get_align_score(read, consensus, 0, n-1) == get_align_score_mid  (reference src/bin_seq.cpp:860-893)
     float score = 0.f;
-    for (int i = 0; i < rd.n; ++i) {
-        float4 p = rd.pwm_row(T, i);
-        uint8_t ch = rd.seq[i];                  // GetConsensus(): read.seq (reference src/Driver.cpp:352-356)
-        const float *s = T.S + 4 * (int)ch;
-        float t = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(p.x, s[0]), __fmul_rn(p.y, s[1])), __fmul_rn(p.z, s[2])), __fmul_rn(p.w, s[3]));
-        score = __fadd_rn(score, t);
+    if (staged) {
+        const int64_t at = R.offsets[r] + lead;
+        for (int i = 0; i < rd.n; ++i)
+            score = __fadd_rn(score, __ldg(T.self + (int)s_seq[at + i] * GMX_NQ + gmx_qidx(s_qual[at + i], 0)));
+    } else {
+        for (int i = 0; i < rd.n; ++i) {
+            float4 p = rd.pwm_row(T, i);
+            uint8_t ch = rd.seq[i];                  // GetConsensus(): read.seq (reference src/Driver.cpp:352-356)
+            const float *s = T.S + 4 * (int)ch;
+            float t = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(p.x, s[0]), __fmul_rn(p.y, s[1])), __fmul_rn(p.z, s[2])), __fmul_rn(p.w, s[3]));
+            score = __fadd_rn(score, t);
+        }
     }
     out.max_align = score;
     double max_align = (double)score;
