@@ -809,10 +809,8 @@ static int phase_a(gmx_ctx *ctx, const gmx_reads *reads, int32_t lo, int32_t hi,
 
     // buffers
     CK(ctx->d_prep.ensure((size_t)n * sizeof(ReadPrep)));
-    CK(ctx->d_seed_rank.ensure((size_t)max_seeds * n_tasks * 4));
-    CK(ctx->d_seed_count.ensure((size_t)max_seeds * n_tasks * 4));
+    CK(ctx->d_seed_rank.ensure((size_t)max_seeds * n_tasks * 16));        // SeedStore::rec
     CK(ctx->d_seed_off.ensure((size_t)max_seeds * n_tasks * 2));
-    CK(ctx->d_seed_code.ensure((size_t)max_seeds * n_tasks * 8));
     CK(ctx->d_seed_n.ensure((size_t)n_tasks));
     CK(ctx->d_seed_hits.ensure((size_t)n_tasks * 4));
     CK(ctx->d_cls_list.ensure((size_t)2 * GMX_N_CLASSES * n_tasks * 4));
@@ -823,7 +821,7 @@ static int phase_a(gmx_ctx *ctx, const gmx_reads *reads, int32_t lo, int32_t hi,
     Counters *dc = ctx->d_counters.as<Counters>();
     ChunkStats *ds = reinterpret_cast<ChunkStats *>(dc + 1);
     SeedStore S;
-    S.rank = ctx->d_seed_rank.as<uint32_t>(); S.count = ctx->d_seed_count.as<uint32_t>(); S.offset = ctx->d_seed_off.as<uint16_t>(); S.code = ctx->d_seed_code.as<unsigned long long>();
+    S.rec = ctx->d_seed_rank.as<uint4>(); S.offset = ctx->d_seed_off.as<uint16_t>();
     S.n_seeds = ctx->d_seed_n.as<uint8_t>(); S.hits = ctx->d_seed_hits.as<uint32_t>(); S.max_seeds = max_seeds; S.n_tasks = n_tasks;
     ClassLists C;
     C.list = ctx->d_cls_list.as<uint32_t>(); C.count = dc->cls_count; C.cursor = dc->cls_cursor; C.n_tasks = n_tasks;

@@ -106,10 +106,9 @@ __global__ void __launch_bounds__(GMX_PREP_THREADS) k_prep_reads(DevReads R, Dev
 // One thread per task = (read, strand).  The walk is sequentially data dependent (the next offset
 // depends on whether the previous k-mer hit), so the parallelism is across the 2 x n_reads tasks.
 struct SeedStore {
-    uint32_t *rank;    // [n_tasks][max_seeds] first SA rank of the interval
-    uint32_t *count;   // [n_tasks][max_seeds] interval size
+    uint4 *rec;        // [n_tasks][max_seeds] {first SA rank of the interval, interval size, the k-mer itself (low, high word):
+                       //   2 bits per base, first base most significant} -- one 16-byte store / load per k-mer
     uint16_t *offset;  // [n_tasks][max_seeds] k-mer offset i in the oriented read
-    unsigned long long *code;  // [n_tasks][max_seeds] the k-mer itself, 2 bits per base, first base most significant
     uint8_t  *n_seeds; // [n_tasks]
     uint32_t *hits;    // [n_tasks] total SA hits of the task
     int max_seeds;
@@ -133,8 +132,13 @@ __global__ void k_seed_walk(DevIndex ix, DevReads R, DevParams P, const ReadPrep
         const uint8_t *seq = R.seq + off;
         // oriented consensus symbol: POS = nt4(seq[x]); NEG = complement of seq[n-1-x]
         // (reverse_comp maps every non-acgt character to 'n', which never matches)
+        // bytes come through an 8-byte register buffer: a byte load per base costs a full L1 wavefront per lane
+        // (the lanes of a warp sit one read apart), an aligned 8-byte load serves 8 bases of the walk
+        unsigned long long buf = 0; uintptr_t buf_at = ~(uintptr_t)0;
         auto sym_at = [&](int x) -> uint32_t {
-            int c = gmx_nt4(seq[neg ? n - 1 - x : x]);
+            const uintptr_t a = (uintptr_t)(seq + (neg ? n - 1 - x : x));
+            if ((a >> 3) != buf_at) { buf_at = a >> 3; buf = __ldg(reinterpret_cast<const unsigned long long *>(buf_at << 3)); }
+            int c = gmx_nt4((uint8_t)(buf >> ((a & 7u) * 8u)));
             return (uint32_t)((neg && c < 4) ? 3 - c : c);
         };
         // rolling window: the k-mer at `wbase`, 2 bits per base (first base most significant), and its non-ACGT mask.
@@ -171,10 +175,8 @@ __global__ void k_seed_walk(DevIndex ix, DevReads R, DevParams P, const ReadPrep
             i += j;
             if (!found) break;
             if (ns < S.max_seeds) {
-                S.rank[S.at(task, ns)] = (uint32_t)k;
-                S.count[S.at(task, ns)] = (uint32_t)(l - k + 1);
+                S.rec[S.at(task, ns)] = make_uint4((uint32_t)k, (uint32_t)(l - k + 1), (uint32_t)wcode, (uint32_t)(wcode >> 32));   // the window is at i
                 S.offset[S.at(task, ns)] = (uint16_t)i;
-                S.code[S.at(task, ns)] = wcode;                   // the window is at i: the k-mer just found
                 total += (uint32_t)(l - k + 1);
                 ns++;
             }
@@ -276,8 +278,8 @@ __device__ __forceinline__ void gmx_vote_task(const DevIndex &ix, const SeedStor
 {
     int ns = S.n_seeds[task];
     for (int s = 0; s < ns; ++s) {
-        uint32_t rank0 = S.rank[S.at(task, s)];
-        uint32_t cnt = S.count[S.at(task, s)];
+        const uint4 rec = S.rec[S.at(task, s)];
+        uint32_t rank0 = rec.x, cnt = rec.y;
         uint32_t off = S.offset[S.at(task, s)];
         for (uint32_t t0 = 0; t0 < cnt; t0 += 32) {
             uint32_t t = t0 + lane;
@@ -391,7 +393,8 @@ __global__ void __launch_bounds__(WARPS * 32) k_vote_smem(DevIndex ix, SeedStore
         const int ns = S.n_seeds[task];
         // pull every suffix-array line this task will read into L2 while the table is being cleared
         for (int s = 0; s < ns; ++s) {
-            const uint32_t rank0 = S.rank[S.at(task, s)], cnt = S.count[S.at(task, s)];
+            const uint4 rec = S.rec[S.at(task, s)];
+            const uint32_t rank0 = rec.x, cnt = rec.y;
             for (uint32_t t = (uint32_t)lane * 32u; t < cnt; t += 1024u)
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(ix.sa_full + rank0 + t));
         }
@@ -401,8 +404,8 @@ __global__ void __launch_bounds__(WARPS * 32) k_vote_smem(DevIndex ix, SeedStore
         for (uint32_t x = lane; x < SLOTS / 16; x += 32) c4[x] = make_uint4(0, 0, 0, 0);
         __syncwarp();
         for (int s = 0; s < ns; ++s) {
-            const uint32_t rank0 = S.rank[S.at(task, s)];
-            const uint32_t cnt = S.count[S.at(task, s)];
+            const uint4 rec = S.rec[S.at(task, s)];
+            const uint32_t rank0 = rec.x, cnt = rec.y;
             const uint32_t off = S.offset[S.at(task, s)];
             for (uint32_t t0 = 0; t0 < cnt; t0 += 32u * GMX_VOTE_UNROLL) {
                 uint32_t sa[GMX_VOTE_UNROLL];
@@ -554,7 +557,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_vote_filter(DevIndex ix, uint
             m.rank[h] = 0u; m.cnt[h] = 0u; m.off[h] = 0u; m.code[h] = 0ull;
             if (h == 1 && !two_halves) break;
             const int64_t at = min(S.at(task, lane + 32 * h), last_seed);
-            m.rank[h] = S.rank[at]; m.cnt[h] = S.count[at]; m.off[h] = S.offset[at]; m.code[h] = S.code[at];
+            const uint4 rec = S.rec[at];
+            m.rank[h] = rec.x; m.cnt[h] = rec.y; m.off[h] = S.offset[at]; m.code[h] = ((unsigned long long)rec.w << 32) | rec.z;
         }
     };
 
