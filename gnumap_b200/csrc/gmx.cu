@@ -82,6 +82,7 @@ struct gmx_ctx {
     cudaEvent_t done_ev[2] = {nullptr, nullptr};          // last kernel that reads buffer set [slot] has been issued
     DevReads up_view[2];
     int32_t up_max_len[2] = {0, 0};
+    struct PendingScan { const gmx_reads *reads = nullptr; int32_t lo = 0, hi = 0; } up_scan[2];   // longest-read scan owed for a buffer set
     DevReads dreads;
     // pipeline buffers
     DevBuf d_seed_code;
@@ -524,9 +525,18 @@ static int issue_upload(gmx_ctx *ctx, const gmx_reads *reads, int32_t lo, int32_
         }
     }
     CK(cudaEventRecord(ctx->up_ev[slot], stream));
-    // the chunk's longest read is found on the host while the copies run
+    // the chunk's longest read is found on the host later, at a point where the GPU has work queued (finish_scan)
+    ctx->up_scan[slot].reads = reads; ctx->up_scan[slot].lo = lo; ctx->up_scan[slot].hi = hi;
+    return GMX_OK;
+}
+
+static int finish_scan(gmx_ctx *ctx, int slot)
+{
+    gmx_ctx::PendingScan &p = ctx->up_scan[slot];
+    if (!p.reads) return GMX_OK;
     int32_t max_len = 0;
-    int r = scan_max_len(ctx, reads, lo, hi, &max_len);
+    int r = scan_max_len(ctx, p.reads, p.lo, p.hi, &max_len);
+    p.reads = nullptr;
     if (r != GMX_OK) return r;
     ctx->up_max_len[slot] = max_len;
     return GMX_OK;
@@ -536,6 +546,7 @@ static int issue_upload(gmx_ctx *ctx, const gmx_reads *reads, int32_t lo, int32_
 static int upload_reads(gmx_ctx *ctx, const gmx_reads *reads, int32_t lo, int32_t hi, int32_t *max_len_out)
 {
     int r = issue_upload(ctx, reads, lo, hi, 0, ctx->stream);
+    if (r == GMX_OK) r = finish_scan(ctx, 0);
     if (r != GMX_OK) return r;
     ctx->dreads = ctx->up_view[0];
     if (max_len_out) *max_len_out = ctx->up_max_len[0];
@@ -796,6 +807,7 @@ static int phase_a(gmx_ctx *ctx, const gmx_reads *reads, int32_t lo, int32_t hi,
     stage_begin(ctx, ST_UPLOAD);
     CK(cudaStreamWaitEvent(ctx->stream, ctx->up_ev[slot], 0));
     ctx->dreads = ctx->up_view[slot];
+    { int r = finish_scan(ctx, slot); if (r != GMX_OK) return r; }           // only the batch's first chunk still owes it here
     max_len = ctx->up_max_len[slot];
     int64_t total_bases = reads->on_device ? (int64_t)n * max_len : reads->offsets[hi] - reads->offsets[lo];
     uint64_t up_bytes = reads->on_device ? 0 : (uint64_t)total_bases * (reads->qual ? 2 : 1) + (reads->pwm ? 16ull * total_bases : 0) + 8ull * n;
@@ -898,6 +910,7 @@ static int phase_a(gmx_ctx *ctx, const gmx_reads *reads, int32_t lo, int32_t hi,
         }
         stage_end(ctx, ST_VOTE, 0, 0, use_filter ? 12 : 6);
         CK(cudaMemcpyAsync(&hc, dc, sizeof(hc), cudaMemcpyDeviceToHost, ctx->stream));
+        { int r = finish_scan(ctx, slot ^ 1); if (r != GMX_OK) return r; }      // host work for the next chunk while the vote runs
         CK(cudaStreamSynchronize(ctx->stream));
         stage_collect(ctx);
         if (hc.c.arena_overflow) {
