@@ -392,12 +392,23 @@ __device__ int gmx_nw_traceback(const ReadView &rd, const WindowView &win, const
             if (c_type == type) c_counter++;
             else { if (c_counter && n_ops < 48) ops[n_ops++] = (uint16_t)((c_counter << 2) | c_type); c_type = type; c_counter = 1; }
         };
+        // the walk visits the rows in descending order, at most one new row per step: eight move words are fetched
+        // at once (independent loads) instead of one dependent load per step
         while (i != 0 && j != 0) {
-            uint32_t mv = (moves[(int64_t)i * mv_stride] >> (2 * (j - i + G))) & 3u;
-            if (mv == GMX_MV_D) { push(0); i--; j--; }
-            else if (mv == GMX_MV_U) { push(1); i--; }
-            else { push(2); j--; }
-            alen++;
+            uint32_t rows[8];
+            const int top = i;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) rows[k] = top - k >= 1 ? moves[(int64_t)(top - k) * mv_stride] : 0u;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                while (i == top - k && i != 0 && j != 0) {
+                    uint32_t mv = (rows[k] >> (2 * (j - i + G))) & 3u;
+                    if (mv == GMX_MV_D) { push(0); i--; j--; }
+                    else if (mv == GMX_MV_U) { push(1); i--; }
+                    else { push(2); j--; }
+                    alen++;
+                }
+            }
         }
         while (i > 0) { push(1); i--; alen++; }
         while (j > 0) { push(2); j--; alen++; }
@@ -408,10 +419,19 @@ __device__ int gmx_nw_traceback(const ReadView &rd, const WindowView &win, const
         int i = n, j = m, k = 0;
         auto put = [&](uint8_t ch) { int at = alen - 1 - k; if (at < out.aligned_cap) out.aligned[at] = ch; k++; };
         while (i != 0 && j != 0) {
-            uint32_t mv = (moves[(int64_t)i * mv_stride] >> (2 * (j - i + G))) & 3u;
-            if (mv == GMX_MV_D) { put(cons.at(rd, T, i - 1)); i--; j--; }
-            else if (mv == GMX_MV_U) { put(cons.at(rd, T, i)); i--; }      // sic: consense[i]
-            else { put('-'); j--; }
+            uint32_t rows[8];
+            const int top = i;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) rows[k] = top - k >= 1 ? moves[(int64_t)(top - k) * mv_stride] : 0u;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                while (i == top - k && i != 0 && j != 0) {
+                    uint32_t mv = (rows[k] >> (2 * (j - i + G))) & 3u;
+                    if (mv == GMX_MV_D) { put(cons.at(rd, T, i - 1)); i--; j--; }
+                    else if (mv == GMX_MV_U) { put(cons.at(rd, T, i)); i--; }      // sic: consense[i]
+                    else { put('-'); j--; }
+                }
+            }
         }
         while (i > 0) { put(cons.at(rd, T, i)); i--; }
         while (j > 0) { put('-'); j--; }
