@@ -65,7 +65,10 @@ def emit(line: dict):
 # workload: i.i.d. genome seed 100, reads seed 101, 1 % substitutions, Q15..40
 # ------------------------------------------------------------------------------------------------
 def workload_name(a):
-    return f"synthetic {a.genome // 1_000_000} Mb genome, {a.reads} x {a.read_len} bp reads, {a.mode} mode (BASELINE configs[1] shape)"
+    shape = {("normal", 100_000_000, 100): "BASELINE configs[1] shape", ("normal", 156_000_000, 150): "BASELINE configs[2] shape, one shard",
+             ("snp", 156_000_000, 150): "BASELINE configs[3] shape, one shard", ("bs", 100_000_000, 100): "BASELINE configs[4] shape, one shard"}
+    tag = shape.get((a.mode, a.genome, a.read_len), "custom shape")
+    return f"synthetic {a.genome // 1_000_000} Mb genome, {a.reads} x {a.read_len} bp reads, {a.mode} mode ({tag})"
 
 
 def get_index(a, device):
@@ -470,9 +473,9 @@ def own_arm(a):
                     "algorithmic_bytes_per_step": st["bytes"][top] / a.steps, "ms_per_step": st["ms"][top] / a.steps,
                     "launches_per_step": launches / a.steps,
                     "algorithmic_bytes_per_loaded_launch": st["bytes"][top] / max(launches / 12, 1) if top == "locate_vote" else st["bytes"][top] / max(launches, 1),
-                    "note": "stage = 12 launches per chunk of 524288 reads (6 filter + 6 exact classes); one of them (k_vote_filter<13,4,true> on this "
+                    "note": "stage = 12 launches per chunk (6 filter + 6 exact classes; chunks of up to 524288 reads); one of them (k_vote_filter<13,4,true> on this "
                             "workload) carries ~all tasks, the rest find empty lists (~5 us each); achieved/traffic are per loaded launch; "
-                            "the kernel is ALU/LSU-bound (profiles/r01_ncu_raw_k_vote_filter_v7.txt), not HBM-bound",
+                            "the kernel is instruction/latency-bound (profiles/r01_ncu_raw_k_vote_filter_final.txt), not HBM-bound",
                     "stages_ms_per_step": {k: round(v / a.steps, 3) for k, v in st["ms"].items()},
                     "stages_units_per_step": {k: v // a.steps for k, v in st["units"].items()}}
         # per-kernel table: algorithmic bytes (or cell updates) / CUDA-event time, against the measured HBM peak or the

@@ -116,7 +116,9 @@ typedef struct gmx_reads {
     const uint8_t *qual;
     const float   *pwm;
     int32_t        on_device; /* 0: the four arrays are host memory (copied to the GPU inside the call);
-                                 1: they already live in the memory of the context's GPU             */
+                                 1: they already live in the memory of the context's GPU (seq / qual are
+                                    read in aligned 8-byte words: the last word may reach up to 7 bytes past the
+                                    final base, inside the allocation granule of any cudaMalloc'd buffer)  */
     int32_t        max_len;   /* longest read of the batch; 0 = let the library scan offsets (host only) */
     /* Reads used in place inside a larger text (FASTQ): device-resident batches only.  When `lens` is given, read r
      * is seq[offsets[r] .. +lens[r]) and offsets has n_reads entries; when `qual_offsets` is given its quality string
