@@ -440,11 +440,8 @@ __global__ void __launch_bounds__(WARPS * 32) k_vote_smem(DevIndex ix, SeedStore
 #define GMX_FILTER_MAX_SEEDS 64
 #define GMX_FILTER_MAX_SPAN 448  // max k-mer offset + mer: the window words must fit the 32 lanes ((15 + span) / 16 + 2 < 32)
 
-// shared-window accessors (32-bit shared addresses)
-__device__ __forceinline__ uint32_t gmx_lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
-__device__ __forceinline__ void gmx_sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+// returning OR on a 32-bit shared-window address
 __device__ __forceinline__ uint32_t gmx_atoms_or32(uint32_t a, uint32_t v) { uint32_t o; asm volatile("atom.shared.or.b32 %0, [%1], %2;" : "=r"(o) : "r"(a), "r"(v) : "memory"); return o; }
-__device__ __forceinline__ void gmx_reds_or32(uint32_t a, uint32_t v) { asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 
 struct FilterSmem {              // per-warp layout behind the filter bytes
     uint32_t queue[GMX_FQ_CAP];
