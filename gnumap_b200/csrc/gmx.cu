@@ -38,6 +38,14 @@ struct DevBuf {
     template <class T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
+// function-local scratch: freed on every return path (the context's own buffers are released by gmx_destroy)
+struct ScratchBuf : DevBuf {
+    ScratchBuf() = default;
+    ScratchBuf(const ScratchBuf &) = delete;
+    ScratchBuf &operator=(const ScratchBuf &) = delete;
+    ~ScratchBuf() { release(); }
+};
+
 struct HostBuf {                                   // pinned host staging
     void *p = nullptr;
     size_t cap = 0;
@@ -561,7 +569,7 @@ extern "C" int gmx_fm_search(gmx_ctx *ctx, const uint8_t *kmers, int32_t len, in
     if (!ctx || !kmers || !k_out || !l_out || len < 1 || len > 64 || n < 0) return GMX_ERR_INVALID;
     if (n == 0) return GMX_OK;
     CK(cudaSetDevice(ctx->device));
-    DevBuf in, ko, lo;
+    ScratchBuf in, ko, lo;
     CK(in.ensure((size_t)n * len)); CK(ko.ensure((size_t)n * 8)); CK(lo.ensure((size_t)n * 8));
     CK(cudaMemcpyAsync(in.p, kmers, (size_t)n * len, cudaMemcpyHostToDevice, ctx->stream));
     k_fm_search<<<nblk(n, 128), 128, 0, ctx->stream>>>(ctx->ix, in.as<uint8_t>(), len, n, ko.as<uint64_t>(), lo.as<uint64_t>());
@@ -579,7 +587,7 @@ extern "C" int gmx_sa_locate(gmx_ctx *ctx, const uint64_t *ranks, int64_t n, int
     if (n == 0) return GMX_OK;
     for (int64_t i = 0; i < n; ++i) if (ranks[i] > ctx->ix.seq_len) { ctx->err = "rank out of range"; return GMX_ERR_INVALID; }
     CK(cudaSetDevice(ctx->device));
-    DevBuf in, po;
+    ScratchBuf in, po;
     CK(in.ensure((size_t)n * 8)); CK(po.ensure((size_t)n * 8));
     CK(cudaMemcpyAsync(in.p, ranks, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
     k_sa_locate<<<nblk(n, 128), 128, 0, ctx->stream>>>(ctx->ix, in.as<uint64_t>(), n, mode, po.as<uint64_t>());
@@ -595,7 +603,7 @@ extern "C" int gmx_get_windows(gmx_ctx *ctx, const uint64_t *begin, int64_t n, i
     if (!ctx || !begin || !chars_out || !len_out || n < 0 || size < 1) return GMX_ERR_INVALID;
     if (n == 0) return GMX_OK;
     CK(cudaSetDevice(ctx->device));
-    DevBuf in, ch, ln;
+    ScratchBuf in, ch, ln;
     CK(in.ensure((size_t)n * 8)); CK(ch.ensure((size_t)n * size)); CK(ln.ensure((size_t)n * 4));
     CK(cudaMemcpyAsync(in.p, begin, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
     k_get_windows<<<nblk(n, 128), 128, 0, ctx->stream>>>(ctx->ix, in.as<uint64_t>(), n, size, ch.as<uint8_t>(), ln.as<int32_t>());
@@ -652,7 +660,7 @@ __global__ void __launch_bounds__(128) k_traceback_tasks(DevReads R, DevTables T
 }
 
 struct TaskUpload {
-    DevBuf ridx, strand, windows, cons;
+    ScratchBuf ridx, strand, windows, cons;
 };
 
 static int upload_tasks(gmx_ctx *ctx, TaskUpload &u, const gmx_reads *reads, int64_t n_tasks, const int32_t *read_idx, const uint8_t *strand,
@@ -679,7 +687,7 @@ extern "C" int gmx_nw_score(gmx_ctx *ctx, const gmx_reads *reads, int64_t n_task
     if (!ctx || !reads || !read_idx || !windows || !score_out || n_tasks < 0 || win_stride < 1) return GMX_ERR_INVALID;
     if (n_tasks == 0) return GMX_OK;
     CK(cudaSetDevice(ctx->device));
-    TaskUpload u; DevBuf out;
+    TaskUpload u; ScratchBuf out;
     int r = upload_tasks(ctx, u, reads, n_tasks, read_idx, strand, windows, win_stride, nullptr, nullptr);
     if (r != GMX_OK) return r;
     CK(out.ensure((size_t)n_tasks * 4));
@@ -701,7 +709,7 @@ extern "C" int gmx_nw_traceback(gmx_ctx *ctx, const gmx_reads *reads, int64_t n_
         return GMX_ERR_INVALID;
     if (n_tasks == 0) return GMX_OK;
     CK(cudaSetDevice(ctx->device));
-    TaskUpload u; DevBuf al, ln, cg, mv;
+    TaskUpload u; ScratchBuf al, ln, cg, mv;
     int32_t max_len = 0;
     int r = upload_tasks(ctx, u, reads, n_tasks, read_idx, strand, windows, win_stride, consensus, &max_len);
     if (r != GMX_OK) return r;
@@ -727,7 +735,7 @@ extern "C" int gmx_pair_hmm(gmx_ctx *ctx, const gmx_reads *reads, int64_t n_task
     if (!ctx || !reads || !read_idx || !windows || !post_out || n_tasks < 0 || win_stride < 1) return GMX_ERR_INVALID;
     if (n_tasks == 0) return GMX_OK;
     CK(cudaSetDevice(ctx->device));
-    TaskUpload u; DevBuf out, scratch;
+    TaskUpload u; ScratchBuf out, scratch;
     int32_t max_len = 0;
     int r = upload_tasks(ctx, u, reads, n_tasks, read_idx, strand, windows, win_stride, nullptr, &max_len);
     if (r != GMX_OK) return r;
@@ -1680,7 +1688,7 @@ extern "C" int gmx_format_sgr(gmx_ctx *ctx, const char *const *chrom_names, doub
     const uint64_t nb = ctx->acc.n_amount;
     if (nb >= 0x7fffffffull) { ctx->err = "more than 2^31 accumulator bins"; return GMX_ERR_UNSUPPORTED; }
     // printable bins, in order, selected on the device
-    DevBuf d_idx, d_val, d_cnt, d_tmp;
+    ScratchBuf d_idx, d_val, d_cnt, d_tmp;
     CK(d_idx.ensure((size_t)nb * 4 + 16)); CK(d_cnt.ensure(16));
     thrust::counting_iterator<uint32_t> it(0);
     SgrRowSelect pred{ctx->acc.amount, min_print};            // float > double literal, compared in double as the reference does
@@ -1754,7 +1762,7 @@ extern "C" int gmx_format_gmp(gmx_ctx *ctx, const char *const *chrom_names, int 
     const uint64_t gs = ctx->params.gen_size;
     const uint64_t l_pac = (uint64_t)ctx->h_seq_offset.back();
     // printable rows, in genome order, selected and gathered on the device
-    DevBuf d_idx, d_rows, d_base, d_cnt, d_tmp;
+    ScratchBuf d_idx, d_rows, d_base, d_cnt, d_tmp;
     CK(d_idx.ensure((size_t)nb * 4 + 16)); CK(d_cnt.ensure(16));
     thrust::counting_iterator<uint32_t> it(0);
     GmpRowSelect pred{ctx->acc.amount, ctx->ix.pac, gs, l_pac, min_print, snp ? -1 : target_base};
