@@ -203,6 +203,17 @@ __device__ float gmx_nw_band_score_any(const ReadView &rd, const WindowView &win
 // (7 live columns + the one entering), the 8 row phases are unrolled so every slot index is a compile-time
 // constant, and the 4-way choice of the substitution value by the genome base is three byte-permutes with
 // selectors kept per slot.
+// eight bytes starting at any address, from the one or two aligned 64-bit words that hold them
+__device__ __forceinline__ unsigned long long gmx_load8_unaligned(const uint8_t *p)
+{
+    const uintptr_t a = (uintptr_t)p;
+    const unsigned long long *w = reinterpret_cast<const unsigned long long *>(a & ~(uintptr_t)7);
+    const unsigned sh = (unsigned)(a & 7u) * 8u;
+    unsigned long long v = __ldg(w);
+    if (sh) v = (v >> sh) | (__ldg(w + 1) << (64u - sh));
+    return v;
+}
+
 struct NwFastState {
     float S[8];            // nm[i+1][j] of the live columns, slot j & 7
     uint32_t A[8], B[8];   // PRMT selectors of the slot's genome base: bit 0 / bit 1
@@ -216,15 +227,17 @@ __device__ __forceinline__ float gmx_nw_pick(const float4 &sub, uint32_t selA, u
 }
 
 // one row i with i & 7 == P.  INTERIOR: 3 <= i <= n - 5 (every band column inside [0, n-1], right guard outside)
+// g_in: the genome base of the entering column when the caller has it already (interior rows), else -1
 template <int P, bool INTERIOR>
-__device__ __forceinline__ void gmx_nw_fast_row(NwFastState &st, int i, int n, const float4 &sub, const uint8_t *pac, int64_t pos, float gap)
+__device__ __forceinline__ void gmx_nw_fast_row(NwFastState &st, int i, int n, const float4 &sub, const uint8_t *pac, int64_t pos, float gap, int g_in = -1)
 {
     // the column entering the band on the left: j = i - 3, slot (P + 5) & 7
     {
         constexpr int sn = (P + 5) & 7;
         const int jn = i - 3;
         int g = 0;
-        if (INTERIOR || jn >= 0) g = gmx_pac_base(pac, pos + jn);
+        if (INTERIOR) g = g_in;
+        else if (jn >= 0) g = gmx_pac_base(pac, pos + jn);
         st.A[sn] = (g & 1) ? 0x7654u : 0x3210u;
         st.B[sn] = (g & 2) ? 0x7654u : 0x3210u;
         st.S[sn] = (!INTERIOR && i == n - 1) ? __fmul_rn(gap, 4.f) : GMX_NEG_INF;       // nm[n][n-4] is a border cell
@@ -263,14 +276,34 @@ __device__ float gmx_nw_band_score_fast3(const ReadView &rd, const uint8_t *pac,
     int i = n - 1;
     while (i >= 0) {
         if ((i & 7) == 7 && i <= n - 5 && i - 7 >= 3) {
-            gmx_nw_fast_row<7, true>(st, i, n, rd.sub_row(T, i), pac, pos, gap);
-            gmx_nw_fast_row<6, true>(st, i - 1, n, rd.sub_row(T, i - 1), pac, pos, gap);
-            gmx_nw_fast_row<5, true>(st, i - 2, n, rd.sub_row(T, i - 2), pac, pos, gap);
-            gmx_nw_fast_row<4, true>(st, i - 3, n, rd.sub_row(T, i - 3), pac, pos, gap);
-            gmx_nw_fast_row<3, true>(st, i - 4, n, rd.sub_row(T, i - 4), pac, pos, gap);
-            gmx_nw_fast_row<2, true>(st, i - 5, n, rd.sub_row(T, i - 5), pac, pos, gap);
-            gmx_nw_fast_row<1, true>(st, i - 6, n, rd.sub_row(T, i - 6), pac, pos, gap);
-            gmx_nw_fast_row<0, true>(st, i - 7, n, rd.sub_row(T, i - 7), pac, pos, gap);
+            // Eight interior rows.  The lanes of a warp sit on different reads and genome positions, so every byte
+            // load costs a wavefront per lane: the 8 sequence bytes, the 8 quality bytes and the 8 entering genome
+            // bases of the block come from two aligned 64-bit words each (two 32-bit words for the packed genome).
+            const uint8_t *a_seq = rd.seq + (rd.neg ? n - 1 - i : i - 7), *a_qual = rd.qual + (rd.neg ? n - 1 - i : i - 7);
+            const unsigned long long sq = gmx_load8_unaligned(a_seq), ql = gmx_load8_unaligned(a_qual);
+            const int64_t x0 = pos + i - 10;                                   // first (lowest) entering column of the block
+            const uintptr_t pa = (uintptr_t)(pac + (x0 >> 2));
+            const uint32_t *pw = reinterpret_cast<const uint32_t *>(pa & ~(uintptr_t)3);
+            const unsigned long long gw = ((unsigned long long)__ldg(pw + 1) << 32) | __ldg(pw);
+            const int64_t xb = 4 * ((x0 >> 2) - (int64_t)(pa & 3));               // genome index of the first base of byte 0 of gw
+            const float4 *lut = reinterpret_cast<const float4 *>(rd.neg ? T.sub_neg : T.sub_pos);
+            auto row_sub = [&](int k) -> float4 {                               // row i - k
+                const int b = rd.neg ? k : 7 - k;
+                return __ldg(lut + gmx_nt4((uint8_t)(sq >> (8 * b))) * GMX_NQ + gmx_qidx((uint8_t)(ql >> (8 * b)), 0));
+            };
+            auto row_g = [&](int k) -> int {                                    // genome base of column i - k - 3
+                const int64_t x = pos + i - k - 3;
+                const int rel = (int)(x - xb);                                  // bases from the start of gw: 4 per byte, first base in the top bits
+                return (int)((gw >> (8 * (rel >> 2) + 2 * (3 - (rel & 3)))) & 3ull);
+            };
+            gmx_nw_fast_row<7, true>(st, i, n, row_sub(0), pac, pos, gap, row_g(0));
+            gmx_nw_fast_row<6, true>(st, i - 1, n, row_sub(1), pac, pos, gap, row_g(1));
+            gmx_nw_fast_row<5, true>(st, i - 2, n, row_sub(2), pac, pos, gap, row_g(2));
+            gmx_nw_fast_row<4, true>(st, i - 3, n, row_sub(3), pac, pos, gap, row_g(3));
+            gmx_nw_fast_row<3, true>(st, i - 4, n, row_sub(4), pac, pos, gap, row_g(4));
+            gmx_nw_fast_row<2, true>(st, i - 5, n, row_sub(5), pac, pos, gap, row_g(5));
+            gmx_nw_fast_row<1, true>(st, i - 6, n, row_sub(6), pac, pos, gap, row_g(6));
+            gmx_nw_fast_row<0, true>(st, i - 7, n, row_sub(7), pac, pos, gap, row_g(7));
             i -= 8;
             continue;
         }
