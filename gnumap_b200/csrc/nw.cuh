@@ -374,9 +374,9 @@ __device__ __forceinline__ void gmx_nw_fill_moves(const ReadView &rd, const Wind
     int gb[2 * GMAX + 3];
 #pragma unroll
     for (int x = 0; x < 2 * GMAX + 3; ++x) { int j = 1 + (x - G - 1) - 1; gb[x] = (x <= 2 * G + 1 && j >= 0 && j < m) ? win.base(j) : 0; }
-    for (int i = 1; i <= n; ++i) {
-        float4 sub = rd.sub_row(T, i - 1);
-        const float other = win.pac ? 0.f : rd.sub_other(T, i - 1);
+    // one row of the fill; g_enter: the genome base of the column entering the band on the right if the caller has
+    // it already, else -1
+    auto do_row = [&](int i, const float4 &sub, float other, int g_enter) {
         uint32_t mv = 0;
         // guard cell left of the band: column 0 carries gap*i for i <= G+2, otherwise NEG_INF
         cur[0] = (i - G - 1 == 0) ? __fmul_rn(gap, (float)i) : GMX_NEG_INF;
@@ -404,8 +404,36 @@ __device__ __forceinline__ void gmx_nw_fill_moves(const ReadView &rd, const Wind
         for (int x = 0; x < 2 * GMAX + 3; ++x) { if (x == 2 * G + 2) cur[x] = GMX_NEG_INF; if (x <= 2 * G + 2) prev[x] = cur[x]; }
 #pragma unroll
         for (int x = 0; x < 2 * GMAX + 2; ++x) gb[x] = gb[x + 1];
-        { int j = (i + 1) + G - 1; if (2 * G + 1 < 2 * GMAX + 3) gb[2 * G + 1] = j < m ? win.base(j) : 0; }
+        { int j = (i + 1) + G - 1; if (2 * G + 1 < 2 * GMAX + 3) gb[2 * G + 1] = j < m ? (g_enter >= 0 ? g_enter : win.base(j)) : 0; }
         moves[(int64_t)i * mv_stride] = mv;
+    };
+    int i = 1;
+    while (i <= n) {
+        if (G_T == 3 && win.pac && !rd.pwm && i + 6 <= n - 1) {
+            // Eight rows whose sequence / quality bytes and entering genome bases are fetched together (the lanes of a
+            // warp sit on different reads and genome positions: a byte load is a wavefront per lane), as in K2a.
+            const int r = i - 1;                                                 // read rows r .. r + 7
+            const uint8_t *a_seq = rd.seq + (rd.neg ? n - 1 - r - 7 : r), *a_qual = rd.qual + (rd.neg ? n - 1 - r - 7 : r);
+            const unsigned long long sq = gmx_load8_unaligned(a_seq), ql = gmx_load8_unaligned(a_qual);
+            const int64_t x0 = win.pos + i + G;                                  // entering column of row i (the lowest of the block)
+            const uintptr_t pa = (uintptr_t)(win.pac + (x0 >> 2));
+            const uint32_t *pw = reinterpret_cast<const uint32_t *>(pa & ~(uintptr_t)3);
+            const unsigned long long gw = ((unsigned long long)__ldg(pw + 1) << 32) | __ldg(pw);
+            const int64_t xb = 4 * ((x0 >> 2) - (int64_t)(pa & 3));               // genome index of the first base of byte 0 of gw
+            const float4 *lut = reinterpret_cast<const float4 *>(rd.neg ? T.sub_neg : T.sub_pos);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int bsel = rd.neg ? 7 - k : k;
+                const float4 sub = __ldg(lut + gmx_nt4((uint8_t)(sq >> (8 * bsel))) * GMX_NQ + gmx_qidx((uint8_t)(ql >> (8 * bsel)), 0));
+                const int rel = (int)(x0 + k - xb);
+                const int g = (int)((gw >> (8 * (rel >> 2) + 2 * (3 - (rel & 3)))) & 3ull);
+                do_row(i + k, sub, 0.f, g);
+            }
+            i += 8;
+            continue;
+        }
+        do_row(i, rd.sub_row(T, i - 1), win.pac ? 0.f : rd.sub_other(T, i - 1), -1);
+        ++i;
     }
 }
 
