@@ -95,8 +95,8 @@ struct FastqLines {            // std::getline over a memory buffer, with ifstre
     const char *t; int64_t len, pos; bool eof;
     void getline(int64_t &off, int64_t &n)
     {
+        if (eof) return;               // the stream is no longer good: std::getline leaves the string as it was
         off = pos; n = 0;
-        if (eof) return;
         const char *q = (const char *)memchr(t + pos, '\n', (size_t)(len - pos));
         if (q) { n = (q - t) - pos; pos = (q - t) + 1; }
         else { n = len - pos; pos = len; eof = true; }

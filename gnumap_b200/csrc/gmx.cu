@@ -1385,9 +1385,12 @@ extern "C" int gmx_fastq_scan_host(const char *text, int64_t len, int illumina, 
     int64_t n = 0;
     int rc = GMX_OK;
     int qbase = illumina ? 64 : 33;
+    // the four line buffers live across records, as the reference's strings do (:1049): a getline on a stream that
+    // already hit end-of-file leaves its string untouched, so a truncated last record can pick up the previous
+    // record's lines -- the reference emits such reads, and so does this scan
+    int64_t no = 0, nn = 0, so = 0, sn = 0, po = 0, pn = 0, qo = 0, qn = 0;
     while (true) {
         if (in.eof) break;                                         // :1060
-        int64_t no, nn, so, sn, po, pn, qo, qn;
         in.getline(no, nn);                                        // :1070
         while (nn == 0 && !in.eof) in.getline(no, nn);             // :1073-1076 blank lines
         if (in.eof) break;                                         // :1079

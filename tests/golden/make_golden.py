@@ -254,6 +254,10 @@ def fastq_cases():
         "lowercase_and_other_letters": b"@x\nacgtRYKM\n+\nIIIIIIII\n",
         "bad_quality_char": b"@x\nACGT\n+\nII I\n",
         "empty_file": b"",
+        # a getline on a stream that already hit end-of-file leaves its string untouched: the reference then emits
+        # the truncated last record with the previous record's lines
+        "truncated_after_plus_no_newline": rec(b"a", 30) + rec(b"b", 12)[: -14],
+        "stale_lines_at_eof": b"@r2\nnntAc\n+\n@extra\n@#-2+?/B\n",
     }
     return cases
 

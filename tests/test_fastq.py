@@ -36,6 +36,59 @@ def test_host_scan_matches_the_reference_reader():
         assert got == c["reads"], f"{name}: {got[:3]} vs {c['reads'][:3]}"
 
 
+def test_host_scan_fuzz_against_the_reference_reader(tmp_path):
+    """Differential fuzz where the compiled reference is present (oracle/_ref/libref_probe.so, built by
+    __graft_entry__.build() next to /root/reference): random FASTQ texts with deleted, blank, garbage, shortened,
+    lengthened and duplicated lines through the reference's own SeqReader and through gmx_fastq_scan_host."""
+    import ctypes as C
+    from oracle import oracle as O
+    if not os.path.exists(O.REF_PROBE):
+        pytest.skip("oracle/_ref/libref_probe.so has not been built (needs /root/reference at build time)")
+    L = C.CDLL(O.REF_PROBE)
+    rng = np.random.default_rng(2718)
+    fn = str(tmp_path / "f.fq")
+    buf = C.create_string_buffer(1 << 18)
+
+    def rec(i):
+        n = int(rng.integers(1, 40))
+        return [b"@r%d" % i, bytes(b"ACGTNacgtn"[int(c)] for c in rng.integers(0, 10, size=n)), b"+",
+                bytes(int(x) + 33 for x in rng.integers(0, 41, size=n))]
+
+    checked = recovered = 0
+    while checked < 400:
+        lines = []
+        for i in range(int(rng.integers(1, 8))):
+            lines += rec(i)
+        for _ in range(int(rng.integers(0, 4))):
+            if not lines:
+                break
+            op, k = int(rng.integers(0, 8)), int(rng.integers(0, len(lines)))
+            if op == 0: del lines[k]
+            elif op == 1: lines.insert(k, b"")
+            elif op == 2: lines.insert(k, b"GARBAGE")
+            elif op == 3: lines[k] = lines[k][: max(0, len(lines[k]) - int(rng.integers(1, 5)))]
+            elif op == 4: lines[k] = lines[k] + b"XX"
+            elif op == 5: lines.insert(k, b"@extra")
+            elif op == 6: lines.insert(k, b"+")
+            else: lines[k] = b"@" + lines[k]
+        text = b"\n".join(lines) + (b"\n" if rng.random() < 0.8 else b"")
+        if not text.startswith(b"@"):
+            continue                                      # the reference sniffs the format from the first character
+        with open(fn, "wb") as f:
+            f.write(text)
+        n = L.refp_read_fastq(fn.encode(), buf, 1 << 18)
+        want = None if n < 0 else ([ln.split("\t") for ln in buf.value.decode("latin-1").split("\n")[:-1]] if n > 0 else [])
+        try:
+            got = fields(text, api.fastq_scan_host(text))
+        except api.GmxError as e:
+            assert e.code == _abi.GMX_ERR_FORMAT
+            got = None
+        assert got == want, (text, got, want)
+        checked += 1
+        recovered += want is not None and len(want) != text.count(b"@r")
+    assert recovered > 50
+
+
 def test_illumina_offset_falls_back_like_the_reference():
     # quality chars below 64 with --illumina: the reference turns the flag off and re-reads at offset 33 (SeqReader.cpp:1180-1188)
     text = b"@a\nACGT\n+\n5555\n"
