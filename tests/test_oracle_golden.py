@@ -154,3 +154,35 @@ def test_whole_program_matches_reference(mode):
             # accumulators: posteriors and accumulated scores within 1e-5 relative; the text
             # file is printed with five decimals (half a unit of the last place = 5e-6)
             assert np.allclose(np.array(g[2:8], dtype=np.float64), np.array([float(x) for x in w[2:8]]), rtol=1e-5, atol=6e-6), (g, w)
+
+
+def test_index_builder_against_live_bwa_index(tmp_path):
+    """SURVEY.md 8(f) rank 4, where the compiled reference is present: random genomes (1-5 contigs, lengths around the
+    occ-block and SA-sample boundaries, a homopolymer, a tandem repeat) through the reference's own bwa_index and through
+    gnumap_b200/index.py: the five index files byte for byte."""
+    if not O.have_ref_binary():
+        pytest.skip("oracle/_ref/gnumap has not been built (needs /root/reference at build time)")
+    rng = np.random.default_rng(4242)
+    shapes = [[127], [128, 129], [31, 32, 33], [1000, 1, 64], [4097], [255, 256, 257, 4, 12]]
+    for k, lens in enumerate(shapes):
+        contigs = []
+        for j, n in enumerate(lens):
+            c = rng.integers(0, 4, size=n, dtype=np.uint8)
+            if k == 3 and j == 0:
+                c[100:400] = 0                                     # homopolymer
+            if k == 4:
+                c[1000:1600] = np.tile(c[1000:1012], 50)            # tandem repeat
+            contigs.append((f"c{k}_{j}", c))
+        d = tmp_path / f"g{k}"
+        d.mkdir()
+        fa = str(d / "g.fa")
+        synth.write_fasta(fa, contigs)
+        empty = str(d / "e.fq")
+        open(empty, "w").close()
+        O.run_reference(fa, empty, str(d / "out"), threads=1, mmap_threshold=1024)
+        mine = str(d / "mine.fa")
+        index.save_index(index.build_index(contigs), mine)
+        for ext in ("bwt", "sa", "pac", "ann", "amb"):
+            want = np.fromfile(fa + ".gnumap." + ext, dtype=np.uint8)
+            got = np.fromfile(mine + ".gnumap." + ext, dtype=np.uint8)
+            assert np.array_equal(got, want), f"genome {k} ({lens}): .gnumap.{ext} differs from bwa_index's"
