@@ -43,10 +43,6 @@ __global__ void k_count_newlines(const char *text, int64_t len, unsigned long lo
     if ((threadIdx.x & 31) == 0 && n) atomicAdd(count, n);
 }
 
-struct AboveThreshold {
-    const float *v; float t;
-    __host__ __device__ bool operator()(uint32_t i) const { return v[i] > t; }
-};
 
 __global__ void k_gather_f32(const float *v, const uint32_t *idx, uint32_t n, float *out)
 {

@@ -93,9 +93,8 @@ struct gmx_ctx {
     struct PendingScan { const gmx_reads *reads = nullptr; int32_t lo = 0, hi = 0; } up_scan[2];   // longest-read scan owed for a buffer set
     DevReads dreads;
     // pipeline buffers
-    DevBuf d_seed_code;
     DevBuf d_fq_text, d_fq_nl, d_fq_tmp, d_fq_seq_off, d_fq_qual_off, d_fq_len, d_fq_recs, d_fq_flags, d_fq_count;   // FASTQ indexer
-    DevBuf d_prep, d_seed_rank, d_seed_count, d_seed_off, d_seed_n, d_seed_hits, d_cls_list, d_cls_meta;
+    DevBuf d_prep, d_seed_rank, d_seed_off, d_seed_n, d_seed_hits, d_cls_list, d_cls_meta;
     DevBuf d_keys, d_keys_alt, d_sort_tmp, d_score, d_leader, d_slot, d_lead_cand, d_hashes, d_expv, d_counters;
     DevBuf d_results, d_alen, d_aligned, d_cigar, d_hmm, d_moves, d_arena, d_phmm_scratch;
     size_t cand_cap = 0;
@@ -417,10 +416,10 @@ extern "C" void gmx_destroy(gmx_ctx *ctx)
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     DevBuf *bufs[] = {&ctx->d_bwt, &ctx->d_sa_full, &ctx->d_sa_samp, &ctx->d_pac, &ctx->d_seq_offset, &ctx->d_tables, &ctx->d_amount,
                       &ctx->d_planes, &ctx->d_offsets[0], &ctx->d_seq[0], &ctx->d_qual[0], &ctx->d_pwm[0], &ctx->d_offsets[1], &ctx->d_seq[1], &ctx->d_qual[1], &ctx->d_pwm[1], &ctx->d_prep, &ctx->d_seed_rank,
-                      &ctx->d_seed_count, &ctx->d_seed_off, &ctx->d_seed_n, &ctx->d_seed_hits, &ctx->d_cls_list, &ctx->d_cls_meta,
+                      &ctx->d_seed_off, &ctx->d_seed_n, &ctx->d_seed_hits, &ctx->d_cls_list, &ctx->d_cls_meta,
                       &ctx->d_keys, &ctx->d_keys_alt, &ctx->d_sort_tmp, &ctx->d_score, &ctx->d_leader, &ctx->d_slot, &ctx->d_lead_cand,
                       &ctx->d_hashes, &ctx->d_expv, &ctx->d_counters, &ctx->d_results, &ctx->d_alen, &ctx->d_aligned, &ctx->d_cigar,
-                      &ctx->d_hmm, &ctx->d_moves, &ctx->d_arena, &ctx->d_phmm_scratch, &ctx->d_best_cigar[0], &ctx->d_best_cigar[1], &ctx->d_out_results[0], &ctx->d_out_results[1], &ctx->d_seed_code, &ctx->d_kmer_tab, &ctx->d_multi, &ctx->d_multi_count, &ctx->d_ranges, &ctx->d_groups, &ctx->d_read_base, &ctx->d_fq_text, &ctx->d_fq_nl, &ctx->d_fq_tmp, &ctx->d_fq_seq_off, &ctx->d_fq_qual_off, &ctx->d_fq_len, &ctx->d_fq_recs, &ctx->d_fq_flags, &ctx->d_fq_count};
+                      &ctx->d_hmm, &ctx->d_moves, &ctx->d_arena, &ctx->d_phmm_scratch, &ctx->d_best_cigar[0], &ctx->d_best_cigar[1], &ctx->d_out_results[0], &ctx->d_out_results[1], &ctx->d_kmer_tab, &ctx->d_multi, &ctx->d_multi_count, &ctx->d_ranges, &ctx->d_groups, &ctx->d_read_base, &ctx->d_fq_text, &ctx->d_fq_nl, &ctx->d_fq_tmp, &ctx->d_fq_seq_off, &ctx->d_fq_qual_off, &ctx->d_fq_len, &ctx->d_fq_recs, &ctx->d_fq_flags, &ctx->d_fq_count};
     for (DevBuf *b : bufs) b->release();
     ctx->h_best_cigar.release();
     ctx->h_counters.release();
