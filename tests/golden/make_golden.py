@@ -195,6 +195,38 @@ def make_program(tmp):
         print(f"ref_program_{mode}.json.gz: {len(sam)} SAM records, matched {rec['matched']}")
 
 
+def make_program_snpdepth(tmp):
+    """Whole-program `--snp` run at 15x coverage over a two-haplotype sample with planted homozygous and heterozygous
+    SNPs, so that the .gmp carries confident mono- and diploid calls (the 1.7x fixtures above carry none)."""
+    d = os.path.join(tmp, "snpdepth")
+    os.makedirs(d)
+    contigs = synth.make_genome(6000, 77, n_contigs=2)
+    codes = np.concatenate([c for _, c in contigs])
+    hap_a = codes.copy(); hap_b = codes.copy()
+    hom = np.arange(150, 5900, 300); het = np.arange(300, 5900, 300)
+    hap_a[hom] = (hap_a[hom] + 1) & 3; hap_b[hom] = hap_a[hom]
+    hap_b[het] = (hap_b[het] + 2) & 3
+    ra = synth.simulate_reads(hap_a, 750, 62, 78, sub_rate=0.01)
+    rb = synth.simulate_reads(hap_b, 750, 62, 79, sub_rate=0.01)
+    reads = {k: np.concatenate([ra[k], rb[k]]) for k in ra}
+    fa = os.path.join(d, "g.fa"); fq = os.path.join(d, "r.fq")
+    synth.write_fasta(fa, contigs); synth.write_fastq(fq, reads)
+    empty = os.path.join(d, "empty.fq")
+    open(empty, "w").close()
+    O.run_reference(fa, empty, os.path.join(d, "warm"), threads=1, extra=["--snp"], mmap_threshold=1024)
+    log = O.run_reference(fa, fq, os.path.join(d, "out"), threads=1, extra=["--snp"], mmap_threshold=1024)
+    rec = {"mode": "snp", "extra": ["--snp"], "genome_seed": 77,
+           "contigs": [[n, "".join("ACGT"[c] for c in cs)] for n, cs in contigs],
+           "reads": [[nm, s.decode(), q.decode()] for nm, (s, q) in zip(*synth.read_fastq(fq))],
+           "sam": [ln.rstrip("\n") for ln in open(os.path.join(d, "out.sam")) if not ln.startswith("@")],
+           "matched": int([ln for ln in log.splitlines() if "Sequences matched" in ln][0].split(":")[1]),
+           "gmp": [ln.rstrip("\n") for ln in open(os.path.join(d, "out.gmp"))]}
+    with gzip.GzipFile(os.path.join(HERE, "ref_program_snpdepth.json.gz"), "wb", mtime=0) as f:
+        f.write(json.dumps(rec).encode())
+    calls = [ln.split("\t")[-1][:2] for ln in rec["gmp"]]
+    print("ref_program_snpdepth.json.gz:", len(rec["gmp"]), "rows,", sum(c == "Y:" for c in calls), "Y calls,", sum("/" in ln.split("\t")[-1] for ln in rec["gmp"]), "diploid")
+
+
 def make_snp_calls(tmp):
     """Call columns of GenomeBwt::PrintSNPCall (reference src/GenomeBwt.cpp:1011-1092 over is_snp / LRT / dipLRT
     :739-898) for random read-count vectors, through the unmodified reference objects.  gsl_cdf_chisq_P comes from
@@ -289,6 +321,7 @@ def main():
         make_functions(tmp)
         make_index(tmp)
         make_program(tmp)
+        make_program_snpdepth(tmp)
         make_snp_calls(tmp)
     finally:
         shutil.rmtree(tmp, ignore_errors=True)

@@ -198,7 +198,7 @@ def test_native_sgr_equals_the_reference_binary():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("mode", ["snp", "bs"])
+@pytest.mark.parametrize("mode", ["snp", "bs", "snpdepth"])
 def test_native_gmp_rows_and_calls(mode):
     """SURVEY.md §8(f) rank 3 (SNP / bisulfite part): gmx_format_gmp -- rows selected and gathered on the device --
     against the restated row printer on the same accumulators (text equality; the call column through gmx_snp_call,
@@ -210,19 +210,19 @@ def test_native_gmp_rows_and_calls(mode):
     lut = {c: i for i, c in enumerate("ACGT")}
     contigs = [(n, np.array([lut[c] for c in s], dtype=np.uint8)) for n, s in rec["contigs"]]
     ix = index.build_index(contigs)
-    p = common.set_mode(api.default_params(), _abi.MODE_SNP if mode == "snp" else _abi.MODE_BS)
+    p = common.set_mode(api.default_params(), _abi.MODE_BS if mode == "bs" else _abi.MODE_SNP)
     text = "".join(f"@{nm}\n{s}\n+\n{q}\n" for nm, s, q in rec["reads"]).encode()
     m = api.Mapper(ix, p)
     m.process_fastq(text, fetch=False)
-    got = m.format_gmp(target_base=-1 if mode == "snp" else 1).decode().split("\n")
+    got = m.format_gmp(target_base=1 if mode == "bs" else -1).decode().split("\n")
     assert got[-1] == "" and len(got) > 1000
     got = got[:-1]
     amount, planes = m.finish()
     codes = ix.codes()
     want = []
     for r in output.gmp_rows(ix, amount, planes, p.mode):
-        line = ("%s\t%d\t%.5f" if mode == "snp" else "%s\t%d\t%f") % r[:3] + "".join("\t%.5f" % x for x in r[3:8])
-        if mode == "snp":
+        line = ("%s\t%d\t%f" if mode == "bs" else "%s\t%d\t%.5f") % r[:3] + "".join("\t%.5f" % x for x in r[3:8])
+        if mode != "bs":
             pos = int(ix.seq_offset[ix.names.index(r[0])]) + r[1] - 1
             line += api.snp_call(np.array(r[3:8], dtype=np.float32), int(codes[pos]))[4].decode()
         want.append(line)
@@ -236,6 +236,8 @@ def test_native_gmp_rows_and_calls(mode):
         assert np.allclose([float(x) for x in mine[k][2:8]], [float(x) for x in ref[k][2:8]], rtol=1e-5, atol=1.1e-5), (mine[k], ref[k])
         same += mine[k][8:] == ref[k][8:]
     assert same >= 0.995 * len(both)
+    if mode == "snpdepth":                                 # 15x two-haplotype sample: confident mono- and diploid calls
+        assert sum(mine[k][8].startswith("Y:") for k in both) >= 30 and sum("/" in mine[k][8] for k in both) >= 10
     m.close()
     m0 = api.Mapper(ix)
     with pytest.raises(api.GmxError):

@@ -186,3 +186,31 @@ def test_index_builder_against_live_bwa_index(tmp_path):
             want = np.fromfile(fa + ".gnumap." + ext, dtype=np.uint8)
             got = np.fromfile(mine + ".gnumap." + ext, dtype=np.uint8)
             assert np.array_equal(got, want), f"genome {k} ({lens}): .gnumap.{ext} differs from bwa_index's"
+
+
+def test_snp_calls_at_depth_match_reference_binary():
+    """15x two-haplotype sample (tests/golden/ref_program_snpdepth.json.gz, written by the unmodified reference binary with
+    `--snp`): the oracle's accumulators give the reference's .gmp numbers, and the library's likelihood-ratio call
+    (gmx_snp_call, host arithmetic) on those accumulators gives the reference's call column -- confident mono- and
+    diploid SNPs included."""
+    from gnumap_b200 import api
+    rec = load_program("snpdepth")
+    ix, names, batch, p, res = run_oracle_program(rec)
+    assert int((res["results"]["status"] == _abi.READ_MAPPED).sum()) == rec["matched"]
+    want = [ln.split("\t") for ln in rec["gmp"]]
+    got = list(output.gmp_rows(ix, res["amount"], res["planes"], p.mode))
+    assert len(got) == len(want)
+    codes = ix.codes()
+    same = y_calls = dip = 0
+    for g, w in zip(got, want):
+        assert g[0] == w[0] and g[1] == int(w[1])
+        assert np.allclose(np.array(g[2:8], dtype=np.float64), np.array([float(x) for x in w[2:8]]), rtol=1e-5, atol=6e-6), (g, w)
+        pos = int(ix.seq_offset[ix.names.index(g[0])]) + g[1] - 1
+        call = api.snp_call(np.array(g[3:8], dtype=np.float32), int(codes[pos]))[4].decode().lstrip("\t")
+        same += call == w[8]
+        y_calls += w[8].startswith("Y:")
+        dip += "/" in w[8]
+        if w[8].startswith("Y:"):                          # a confident call never changes its letters
+            assert call.split(" ")[0] == w[8].split(" ")[0], (g, call, w[8])
+    assert y_calls >= 30 and dip >= 10
+    assert same >= 0.995 * len(want), (same, len(want))
