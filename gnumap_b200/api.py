@@ -35,7 +35,7 @@ EXPORTS = [
     "gmx_get_stage_stats", "gmx_set_option", "gmx_fastq_scan_host", "gmx_fastq_scan", "gmx_process_fastq", "gmx_format_sam", "gmx_format_sgr", "gmx_format_gmp", "gmx_snp_call",
 ]
 
-OPT_COLLECT_HITS, OPT_CHUNK_READS, OPT_VOTE_FILTER, OPT_FILTER_SHIFT = 1, 2, 3, 4
+OPT_COLLECT_HITS, OPT_CHUNK_READS, OPT_VOTE_FILTER, OPT_FILTER_SHIFT, OPT_CIGAR_STRIDE = 1, 2, 3, 4, 5
 
 
 class GmxError(RuntimeError):

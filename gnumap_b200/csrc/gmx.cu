@@ -63,7 +63,7 @@ struct HostBuf {                                   // pinned host staging
     template <class T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
-#define GMX_CIGAR_STRIDE 64
+#define GMX_CIGAR_STRIDE (ctx->cigar_stride)     // bytes per CIGAR slot (GMX_OPT_CIGAR_STRIDE, default 64)
 
 enum Stage { ST_UPLOAD = 0, ST_PREP, ST_SEED, ST_CLASSIFY, ST_VOTE, ST_SORT, ST_NW, ST_FINALIZE, ST_TRACEBACK, ST_PHMM, ST_SCATTER, ST_DOWNLOAD, ST_COUNT };
 static const char *kStageNames[ST_COUNT] = {"upload", "prep_reads", "seed_walk", "classify", "locate_vote", "sort_candidates",
@@ -104,7 +104,8 @@ struct gmx_ctx {
     int32_t last_max_len = 0;
     std::vector<gmx_read_result> h_results;
     std::vector<gmx_hit> h_hits;
-    HostBuf h_best_cigar;                      // pinned [n_reads][GMX_CIGAR_STRIDE]
+    int cigar_stride = 64;                     // GMX_OPT_CIGAR_STRIDE
+    HostBuf h_best_cigar;                      // pinned [n_reads][cigar_stride]
     HostBuf h_counters;                        // pinned staging of the per-chunk device counters
     std::vector<uint8_t> h_best_aligned;       // [n_reads][a_stride]  (collect_hits only)
     int h_a_stride = 0;
@@ -488,7 +489,12 @@ static int scan_max_len(gmx_ctx *ctx, const gmx_reads *reads, int32_t lo, int32_
     int32_t max_len = reads->max_len;
     if (!reads->on_device) {
         max_len = 0;
-        for (int32_t i = lo; i < hi; ++i) max_len = std::max<int32_t>(max_len, (int32_t)(reads->offsets[i + 1] - reads->offsets[i]));
+        for (int32_t i = lo; i < hi; ++i) {
+            const int64_t len = reads->offsets[i + 1] - reads->offsets[i];
+            if (len < 0) { ctx->err = "gmx_reads.offsets must be non-decreasing"; return GMX_ERR_INVALID; }
+            if (len > GMX_MAX_READ_LEN) { ctx->err = "read longer than GMX_MAX_READ_LEN"; return GMX_ERR_UNSUPPORTED; }
+            max_len = std::max<int32_t>(max_len, (int32_t)len);
+        }
     } else if (max_len <= 0) { ctx->err = "device-resident gmx_reads need max_len"; return GMX_ERR_INVALID; }
     if (max_len > GMX_MAX_READ_LEN) { ctx->err = "read longer than GMX_MAX_READ_LEN"; return GMX_ERR_UNSUPPORTED; }
     *max_len_out = max_len;
@@ -506,8 +512,9 @@ static int issue_upload(gmx_ctx *ctx, const gmx_reads *reads, int32_t lo, int32_
     if (!reads->qual && !reads->pwm) { ctx->err = "gmx_reads needs qual or pwm"; return GMX_ERR_INVALID; }
     DevReads &v = ctx->up_view[slot];
     v.n_reads = n; v.qbase = ctx->params.illumina ? 64 : 33;
-    v.qual = nullptr; v.pwm = nullptr; v.qoffsets = nullptr; v.lens = nullptr;
+    v.qual = nullptr; v.pwm = nullptr; v.qoffsets = nullptr; v.lens = nullptr; v.max_len = 0;
     if (reads->on_device) {
+        v.max_len = reads->max_len;
         v.offsets = reads->offsets + lo;
         v.seq = reads->seq; v.qual = reads->qual; v.pwm = reads->pwm;
         v.qoffsets = reads->qual_offsets ? reads->qual_offsets + lo : nullptr;
@@ -625,7 +632,7 @@ extern "C" int gmx_self_score(gmx_ctx *ctx, const gmx_reads *reads, float *score
     CK(ctx->d_prep.ensure((size_t)n * sizeof(ReadPrep)));
     DevParams dp = ctx->dparams; dp.mer = 0;             // score every read regardless of length
     dp.cutoff = -INFINITY;
-    k_prep_reads<<<nblk(n, GMX_PREP_THREADS), GMX_PREP_THREADS, 0, ctx->stream>>>(ctx->dreads, ctx->tab, dp, ctx->d_prep.as<ReadPrep>());
+    k_prep_reads<<<nblk(n, GMX_PREP_THREADS), GMX_PREP_THREADS, 0, ctx->stream>>>(ctx->dreads, ctx->tab, dp, ctx->d_prep.as<ReadPrep>(), nullptr);
     CK(cudaGetLastError());
     std::vector<ReadPrep> h(n);
     CK(cudaMemcpyAsync(h.data(), ctx->d_prep.p, (size_t)n * sizeof(ReadPrep), cudaMemcpyDeviceToHost, ctx->stream));
@@ -655,6 +662,7 @@ __global__ void __launch_bounds__(128) k_traceback_tasks(DevReads R, DevTables T
     WindowView win; win.pac = nullptr; win.pos = 0; win.chars = windows + t * win_stride;
     ConsView cons; cons.explicit_chars = consensus ? consensus + t * win_stride : nullptr;
     TracebackOut o; o.aligned = aligned + t * a_stride; o.aligned_cap = a_stride; o.cigar = cigar + t * c_stride; o.cigar_cap = c_stride; o.fix_deletions = 0;
+    o.truncated = nullptr;
     alen[t] = gmx_nw_traceback(rd, win, cons, T, P.gap, P.max_gap, moves + t, n_tasks, o);
 }
 
@@ -852,7 +860,7 @@ static int phase_a(gmx_ctx *ctx, const gmx_reads *reads, int32_t lo, int32_t hi,
     // a3 + status
     stage_begin(ctx, ST_PREP);
     CK(cudaMemsetAsync(ds, 0, sizeof(ChunkStats), ctx->stream));
-    k_prep_reads<<<nblk(n, GMX_PREP_THREADS), GMX_PREP_THREADS, 0, ctx->stream>>>(ctx->dreads, ctx->tab, P, ctx->d_prep.as<ReadPrep>());
+    k_prep_reads<<<nblk(n, GMX_PREP_THREADS), GMX_PREP_THREADS, 0, ctx->stream>>>(ctx->dreads, ctx->tab, P, ctx->d_prep.as<ReadPrep>(), &ds->v[3]);
     CK(cudaGetLastError());
     stage_end(ctx, ST_PREP, (uint64_t)n, (uint64_t)total_bases * 2, 1);
 
@@ -935,6 +943,7 @@ static int phase_a(gmx_ctx *ctx, const gmx_reads *reads, int32_t lo, int32_t hi,
         n_cand = hc.c.n_cand;
         break;
     }
+    if (hc.s.v[3]) { ctx->err = "device-resident gmx_reads: a read is longer than gmx_reads.max_len (or has a negative length)"; return GMX_ERR_INVALID; }
     // algorithmic work of the seed / vote stages (DESIGN.md "Roofline"): every backward-search step reads two
     // 64-byte occ blocks; every SA hit reads one 4-byte entry of the de-sampled suffix array
     ctx->stage_units[ST_SEED] += hc.s.v[0]; ctx->stage_bytes[ST_SEED] += hc.s.v[1] * 128ull + (ctx->ix.tab_len > 0 ? hc.s.v[0] * 8ull : 0ull);
@@ -1024,7 +1033,7 @@ static int phase_b(gmx_ctx *ctx)
     const int want_aligned = (P.mode == GMX_MODE_BS || ctx->collect_hits) ? 1 : 0;
     stage_begin(ctx, ST_TRACEBACK);
     k_traceback<<<nblk(n_leaders, 128), 128, 0, ctx->stream>>>(ctx->ix, ctx->dreads, ctx->tab, P, cs.keys, n_leaders, L,
-                                                              ctx->d_moves.as<uint32_t>(), want_aligned);
+                                                              ctx->d_moves.as<uint32_t>(), want_aligned, ctx->d_multi_count.as<uint32_t>() + 1);
     CK(cudaGetLastError());
     stage_end(ctx, ST_TRACEBACK, (uint64_t)n_leaders * (uint64_t)std::max(7 * max_len - 12, 0), 0, 1);
     if (P.mode == GMX_MODE_SNP) {
@@ -1075,6 +1084,13 @@ static int download_chunk(gmx_ctx *ctx, bool scored, gmx_read_result *results_ou
     const int32_t n = cs.n, lo = cs.lo;
     const uint32_t n_cand = cs.n_cand, n_leaders = cs.n_leaders;
     LeaderStore &L = cs.L;
+    // the library's own result storage is the destination when the caller passes none and the staging area of the
+    // hit-collecting path: size it here, since a gmx_score_batch may follow a gmx_map_batch that did not need it
+    if ((!results_out || ctx->collect_hits) && ctx->h_results.size() < (size_t)ctx->last_n_reads) ctx->h_results.resize((size_t)ctx->last_n_reads);
+    if (ctx->collect_hits && ctx->h_best_aligned.size() < (size_t)ctx->last_n_reads * (size_t)ctx->h_a_stride) {
+        ctx->h_best_aligned.assign((size_t)ctx->last_n_reads * (size_t)ctx->h_a_stride, 0);
+        memset(ctx->h_best_cigar.p, 0, (size_t)std::max(ctx->last_n_reads, 1) * GMX_CIGAR_STRIDE);
+    }
     stage_begin(ctx, ST_DOWNLOAD);
     if (!ctx->collect_hits) {
         // fast path: fixed-size records only, staged and copied out on a second stream while the next chunk computes
@@ -1170,10 +1186,48 @@ static int batch_max_len(gmx_ctx *ctx, const gmx_reads *reads, int32_t *out)
     return scan_max_len(ctx, reads, 0, reads->n_reads, out);
 }
 
-// phases: 1 = PHASE A only, 3 = PHASE A + PHASE B
+static int run_batch_impl(gmx_ctx *ctx, const gmx_reads *reads, gmx_read_result *results, bool do_score);
+
+// end of a batch (streams idle): the multi-position list of the fast download path and the truncated-CIGAR count
+static int collect_batch_counters(gmx_ctx *ctx)
+{
+    uint32_t c[2] = {0, 0};
+    CK(cudaMemcpy(c, ctx->d_multi_count.p, 8, cudaMemcpyDeviceToHost));
+    if (ctx->multi_cap) {
+        uint32_t nm = c[0];
+        if (nm > ctx->multi_cap) { ctx->multi_overflow = true; nm = ctx->multi_cap; }
+        ctx->h_multi.resize(nm);
+        if (nm) CK(cudaMemcpy(ctx->h_multi.data(), ctx->d_multi.p, (size_t)nm * sizeof(MultiPos), cudaMemcpyDeviceToHost));
+    }
+    if (c[1]) {
+        char b[160];
+        snprintf(b, sizeof(b), "%u alignment(s) need a CIGAR longer than the %d-byte slot: raise GMX_OPT_CIGAR_STRIDE", c[1], ctx->cigar_stride);
+        ctx->err = b;
+        return GMX_ERR_OVERFLOW;
+    }
+    return GMX_OK;
+}
+
+// PHASE A (+ PHASE B when do_score).  Every error leaves through one cleanup path: copies on the upload / download
+// streams may still be reading the caller's reads or writing the caller's results, so all three streams are drained
+// and the batch state is invalidated before the error code goes back.
 static int run_batch(gmx_ctx *ctx, const gmx_reads *reads, gmx_read_result *results, bool do_score)
 {
     if (!ctx || !reads || reads->n_reads < 0 || (reads->n_reads > 0 && !reads->offsets)) return GMX_ERR_INVALID;
+    const int r = run_batch_impl(ctx, reads, results, do_score);
+    if (r != GMX_OK) {
+        const std::string why = ctx->err;
+        cudaStreamSynchronize(ctx->stream); cudaStreamSynchronize(ctx->copy_stream); cudaStreamSynchronize(ctx->d2h_stream);
+        cudaGetLastError();
+        ctx->cs.valid = false; ctx->mapped = false; ctx->scored = false; ctx->keep_valid = false;
+        ctx->up_scan[0].reads = nullptr; ctx->up_scan[1].reads = nullptr;
+        ctx->err = why;
+    }
+    return r;
+}
+
+static int run_batch_impl(gmx_ctx *ctx, const gmx_reads *reads, gmx_read_result *results, bool do_score)
+{
     CK(cudaSetDevice(ctx->device));
     const int32_t n = reads->n_reads;
     int32_t max_len = 0;       // of the whole batch: only the hit-collecting download needs it before the first chunk runs
@@ -1182,10 +1236,11 @@ static int run_batch(gmx_ctx *ctx, const gmx_reads *reads, gmx_read_result *resu
     ctx->h_hits.clear();
     ctx->h_multi.clear();
     ctx->multi_overflow = false; ctx->multi_cap = 0;
+    CK(ctx->d_multi_count.ensure(16));                                       // [0] multi-position entries, [1] truncated CIGARs
+    CK(cudaMemsetAsync(ctx->d_multi_count.p, 0, 16, ctx->stream));
     if (!ctx->collect_hits && do_score && n > 0) {
         ctx->multi_cap = (uint32_t)std::min<int64_t>(4ll * n + 65536, 0x7fffffffll);
-        CK(ctx->d_multi.ensure((size_t)ctx->multi_cap * sizeof(MultiPos))); CK(ctx->d_multi_count.ensure(16));
-        CK(cudaMemsetAsync(ctx->d_multi_count.p, 0, 4, ctx->stream));
+        CK(ctx->d_multi.ensure((size_t)ctx->multi_cap * sizeof(MultiPos)));
     }
     ctx->h_a_stride = max_len + 2 * ctx->params.max_gap + 8;
     CK(ctx->h_best_cigar.ensure((size_t)std::max(n, 1) * GMX_CIGAR_STRIDE));
@@ -1239,13 +1294,8 @@ static int run_batch(gmx_ctx *ctx, const gmx_reads *reads, gmx_read_result *resu
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaStreamSynchronize(ctx->d2h_stream));
     stage_collect(ctx);
-    if (ctx->multi_cap) {                                                   // the batch's multi-position list: one small copy
-        uint32_t nm = 0;
-        CK(cudaMemcpy(&nm, ctx->d_multi_count.p, 4, cudaMemcpyDeviceToHost));
-        if (nm > ctx->multi_cap) { ctx->multi_overflow = true; nm = ctx->multi_cap; }
-        ctx->h_multi.resize(nm);
-        if (nm) CK(cudaMemcpy(ctx->h_multi.data(), ctx->d_multi.p, (size_t)nm * sizeof(MultiPos), cudaMemcpyDeviceToHost));
-    }
+    int r = collect_batch_counters(ctx);
+    if (r != GMX_OK) return r;
     ctx->mapped = true; ctx->scored = do_score;
     return GMX_OK;
 }
@@ -1285,10 +1335,11 @@ extern "C" int gmx_score_batch(gmx_ctx *ctx, gmx_read_result *results)
     if (ctx->cs.valid) {
         ctx->h_hits.clear();
         ctx->h_multi.clear(); ctx->multi_overflow = false; ctx->multi_cap = 0;
+        CK(ctx->d_multi_count.ensure(16));
+        CK(cudaMemsetAsync(ctx->d_multi_count.p, 0, 16, ctx->stream));
         if (!ctx->collect_hits) {
             ctx->multi_cap = (uint32_t)std::min<int64_t>(4ll * ctx->last_n_reads + 65536, 0x7fffffffll);
-            CK(ctx->d_multi.ensure((size_t)ctx->multi_cap * sizeof(MultiPos))); CK(ctx->d_multi_count.ensure(16));
-            CK(cudaMemsetAsync(ctx->d_multi_count.p, 0, 4, ctx->stream));
+            CK(ctx->d_multi.ensure((size_t)ctx->multi_cap * sizeof(MultiPos)));
         }
         int r = phase_b(ctx);
         if (r != GMX_OK) return r;
@@ -1297,13 +1348,8 @@ extern "C" int gmx_score_batch(gmx_ctx *ctx, gmx_read_result *results)
         CK(cudaStreamSynchronize(ctx->stream));
         CK(cudaStreamSynchronize(ctx->d2h_stream));
         stage_collect(ctx);
-        if (ctx->multi_cap) {
-            uint32_t nm = 0;
-            CK(cudaMemcpy(&nm, ctx->d_multi_count.p, 4, cudaMemcpyDeviceToHost));
-            if (nm > ctx->multi_cap) { ctx->multi_overflow = true; nm = ctx->multi_cap; }
-            ctx->h_multi.resize(nm);
-            if (nm) CK(cudaMemcpy(ctx->h_multi.data(), ctx->d_multi.p, (size_t)nm * sizeof(MultiPos), cudaMemcpyDeviceToHost));
-        }
+        r = collect_batch_counters(ctx);
+        if (r != GMX_OK) return r;
         ctx->cs.valid = false; ctx->scored = true;
         return GMX_OK;
     }
@@ -1322,6 +1368,9 @@ extern "C" int gmx_set_option(gmx_ctx *ctx, int option, int64_t value)
             if (value < 1 || value > (1 << 22)) { ctx->err = "chunk_reads must be in 1..4194304"; return GMX_ERR_INVALID; }
             ctx->chunk_reads = (size_t)value; return GMX_OK;
         case GMX_OPT_VOTE_FILTER: ctx->use_filter = value != 0; return GMX_OK;
+        case GMX_OPT_CIGAR_STRIDE:
+            if (value < 16 || value > 2048 || (value & 15)) { ctx->err = "cigar_stride must be a multiple of 16 in 16..2048"; return GMX_ERR_INVALID; }
+            ctx->cigar_stride = (int)value; ctx->mapped = false; ctx->scored = false; ctx->cs.valid = false; return GMX_OK;
         case GMX_OPT_FILTER_SHIFT:
             if (value < -2 || value > 2) { ctx->err = "filter_shift must be in -2..2"; return GMX_ERR_INVALID; }
             ctx->filter_shift = (int)value; return GMX_OK;

@@ -53,6 +53,8 @@ struct DevReads {
     const int32_t *lens;     // optional: explicit read lengths (reads not contiguous in `seq`)
     int32_t n_reads;
     int32_t qbase;           // 33, or 64 with --illumina
+    int32_t max_len;         // > 0: the caller's bound for device-resident reads (checked by k_prep_reads); 0: lengths were
+                             // validated on the host
 };
 
 __device__ __forceinline__ int gmx_read_len(const DevReads &R, int r)

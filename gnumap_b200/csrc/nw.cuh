@@ -343,7 +343,10 @@ struct TracebackOut {
     char *cigar;           // this task's CIGAR text (capacity cigar_cap, NUL terminated), may be null
     int cigar_cap;
     int fix_deletions;     // apply fix_CIGAR_for_deletions (reference SequenceOperations.h:32-42) + "*" for empty
+    uint32_t *truncated;   // may be null: counts the tasks whose CIGAR did not fit (more runs than GMX_CIGAR_MAX_OPS or more
+                           // text than cigar_cap) -- the reference builds the string unbounded (MAX_CIGAR_SZ 1024 in TopReadOutput)
 };
+#define GMX_CIGAR_MAX_OPS 256
 
 // consensus character of oriented row i; i == n yields the std::string terminator the reference
 // reads at src/bin_seq.cpp:607,660
@@ -445,13 +448,17 @@ __device__ int gmx_nw_traceback(const ReadView &rd, const WindowView &win, const
     else gmx_nw_fill_moves<0>(rd, win, T, gap, G, moves, mv_stride);
 
     // pass 1: path length and run-length ops, walking back from (n, m)  (reference :571-698)
-    uint16_t ops[48];                                  // (count << 2) | type, in backward order
+    uint16_t ops[GMX_CIGAR_MAX_OPS];                   // (count << 2) | type, in backward order
     int n_ops = 0, alen = 0;
+    bool cut = false;
     {
         int i = n, j = m, c_type = 0, c_counter = 0;
         auto push = [&](int type) {
             if (c_type == type) c_counter++;
-            else { if (c_counter && n_ops < 48) ops[n_ops++] = (uint16_t)((c_counter << 2) | c_type); c_type = type; c_counter = 1; }
+            else {
+                if (c_counter) { if (n_ops < GMX_CIGAR_MAX_OPS) ops[n_ops++] = (uint16_t)((c_counter << 2) | c_type); else cut = true; }
+                c_type = type; c_counter = 1;
+            }
         };
         // the walk visits the rows in descending order, at most one new row per step: eight move words are fetched
         // at once (independent loads) instead of one dependent load per step
@@ -473,7 +480,7 @@ __device__ int gmx_nw_traceback(const ReadView &rd, const WindowView &win, const
         }
         while (i > 0) { push(1); i--; alen++; }
         while (j > 0) { push(2); j--; alen++; }
-        if (c_counter > 0 && n_ops < 48) ops[n_ops++] = (uint16_t)((c_counter << 2) | c_type);
+        if (c_counter > 0) { if (n_ops < GMX_CIGAR_MAX_OPS) ops[n_ops++] = (uint16_t)((c_counter << 2) | c_type); else cut = true; }
     }
     // pass 2: the gapped read string, written at its final (reversed) positions
     if (out.aligned) {
@@ -507,9 +514,11 @@ __device__ int gmx_nw_traceback(const ReadView &rd, const WindowView &win, const
             int cnt = ops[o] >> 2, type = ops[o] & 3;
             char digits[8]; int nd = 0;
             do { digits[nd++] = (char)('0' + cnt % 10); cnt /= 10; } while (cnt);
-            while (nd && p < out.cigar_cap - 1) out.cigar[p++] = digits[--nd];
-            if (p < out.cigar_cap - 1) out.cigar[p++] = type == 0 ? 'M' : (type == 1 ? 'I' : 'D');
+            if (p + nd + 1 > out.cigar_cap - 1) { cut = true; break; }
+            while (nd) out.cigar[p++] = digits[--nd];
+            out.cigar[p++] = type == 0 ? 'M' : (type == 1 ? 'I' : 'D');
         }
+        if (cut && out.truncated) atomicAdd(out.truncated, 1u);
         if (p == 0 && out.fix_deletions && n_ops == 0 && p < out.cigar_cap - 1) out.cigar[p++] = '*';
         out.cigar[p] = 0;
     }

@@ -51,7 +51,7 @@ __device__ __forceinline__ ReadView gmx_read_view(const DevReads &R, int r, int 
 // get_val(pwm(base, Q), seq[i]) is a pure function of the two characters and comes from a 96 KB table.
 #define GMX_PREP_THREADS 128
 #define GMX_PREP_STAGE_BYTES (GMX_PREP_THREADS * 176)        // reads of up to 176 bases on average per block
-__global__ void __launch_bounds__(GMX_PREP_THREADS) k_prep_reads(DevReads R, DevTables T, DevParams P, ReadPrep *prep)
+__global__ void __launch_bounds__(GMX_PREP_THREADS) k_prep_reads(DevReads R, DevTables T, DevParams P, ReadPrep *prep, unsigned long long *bad_len)
 {
     __shared__ __align__(16) uint8_t s_seq[GMX_PREP_STAGE_BYTES + 8], s_qual[GMX_PREP_STAGE_BYTES + 8];
     const int r0 = blockIdx.x * blockDim.x;
@@ -79,6 +79,12 @@ __global__ void __launch_bounds__(GMX_PREP_THREADS) k_prep_reads(DevReads R, Dev
     if (r >= R.n_reads) return;
     ReadView rd = gmx_read_view(R, r, 0);
     ReadPrep out; out.min_align = 0; out.max_align = 0; out.status = GMX_READ_MAPPED;
+    // device-resident input: a read longer than the caller's max_len (or a negative length) would overrun every buffer
+    // sized from it -- it takes no part in the batch and the host turns the count into GMX_ERR_INVALID
+    if (R.max_len > 0 && (rd.n < 0 || rd.n > R.max_len)) {
+        if (bad_len) atomicAdd(bad_len, 1ull);
+        out.status = GMX_READ_TOO_SHORT; prep[r] = out; return;
+    }
     if ((unsigned)rd.n < (unsigned)P.mer) { out.status = GMX_READ_TOO_SHORT; prep[r] = out; return; }
     // get_align_score(read, consensus, 0, n-1) == get_align_score_mid  (reference src/bin_seq.cpp:860-893)
     float score = 0.f;
@@ -1221,7 +1227,7 @@ struct LeaderStore {
 // adjacent words (404 MB per million 100-bp groups: noise next to the ALU work)
 __global__ void __launch_bounds__(128) k_traceback(DevIndex ix, DevReads R, DevTables T, DevParams P,
                                                    const unsigned long long *keys, uint32_t n_leaders, LeaderStore L,
-                                                   uint32_t *moves, int want_aligned)
+                                                   uint32_t *moves, int want_aligned, uint32_t *truncated)
 {
     uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n_leaders) return;
@@ -1232,7 +1238,7 @@ __global__ void __launch_bounds__(128) k_traceback(DevIndex ix, DevReads R, DevT
     ConsView cons; cons.explicit_chars = nullptr;          // score(): max_char consensus of the oriented PWM
     TracebackOut out;
     out.aligned = want_aligned ? L.aligned + (size_t)s * L.a_stride : nullptr; out.aligned_cap = L.a_stride;
-    out.cigar = L.cigar + (size_t)s * L.c_stride; out.cigar_cap = L.c_stride; out.fix_deletions = 1;
+    out.cigar = L.cigar + (size_t)s * L.c_stride; out.cigar_cap = L.c_stride; out.fix_deletions = 1; out.truncated = truncated;
     L.alen[s] = gmx_nw_traceback(rd, win, cons, T, P.gap, P.max_gap, moves + s, (int64_t)n_leaders, out);
 }
 

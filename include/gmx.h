@@ -320,6 +320,10 @@ int gmx_snp_call(const float counts[5], int genome_base, int snp_monoploid, floa
 #define GMX_OPT_VOTE_FILTER  3   /* 1 (default): counting-filter + exact-verification vote kernel with the exact
                                     hash-table kernels as its overflow path; 0: exact hash tables for every task  */
 #define GMX_OPT_FILTER_SHIFT 4   /* tuning: log2 scale of the kmin == 2 vote filter (default 0 = 4 bytes per SA hit)     */
+#define GMX_OPT_CIGAR_STRIDE  5   /* bytes per CIGAR slot of the batch pipeline (default 64, a multiple of 16 up to 2048).  The
+                                    reference builds CIGARs unbounded (TopReadOutput::CIGAR holds MAX_CIGAR_SZ = 1024); a batch in
+                                    which some alignment needs more text than the slot fails with GMX_ERR_OVERFLOW instead of
+                                    returning a cut string */
 int gmx_set_option(gmx_ctx *ctx, int option, int64_t value);
 
 /* ---- instrumentation ---------------------------------------------------------------------- */

@@ -6,7 +6,7 @@ Mirrors, for the fields the hot path produces:
   * the SAM writer `single_write_cond_wait` (reference src/Driver.cpp:2146-2217);
   * `GenomeBwt::PrintFinalSGR` (reference src/GenomeBwt.cpp:1212-1273).
 
-These are host-side formatters over the device results; they exist so that whole-program parity
+TEST INFRASTRUCTURE (the product formatters are gmx_format_sam / _sgr / _gmp): they exist so that whole-program parity
 (SAM body, .sgr) can be checked against the compiled reference.
 """
 from __future__ import annotations
@@ -15,7 +15,7 @@ import math
 
 import numpy as np
 
-from . import _abi
+from gnumap_b200 import _abi
 
 _RC = bytes.maketrans(b"acgtACGT-", b"tgcaTGCA-")
 

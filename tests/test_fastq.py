@@ -176,7 +176,7 @@ def test_native_sgr_equals_the_reference_binary():
     FP32 atomics reorder the sums, so values are compared numerically at the file's five decimals; the set of printed
     bins may differ only where the value sits on the MIN_PRINT threshold."""
     from tests import test_oracle_golden as G
-    from gnumap_b200 import output
+    from tests import ref_text as output
     rec = G.load_program("normal")
     lut = {c: i for i, c in enumerate("ACGT")}
     contigs = [(n, np.array([lut[c] for c in s], dtype=np.uint8)) for n, s in rec["contigs"]]
@@ -205,7 +205,7 @@ def test_native_gmp_rows_and_calls(mode):
     itself pinned to the reference's PrintSNPCall by tests/test_host_logic.py), and against the .gmp the unmodified
     reference binary wrote (numbers at the file's decimals: FP32 atomics reorder the sums)."""
     from tests import test_oracle_golden as G, common
-    from gnumap_b200 import output
+    from tests import ref_text as output
     rec = G.load_program(mode)
     lut = {c: i for i, c in enumerate("ACGT")}
     contigs = [(n, np.array([lut[c] for c in s], dtype=np.uint8)) for n, s in rec["contigs"]]

