@@ -33,9 +33,11 @@ EXPORTS = [
     "gmx_nw_score", "gmx_nw_traceback", "gmx_pair_hmm", "gmx_map_batch", "gmx_score_batch", "gmx_process_batch",
     "gmx_get_hits", "gmx_get_best_alignments", "gmx_accumulators_device", "gmx_reset_accumulators", "gmx_finish",
     "gmx_get_stage_stats", "gmx_set_option", "gmx_fastq_scan_host", "gmx_fastq_scan", "gmx_process_fastq", "gmx_format_sam", "gmx_format_sgr", "gmx_format_gmp", "gmx_snp_call",
+    "gmx_comm_create", "gmx_comm_reduce", "gmx_comm_stats", "gmx_comm_destroy",
 ]
 
 OPT_COLLECT_HITS, OPT_CHUNK_READS, OPT_VOTE_FILTER, OPT_FILTER_SHIFT, OPT_CIGAR_STRIDE = 1, 2, 3, 4, 5
+COMM_AUTO, COMM_PEER, COMM_NCCL = 0, 1, 2
 
 
 class GmxError(RuntimeError):
@@ -85,6 +87,11 @@ def load_library():
         L.gmx_snp_call.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double), C.c_char_p, C.c_int]
         L.gmx_format_gmp.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_float, C.c_int, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
         L.gmx_process_fastq.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.c_void_p]
+        L.gmx_comm_create.argtypes = [C.POINTER(C.c_void_p), C.c_void_p, C.c_int, C.c_int]
+        L.gmx_comm_reduce.argtypes = [C.c_void_p, C.c_int]
+        L.gmx_comm_stats.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_uint64), C.POINTER(C.c_int)]
+        L.gmx_comm_destroy.argtypes = [C.c_void_p]
+        L.gmx_comm_destroy.restype = None
         _lib = L
     return _lib
 
@@ -367,3 +374,39 @@ class Mapper:
         s = GmxStageStats()
         self._ck(self.L.gmx_get_stage_stats(self._ctx, C.byref(s)), "gmx_get_stage_stats")
         return {s.name[i].decode(): dict(ms=s.ms[i], units=s.units[i], bytes=s.bytes[i], launches=s.launches[i]) for i in range(s.n_stages)}
+
+
+class Comm:
+    """Several Mappers (one per GPU, or several on one GPU) of ONE process whose accumulators are terms of one sum --
+    the in-process counterpart of the reference's MPI reduce (reference src/Driver.cpp:1615-1811).  mappers[0] is the
+    root: its finish() reduces first."""
+
+    def __init__(self, mappers, backend: int = COMM_AUTO):
+        self.L = load_library()
+        self.mappers = list(mappers)
+        arr = (C.c_void_p * len(self.mappers))(*[m._ctx for m in self.mappers])
+        self._comm = C.c_void_p()
+        rc = self.L.gmx_comm_create(C.byref(self._comm), arr, len(self.mappers), backend)
+        if rc != 0:
+            raise GmxError(rc, "gmx_comm_create", self.L.gmx_last_error(self.mappers[0]._ctx).decode() or self.L.gmx_strerror(rc).decode())
+
+    def reduce(self, all: bool = False):
+        rc = self.L.gmx_comm_reduce(self._comm, int(all))
+        if rc != 0:
+            raise GmxError(rc, "gmx_comm_reduce", self.L.gmx_last_error(self.mappers[0]._ctx).decode())
+
+    def stats(self):
+        ms, nb, be = C.c_float(0), C.c_uint64(0), C.c_int(0)
+        self.L.gmx_comm_stats(self._comm, C.byref(ms), C.byref(nb), C.byref(be))
+        return dict(ms=ms.value, bytes=nb.value, backend={COMM_PEER: "peer", COMM_NCCL: "nccl"}.get(be.value, str(be.value)))
+
+    def close(self):
+        if self._comm:
+            self.L.gmx_comm_destroy(self._comm)
+            self._comm = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

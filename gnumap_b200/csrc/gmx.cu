@@ -18,6 +18,8 @@
 #include "fastq.cuh"
 #include "gmp_out.cuh"
 
+struct gmx_comm;
+
 // ------------------------------------------------------------------------------------------------
 // small utilities
 // ------------------------------------------------------------------------------------------------
@@ -141,6 +143,7 @@ struct gmx_ctx {
     cudaEvent_t gather_ev[2] = {nullptr, nullptr}, dl_ev[2] = {nullptr, nullptr};
     int dl_slot = 0;
     // input of the last multi-chunk gmx_map_batch (gmx_score_batch re-runs the batch from it)
+    gmx_comm *comm = nullptr;                  // set by gmx_comm_create: this context's accumulators are one term of a sum
     gmx_reads keep; bool keep_valid = false;
     std::vector<int64_t> keep_offsets; std::vector<uint8_t> keep_seq, keep_qual; std::vector<float> keep_pwm;
 };
@@ -410,9 +413,12 @@ extern "C" int gmx_create(gmx_ctx **out, const gmx_index *index, const gmx_param
     return GMX_OK;
 }
 
+static void comm_detach(gmx_ctx *ctx);
+
 extern "C" void gmx_destroy(gmx_ctx *ctx)
 {
     if (!ctx) return;
+    if (ctx->comm) comm_detach(ctx);
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     DevBuf *bufs[] = {&ctx->d_bwt, &ctx->d_sa_full, &ctx->d_sa_samp, &ctx->d_pac, &ctx->d_seq_offset, &ctx->d_tables, &ctx->d_amount,
@@ -469,9 +475,12 @@ extern "C" int gmx_accumulators_device(gmx_ctx *ctx, void **amount, uint64_t *n_
     return GMX_OK;
 }
 
+static int comm_reduce_for_finish(gmx_ctx *ctx);
+
 extern "C" int gmx_finish(gmx_ctx *ctx, float *amount_genome, float *const planes[5])
 {
     if (!ctx || !amount_genome) return GMX_ERR_INVALID;
+    if (ctx->comm) { int r = comm_reduce_for_finish(ctx); if (r != GMX_OK) return r; }
     CK(cudaSetDevice(ctx->device));
     CK(cudaMemcpyAsync(amount_genome, ctx->acc.amount, ctx->acc.n_amount * 4, cudaMemcpyDeviceToHost, ctx->stream));
     if (planes && ctx->acc.planes[0])
@@ -1638,7 +1647,8 @@ void sam_format_range(const gmx_ctx *ctx, const char *text, const gmx_fastq_rec 
     std::string rcig, seq_rc, qual_rv;
     for (int64_t r = lo; r < hi; ++r) {
         const gmx_read_result &res = results[r];
-        if (res.status != GMX_READ_MAPPED) continue;                        // unmapped reads print nothing (Driver.cpp:620-629)
+        if (!GMX_READ_PRINTS_SAM(res)) continue;                            // unmapped reads print nothing (Driver.cpp:620-629); nor
+                                                                            // does a best group below top - SAME_DIFF (:695)
         const gmx_fastq_rec &rec = recs[r];
         const char *cigar = best_cigar + (size_t)r * GMX_CIGAR_STRIDE;
         const double total = exp((double)res.best_score) / res.denominator;
@@ -1717,7 +1727,7 @@ extern "C" int gmx_format_sam(gmx_ctx *ctx, const char *text, const gmx_fastq_re
         const int64_t a = n_reads * t / nt, b = n_reads * (t + 1) / nt;
         size_t est = 0;
         for (int64_t r = a; r < b; ++r)
-            if (results[r].status == GMX_READ_MAPPED) est += (size_t)(recs[r].name_len + recs[r].seq_len + recs[r].qual_len + 96) * (size_t)std::max(results[r].best_n_positions, 1);
+            if (GMX_READ_PRINTS_SAM(results[r])) est += (size_t)(recs[r].name_len + recs[r].seq_len + recs[r].qual_len + 96) * (size_t)std::max(results[r].best_n_positions, 1);
         parts[t].reserve(est);
         sam_format_range(ctx, text, recs, results, a, b, chrom_names, &multi_of, multi_index, parts[t]);
     });
@@ -1892,4 +1902,157 @@ extern "C" int gmx_snp_call(const float counts[5], int genome_base, int snp_mono
         memcpy(text, buf, (size_t)n); text[n] = 0;
     }
     return GMX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// several GPUs in one process: accumulator reduce
+// ------------------------------------------------------------------------------------------------
+#include "comm.cuh"
+
+#define CCK(call)                                                                                    \
+    do {                                                                                             \
+        cudaError_t e__ = (call);                                                                    \
+        if (e__ != cudaSuccess) {                                                                    \
+            char b__[512];                                                                           \
+            snprintf(b__, sizeof(b__), "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            comm->err = b__; comm->ctx[0]->err = b__;                                                \
+            return GMX_ERR_CUDA;                                                                     \
+        }                                                                                            \
+    } while (0)
+
+extern "C" int gmx_comm_create(gmx_comm **out, gmx_ctx *const *ctxs, int n, int backend)
+{
+    if (!out || !ctxs || n < 1 || n > GMX_COMM_MAX || backend < GMX_COMM_AUTO || backend > GMX_COMM_NCCL) return GMX_ERR_INVALID;
+    *out = nullptr;
+    for (int i = 0; i < n; ++i) {
+        if (!ctxs[i] || ctxs[i]->comm) return GMX_ERR_INVALID;
+        for (int j = 0; j < i; ++j) if (ctxs[j] == ctxs[i]) return GMX_ERR_INVALID;
+        // every context must accumulate the same arrays
+        if (ctxs[i]->acc.n_amount != ctxs[0]->acc.n_amount || ctxs[i]->n_plane != ctxs[0]->n_plane || ctxs[i]->params.mode != ctxs[0]->params.mode) {
+            ctxs[0]->err = "gmx_comm_create: the contexts do not share one accumulator layout (genome, mode, gen_size)";
+            return GMX_ERR_INVALID;
+        }
+    }
+    bool distinct = true;
+    for (int i = 0; i < n; ++i) for (int j = 0; j < i; ++j) if (ctxs[i]->device == ctxs[j]->device) distinct = false;
+    gmx_comm *comm = new gmx_comm();
+    comm->n = n;
+    for (int i = 0; i < n; ++i) comm->ctx[i] = ctxs[i];
+    if (backend == GMX_COMM_NCCL && (!distinct || n < 2)) { ctxs[0]->err = "GMX_COMM_NCCL needs two or more contexts on distinct devices"; delete comm; return GMX_ERR_INVALID; }
+    if (backend == GMX_COMM_AUTO) backend = GMX_COMM_PEER;
+    if (backend == GMX_COMM_NCCL) {
+        if (!comm->nccl.load()) { ctxs[0]->err = "libnccl.so.2 could not be opened"; delete comm; return GMX_ERR_UNSUPPORTED; }
+        int devs[GMX_COMM_MAX];
+        for (int i = 0; i < n; ++i) devs[i] = ctxs[i]->device;
+        ncclResult_t r = comm->nccl.CommInitAll(comm->comms, n, devs);
+        if (r != ncclSuccess) { ctxs[0]->err = std::string("ncclCommInitAll: ") + comm->nccl.GetErrorString(r); delete comm; return GMX_ERR_CUDA; }
+        comm->have_comms = true;
+    } else {
+        // peer access between every pair of distinct devices (NVLink / NVSwitch on a B200 box)
+        for (int i = 0; i < n; ++i)
+            for (int j = 0; j < n; ++j) {
+                const int a = ctxs[i]->device, b = ctxs[j]->device;
+                if (a == b) continue;
+                int can = 0;
+                CCK(cudaDeviceCanAccessPeer(&can, a, b));
+                if (!can) { ctxs[0]->err = "GMX_COMM_PEER: the devices cannot access each other's memory (use GMX_COMM_NCCL)"; delete comm; return GMX_ERR_UNSUPPORTED; }
+                CCK(cudaSetDevice(a));
+                cudaError_t e = cudaDeviceEnablePeerAccess(b, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { CCK(e); }
+                cudaGetLastError();
+            }
+    }
+    comm->backend = backend;
+    CCK(cudaSetDevice(ctxs[0]->device));
+    CCK(cudaEventCreate(&comm->ev[0])); CCK(cudaEventCreate(&comm->ev[1]));
+    for (int i = 0; i < n; ++i) ctxs[i]->comm = comm;
+    *out = comm;
+    return GMX_OK;
+}
+
+extern "C" int gmx_comm_reduce(gmx_comm *comm, int all)
+{
+    if (!comm) return GMX_ERR_INVALID;
+    const int n = comm->n;
+    for (int i = 0; i < n; ++i) if (!comm->ctx[i]) return GMX_ERR_STATE;
+    gmx_ctx *root = comm->ctx[0];
+    // every context's kernels must have finished scattering
+    for (int i = 0; i < n; ++i) { CCK(cudaSetDevice(comm->ctx[i]->device)); CCK(cudaStreamSynchronize(comm->ctx[i]->stream)); }
+    const uint64_t n_amount = root->acc.n_amount, n_planes = root->acc.planes[0] ? 5ull * root->n_plane : 0ull;
+    CCK(cudaSetDevice(root->device));
+    CCK(cudaEventRecord(comm->ev[0], root->stream));
+    if (n > 1 && comm->backend == GMX_COMM_NCCL) {
+        ncclResult_t r = comm->nccl.GroupStart();
+        for (int i = 0; i < n && r == ncclSuccess; ++i) {
+            gmx_ctx *c = comm->ctx[i];
+            CCK(cudaSetDevice(c->device));
+            // amount_genome is all-reduced in the reference (src/Driver.cpp:1672), the planes reduced to rank 0 (:1719-1767)
+            r = all ? comm->nccl.AllReduce(c->acc.amount, c->acc.amount, n_amount, ncclFloat, ncclSum, comm->comms[i], c->stream)
+                    : comm->nccl.Reduce(c->acc.amount, c->acc.amount, n_amount, ncclFloat, ncclSum, 0, comm->comms[i], c->stream);
+            if (r == ncclSuccess && n_planes)
+                r = all ? comm->nccl.AllReduce(c->acc.planes[0], c->acc.planes[0], n_planes, ncclFloat, ncclSum, comm->comms[i], c->stream)
+                        : comm->nccl.Reduce(c->acc.planes[0], c->acc.planes[0], n_planes, ncclFloat, ncclSum, 0, comm->comms[i], c->stream);
+        }
+        ncclResult_t r2 = comm->nccl.GroupEnd();
+        if (r != ncclSuccess || r2 != ncclSuccess) { comm->err = std::string("nccl reduce: ") + comm->nccl.GetErrorString(r != ncclSuccess ? r : r2); root->err = comm->err; return GMX_ERR_CUDA; }
+    } else if (n > 1) {
+        // GPU g owns slice g of both arrays
+        for (int pass = 0; pass < 2; ++pass) {
+            const uint64_t total = pass == 0 ? n_amount : n_planes;
+            if (!total) continue;
+            PeerBufs B; B.n = n;
+            for (int i = 0; i < n; ++i) B.buf[i] = pass == 0 ? comm->ctx[i]->acc.amount : comm->ctx[i]->acc.planes[0];
+            for (int g = 0; g < n; ++g) {
+                gmx_ctx *c = comm->ctx[g];
+                uint64_t lo = total * (uint64_t)g / (uint64_t)n, hi = total * (uint64_t)(g + 1) / (uint64_t)n;
+                lo &= ~3ull; if (g + 1 < n) hi &= ~3ull;                        // slice borders on float4 boundaries
+                if (hi <= lo) continue;
+                CCK(cudaSetDevice(c->device));
+                const unsigned blocks = (unsigned)std::min<uint64_t>((uint64_t)c->n_sm * 8, ((hi - lo) / 4 + 255) / 256 + 1);
+                k_reduce_slice<<<blocks, 256, 0, c->stream>>>(B, lo, hi, all ? 1 : 0);
+                CCK(cudaGetLastError());
+            }
+        }
+    }
+    // the root's stream waits for every slice owner
+    for (int i = 1; i < n; ++i) { CCK(cudaSetDevice(comm->ctx[i]->device)); CCK(cudaStreamSynchronize(comm->ctx[i]->stream)); }
+    CCK(cudaSetDevice(root->device));
+    CCK(cudaEventRecord(comm->ev[1], root->stream));
+    CCK(cudaStreamSynchronize(root->stream));
+    float ms = 0; cudaEventElapsedTime(&ms, comm->ev[0], comm->ev[1]);
+    comm->last_ms = ms; comm->last_bytes = 4ull * (n_amount + n_planes);
+    if (!all)      // the sum now lives in the root: the other terms start again from zero, so a later reduce adds only what is new
+        for (int i = 1; i < n; ++i) { int r = gmx_reset_accumulators(comm->ctx[i]); if (r != GMX_OK) return r; CCK(cudaStreamSynchronize(comm->ctx[i]->stream)); }
+    return GMX_OK;
+}
+
+static void comm_detach(gmx_ctx *ctx)
+{   // a context destroyed before its communicator: the communicator is unusable from then on
+    gmx_comm *comm = ctx->comm;
+    for (int i = 0; i < comm->n; ++i) if (comm->ctx[i] == ctx) comm->ctx[i] = nullptr;
+    ctx->comm = nullptr;
+}
+
+static int comm_reduce_for_finish(gmx_ctx *ctx)
+{
+    if (ctx->comm->ctx[0] != ctx) { ctx->err = "gmx_finish: only the first context of a communicator holds the sum"; return GMX_ERR_STATE; }
+    return gmx_comm_reduce(ctx->comm, 0);
+}
+
+extern "C" int gmx_comm_stats(const gmx_comm *comm, float *ms, uint64_t *bytes, int *backend)
+{
+    if (!comm) return GMX_ERR_INVALID;
+    if (ms) *ms = comm->last_ms;
+    if (bytes) *bytes = comm->last_bytes;
+    if (backend) *backend = comm->backend;
+    return GMX_OK;
+}
+
+extern "C" void gmx_comm_destroy(gmx_comm *comm)
+{
+    if (!comm) return;
+    for (int i = 0; i < comm->n; ++i) if (comm->ctx[i]) comm->ctx[i]->comm = nullptr;
+    if (comm->have_comms) for (int i = 0; i < comm->n; ++i) comm->nccl.CommDestroy(comm->comms[i]);
+    if (comm->ev[0]) { if (comm->ctx[0]) cudaSetDevice(comm->ctx[0]->device); cudaEventDestroy(comm->ev[0]); cudaEventDestroy(comm->ev[1]); }
+    delete comm;
 }

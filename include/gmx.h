@@ -148,6 +148,13 @@ typedef struct gmx_read_result {
     int32_t  best_aligned_len; /* length of the gapped `aligned` string of the best group          */
 } gmx_read_result;
 
+/* create_match_output hands a read's best group to the SAM writer only when that group's score (the NW score of its
+ * FIRST hit, ScoredSeq::align_score) lies within SAME_DIFF of the read's top NW score (reference src/Driver.cpp:695,
+ * inc/const_include.h:188); a mapped read whose best group misses that test -- e.g. a group whose later member, on the
+ * other strand, scored a few ulps higher -- counts as matched and scores into the accumulators but prints nothing. */
+#define GMX_SAME_DIFF 0.00001
+#define GMX_READ_PRINTS_SAM(res) ((res).status == GMX_READ_MAPPED && (double)(res).best_score > (res).top_score - GMX_SAME_DIFF)
+
 /* One accepted (position, strand) of one group (== one element of ScoredSeq::positions). */
 typedef struct gmx_hit {
     uint64_t pos;              /* absolute 0-based genome position                                 */
@@ -245,8 +252,36 @@ int gmx_reset_accumulators(gmx_ctx *ctx);
 
 /* Before gGen.PrintFinal (Driver.cpp:1820-1823): synchronise and download the accumulators into
  * the host arrays GetGenomeAmtPtr() / GetGenome{A,C,G,T,N}Ptr() (GenomeBwt.h:199-209).
- * planes may be NULL in Normal mode. */
+ * planes may be NULL in Normal mode.  On the root context of a gmx_comm the accumulators of all its contexts are
+ * summed into the root first (replacing the MPI block, Driver.cpp:1615-1811). */
 int gmx_finish(gmx_ctx *ctx, float *amount_genome, float *const planes[5]);
+
+/* ---- several GPUs behind one process ------------------------------------------------
+ * The reference's worker threads (`-c N`, src/Driver.cpp:1527-1554) share one set of accumulators under a mutex; its
+ * MPI nodes sum theirs at the end (MPI_Allreduce of amount_genome src/Driver.cpp:1660-1672, MPI_Reduce of the five read
+ * planes to rank 0 :1719-1767).  Here every GPU has its own context (worker thread t drives context t % n) and the
+ * contexts' accumulators are terms of one sum.  gmx_comm_create ties n contexts (same genome, mode and gen_size; at
+ * most 16) together; ctxs[0] is the root.  gmx_finish on the root first reduces into it, so the patched driver's call
+ * sequence stays create / process ... / finish.
+ *   GMX_COMM_PEER  the library's own reduce kernels over peer memory: GPU g sums slice g of every context's arrays with
+ *                  direct NVLink loads, in context order (deterministic), and stores the sums into the root's memory.
+ *                  Also works for contexts that share a device.
+ *   GMX_COMM_NCCL  ncclCommInitAll over the contexts' devices + ncclReduce (ncclAllReduce when all != 0); libnccl.so.2
+ *                  is opened at run time.  Needs distinct devices.
+ *   GMX_COMM_AUTO  = GMX_COMM_PEER.
+ * gmx_comm_reduce(comm, 0) leaves the sum in the root and zeroes the other contexts' accumulators (a later reduce adds
+ * only what is new); gmx_comm_reduce(comm, 1) leaves the sum in every context (terminal: do not accumulate further).
+ * One process per GPU (torchrun / MPI) does not need a gmx_comm: run the collective of your launcher on
+ * gmx_accumulators_device(). */
+typedef struct gmx_comm gmx_comm;
+#define GMX_COMM_AUTO 0
+#define GMX_COMM_PEER 1
+#define GMX_COMM_NCCL 2
+int  gmx_comm_create(gmx_comm **comm, gmx_ctx *const *ctxs, int n, int backend);
+int  gmx_comm_reduce(gmx_comm *comm, int all);
+/* CUDA-event time and bytes per context of the last reduce, and the backend in use. */
+int  gmx_comm_stats(const gmx_comm *comm, float *ms, uint64_t *bytes, int *backend);
+void gmx_comm_destroy(gmx_comm *comm);      /* before gmx_destroy of its contexts */
 
 /* ---- next row: FASTQ text -> reads -------------------------------------------
  * SeqReader::get_more_fastq (reference src/SeqReader.cpp:1023-1292).  One record per read, offsets into the text. */

@@ -1,15 +1,22 @@
-// gnumap_gmx_bridge.cpp -- the reference-side binding of INTEGRATION.md as a compilable translation unit.
+// gnumap_gmx_bridge.cpp -- the reference-side binding: what a GNUMAP maintainer adds next to src/Driver.cpp.
 //
-// This file is what a GNUMAP maintainer adds next to src/Driver.cpp: it sees the reference's own headers and globals
-// and talks to libgmx.so only through the C ABI of include/gmx.h.  It contains no reference code; it is compiled (not
-// linked) against the headers under /root/reference/inc by tests/test_abi.py::test_reference_side_binding_compiles
-// to prove that the binding matches the reference's real types.
+// It sees the reference's own headers and globals and talks to libgmx.so only through the C ABI of include/gmx.h.  It
+// contains no reference code.  integration/driver_gmx.patch makes src/Driver.cpp call it at four points:
+//
+//   (1) after gGen.LoadGenome()                  src/Driver.cpp:1428-1429  -> gmx_attach()      contexts (one per GPU) + communicator
+//   (2)+(3) the two per-slice loops of parallel_thread_run  :2344-2373     -> gmx_run_slice()   PHASE A + PHASE B of one slice
+//   (4) before gGen.PrintFinal                   :1820-1823 (in place of the MPI block :1615-1811) -> gmx_collect()
+//   and the slice size of the worker threads     :970, :2307               -> gmx_slice_reads()
+//
+// `make -C oracle patched` applies the patch to a copy of the reference's Driver.cpp and links the UNMODIFIED other
+// objects with this file and libgmx.so into oracle/_ref/gnumap_gmx: the reference program, all of its options, on GPUs.
 //
 //   g++ -std=c++0x -I<reference>/inc -I<repo>/oracle/gsl_stub -I<repo>/include -DGMX_BRIDGE_TEST_ACCESS -c gnumap_gmx_bridge.cpp
 //
-// Patch points (reference file:line): (1) after gGen.LoadGenome() src/Driver.cpp:1428-1429 -> gmx_attach();
-// (2)+(3) the two per-slice loops of parallel_thread_run src/Driver.cpp:2344-2373 -> gmx_run_slice();
-// (4) instead of the MPI block src/Driver.cpp:1615-1811, before gGen.PrintFinal :1820 -> gmx_collect().
+// Environment of the patched binary: GMX_DISABLE=1 runs the reference's own CPU loops (A/B runs with one binary);
+// GMX_GPUS=n caps the GPUs used (default: min(threads, devices)); GMX_SLICE_READS=n reads per worker-thread slice
+// (default 65536; the reference's READS_PER_PROC is 2048); GMX_COMM=peer|nccl picks the reduce backend;
+// GMX_NATIVE_PRINT=1 also writes <out>.native.sgr / .gmp with the library's printers.
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -21,15 +28,17 @@
 #include <sstream>
 #include <string>
 #include <vector>
+#include <pthread.h>
 
 #ifdef GMX_BRIDGE_TEST_ACCESS
-// GenomeBwt::index is private (inc/GenomeBwt.h:277); the real patch adds `bwaidx_t* GetIndex() { return index; }`
+// GenomeBwt::index is private (inc/GenomeBwt.h:277); a maintainer adds `bwaidx_t* GetIndex() { return index; }` instead
 #define private public
 #define protected public
 #endif
 #include "const_include.h"
 #include "GenomeBwt.h"
 #include "ScoredSeq.h"
+#include "SequenceOperations.h"
 #ifdef GMX_BRIDGE_TEST_ACCESS
 #undef private
 #undef protected
@@ -49,18 +58,44 @@ extern unsigned int gJUMP_SIZE, gMAX_MATCHES;
 extern int gMIN_JUMP_MATCHES;
 extern float gCUTOFF_SCORE;
 extern bool gFAST;
+extern bool gPRINT_ALL_SAM;
 
-static gmx_ctx *gGmx = 0;
+#define GMX_BRIDGE_MAX_GPUS 16
+static gmx_ctx *gGmx[GMX_BRIDGE_MAX_GPUS];
+static pthread_mutex_t gGmxLock[GMX_BRIDGE_MAX_GPUS];        // worker threads that share a GPU take turns on its context
+static int gGmxN = 0;
+static gmx_comm *gGmxComm = 0;
+static int gGmxIllumina = 0;                                  // gILLUMINA when the contexts were created
 
-static void gmx_die(const char *what)
+// consensus character of one PWM row, as GetConsensus() picks it (src/Driver.cpp:317-347)
+static char gmx_row_char(const float *c)
 {
-    fprintf(stderr, "gmx: %s: %s\n", what, gGmx ? gmx_last_error(gGmx) : "no context");
+    if (c[0] == c[1] && c[0] == c[2] && c[0] == c[3]) return 'n';
+    if (c[0] >= c[1]) return c[0] >= c[2] ? (c[0] >= c[3] ? 'a' : 't') : (c[2] >= c[3] ? 'g' : 't');
+    return c[1] >= c[2] ? (c[1] >= c[3] ? 'c' : 't') : (c[2] >= c[3] ? 'g' : 't');
+}
+
+static void gmx_die(const char *what, gmx_ctx *ctx)
+{
+    fprintf(stderr, "gmx: %s: %s\n", what, ctx ? gmx_last_error(ctx) : "no context");
     exit(1);
 }
 
-// patch point 1 ---------------------------------------------------------------------------------------------------
-void gmx_attach(GenomeBwt &gen, int device)
+bool gmx_enabled() { const char *e = getenv("GMX_DISABLE"); return !(e && *e && *e != '0'); }
+
+// reads per worker-thread slice: the GPU wants slices far larger than the reference's READS_PER_PROC (2048)
+unsigned gmx_slice_reads(unsigned reference_default)
 {
+    if (!gmx_enabled()) return reference_default;
+    const char *e = getenv("GMX_SLICE_READS");
+    long v = e ? atol(e) : 65536;
+    return (unsigned)(v < 1 ? 1 : v);
+}
+
+// patch point 1 ---------------------------------------------------------------------------------------------------
+void gmx_attach(GenomeBwt &gen, unsigned n_threads)
+{
+    if (gPRINT_ALL_SAM) { fprintf(stderr, "gmx: --print_all_sam is not carried by the GPU path (run with GMX_DISABLE=1)\n"); exit(1); }
     bwaidx_t *ix = GMX_GENOME_INDEX(gen);
     std::vector<int64_t> off(ix->bns->n_seqs);
     std::vector<int32_t> len(ix->bns->n_seqs);
@@ -83,42 +118,94 @@ void gmx_attach(GenomeBwt &gen, int device)
     gp.match_pos = gMATCH_POS_STRAND; gp.match_neg = gMATCH_NEG_STRAND; gp.unique_only = gUNIQUE; gp.fast = gFAST;
     gp.use_nw = gNW; gp.illumina = gILLUMINA; gp.adjust = gADJUST;
     gp.mode = gSNP ? GMX_MODE_SNP : ((gBISULFITE || gATOG) ? GMX_MODE_BS : GMX_MODE_NORMAL);
-    if (gmx_create(&gGmx, &gi, &gp, device) != GMX_OK) gmx_die("gmx_create");
+    gGmxIllumina = gILLUMINA;
+
+    // one context per GPU; worker thread t drives context t % n (the reference's threads share gGen under a mutex instead)
+    int want = (int)n_threads;
+    if (const char *e = getenv("GMX_GPUS")) want = atoi(e) < want ? atoi(e) : want;
+    if (want < 1) want = 1;
+    if (want > GMX_BRIDGE_MAX_GPUS) want = GMX_BRIDGE_MAX_GPUS;
+    gGmxN = 0;
+    for (int d = 0; d < want; ++d) {
+        gmx_ctx *c = 0;
+        int rc = gmx_create(&c, &gi, &gp, d);
+        if (rc != GMX_OK) {
+            if (d == 0 || rc != GMX_ERR_INVALID) {                                  // fewer devices than threads: use what is there
+                fprintf(stderr, "gmx: gmx_create on device %d: %s\n", d, c && *gmx_last_error(c) ? gmx_last_error(c) : gmx_strerror(rc));
+                exit(1);
+            }
+            gmx_destroy(c);
+            break;
+        }
+        pthread_mutex_init(&gGmxLock[d], NULL);
+        gGmx[gGmxN++] = c;
+    }
+    if (gGmxN > 1) {
+        int backend = GMX_COMM_AUTO;
+        if (const char *e = getenv("GMX_COMM")) backend = !strcmp(e, "nccl") ? GMX_COMM_NCCL : GMX_COMM_PEER;
+        if (gmx_comm_create(&gGmxComm, gGmx, gGmxN, backend) != GMX_OK) gmx_die("gmx_comm_create", gGmx[0]);
+    }
+    fprintf(stderr, "gmx: %d GPU context(s) for %u worker thread(s)\n", gGmxN, n_threads);
 }
 
 // patch points 2 + 3 ------------------------------------------------------------------------------------------------
-// One call per slice of <= READS_PER_PROC reads; fills what set_top_matches / create_match_output leave behind:
-// gTopReadScore / gReadDenominator (incl. the status sentinels), the matched / not-matched counters and one
-// TopReadOutput per (position, strand) of the best group for the SAM writer.
-void gmx_run_slice(GenomeBwt &gen, unsigned read_begin, unsigned read_end, unsigned &good_seqs, unsigned &bad_seqs, std::vector<TopReadOutput> &sam_out)
+// One call per worker-thread slice; fills what set_top_matches / create_match_output leave behind: gTopReadScore /
+// gReadDenominator (incl. the status sentinels), the matched / not-matched counters, the thread's NW count (DEBUG_NW)
+// and one TopReadOutput per (position, strand) of the best group for the SAM writer.
+void gmx_run_slice(GenomeBwt &gen, unsigned thread_id, unsigned read_begin, unsigned read_end, unsigned &good_seqs, unsigned &bad_seqs,
+                   unsigned &n_nw, std::vector<TopReadOutput> &sam_out)
 {
+    // FASTQ reads: the PWM is a function of (base, quality char) and two bytes per base go to the GPU.  Anything else
+    // (PRB / INT / FASTA reads, or a reader that changed its quality offset on the way: src/SeqReader.cpp:1180-1188)
+    // goes as the raw PWM rows the reader built, with GetConsensus() as the sequence (src/Driver.cpp:352-364).
+    unsigned n = 0;
+    bool as_pwm = (int)gILLUMINA != gGmxIllumina;
+    for (unsigned k = read_begin; k < read_end && gReadArray[k]; ++k, ++n) {
+        const Read *r = gReadArray[k];
+        if (r->seq.size() != r->length || r->fq.size() < r->seq.size()) as_pwm = true;
+    }
     std::vector<int64_t> off(1, 0);
     std::string seq, qual;
-    unsigned n = 0;
-    for (unsigned k = read_begin; k < read_end && gReadArray[k]; ++k, ++n) {       // FASTQ reads: PWM == f(base, quality)
+    std::vector<float> pwm;
+    for (unsigned k = read_begin; k < read_begin + n; ++k) {
         const Read *r = gReadArray[k];
-        seq += r->seq;
-        qual += r->fq.substr(0, r->seq.size());
+        if (!as_pwm) { seq += r->seq; qual.append(r->fq, 0, r->seq.size()); }
+        else {
+            if (r->seq.size() == r->length) seq += r->seq;
+            else for (unsigned i = 0; i < r->length; ++i) seq += gmx_row_char(r->pwm[i]);
+            for (unsigned i = 0; i < r->length; ++i) pwm.insert(pwm.end(), r->pwm[i], r->pwm[i] + 4);
+        }
         off.push_back((int64_t)seq.size());
-    }                                                                             // PRB / INT reads: fill gmx_reads.pwm instead
+    }
     gmx_reads in;
     memset(&in, 0, sizeof(in));
     in.n_reads = (int32_t)n; in.offsets = &off[0];
-    in.seq = (const uint8_t *)seq.data(); in.qual = (const uint8_t *)qual.data();
+    in.seq = (const uint8_t *)seq.data();
+    in.qual = as_pwm ? 0 : (const uint8_t *)qual.data();
+    in.pwm = as_pwm && !pwm.empty() ? &pwm[0] : 0;
     std::vector<gmx_read_result> res(n);
-    if (gmx_process_batch(gGmx, &in, n ? &res[0] : 0) != GMX_OK) gmx_die("gmx_process_batch");
-    int64_t nh = 0;
-    if (gmx_get_hits(gGmx, 0, 0, &nh) != GMX_OK) gmx_die("gmx_get_hits");
-    std::vector<gmx_hit> hits((size_t)nh + 1);
-    if (gmx_get_hits(gGmx, &hits[0], nh + 1, &nh) != GMX_OK) gmx_die("gmx_get_hits");
+    std::vector<gmx_hit> hits;
     std::vector<char> cigar((size_t)n * 64 + 64);
-    if (n && gmx_get_best_alignments(gGmx, &cigar[0], 64, 0, 0) != GMX_OK) gmx_die("gmx_get_best_alignments");
+
+    const int g = (int)(thread_id % (unsigned)gGmxN);
+    gmx_ctx *ctx = gGmx[g];
+    pthread_mutex_lock(&gGmxLock[g]);
+    if (n && gmx_process_batch(ctx, &in, &res[0]) != GMX_OK) gmx_die("gmx_process_batch", ctx);
+    int64_t nh = 0;
+    if (n && gmx_get_hits(ctx, 0, 0, &nh) != GMX_OK) gmx_die("gmx_get_hits", ctx);
+    hits.resize((size_t)nh + 1);
+    if (n && gmx_get_hits(ctx, &hits[0], nh + 1, &nh) != GMX_OK) gmx_die("gmx_get_hits", ctx);
+    if (n && gmx_get_best_alignments(ctx, &cigar[0], 64, 0, 0) != GMX_OK) gmx_die("gmx_get_best_alignments", ctx);
+    pthread_mutex_unlock(&gGmxLock[g]);
+
     for (unsigned i = 0; i < n; ++i) {
         const unsigned k = read_begin + i;
         gTopReadScore[k] = res[i].top_score;                                       // incl. READ_TOO_SHORT / _POOR / _MANY
         gReadDenominator[k] = res[i].denominator;
+        n_nw += (unsigned)res[i].n_candidates;
         if (res[i].status != GMX_READ_MAPPED) { bad_seqs++; continue; }
         good_seqs++;
+        if (!GMX_READ_PRINTS_SAM(res[i])) continue;                                // src/Driver.cpp:695: best group below top - SAME_DIFF
         // what ScoredSeq::get_SAM fills (inc/ScoredSeq.h:293-404): one TopReadOutput per (position, strand) of the best group
         const double total = exp((double)res[i].best_score) / res[i].denominator;
         // the denominator was summed from the device's exp(): the host's exp() may differ in the last place, so a
@@ -136,8 +223,8 @@ void gmx_run_slice(GenomeBwt &gen, unsigned read_begin, unsigned read_end, unsig
             out.MAPQ = mapq;
             strncpy(out.CIGAR, &cigar[(size_t)i * 64], MAX_CIGAR_SZ - 1); out.CIGAR[MAX_CIGAR_SZ - 1] = '\0';
             out.readIndex = k;
-            out.consensus = gReadArray[k]->seq;
-            out.qual = gReadArray[k]->fq;
+            out.consensus = seq.substr((size_t)off[i], (size_t)(off[i + 1] - off[i]));        // GetConsensus(read)
+            out.qual = str2qual(*gReadArray[k]);
             out.A_SCORE = res[i].best_score;
             out.SIM_MATCHES = res[i].best_n_positions;
             out.POST_PROB = res[i].best_posterior;
@@ -151,6 +238,7 @@ void gmx_run_slice(GenomeBwt &gen, unsigned read_begin, unsigned read_end, unsig
 // accumulators where they are, so the 4-24 B per genome position never cross to the host.
 void gmx_print_final(GenomeBwt &gen, const char *fn)
 {
+    if (gGmxComm && gmx_comm_reduce(gGmxComm, 0) != GMX_OK) gmx_die("gmx_comm_reduce", gGmx[0]);
     const bntseq_t *bns = GMX_GENOME_INDEX(gen)->bns;
     std::vector<const char *> names((size_t)bns->n_seqs);
     for (int i = 0; i < bns->n_seqs; ++i) names[(size_t)i] = bns->anns[i].name;
@@ -161,10 +249,10 @@ void gmx_print_final(GenomeBwt &gen, const char *fn)
     std::vector<char> text;
     int64_t len = 0;
     for (int pass = 0; pass < 2; ++pass) {            // first pass sizes the buffer
-        const int rc = gmp ? gmx_format_gmp(gGmx, &names[0], target, 0.001, gSNP_PVAL, gSNP_MONOP ? 1 : 0, text.empty() ? 0 : &text[0], (int64_t)text.size(), &len)
-                           : gmx_format_sgr(gGmx, &names[0], 0.001, text.empty() ? 0 : &text[0], (int64_t)text.size(), &len);
+        const int rc = gmp ? gmx_format_gmp(gGmx[0], &names[0], target, 0.001, gSNP_PVAL, gSNP_MONOP ? 1 : 0, text.empty() ? 0 : &text[0], (int64_t)text.size(), &len)
+                           : gmx_format_sgr(gGmx[0], &names[0], 0.001, text.empty() ? 0 : &text[0], (int64_t)text.size(), &len);
         if (rc == GMX_OK) break;
-        if (rc != GMX_ERR_OVERFLOW || pass) gmx_die(gmp ? "gmx_format_gmp" : "gmx_format_sgr");
+        if (rc != GMX_ERR_OVERFLOW || pass) gmx_die(gmp ? "gmx_format_gmp" : "gmx_format_sgr", gGmx[0]);
         text.resize((size_t)len);
     }
     const std::string path = std::string(fn) + (gmp ? ".gmp" : ".sgr");
@@ -175,17 +263,20 @@ void gmx_print_final(GenomeBwt &gen, const char *fn)
 }
 
 // patch point 4 ---------------------------------------------------------------------------------------------------
-void gmx_collect(GenomeBwt &gen)
+// The sum over the GPUs' accumulators (gmx_finish on the root context reduces first: the library-side counterpart of the
+// MPI block, src/Driver.cpp:1615-1811) lands in the arrays GenomeBwt::PrintFinal reads.
+void gmx_collect(GenomeBwt &gen, const char *out_prefix)
 {
+    if (getenv("GMX_NATIVE_PRINT")) gmx_print_final(gen, (std::string(out_prefix) + ".native").c_str());
     float *planes[5] = {gen.GetGenomeAPtr(), gen.GetGenomeCPtr(), gen.GetGenomeGPtr(), gen.GetGenomeTPtr(), gen.GetGenomeNPtr()};
-    // several GPUs: one process per GPU, ncclAllReduce(sum, f32) on gmx_accumulators_device() first.
     // The library keeps ceil(l_pac / gGEN_SIZE) bins; the reference allocates l_pac / gGEN_SIZE floats (src/GenomeBwt.cpp:323).
     uint64_t n_amount = 0, n_plane = 0;
-    if (gmx_accumulators_device(gGmx, 0, &n_amount, 0, &n_plane) != GMX_OK) gmx_die("gmx_accumulators_device");
+    if (gmx_accumulators_device(gGmx[0], 0, &n_amount, 0, &n_plane) != GMX_OK) gmx_die("gmx_accumulators_device", gGmx[0]);
     std::vector<float> amount((size_t)n_amount);
-    if (gmx_finish(gGmx, n_amount ? &amount[0] : 0, planes) != GMX_OK) gmx_die("gmx_finish");
+    if (gmx_finish(gGmx[0], n_amount ? &amount[0] : 0, planes) != GMX_OK) gmx_die("gmx_finish", gGmx[0]);
     const uint64_t ref_bins = (uint64_t)GMX_GENOME_INDEX(gen)->bns->l_pac / gGEN_SIZE;
     memcpy(gen.GetGenomeAmtPtr(), amount.data(), sizeof(float) * (size_t)(ref_bins < n_amount ? ref_bins : n_amount));
-    gmx_destroy(gGmx);
-    gGmx = 0;
+    if (gGmxComm) { gmx_comm_destroy(gGmxComm); gGmxComm = 0; }
+    for (int i = 0; i < gGmxN; ++i) { gmx_destroy(gGmx[i]); gGmx[i] = 0; }
+    gGmxN = 0;
 }

@@ -67,6 +67,8 @@ def sam_records(index, names, batch: _abi.ReadBatch, results: np.ndarray, hits: 
         res = results[r]
         if res["status"] != _abi.READ_MAPPED or res["best_group"] < 0:
             continue
+        if not float(res["best_score"]) > float(res["top_score"]) - 0.00001:     # SAME_DIFF, reference src/Driver.cpp:695
+            continue
         a, b = int(batch.offsets[r]), int(batch.offsets[r + 1])
         seq = batch.seq[a:b].tobytes()
         qual = batch.qual[a:b].tobytes() if batch.qual is not None else b"*"

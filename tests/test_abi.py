@@ -123,9 +123,26 @@ def test_reference_side_binding_compiles(tmp_path):
     subprocess.check_call(["g++", "-std=c++0x", "-w", "-I", ref_inc, "-I", os.path.join(ROOT, "oracle", "gsl_stub"),
                            "-I", os.path.join(ROOT, "include"), "-DGMX_BRIDGE_TEST_ACCESS", "-c", src, "-o", str(obj)])
     syms = subprocess.check_output(["nm", "-C", str(obj)], text=True)
-    for fn in ("gmx_attach(GenomeBwt&, int)", "gmx_run_slice(GenomeBwt&", "gmx_collect(GenomeBwt&)"):
+    for fn in ("gmx_attach(GenomeBwt&, unsigned int)", "gmx_run_slice(GenomeBwt&", "gmx_collect(GenomeBwt&, char const*)", "gmx_slice_reads(unsigned int)"):
         assert fn in syms
-    for dep in ("gmx_create", "gmx_process_batch", "gmx_get_hits", "gmx_get_best_alignments", "gmx_finish", "gmx_destroy"):
+    for dep in ("gmx_create", "gmx_process_batch", "gmx_get_hits", "gmx_get_best_alignments", "gmx_finish", "gmx_destroy", "gmx_comm_create"):
         assert f"U {dep}" in syms, f"the binding should call {dep} through the C ABI"
-    # the stub in INTEGRATION.md is this file, verbatim
-    assert open(src).read() in open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    # INTEGRATION.md shows this file and the Driver.cpp patch, verbatim
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    assert open(src).read() in doc
+    assert open(os.path.join(ROOT, "integration", "driver_gmx.patch")).read() in doc
+
+
+def test_driver_patch_applies_to_the_reference(tmp_path):
+    """integration/driver_gmx.patch applies cleanly to the reference's src/Driver.cpp and the result compiles."""
+    ref = "/root/reference"
+    if not os.path.isdir(ref):
+        pytest.skip("the reference checkout is not present on this machine")
+    work = tmp_path / "Driver.cpp"
+    work.write_bytes(open(os.path.join(ref, "src", "Driver.cpp"), "rb").read())
+    subprocess.check_call(["patch", "-s", "-p2", str(work), os.path.join(ROOT, "integration", "driver_gmx.patch")])
+    txt = work.read_text()
+    for call in ("gmx_attach(gGen, gNUM_THREADS)", "gmx_run_slice(", "gmx_collect(gGen, output_file)", "gmx_slice_reads(READS_PER_PROC)"):
+        assert call in txt
+    subprocess.check_call(["g++", "-std=c++0x", "-w", "-DDEBUG_NW", "-DDEBUG_TIME", "-I", os.path.join(ref, "inc"),
+                           "-I", os.path.join(ROOT, "oracle", "gsl_stub"), "-fsyntax-only", str(work)])

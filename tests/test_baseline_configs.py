@@ -53,17 +53,21 @@ def _full_sam(fx, stripped):
 
 
 def test_cfg0_oracle_matches_reference_binary(cfg0):
-    """CPU: the oracle on a slice of the example reads against the reference binary's SAM."""
+    """CPU: the oracle on all 24 869 example reads against the reference binary's SAM, matched count and NW count."""
     from oracle import oracle as O
-    lo, hi = 0, 3000
-    batch = _abi.ReadBatch([cfg0["seq"][i].tobytes() for i in range(lo, hi)], [cfg0["qual"][i].tobytes() for i in range(lo, hi)])
+    n = len(cfg0["names"])
+    batch = _abi.ReadBatch([cfg0["seq"][i].tobytes() for i in range(n)], [cfg0["qual"][i].tobytes() for i in range(n)])
     p = O.default_params()
     got = O.process_batch(O.OracleIndex(cfg0["index"]), p, batch)
-    names = cfg0["names"][lo:hi]
-    sam = sorted(ref_text.sam_records(cfg0["index"], names, batch, got["results"], got["hits"], got["cigars"], p.adjust))
-    want = sorted(s for s in _full_sam(cfg0, cfg0["sam_stripped"]) if s.split("\t", 1)[0] in set(names))
-    assert len(want) > 2500
-    assert sam == want
+    r = got["results"]
+    sam = sorted(ref_text.sam_records(cfg0["index"], cfg0["names"], batch, r, got["hits"], got["cigars"], p.adjust))
+    assert sam == sorted(_full_sam(cfg0, cfg0["sam_stripped"]))
+    assert int((r["status"] == _abi.READ_MAPPED).sum()) == cfg0["matched"]
+    assert int(r["n_candidates"].sum()) == cfg0["total_nw"]                     # DEBUG_NW "Total NW", src/Driver.cpp:1596
+    # the example reads hold two mapped reads whose best group scores a few ulps under the read's top NW score (one genome
+    # string met on both strands): the reference prints no SAM record for them (SAME_DIFF, src/Driver.cpp:695)
+    silent = (r["status"] == _abi.READ_MAPPED) & ~(r["best_score"].astype(np.float64) > r["top_score"] - 0.00001)
+    assert int(silent.sum()) == 2
 
 
 @pytest.mark.gpu
