@@ -33,7 +33,7 @@ EXPORTS = [
     "gmx_nw_score", "gmx_nw_traceback", "gmx_pair_hmm", "gmx_map_batch", "gmx_score_batch", "gmx_process_batch",
     "gmx_get_hits", "gmx_get_best_alignments", "gmx_accumulators_device", "gmx_reset_accumulators", "gmx_finish",
     "gmx_get_stage_stats", "gmx_set_option", "gmx_fastq_scan_host", "gmx_fastq_scan", "gmx_process_fastq", "gmx_format_sam", "gmx_format_sgr", "gmx_format_gmp", "gmx_snp_call",
-    "gmx_comm_create", "gmx_comm_reduce", "gmx_comm_stats", "gmx_comm_destroy",
+    "gmx_comm_create", "gmx_comm_reduce", "gmx_comm_stats", "gmx_comm_destroy", "gmx_measure_alu_peak",
 ]
 
 OPT_COLLECT_HITS, OPT_CHUNK_READS, OPT_VOTE_FILTER, OPT_FILTER_SHIFT, OPT_CIGAR_STRIDE = 1, 2, 3, 4, 5
@@ -87,6 +87,7 @@ def load_library():
         L.gmx_snp_call.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double), C.c_char_p, C.c_int]
         L.gmx_format_gmp.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_float, C.c_int, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
         L.gmx_process_fastq.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.c_void_p]
+        L.gmx_measure_alu_peak.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
         L.gmx_comm_create.argtypes = [C.POINTER(C.c_void_p), C.c_void_p, C.c_int, C.c_int]
         L.gmx_comm_reduce.argtypes = [C.c_void_p, C.c_int]
         L.gmx_comm_stats.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_uint64), C.POINTER(C.c_int)]
@@ -369,6 +370,12 @@ class Mapper:
             pl[b] = planes[b].ctypes.data if planes is not None else None
         self._ck(self.L.gmx_finish(self._ctx, ptr(amount), pl), "gmx_finish")
         return amount, planes
+
+    def alu_peak(self, kind: int = 0) -> float:
+        """Measured tera lane-operations per second: 0 = FP32 mul + add (no FMA), 1 = FP32 add + max, 2 = FP64 mul + add."""
+        v = C.c_double(0.0)
+        self._ck(self.L.gmx_measure_alu_peak(self._ctx, kind, C.byref(v)), "gmx_measure_alu_peak")
+        return v.value
 
     def stage_stats(self):
         s = GmxStageStats()

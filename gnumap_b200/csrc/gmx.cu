@@ -1905,6 +1905,60 @@ extern "C" int gmx_snp_call(const float counts[5], int genome_base, int snp_mono
 }
 
 // ------------------------------------------------------------------------------------------------
+// measured ALU ceilings for the roofline of the NW kernels ("measure with a mul/add micro-kernel")
+// ------------------------------------------------------------------------------------------------
+// K2a / K2b are bit-exact FP32 with separate multiplies and adds (no FMA); K2c runs on the FP64 pipe.  Eight independent
+// chains per thread keep the pipes full; the result is stored so that nothing is optimised away.
+template <int KIND>
+__global__ void __launch_bounds__(256) k_alu_peak(float *out, int iters, float x, float y)
+{
+    float a[8]; double d[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { a[k] = (float)(threadIdx.x + k) * 1e-3f; d[k] = (double)a[k]; }
+    const double dx = (double)x, dy = (double)y;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (KIND == 0) a[k] = __fadd_rn(__fmul_rn(a[k], x), y);              // FMUL + FADD: 2 flops, 2 instructions
+            else if (KIND == 1) a[k] = fmaxf(__fadd_rn(a[k], x), y);             // FADD + FMNMX: the max-plus step of the NW cell
+            else d[k] = __dadd_rn(__dmul_rn(d[k], dx), dy);                       // DMUL + DADD
+        }
+    }
+    float s = 0; double sd = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { s += a[k]; sd += d[k]; }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s + (float)sd;
+}
+
+// kind 0: FP32 multiply + add without FMA (what K2a / K2b issue); 1: FP32 add + max; 2: FP64 multiply + add without FMA.
+// *tera_ops = 1e-12 x arithmetic instructions x 32 lanes / second (one flop per lane per instruction), best of five.
+extern "C" int gmx_measure_alu_peak(gmx_ctx *ctx, int kind, double *tera_ops)
+{
+    if (!ctx || !tera_ops || kind < 0 || kind > 2) return GMX_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    const int blocks = ctx->n_sm * 16, iters = kind == 2 ? 1 << 12 : 1 << 14;
+    ScratchBuf out;
+    CK(out.ensure((size_t)blocks * 256 * 4));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 6; ++rep) {
+        CK(cudaEventRecord(e0, ctx->stream));
+        if (kind == 0) k_alu_peak<0><<<blocks, 256, 0, ctx->stream>>>(out.as<float>(), iters, 0.999f, 0.001f);
+        else if (kind == 1) k_alu_peak<1><<<blocks, 256, 0, ctx->stream>>>(out.as<float>(), iters, 0.999f, 0.001f);
+        else k_alu_peak<2><<<blocks, 256, 0, ctx->stream>>>(out.as<float>(), iters, 0.999f, 0.001f);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(e1, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        float ms = 0; CK(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *tera_ops = (double)blocks * 256.0 * (double)iters * 8.0 * 2.0 / ((double)best * 1e-3) * 1e-12;
+    return GMX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // several GPUs in one process: accumulator reduce
 // ------------------------------------------------------------------------------------------------
 #include "comm.cuh"

@@ -102,3 +102,42 @@ def read_fastq(path: str):
         recs.append((lines[i + 1], lines[i + 3]))
         i += 4
     return names, recs
+
+
+def simulate_reads_torch(codes_t, n_reads: int, read_len: int, seed: int, sub_rate: float = 0.01, qlo: int = 15, qhi: int = 40,
+                         bisulfite: float = 0.0, block_reads: int = 131072, first_block: int = 0):
+    """The same read model on the GPU, for read sets too large for the numpy generator (10 M x 150 bp): reads are made in
+    blocks of `block_reads`, block b from torch seed `seed + b`, so any rank can make any part of the set on its own.
+    `codes_t`: uint8 tensor (codes 0..3) of the concatenated genome on the target device.  Returns dict(seq uint8[n, L] ASCII
+    ACGT, qual uint8[n, L] ASCII Phred+33, pos int64[n], strand uint8[n]) as device tensors."""
+    import torch
+    dev = codes_t.device
+    L = codes_t.numel()
+    lut = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=dev)
+    comp = torch.tensor([3, 2, 1, 0], dtype=torch.uint8, device=dev)
+    ar = torch.arange(read_len, device=dev, dtype=torch.int64)
+    outs = {"seq": [], "qual": [], "pos": [], "strand": []}
+    b = first_block
+    done = 0
+    while done < n_reads:
+        n = min(block_reads, n_reads - done)
+        g = torch.Generator(device=dev)
+        g.manual_seed(seed + b)
+        pos = torch.randint(0, L - read_len - 2, (n,), generator=g, device=dev, dtype=torch.int64)
+        strand = torch.randint(0, 2, (n,), generator=g, device=dev, dtype=torch.uint8)
+        fwd = codes_t[pos[:, None] + ar[None, :]]
+        if bisulfite > 0:
+            conv = torch.rand(fwd.shape, generator=g, device=dev) < bisulfite
+            plus = (strand == 0)[:, None]
+            fwd = torch.where(conv & plus & (fwd == 1), torch.full_like(fwd, 3), fwd)
+            fwd = torch.where(conv & ~plus & (fwd == 2), torch.zeros_like(fwd), fwd)
+        sub = torch.rand(fwd.shape, generator=g, device=dev) < sub_rate
+        delta = torch.randint(1, 4, fwd.shape, generator=g, device=dev, dtype=torch.uint8)
+        fwd = torch.where(sub, (fwd + delta) & 3, fwd)
+        rc = comp[fwd.flip(1).long()]
+        bases = torch.where((strand == 1)[:, None], rc, fwd)
+        quals = torch.randint(qlo, qhi + 1, fwd.shape, generator=g, device=dev, dtype=torch.uint8) + 33
+        outs["seq"].append(lut[bases.long()]); outs["qual"].append(quals); outs["pos"].append(pos); outs["strand"].append(strand)
+        done += n
+        b += 1
+    return {k: torch.cat(v) for k, v in outs.items()}

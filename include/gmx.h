@@ -373,6 +373,11 @@ typedef struct gmx_stage_stats {
 } gmx_stage_stats;
 int gmx_get_stage_stats(gmx_ctx *ctx, gmx_stage_stats *out);
 
+/* Measured ALU ceiling of the context's GPU for the roofline of the NW kernels (a mul/add micro-kernel, best of five):
+ * kind 0 = FP32 multiply + add WITHOUT fused multiply-add (what the bit-exact K2a / K2b issue), 1 = FP32 add + max,
+ * 2 = FP64 multiply + add without FMA (K2c's pipe).  *tera_ops = 1e-12 x lane-operations per second. */
+int gmx_measure_alu_peak(gmx_ctx *ctx, int kind, double *tera_ops);
+
 #ifdef __cplusplus
 }
 #endif
