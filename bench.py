@@ -314,6 +314,8 @@ class Job:
             m.set_option(api.OPT_CHUNK_READS, int(os.environ["GMX_CHUNK_READS"]))
         if os.environ.get("GMX_FILTER_SHIFT"):
             m.set_option(api.OPT_FILTER_SHIFT, int(os.environ["GMX_FILTER_SHIFT"]))
+        if os.environ.get("GMX_VOTE_SLOTS"):
+            m.set_option(api.OPT_VOTE_SLOTS, int(os.environ["GMX_VOTE_SLOTS"]))
         self.stream = torch.cuda.Stream(device=self.dev)
         m.set_stream(self.stream.cuda_stream)
         n = self.n = seq_h.numel() // L

@@ -36,7 +36,7 @@ EXPORTS = [
     "gmx_comm_create", "gmx_comm_reduce", "gmx_comm_stats", "gmx_comm_destroy", "gmx_measure_alu_peak",
 ]
 
-OPT_COLLECT_HITS, OPT_CHUNK_READS, OPT_VOTE_FILTER, OPT_FILTER_SHIFT, OPT_CIGAR_STRIDE = 1, 2, 3, 4, 5
+OPT_COLLECT_HITS, OPT_CHUNK_READS, OPT_VOTE_FILTER, OPT_FILTER_SHIFT, OPT_CIGAR_STRIDE, OPT_VOTE_SLOTS = 1, 2, 3, 4, 5, 6
 COMM_AUTO, COMM_PEER, COMM_NCCL = 0, 1, 2
 
 

@@ -131,6 +131,7 @@ struct gmx_ctx {
     bool collect_hits = true;
     bool use_filter = true;                    // GMX_OPT_VOTE_FILTER
     int filter_shift = 0;                      // GMX_OPT_FILTER_SHIFT
+    int vote_slots = GMX_VOTE_UNROLL;          // GMX_OPT_VOTE_SLOTS: 32-hit slots per step of the vote kernel
     int n_sm = 148;
     DevBuf d_ranges;                           // candidate range per read
     DevBuf d_groups, d_read_base;              // groups per read and their exclusive scan (leader slots)
@@ -396,6 +397,10 @@ extern "C" int gmx_create(gmx_ctx **out, const gmx_index *index, const gmx_param
 
     int r = build_tables(ctx);
     if (r != GMX_OK) return r;
+    {   // vote kernel: slots per step from the expected SA hits of one k-mer
+        const double per_kmer = (double)index->seq_len / pow(4.0, (double)std::min(params->mer, 15));
+        ctx->vote_slots = per_kmer * 1.15 > 32.0 * GMX_VOTE_UNROLL ? 6 : GMX_VOTE_UNROLL;
+    }
 
     // accumulators (zeroed: neutralises the reference's un-initialised malloc)
     ctx->acc.n_amount = ((uint64_t)index->l_pac + params->gen_size - 1) / params->gen_size;
@@ -801,19 +806,19 @@ static cudaError_t launch_vote(gmx_ctx *ctx, const SeedStore &S, const ClassList
     return cudaGetLastError();
 }
 
-template <int FL, int WARPS, bool BITS>
+template <int FL, int WARPS, bool BITS, int U = GMX_VOTE_UNROLL>
 static cudaError_t launch_filter(gmx_ctx *ctx, const SeedStore &S, const ClassLists &F, const ClassLists &E, int cls, const CandSink &sink, int n_sm,
                                  uint32_t pac_words)
 {
     size_t smem = (size_t)WARPS * gmx_filter_warp_bytes(FL);
-    cudaError_t e = cudaFuncSetAttribute(k_vote_filter<FL, WARPS, BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k_vote_filter<FL, WARPS, BITS, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 1;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_vote_filter<FL, WARPS, BITS>, WARPS * 32, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_vote_filter<FL, WARPS, BITS, U>, WARPS * 32, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
-    k_vote_filter<FL, WARPS, BITS><<<n_sm * per_sm, WARPS * 32, smem, ctx->stream>>>(ctx->ix, pac_words, S, F, E, cls, ctx->dparams.kmin,
-                                                                              ctx->dparams.mer, sink);
+    k_vote_filter<FL, WARPS, BITS, U><<<n_sm * per_sm, WARPS * 32, smem, ctx->stream>>>(ctx->ix, pac_words, S, F, E, cls, ctx->dparams.kmin,
+                                                                                 ctx->dparams.mer, sink);
     return cudaGetLastError();
 }
 
@@ -905,7 +910,12 @@ static int phase_a(gmx_ctx *ctx, const gmx_reads *reads, int32_t lo, int32_t hi,
                         case 10: e = launch_filter<10, 8, true>(ctx, S, F, C, c, sink, n_sm, pac_words); break;
                         case 11: e = launch_filter<11, 8, true>(ctx, S, F, C, c, sink, n_sm, pac_words); break;
                         case 12: e = launch_filter<12, 8, true>(ctx, S, F, C, c, sink, n_sm, pac_words); break;
-                        case 13: e = launch_filter<13, 4, true>(ctx, S, F, C, c, sink, n_sm, pac_words); break;
+                        case 13:
+                            // 32-hit slots per step for the expected hits of one k-mer (seq_len / 4^mer on a random genome:
+                            // 95 at 100 Mb, 149 at 156 Mb for mer 10) plus head room
+                            if (ctx->vote_slots >= 6) e = launch_filter<13, 4, true, 6>(ctx, S, F, C, c, sink, n_sm, pac_words);
+                            else e = launch_filter<13, 4, true>(ctx, S, F, C, c, sink, n_sm, pac_words);
+                            break;
                         case 14: e = launch_filter<14, 2, true>(ctx, S, F, C, c, sink, n_sm, pac_words); break;
                         case 15: e = launch_filter<15, 1, true>(ctx, S, F, C, c, sink, n_sm, pac_words); break;
                         default: e = launch_filter<16, 1, true>(ctx, S, F, C, c, sink, n_sm, pac_words); break;
@@ -1050,27 +1060,31 @@ static int phase_b(gmx_ctx *ctx)
         CK(ctx->d_hmm.ensure((size_t)n_leaders * max_len * 5 * 4));
         L.hmm = ctx->d_hmm.as<float>();
         size_t per_task = gmx_phmm_scratch_doubles(max_len);
-        uint32_t wave = std::min<uint32_t>(n_leaders, (uint32_t)ctx->n_sm * 24);     // resident warps: register-bound
-        CK(ctx->d_phmm_scratch.ensure((size_t)wave * per_task * 8));
-        stage_begin(ctx, ST_PHMM);
-        int launches = 0;
         const int C = (max_len + 31) / 32;
-        for (uint32_t s0 = 0; s0 < n_leaders; s0 += wave) {
-            uint32_t cnt = std::min<uint32_t>(wave, n_leaders - s0);
-            double *scr = ctx->d_phmm_scratch.as<double>();
-#define GMX_PHMM_LAUNCH(CT) k_pair_hmm_leaders<CT><<<cnt, GMX_PHMM_THREADS, 0, ctx->stream>>>(ctx->ix, ctx->dreads, ctx->tab, cs.keys, L, s0, cnt, scr, per_task)
-            switch (C) {
-                case 1: GMX_PHMM_LAUNCH(1); break;
-                case 2: GMX_PHMM_LAUNCH(2); break;
-                case 3: GMX_PHMM_LAUNCH(3); break;
-                case 4: GMX_PHMM_LAUNCH(4); break;
-                case 5: GMX_PHMM_LAUNCH(5); break;
-                default: GMX_PHMM_LAUNCH(0); break;
-            }
-#undef GMX_PHMM_LAUNCH
-            CK(cudaGetLastError());
-            launches++;
+        // persistent grid: as many one-warp CTAs as the SMs hold at once (register-bound), each with its own scratch slot
+        int per_sm = 1;
+#define GMX_PHMM_OCC(CT) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pair_hmm_leaders<CT>, GMX_PHMM_THREADS, 0))
+        switch (C) { case 1: GMX_PHMM_OCC(1); break; case 2: GMX_PHMM_OCC(2); break; case 3: GMX_PHMM_OCC(3); break; case 4: GMX_PHMM_OCC(4); break;
+                     case 5: GMX_PHMM_OCC(5); break; default: GMX_PHMM_OCC(0); break; }
+#undef GMX_PHMM_OCC
+        const uint32_t grid = std::min<uint32_t>(n_leaders, (uint32_t)ctx->n_sm * (uint32_t)std::max(per_sm, 1));
+        CK(ctx->d_phmm_scratch.ensure((size_t)grid * per_task * 8 + 16));
+        uint32_t *cursor = reinterpret_cast<uint32_t *>(ctx->d_phmm_scratch.as<char>() + (size_t)grid * per_task * 8);
+        stage_begin(ctx, ST_PHMM);
+        CK(cudaMemsetAsync(cursor, 0, 4, ctx->stream));
+        int launches = 1;
+        double *scr = ctx->d_phmm_scratch.as<double>();
+#define GMX_PHMM_LAUNCH(CT) k_pair_hmm_leaders<CT><<<grid, GMX_PHMM_THREADS, 0, ctx->stream>>>(ctx->ix, ctx->dreads, ctx->tab, cs.keys, L, n_leaders, cursor, scr, per_task)
+        switch (C) {
+            case 1: GMX_PHMM_LAUNCH(1); break;
+            case 2: GMX_PHMM_LAUNCH(2); break;
+            case 3: GMX_PHMM_LAUNCH(3); break;
+            case 4: GMX_PHMM_LAUNCH(4); break;
+            case 5: GMX_PHMM_LAUNCH(5); break;
+            default: GMX_PHMM_LAUNCH(0); break;
         }
+#undef GMX_PHMM_LAUNCH
+        CK(cudaGetLastError());
         stage_end(ctx, ST_PHMM, (uint64_t)n_leaders * (uint64_t)max_len * (uint64_t)max_len, 0, launches);
     }
     stage_begin(ctx, ST_SCATTER);
@@ -1377,6 +1391,9 @@ extern "C" int gmx_set_option(gmx_ctx *ctx, int option, int64_t value)
             if (value < 1 || value > (1 << 22)) { ctx->err = "chunk_reads must be in 1..4194304"; return GMX_ERR_INVALID; }
             ctx->chunk_reads = (size_t)value; return GMX_OK;
         case GMX_OPT_VOTE_FILTER: ctx->use_filter = value != 0; return GMX_OK;
+        case GMX_OPT_VOTE_SLOTS:
+            if (value != 4 && value != 6) { ctx->err = "vote_slots must be 4 or 6"; return GMX_ERR_INVALID; }
+            ctx->vote_slots = (int)value; return GMX_OK;
         case GMX_OPT_CIGAR_STRIDE:
             if (value < 16 || value > 2048 || (value & 15)) { ctx->err = "cigar_stride must be a multiple of 16 in 16..2048"; return GMX_ERR_INVALID; }
             ctx->cigar_stride = (int)value; ctx->mapped = false; ctx->scored = false; ctx->cs.valid = false; return GMX_OK;

@@ -448,6 +448,15 @@ __global__ void __launch_bounds__(WARPS * 32) k_vote_smem(DevIndex ix, SeedStore
 
 // returning OR on a 32-bit shared-window address
 __device__ __forceinline__ uint32_t gmx_atoms_or32(uint32_t a, uint32_t v) { uint32_t o; asm volatile("atom.shared.or.b32 %0, [%1], %2;" : "=r"(o) : "r"(a), "r"(v) : "memory"); return o; }
+// the same under a predicate (0 when the lane sits out): one predicated ATOMS instead of a branch around it -- the
+// compiler's own `if (p)` costs BSSY + BRA + BSYNC per atomic, a fifth of the per-hit instructions of the vote step
+__device__ __forceinline__ uint32_t gmx_atoms_or32_if(uint32_t a, uint32_t v, bool p)
+{
+    uint32_t o;
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %3, 0;\n\tmov.u32 %0, 0;\n\t@q atom.shared.or.b32 %0, [%1], %2;\n\t}"
+                 : "=r"(o) : "r"(a), "r"(v), "r"((uint32_t)p) : "memory");
+    return o;
+}
 
 struct FilterSmem {              // per-warp layout behind the filter bytes
     uint32_t queue[GMX_FQ_CAP];
@@ -522,12 +531,14 @@ __device__ int gmx_round_diag0(const DevIndex &ix, int ns, int mer, int kmin, co
 // diagonal, two bits inside it) -- half the filter bytes of the byte counters at a fifth of their false positives,
 // and ONE shared-memory operation per hit: a returning atomic OR sets the two bits and reports whether both were
 // already there.  Being atomic, lanes that share a word in one step cannot lose each other's bits.
-template <int F_LOG2, int WARPS, bool BITS>
+// U: 32-hit slots per step.  A step handles the hits of ONE k-mer, so U is sized for the genome: a k-mer of a random
+// genome has seq_len / 4^mer hits on average (95 at 100 Mb, 149 at 156 Mb for mer 10); with too few slots most k-mers
+// need a second, mostly empty step.
+template <int F_LOG2, int WARPS, bool BITS, int U = GMX_VOTE_UNROLL>
 __global__ void __launch_bounds__(WARPS * 32, 1) k_vote_filter(DevIndex ix, uint32_t pac_words, SeedStore S, ClassLists F, ClassLists E,
                                                             int cls, int kmin, int mer, CandSink sink)
 {
     constexpr uint32_t FBYTES = 1u << F_LOG2;
-    constexpr int U = GMX_VOTE_UNROLL;
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint8_t *filt = smem_raw + (size_t)warp * gmx_filter_warp_bytes(F_LOG2);
@@ -585,6 +596,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_vote_filter(DevIndex ix, uint
     bool n_ids_pending = true;
     uint32_t slot = 0;
     bool has_cur = g_base < n_list;
+    bool first_task = true;
     if (has_cur) fetch(__shfl_sync(0xffffffffu, g_ids, 0), cur);
     while (has_cur) {
         // step the cursor to the next work item and start loading its k-mers
@@ -610,11 +622,15 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_vote_filter(DevIndex ix, uint
             cur = nxt; has_cur = has_next;
             continue;
         }
-        // pull every suffix-array line this task will read into L2 while the filter is being cleared
+        // the suffix-array lines of a task are pulled into L2 one task ahead (below, once the next task's k-mers have
+        // arrived); only a warp's very first task asks for its own here
+        if (first_task) {
 #pragma unroll
-        for (int h = 0; h < 2; ++h)
-            for (uint32_t t = 0; t < cur.cnt[h]; t += 32u)
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(ix.sa_full + cur.rank[h] + t));
+            for (int h = 0; h < 2; ++h)
+                for (uint32_t t = 0; t < cur.cnt[h]; t += 32u)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(ix.sa_full + cur.rank[h] + t));
+            first_task = false;
+        }
         uint4 *f4 = reinterpret_cast<uint4 *>(filt);
         for (uint32_t x = lane; x < FBYTES / 16; x += 32) f4[x] = make_uint4(0, 0, 0, 0);
         __syncwarp();
@@ -742,7 +758,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_vote_filter(DevIndex ix, uint
                 // were there already (measured on B200: 9.3 ms per step against 9.6 for load + reduction and 10.6 for
                 // load + plain store + re-read + repair; lanes without a hit must skip it, the unit's cost is per lane)
 #pragma unroll
-                for (int u = 0; u < U; ++u) { o[u] = 0u; if (valid[u]) o[u] = gmx_atoms_or32(w[u], b[u]); }
+                for (int u = 0; u < U; ++u) o[u] = gmx_atoms_or32_if(w[u], b[u], valid[u]);
 #pragma unroll
                 for (int u = 0; u < U; ++u) flag[u] = valid[u] && (o[u] & b[u]) == b[u];
             } else {
@@ -765,18 +781,25 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_vote_filter(DevIndex ix, uint
             bool any_flag = false;
 #pragma unroll
             for (int u = 0; u < U; ++u) any_flag |= flag[u];
-            if (__any_sync(0xffffffffu, any_flag)) {
+            // flagged hits are rare (about one lane in every other step): the lanes that hold some append theirs in turn
+            for (uint32_t fl = __ballot_sync(0xffffffffu, any_flag); fl; fl &= fl - 1u) {
+                const int src = __ffs(fl) - 1;
+                uint32_t mine = 0;
+                if (lane == src) {
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const uint32_t fm = __ballot_sync(0xffffffffu, flag[u]);
-                    if (flag[u]) {
-                        const uint32_t at = qn + (uint32_t)__popc(fm & lt);
-                        if (at < GMX_FQ_CAP) fs->queue[at] = diag[u];
-                    }
-                    qn += (uint32_t)__popc(fm);
+                    for (int u = 0; u < U; ++u)
+                        if (flag[u]) { if (qn + mine < GMX_FQ_CAP) fs->queue[qn + mine] = diag[u]; mine++; }
                 }
+                qn += __shfl_sync(0xffffffffu, mine, src);
             }
             __syncwarp();
+            // one task ahead: the next task's k-mers have arrived by now -- ask L2 for its suffix-array lines
+            if (s_cur == 0 && t_cur == 0 && has_next) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+                    for (uint32_t t = 0; t < nxt.cnt[h]; t += 32u)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(ix.sa_full + nxt.rank[h] + t));
+            }
             s_cur = s_n; t_cur = t_n;
         }
         if (s_cur >= ns && d0_hits) {                                  // diagonal 0 joins the last drain

@@ -359,6 +359,7 @@ int gmx_snp_call(const float counts[5], int genome_base, int snp_monoploid, floa
                                     reference builds CIGARs unbounded (TopReadOutput::CIGAR holds MAX_CIGAR_SZ = 1024); a batch in
                                     which some alignment needs more text than the slot fails with GMX_ERR_OVERFLOW instead of
                                     returning a cut string */
+#define GMX_OPT_VOTE_SLOTS   6   /* tuning: 32-hit slots per step of the vote kernel, 4 or 6 (default: from seq_len / 4^mer)  */
 int gmx_set_option(gmx_ctx *ctx, int option, int64_t value);
 
 /* ---- instrumentation ---------------------------------------------------------------------- */

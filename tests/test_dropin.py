@@ -71,12 +71,12 @@ CASES = {
     "max_gap_1": (["--max_gap=1"], 2, {}),
     "gap_penalty": (["-G", "-0.5"], 2, {}),
     "bin_size_4": (["--bin_size=4"], 2, {}),
-    "bin_size_1_unique": (["--bin_size=1", "-u"], 2, {}),
+    "bin_size_1_unique": (["--bin_size=1", "-u", "1"], 2, {}),          # the reference's -u consumes one token (src/Driver.cpp:2767)
     "illumina": (["--illumina"], 2, {"qoff": 64, "qlo": 5}),
     "mer12_jump4_seeds3": (["-m", "12", "-j", "4", "-k", "3"], 2, {}),
     "max_kmer_and_matches": (["-h", "40", "-T", "3"], 2, {}),
     "up_strand_raw": (["--up_strand", "-r", "-a", "60"], 2, {}),
-    "read_quality_fast": (["-q", "70", "--fast"], 2, {}),
+    "read_quality_fast": (["-q", "70", "--fast", "-k", "1"], 2, {}),      # --fast stops at the first k-mer that hits: one seed must do
 }
 
 
