@@ -314,6 +314,8 @@ class Job:
             m.set_option(api.OPT_CHUNK_READS, int(os.environ["GMX_CHUNK_READS"]))
         if os.environ.get("GMX_FILTER_SHIFT"):
             m.set_option(api.OPT_FILTER_SHIFT, int(os.environ["GMX_FILTER_SHIFT"]))
+        if os.environ.get("GMX_VOTE_COMPACT"):
+            m.set_option(api.OPT_VOTE_COMPACT, int(os.environ["GMX_VOTE_COMPACT"]))
         if os.environ.get("GMX_VOTE_SLOTS"):
             m.set_option(api.OPT_VOTE_SLOTS, int(os.environ["GMX_VOTE_SLOTS"]))
         self.stream = torch.cuda.Stream(device=self.dev)
@@ -341,6 +343,34 @@ class Job:
 
     def step(self, batch):
         self.m.process_batch(batch, fetch=False, results=self.res_np)
+
+    def small_calls(self, reads_per_call, calls):
+        """The reference's natural call size: its worker threads hand over 2048 reads each per iteration (src/Driver.cpp:2339),
+        2048 x threads reads per round.  `calls` gmx_process_batch calls of `reads_per_call` reads from pinned host memory,
+        wall clock."""
+        torch = self.torch
+        n = min(reads_per_call, self.n)
+        calls = max(1, min(calls, self.n // n))
+        batches = []
+        for c in range(calls):
+            class B:
+                pass
+            b = B()
+            s = self._abi.GmxReads()
+            s.n_reads = n; s.offsets = self.off_h.data_ptr() + 8 * c * n; s.seq = self.seq_h.data_ptr(); s.qual = self.qual_h.data_ptr(); s.pwm = None
+            s.on_device = 0; s.max_len = self.L
+            b.struct = s; b.n_reads = n
+            batches.append((b, self.res_np[c * n:(c + 1) * n]))
+        for b, r in batches[:2]:
+            self.m.process_batch(b, fetch=False, results=r)
+        torch.cuda.synchronize()
+        t0 = time.time()
+        for b, r in batches:
+            self.m.process_batch(b, fetch=False, results=r)
+        torch.cuda.synchronize()
+        dt = time.time() - t0
+        return {"reads_per_call": n, "calls": calls, "value": n * calls / dt, "unit": "reads/s", "ms_per_call": 1e3 * dt / calls,
+                "what": "gmx_process_batch from pinned host buffers at the reference's call granularity (2048 reads x 16 worker threads per round), wall clock"}
 
     def reduce(self, timed=True):
         """The path's one collective (MPI Allreduce / Reduce of the accumulators, reference src/Driver.cpp:1615-1811)."""
@@ -581,6 +611,7 @@ def own_arm(a):
     clocks = sampler.stop() if sampler else None
     ms_e2e, wall_e2e, _, _ = job.timed(job.host_batch, a.steps, False)
     mapped = int((res_np["status"] == 0).sum())
+    small = job.small_calls(SLICE * 16, 24) if rank == 0 else None
 
     # next row: the same step fed with FASTQ TEXT (pinned host buffer): H2D of the raw text, device record
     # indexer, reads used in place, D2H of the results and of the record index
@@ -667,11 +698,11 @@ def own_arm(a):
         try:   # DRAM bytes per SA hit of the vote kernel from the committed ncu --set full capture, scaled to this launch
             tj = json.load(open(os.path.join(ROOT, "profiles", "vote_kernel_traffic.json")))
             if roofline["kernel"] == "locate_vote":
-                chunks = max(st["launches"]["locate_vote"] / 12, 1)
+                chunks = max(st["launches"].get("classify", 0), 1)          # one k_classify per chunk
                 roofline["traffic"] = tj["dram_bytes_per_sa_hit"] * st["units"]["locate_vote"] / chunks
                 roofline["algorithmic_bytes_per_loaded_launch"] = st["bytes"]["locate_vote"] / chunks
-                roofline["note"] = ("stage = 12 launches per chunk (6 filter + 6 exact classes); one of them carries ~all tasks of a uniform workload, the rest "
-                                    "find empty lists (~5 us each); achieved / traffic are per loaded launch")
+                roofline["note"] = ("stage = one launch per non-empty task class and chunk (6 filter + 6 exact classes exist; a uniform workload fills one); "
+                                    "achieved / traffic are per chunk")
         except (OSError, KeyError, ValueError):
             pass
         nw_cells = st["units"].get("nw_score", 0)
@@ -747,6 +778,7 @@ def own_arm(a):
                     "clock": "wall, max over ranks", "cuda_event_ms_per_step": ms_e2e / a.steps},
             "gpu_launches": int(sum(st["launches"].values())),
             "roofline": roofline,
+            "small_calls": small,
             "alu_peaks": alu,
             "cpu_baseline": cpu,
             "parity_sample": parity,

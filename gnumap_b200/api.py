@@ -23,7 +23,7 @@ from . import _abi
 from ._abi import (GmxIndex, GmxParams, GmxReads, GmxStageStats, HIT_DTYPE, READ_RESULT_DTYPE, IndexHandle, ReadBatch, ptr)
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libgmx.so")
+LIB_PATH = os.environ.get("GMX_LIB") or os.path.join(HERE, "libgmx.so")      # GMX_LIB: an alternative build of the same library (kernel experiments)
 
 _lib = None
 
@@ -36,7 +36,7 @@ EXPORTS = [
     "gmx_comm_create", "gmx_comm_reduce", "gmx_comm_stats", "gmx_comm_destroy", "gmx_measure_alu_peak",
 ]
 
-OPT_COLLECT_HITS, OPT_CHUNK_READS, OPT_VOTE_FILTER, OPT_FILTER_SHIFT, OPT_CIGAR_STRIDE, OPT_VOTE_SLOTS = 1, 2, 3, 4, 5, 6
+OPT_COLLECT_HITS, OPT_CHUNK_READS, OPT_VOTE_FILTER, OPT_FILTER_SHIFT, OPT_CIGAR_STRIDE, OPT_VOTE_SLOTS, OPT_VOTE_COMPACT = 1, 2, 3, 4, 5, 6, 7
 COMM_AUTO, COMM_PEER, COMM_NCCL = 0, 1, 2
 
 

@@ -132,6 +132,8 @@ struct gmx_ctx {
     bool use_filter = true;                    // GMX_OPT_VOTE_FILTER
     int filter_shift = 0;                      // GMX_OPT_FILTER_SHIFT
     int vote_slots = GMX_VOTE_UNROLL;          // GMX_OPT_VOTE_SLOTS: 32-hit slots per step of the vote kernel
+    int vote_compact = 1;                      // GMX_OPT_VOTE_COMPACT
+    uint32_t class_hint = 0xfffu;              // vote classes (6 filter + 6 exact) that held tasks in the previous chunk
     int n_sm = 148;
     DevBuf d_ranges;                           // candidate range per read
     DevBuf d_groups, d_read_base;              // groups per read and their exclusive scan (leader slots)
@@ -806,19 +808,19 @@ static cudaError_t launch_vote(gmx_ctx *ctx, const SeedStore &S, const ClassList
     return cudaGetLastError();
 }
 
-template <int FL, int WARPS, bool BITS, int U = GMX_VOTE_UNROLL>
+template <int FL, int WARPS, bool BITS, int U = GMX_VOTE_UNROLL, bool COMPACT = false>
 static cudaError_t launch_filter(gmx_ctx *ctx, const SeedStore &S, const ClassLists &F, const ClassLists &E, int cls, const CandSink &sink, int n_sm,
                                  uint32_t pac_words)
 {
-    size_t smem = (size_t)WARPS * gmx_filter_warp_bytes(FL);
-    cudaError_t e = cudaFuncSetAttribute(k_vote_filter<FL, WARPS, BITS, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    size_t smem = (size_t)WARPS * (COMPACT ? gmx_filter_warp_bytes_compact() : gmx_filter_warp_bytes(FL));
+    cudaError_t e = cudaFuncSetAttribute(k_vote_filter<FL, WARPS, BITS, U, COMPACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 1;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_vote_filter<FL, WARPS, BITS, U>, WARPS * 32, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_vote_filter<FL, WARPS, BITS, U, COMPACT>, WARPS * 32, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
-    k_vote_filter<FL, WARPS, BITS, U><<<n_sm * per_sm, WARPS * 32, smem, ctx->stream>>>(ctx->ix, pac_words, S, F, E, cls, ctx->dparams.kmin,
-                                                                                 ctx->dparams.mer, sink);
+    k_vote_filter<FL, WARPS, BITS, U, COMPACT><<<n_sm * per_sm, WARPS * 32, smem, ctx->stream>>>(ctx->ix, pac_words, S, F, E, cls, ctx->dparams.kmin,
+                                                                                          ctx->dparams.mer, sink);
     return cudaGetLastError();
 }
 
@@ -897,56 +899,87 @@ static int phase_a(gmx_ctx *ctx, const gmx_reads *reads, int32_t lo, int32_t hi,
         CK(cudaGetLastError());
         stage_end(ctx, ST_CLASSIFY, (uint64_t)n_tasks, (uint64_t)n_tasks * 8, 1);
 
-        // K1b + K1c
+        // K1b + K1c.  Twelve kernels cover the task classes (6 filter + 6 exact); a uniform workload fills one or two of
+        // them.  Only the classes that held tasks in the previous chunk are launched up front; once the counters are back
+        // (the host needs them anyway), a class that turned out non-empty without having been launched is launched then.
         CandSink sink; sink.keys = ctx->d_keys.as<unsigned long long>(); sink.count = &dc->n_cand; sink.overflow = &dc->cand_overflow; sink.cap = (uint32_t)ctx->cand_cap;
-        stage_begin(ctx, ST_VOTE);
-        if (use_filter) {
-            if (P.kmin == 2) {       // blocked Bloom filter over bits: (4 << filter_shift) bytes of filter per SA hit of the class
-                for (int c = 0; c < GMX_N_CLASSES; ++c) {
-                    cudaError_t e = cudaSuccess;
+        auto launch_class = [&](int k) -> cudaError_t {         // k: 0..5 filter classes, 6..11 exact classes
+            if (k < GMX_N_CLASSES) {
+                const int c = k;
+                if (!use_filter) return cudaSuccess;
+                if (P.kmin == 2) {       // blocked Bloom filter over bits: (4 << filter_shift) bytes of filter per SA hit of the class
                     // measured on B200: occupancy beats a sparse filter -- 8 KB (20 warps/SM) up to 8k hits per task
                     static const int kBitsLog2[GMX_N_CLASSES] = {11, 12, 13, 13, 13, 15};
                     switch (std::min(std::max(kBitsLog2[c] + ctx->filter_shift, 10), 16)) {
-                        case 10: e = launch_filter<10, 8, true>(ctx, S, F, C, c, sink, n_sm, pac_words); break;
-                        case 11: e = launch_filter<11, 8, true>(ctx, S, F, C, c, sink, n_sm, pac_words); break;
-                        case 12: e = launch_filter<12, 8, true>(ctx, S, F, C, c, sink, n_sm, pac_words); break;
+                        case 10: return launch_filter<10, 8, true>(ctx, S, F, C, c, sink, n_sm, pac_words);
+                        case 11: return launch_filter<11, 8, true>(ctx, S, F, C, c, sink, n_sm, pac_words);
+                        case 12: return launch_filter<12, 8, true>(ctx, S, F, C, c, sink, n_sm, pac_words);
                         case 13:
                             // 32-hit slots per step for the expected hits of one k-mer (seq_len / 4^mer on a random genome:
                             // 95 at 100 Mb, 149 at 156 Mb for mer 10) plus head room
-                            if (ctx->vote_slots >= 6) e = launch_filter<13, 4, true, 6>(ctx, S, F, C, c, sink, n_sm, pac_words);
-                            else e = launch_filter<13, 4, true>(ctx, S, F, C, c, sink, n_sm, pac_words);
-                            break;
-                        case 14: e = launch_filter<14, 2, true>(ctx, S, F, C, c, sink, n_sm, pac_words); break;
-                        case 15: e = launch_filter<15, 1, true>(ctx, S, F, C, c, sink, n_sm, pac_words); break;
-                        default: e = launch_filter<16, 1, true>(ctx, S, F, C, c, sink, n_sm, pac_words); break;
+                            if (ctx->vote_compact && S.max_seeds <= 32) {      // tasks of at most 32 k-mers: the 24-warp variant
+                                if (ctx->vote_slots >= 6) return launch_filter<13, 4, true, 6, true>(ctx, S, F, C, c, sink, n_sm, pac_words);
+                                return launch_filter<13, 4, true, 4, true>(ctx, S, F, C, c, sink, n_sm, pac_words);
+                            }
+                            if (ctx->vote_slots >= 6) return launch_filter<13, 4, true, 6>(ctx, S, F, C, c, sink, n_sm, pac_words);
+                            return launch_filter<13, 4, true>(ctx, S, F, C, c, sink, n_sm, pac_words);
+                        case 14: return launch_filter<14, 2, true>(ctx, S, F, C, c, sink, n_sm, pac_words);
+                        case 15: return launch_filter<15, 1, true>(ctx, S, F, C, c, sink, n_sm, pac_words);
+                        default: return launch_filter<16, 1, true>(ctx, S, F, C, c, sink, n_sm, pac_words);
                     }
-                    CK(e);
                 }
-            } else {                  // byte counters: 8 bytes of filter per SA hit of the class
-                CK((launch_filter<12, 8, false>(ctx, S, F, C, 0, sink, n_sm, pac_words)));
-                CK((launch_filter<13, 4, false>(ctx, S, F, C, 1, sink, n_sm, pac_words)));
-                CK((launch_filter<14, 2, false>(ctx, S, F, C, 2, sink, n_sm, pac_words)));
-                CK((launch_filter<15, 1, false>(ctx, S, F, C, 3, sink, n_sm, pac_words)));
-                CK((launch_filter<16, 1, false>(ctx, S, F, C, 4, sink, n_sm, pac_words)));
-                CK((launch_filter<17, 1, false>(ctx, S, F, C, 5, sink, n_sm, pac_words)));
+                switch (c) {             // byte counters: 8 bytes of filter per SA hit of the class
+                    case 0: return launch_filter<12, 8, false>(ctx, S, F, C, 0, sink, n_sm, pac_words);
+                    case 1: return launch_filter<13, 4, false>(ctx, S, F, C, 1, sink, n_sm, pac_words);
+                    case 2: return launch_filter<14, 2, false>(ctx, S, F, C, 2, sink, n_sm, pac_words);
+                    case 3: return launch_filter<15, 1, false>(ctx, S, F, C, 3, sink, n_sm, pac_words);
+                    case 4: return launch_filter<16, 1, false>(ctx, S, F, C, 4, sink, n_sm, pac_words);
+                    default: return launch_filter<17, 1, false>(ctx, S, F, C, 5, sink, n_sm, pac_words);
+                }
             }
-        }
-        CK((launch_vote<10, 2>(ctx, S, C, 0, sink, n_sm)));
-        CK((launch_vote<11, 1>(ctx, S, C, 1, sink, n_sm)));
-        CK((launch_vote<12, 1>(ctx, S, C, 2, sink, n_sm)));
-        CK((launch_vote<13, 1>(ctx, S, C, 3, sink, n_sm)));
-        CK((launch_vote<14, 1>(ctx, S, C, 4, sink, n_sm)));
-        {
-            if (ctx->d_arena.cap == 0) CK(ctx->d_arena.ensure((size_t)256 << 20));
-            GlobalTableArena A; A.words = ctx->d_arena.as<uint32_t>(); A.used = &dc->arena_used; A.cap = ctx->d_arena.cap / 4; A.overflow = &dc->arena_overflow;
-            k_vote_gmem<<<n_sm * 4, 128, 0, ctx->stream>>>(ctx->ix, S, C, 5, P.kmin, sink, A);
-            CK(cudaGetLastError());
-        }
-        stage_end(ctx, ST_VOTE, 0, 0, use_filter ? 12 : 6);
+            switch (k - GMX_N_CLASSES) {
+                case 0: return launch_vote<10, 2>(ctx, S, C, 0, sink, n_sm);
+                case 1: return launch_vote<11, 1>(ctx, S, C, 1, sink, n_sm);
+                case 2: return launch_vote<12, 1>(ctx, S, C, 2, sink, n_sm);
+                case 3: return launch_vote<13, 1>(ctx, S, C, 3, sink, n_sm);
+                case 4: return launch_vote<14, 1>(ctx, S, C, 4, sink, n_sm);
+                default: {
+                    if (ctx->d_arena.cap == 0) { cudaError_t e = ctx->d_arena.ensure((size_t)256 << 20); if (e != cudaSuccess) return e; }
+                    GlobalTableArena A; A.words = ctx->d_arena.as<uint32_t>(); A.used = &dc->arena_used; A.cap = ctx->d_arena.cap / 4; A.overflow = &dc->arena_overflow;
+                    k_vote_gmem<<<n_sm * 4, 128, 0, ctx->stream>>>(ctx->ix, S, C, 5, P.kmin, sink, A);
+                    return cudaGetLastError();
+                }
+            }
+        };
+        stage_begin(ctx, ST_VOTE);
+        uint32_t launched = 0;
+        int n_launch = 0;
+        for (int k = 0; k < 2 * GMX_N_CLASSES; ++k)
+            if ((ctx->class_hint >> k) & 1u) { CK(launch_class(k)); launched |= 1u << k; n_launch++; }
+        stage_end(ctx, ST_VOTE, 0, 0, n_launch);
         CK(cudaMemcpyAsync(&hc, dc, sizeof(hc), cudaMemcpyDeviceToHost, ctx->stream));
         { int r = finish_scan(ctx, slot ^ 1); if (r != GMX_OK) return r; }      // host work for the next chunk while the vote runs
         CK(cudaStreamSynchronize(ctx->stream));
         stage_collect(ctx);
+        // classes that hold tasks but were not launched (the filter kernels also hand tasks to the exact classes as they run)
+        for (int pass = 0; pass < 3; ++pass) {
+            uint32_t need = 0;
+            for (int c = 0; c < GMX_N_CLASSES; ++c) {
+                if (hc.c.fcls_count[c]) need |= 1u << c;
+                if (hc.c.cls_count[c]) need |= 1u << (GMX_N_CLASSES + c);
+            }
+            if (pass == 0) ctx->class_hint = need ? need : ctx->class_hint;
+            const uint32_t todo = need & ~launched;
+            if (!todo) break;
+            stage_begin(ctx, ST_VOTE);
+            n_launch = 0;
+            for (int k = 0; k < 2 * GMX_N_CLASSES; ++k)
+                if ((todo >> k) & 1u) { CK(launch_class(k)); launched |= 1u << k; n_launch++; }
+            stage_end(ctx, ST_VOTE, 0, 0, n_launch);
+            CK(cudaMemcpyAsync(&hc, dc, sizeof(hc), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            stage_collect(ctx);
+        }
         if (hc.c.arena_overflow) {
             if (attempt >= 4) { ctx->err = "global vote-table arena overflow"; return GMX_ERR_OVERFLOW; }
             size_t want = ctx->d_arena.cap * 4;
@@ -1394,6 +1427,7 @@ extern "C" int gmx_set_option(gmx_ctx *ctx, int option, int64_t value)
         case GMX_OPT_VOTE_SLOTS:
             if (value != 4 && value != 6) { ctx->err = "vote_slots must be 4 or 6"; return GMX_ERR_INVALID; }
             ctx->vote_slots = (int)value; return GMX_OK;
+        case GMX_OPT_VOTE_COMPACT: ctx->vote_compact = value != 0; return GMX_OK;
         case GMX_OPT_CIGAR_STRIDE:
             if (value < 16 || value > 2048 || (value & 15)) { ctx->err = "cigar_stride must be a multiple of 16 in 16..2048"; return GMX_ERR_INVALID; }
             ctx->cigar_stride = (int)value; ctx->mapped = false; ctx->scored = false; ctx->cs.valid = false; return GMX_OK;

@@ -448,37 +448,33 @@ __global__ void __launch_bounds__(WARPS * 32) k_vote_smem(DevIndex ix, SeedStore
 
 // returning OR on a 32-bit shared-window address
 __device__ __forceinline__ uint32_t gmx_atoms_or32(uint32_t a, uint32_t v) { uint32_t o; asm volatile("atom.shared.or.b32 %0, [%1], %2;" : "=r"(o) : "r"(a), "r"(v) : "memory"); return o; }
-// the same under a predicate (0 when the lane sits out): one predicated ATOMS instead of a branch around it -- the
-// compiler's own `if (p)` costs BSSY + BRA + BSYNC per atomic, a fifth of the per-hit instructions of the vote step
-__device__ __forceinline__ uint32_t gmx_atoms_or32_if(uint32_t a, uint32_t v, bool p)
-{
-    uint32_t o;
-    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %3, 0;\n\tmov.u32 %0, 0;\n\t@q atom.shared.or.b32 %0, [%1], %2;\n\t}"
-                 : "=r"(o) : "r"(a), "r"(v), "r"((uint32_t)p) : "memory");
-    return o;
-}
 
-struct FilterSmem {              // per-warp layout behind the filter bytes
+template <int SEEDS>
+struct FilterSmemT {             // per-warp layout behind the filter bytes; SEEDS = k-mers per task it holds (32 or 64)
     uint32_t queue[GMX_FQ_CAP];
-    unsigned long long codes[GMX_FILTER_MAX_SEEDS];
+    unsigned long long codes[SEEDS];
     unsigned long long outb[32];     // emitted keys, flushed to the candidate list 32 at a time
-    uint32_t rank[GMX_FILTER_MAX_SEEDS];
-    uint32_t cnt[GMX_FILTER_MAX_SEEDS];
-    uint16_t offs[GMX_FILTER_MAX_SEEDS];
+    uint32_t rank[SEEDS];
+    uint32_t cnt[SEEDS];
+    uint16_t offs[SEEDS];
 };
+typedef FilterSmemT<GMX_FILTER_MAX_SEEDS> FilterSmem;
 
 __host__ __device__ constexpr size_t gmx_filter_warp_bytes(int f_log2) { return ((size_t)1 << f_log2) + sizeof(FilterSmem); }
+// the compact variant: filter bytes need not be a power of two, at most 32 k-mers per task
+#define GMX_FILTER_COMPACT_BYTES 7552
+__host__ __device__ constexpr size_t gmx_filter_warp_bytes_compact() { return (size_t)GMX_FILTER_COMPACT_BYTES + sizeof(FilterSmemT<32>); }
 
 // exact vote mask of diagonal d > 0 over the k-mers of the walk (bit s <=> k-mer s hits d), from its window words.
 // Lane l holds k-mers l and l + 32 of the walk in registers: offset, code, and the last diagonal at which the
 // k-mer still fits the genome (seq_len - off - mer).
-template <bool SHORT_MER>
-__device__ __forceinline__ unsigned long long gmx_exact_mask(uint32_t w, uint32_t d, int ns, int mer, const uint32_t off[2],
-                                                             const unsigned long long code[2], const uint32_t limit[2], int lane)
+template <bool SHORT_MER, int H>
+__device__ __forceinline__ unsigned long long gmx_exact_mask(uint32_t w, uint32_t d, int ns, int mer, const uint32_t *off,
+                                                             const unsigned long long *code, const uint32_t *limit, int lane)
 {
     unsigned long long mask = 0;
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
+    for (int h = 0; h < H; ++h) {
         if (h == 1 && ns <= 32) break;
         const bool active = lane + 32 * h < ns;
         const uint32_t bit = 2u * ((d & 15u) + off[h]);
@@ -501,7 +497,8 @@ __device__ __forceinline__ unsigned long long gmx_exact_mask(uint32_t w, uint32_
 
 // round at which diagonal 0 reaches kmin votes, or -1.  Diagonal 0 collects every occurrence of k-mer s at a
 // position p <= off_s (the reference clamps sa - i at 0, inc/align_seq2_raw.cpp:270), several per k-mer.
-__device__ int gmx_round_diag0(const DevIndex &ix, int ns, int mer, int kmin, const FilterSmem *fs, int lane)
+template <class FS>
+__device__ int gmx_round_diag0(const DevIndex &ix, int ns, int mer, int kmin, const FS *fs, int lane)
 {
     uint32_t carry = 0;
     for (int g = 0; g < ns; g += 32) {
@@ -534,22 +531,28 @@ __device__ int gmx_round_diag0(const DevIndex &ix, int ns, int mer, int kmin, co
 // U: 32-hit slots per step.  A step handles the hits of ONE k-mer, so U is sized for the genome: a k-mer of a random
 // genome has seq_len / 4^mer hits on average (95 at 100 Mb, 149 at 156 Mb for mer 10); with too few slots most k-mers
 // need a second, mostly empty step.
-template <int F_LOG2, int WARPS, bool BITS, int U = GMX_VOTE_UNROLL>
-__global__ void __launch_bounds__(WARPS * 32, 1) k_vote_filter(DevIndex ix, uint32_t pac_words, SeedStore S, ClassLists F, ClassLists E,
+// COMPACT (BITS only): the occupancy variant for tasks of at most 32 k-mers -- a 7552-byte filter (the word index is a
+// multiply-high instead of a shift, so the size need not be a power of two), half the k-mer arrays in shared memory and
+// in registers, and a register budget for six CTAs of four warps per SM: 24 warps instead of 20.
+template <int F_LOG2, int WARPS, bool BITS, int U = GMX_VOTE_UNROLL, bool COMPACT = false>
+__global__ void __launch_bounds__(WARPS * 32, COMPACT ? 6 : 1) k_vote_filter(DevIndex ix, uint32_t pac_words, SeedStore S, ClassLists F, ClassLists E,
                                                             int cls, int kmin, int mer, CandSink sink)
 {
-    constexpr uint32_t FBYTES = 1u << F_LOG2;
+    constexpr uint32_t FBYTES = COMPACT ? (uint32_t)GMX_FILTER_COMPACT_BYTES : (1u << F_LOG2);
+    constexpr int SEEDS = COMPACT ? 32 : GMX_FILTER_MAX_SEEDS;
+    constexpr int H = SEEDS / 32;                                   // k-mers per lane
+    typedef FilterSmemT<SEEDS> FS;
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint8_t *filt = smem_raw + (size_t)warp * gmx_filter_warp_bytes(F_LOG2);
-    FilterSmem *fs = reinterpret_cast<FilterSmem *>(filt + FBYTES);
+    uint8_t *filt = smem_raw + (size_t)warp * (FBYTES + sizeof(FS));
+    FS *fs = reinterpret_cast<FS *>(filt + FBYTES);
     const uint32_t n_list = F.count[cls];
     const uint32_t *list = F.list + (int64_t)cls * F.n_tasks;
     const uint32_t lt = (1u << lane) - 1u;
     const int need = kmin - 1;                                       // votes a bucket must already hold
 
     // seeds of a task in registers: seed `lane` and seed `lane + 32`; fetched one task ahead
-    struct Meta { uint32_t task; int ns; uint32_t rank[2], cnt[2], off[2]; unsigned long long code[2]; };
+    struct Meta { uint32_t task; int ns; uint32_t rank[H], cnt[H], off[H]; unsigned long long code[H]; };
     // Work items are taken GRAB at a time (one same-address atomic per task would serialise 2 M returning atomics
     // per step), and nothing on the way to a task's k-mers waits for a load it has just issued: the cursor of the
     // next grab is requested one grab ahead, its task ids (lanes 0..GRAB-1) one task later, and a task's k-mers --
@@ -567,7 +570,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_vote_filter(DevIndex ix, uint
         m.task = task;
         m.ns = S.n_seeds[task];
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < H; ++h) {
             m.rank[h] = 0u; m.cnt[h] = 0u; m.off[h] = 0u; m.code[h] = 0ull;
             if (h == 1 && !two_halves) break;
             const int64_t at = min(S.at(task, lane + 32 * h), last_seed);
@@ -596,7 +599,6 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_vote_filter(DevIndex ix, uint
     bool n_ids_pending = true;
     uint32_t slot = 0;
     bool has_cur = g_base < n_list;
-    bool first_task = true;
     if (has_cur) fetch(__shfl_sync(0xffffffffu, g_ids, 0), cur);
     while (has_cur) {
         // step the cursor to the next work item and start loading its k-mers
@@ -608,12 +610,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_vote_filter(DevIndex ix, uint
 
         const uint32_t task = cur.task;
         const int ns = cur.ns;
-        bool unsupported = ns > GMX_FILTER_MAX_SEEDS;
+        bool unsupported = ns > SEEDS;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < H; ++h) {
             const int s = lane + 32 * h;
-            if (!(s < ns && s < GMX_FILTER_MAX_SEEDS)) { cur.rank[h] = 0u; cur.cnt[h] = 0u; cur.off[h] = 0u; cur.code[h] = 0ull; }
-            if (s < GMX_FILTER_MAX_SEEDS) { fs->rank[s] = cur.rank[h]; fs->cnt[s] = cur.cnt[h]; fs->offs[s] = (uint16_t)cur.off[h]; fs->codes[s] = cur.code[h]; }
+            if (!(s < ns && s < SEEDS)) { cur.rank[h] = 0u; cur.cnt[h] = 0u; cur.off[h] = 0u; cur.code[h] = 0ull; }
+            if (s < SEEDS) { fs->rank[s] = cur.rank[h]; fs->cnt[s] = cur.cnt[h]; fs->offs[s] = (uint16_t)cur.off[h]; fs->codes[s] = cur.code[h]; }
             if (s < ns && cur.off[h] + (uint32_t)mer > GMX_FILTER_MAX_SPAN) unsupported = true;
         }
         unsupported = __any_sync(0xffffffffu, unsupported);
@@ -622,15 +624,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_vote_filter(DevIndex ix, uint
             cur = nxt; has_cur = has_next;
             continue;
         }
-        // the suffix-array lines of a task are pulled into L2 one task ahead (below, once the next task's k-mers have
-        // arrived); only a warp's very first task asks for its own here
-        if (first_task) {
+        // pull every suffix-array line this task will read into L2 while the filter is being cleared (asking one task
+        // ahead instead measured 0.4 ms slower per step: the lines of two tasks per warp then compete for L2)
 #pragma unroll
-            for (int h = 0; h < 2; ++h)
-                for (uint32_t t = 0; t < cur.cnt[h]; t += 32u)
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(ix.sa_full + cur.rank[h] + t));
-            first_task = false;
-        }
+        for (int h = 0; h < H; ++h)
+            for (uint32_t t = 0; t < cur.cnt[h]; t += 32u)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(ix.sa_full + cur.rank[h] + t));
         uint4 *f4 = reinterpret_cast<uint4 *>(filt);
         for (uint32_t x = lane; x < FBYTES / 16; x += 32) f4[x] = make_uint4(0, 0, 0, 0);
         __syncwarp();
@@ -660,9 +659,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_vote_filter(DevIndex ix, uint
             }
 
             // pass 2: exact votes of each distinct diagonal from its genome window, four windows in flight
-            uint32_t limit[2];
+            uint32_t limit[H];
 #pragma unroll
-            for (int h = 0; h < 2; ++h) limit[h] = (uint32_t)ix.seq_len - cur.off[h] - (uint32_t)mer;
+            for (int h = 0; h < H; ++h) limit[h] = (uint32_t)ix.seq_len - cur.off[h] - (uint32_t)mer;
             const uint32_t *pac32 = reinterpret_cast<const uint32_t *>(ix.pac);
             for (uint32_t q0 = 0; q0 < n2; q0 += 4) {
                 uint32_t d[4], raw[4];
@@ -679,8 +678,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_vote_filter(DevIndex ix, uint
                     int round = -1;
                     if (d[i] != 0u) {
                         const uint32_t ww = __byte_perm(raw[i], 0, 0x0123);   // bases are packed most significant first
-                        const unsigned long long m = mer <= 16 ? gmx_exact_mask<true>(ww, d[i], ns, mer, cur.off, cur.code, limit, lane)
-                                                               : gmx_exact_mask<false>(ww, d[i], ns, mer, cur.off, cur.code, limit, lane);
+                        const unsigned long long m = mer <= 16 ? gmx_exact_mask<true, H>(ww, d[i], ns, mer, cur.off, cur.code, limit, lane)
+                                                               : gmx_exact_mask<false, H>(ww, d[i], ns, mer, cur.off, cur.code, limit, lane);
                         if (__popcll(m) >= kmin) {
                             const uint32_t lo = (uint32_t)m, hi = (uint32_t)(m >> 32);
                             const int pl = __popc(lo);
@@ -750,7 +749,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_vote_filter(DevIndex ix, uint
                     // positions are the low five bits of the diagonal itself (hits are unrelated genome positions)
                     // and of the high half of the product -- shifts by a register wrap, so neither needs a mask
                     const unsigned long long pr = (unsigned long long)diag[u] * 0x9E3779B1ull;
-                    const uint32_t idx = (uint32_t)pr >> (32 - (F_LOG2 - 2));
+                    const uint32_t idx = COMPACT ? __umulhi((uint32_t)pr, FBYTES / 4u) : (uint32_t)pr >> (32 - (F_LOG2 - 2));
                     asm("mad.lo.u32 %0, %1, 4, %2;" : "=r"(w[u]) : "r"(idx), "r"(fbase));
                     b[u] = (1u << (diag[u] & 31u)) | (1u << ((uint32_t)(pr >> 32) & 31u));
                 }
@@ -758,7 +757,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_vote_filter(DevIndex ix, uint
                 // were there already (measured on B200: 9.3 ms per step against 9.6 for load + reduction and 10.6 for
                 // load + plain store + re-read + repair; lanes without a hit must skip it, the unit's cost is per lane)
 #pragma unroll
-                for (int u = 0; u < U; ++u) o[u] = gmx_atoms_or32_if(w[u], b[u], valid[u]);
+                for (int u = 0; u < U; ++u) { o[u] = 0u; if (valid[u]) o[u] = gmx_atoms_or32(w[u], b[u]); }
 #pragma unroll
                 for (int u = 0; u < U; ++u) flag[u] = valid[u] && (o[u] & b[u]) == b[u];
             } else {
@@ -781,25 +780,19 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_vote_filter(DevIndex ix, uint
             bool any_flag = false;
 #pragma unroll
             for (int u = 0; u < U; ++u) any_flag |= flag[u];
-            // flagged hits are rare (about one lane in every other step): the lanes that hold some append theirs in turn
-            for (uint32_t fl = __ballot_sync(0xffffffffu, any_flag); fl; fl &= fl - 1u) {
-                const int src = __ffs(fl) - 1;
-                uint32_t mine = 0;
-                if (lane == src) {
+            // (appending the flagged hits lane by lane instead of slot by slot measured 0.5 ms slower per step)
+            if (__any_sync(0xffffffffu, any_flag)) {
 #pragma unroll
-                    for (int u = 0; u < U; ++u)
-                        if (flag[u]) { if (qn + mine < GMX_FQ_CAP) fs->queue[qn + mine] = diag[u]; mine++; }
+                for (int u = 0; u < U; ++u) {
+                    const uint32_t fm = __ballot_sync(0xffffffffu, flag[u]);
+                    if (flag[u]) {
+                        const uint32_t at = qn + (uint32_t)__popc(fm & lt);
+                        if (at < GMX_FQ_CAP) fs->queue[at] = diag[u];
+                    }
+                    qn += (uint32_t)__popc(fm);
                 }
-                qn += __shfl_sync(0xffffffffu, mine, src);
             }
             __syncwarp();
-            // one task ahead: the next task's k-mers have arrived by now -- ask L2 for its suffix-array lines
-            if (s_cur == 0 && t_cur == 0 && has_next) {
-#pragma unroll
-                for (int h = 0; h < 2; ++h)
-                    for (uint32_t t = 0; t < nxt.cnt[h]; t += 32u)
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(ix.sa_full + nxt.rank[h] + t));
-            }
             s_cur = s_n; t_cur = t_n;
         }
         if (s_cur >= ns && d0_hits) {                                  // diagonal 0 joins the last drain

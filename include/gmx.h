@@ -43,7 +43,8 @@ extern "C" {
 #define GMX_READ_UNMATCHED  1    /* no accepted hit                         top = 0               */
 #define GMX_READ_TOO_SHORT  2    /* length < mer            (READ_TOO_SHORT) top = -2             */
 #define GMX_READ_TOO_POOR   3    /* self score < cutoff     (READ_TOO_POOR)  top = -3             */
-#define GMX_READ_TOO_MANY   4    /* > max_matches or !unique (READ_TOO_MANY) top = 999999         */
+#define GMX_READ_TOO_MANY   4    /* > max_matches or !unique (READ_TOO_MANY) top = 999999; the reference's
+                                    "Sequences matched" line counts these (num_matched++, Driver.cpp:520,579)       */
 
 #define GMX_POS_STRAND 0         /* reference inc/const_include.h:190-191 */
 #define GMX_NEG_STRAND 1
@@ -360,6 +361,7 @@ int gmx_snp_call(const float counts[5], int genome_base, int snp_monoploid, floa
                                     which some alignment needs more text than the slot fails with GMX_ERR_OVERFLOW instead of
                                     returning a cut string */
 #define GMX_OPT_VOTE_SLOTS   6   /* tuning: 32-hit slots per step of the vote kernel, 4 or 6 (default: from seq_len / 4^mer)  */
+#define GMX_OPT_VOTE_COMPACT 7   /* tuning: 1 (default) = the 24-warps-per-SM variant of the vote kernel for tasks of <= 32 k-mers      */
 int gmx_set_option(gmx_ctx *ctx, int option, int64_t value);
 
 /* ---- instrumentation ---------------------------------------------------------------------- */

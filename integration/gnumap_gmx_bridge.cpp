@@ -203,6 +203,8 @@ void gmx_run_slice(GenomeBwt &gen, unsigned thread_id, unsigned read_begin, unsi
         gTopReadScore[k] = res[i].top_score;                                       // incl. READ_TOO_SHORT / _POOR / _MANY
         gReadDenominator[k] = res[i].denominator;
         n_nw += (unsigned)res[i].n_candidates;
+        // READ_TOO_MANY counts as matched in the reference's statistics (num_matched++, src/Driver.cpp:520,579) and prints nothing
+        if (res[i].status == GMX_READ_TOO_MANY) { good_seqs++; continue; }
         if (res[i].status != GMX_READ_MAPPED) { bad_seqs++; continue; }
         good_seqs++;
         if (!GMX_READ_PRINTS_SAM(res[i])) continue;                                // src/Driver.cpp:695: best group below top - SAME_DIFF
