@@ -132,7 +132,7 @@ struct gmx_ctx {
     bool use_filter = true;                    // GMX_OPT_VOTE_FILTER
     int filter_shift = 0;                      // GMX_OPT_FILTER_SHIFT
     int vote_slots = GMX_VOTE_UNROLL;          // GMX_OPT_VOTE_SLOTS: 32-hit slots per step of the vote kernel
-    int vote_compact = 1;                      // GMX_OPT_VOTE_COMPACT
+    int vote_compact = 2;                      // GMX_OPT_VOTE_COMPACT: 0 off, 1 two-bit variant, 2 three-bit variants (default)
     uint32_t class_hint = 0xfffu;              // vote classes (6 filter + 6 exact) that held tasks in the previous chunk
     int n_sm = 148;
     DevBuf d_ranges;                           // candidate range per read
@@ -808,11 +808,11 @@ static cudaError_t launch_vote(gmx_ctx *ctx, const SeedStore &S, const ClassList
     return cudaGetLastError();
 }
 
-template <int FL, int WARPS, bool BITS, int U = GMX_VOTE_UNROLL, bool COMPACT = false>
+template <int FL, int WARPS, bool BITS, int U = GMX_VOTE_UNROLL, int COMPACT = 0>
 static cudaError_t launch_filter(gmx_ctx *ctx, const SeedStore &S, const ClassLists &F, const ClassLists &E, int cls, const CandSink &sink, int n_sm,
                                  uint32_t pac_words)
 {
-    size_t smem = (size_t)WARPS * (COMPACT ? gmx_filter_warp_bytes_compact() : gmx_filter_warp_bytes(FL));
+    size_t smem = (size_t)WARPS * (COMPACT ? gmx_filter_warp_bytes_compact(COMPACT) : gmx_filter_warp_bytes(FL));
     cudaError_t e = cudaFuncSetAttribute(k_vote_filter<FL, WARPS, BITS, U, COMPACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 1;
@@ -917,9 +917,14 @@ static int phase_a(gmx_ctx *ctx, const gmx_reads *reads, int32_t lo, int32_t hi,
                         case 13:
                             // 32-hit slots per step for the expected hits of one k-mer (seq_len / 4^mer on a random genome:
                             // 95 at 100 Mb, 149 at 156 Mb for mer 10) plus head room
-                            if (ctx->vote_compact && S.max_seeds <= 32) {      // tasks of at most 32 k-mers: the 24-warp variant
-                                if (ctx->vote_slots >= 6) return launch_filter<13, 4, true, 6, true>(ctx, S, F, C, c, sink, n_sm, pac_words);
-                                return launch_filter<13, 4, true, 4, true>(ctx, S, F, C, c, sink, n_sm, pac_words);
+                            if (ctx->vote_compact && S.max_seeds <= 32) {
+                                // tasks of at most 32 k-mers: the occupancy variants.  Up to 2 k hits per task (class 2) a 5 KB
+                                // filter with three bits per diagonal (32 warps / SM); above, 7.4 KB (24 warps / SM)
+                                const int variant = ctx->vote_compact >= 2 ? (c <= 2 ? 2 : 3) : 1;
+                                const bool six = ctx->vote_slots >= 6;
+                                if (variant == 2) return six ? launch_filter<13, 4, true, 6, 2>(ctx, S, F, C, c, sink, n_sm, pac_words) : launch_filter<13, 4, true, 4, 2>(ctx, S, F, C, c, sink, n_sm, pac_words);
+                                if (variant == 3) return six ? launch_filter<13, 4, true, 6, 3>(ctx, S, F, C, c, sink, n_sm, pac_words) : launch_filter<13, 4, true, 4, 3>(ctx, S, F, C, c, sink, n_sm, pac_words);
+                                return six ? launch_filter<13, 4, true, 6, 1>(ctx, S, F, C, c, sink, n_sm, pac_words) : launch_filter<13, 4, true, 4, 1>(ctx, S, F, C, c, sink, n_sm, pac_words);
                             }
                             if (ctx->vote_slots >= 6) return launch_filter<13, 4, true, 6>(ctx, S, F, C, c, sink, n_sm, pac_words);
                             return launch_filter<13, 4, true>(ctx, S, F, C, c, sink, n_sm, pac_words);
@@ -1427,7 +1432,7 @@ extern "C" int gmx_set_option(gmx_ctx *ctx, int option, int64_t value)
         case GMX_OPT_VOTE_SLOTS:
             if (value != 4 && value != 6) { ctx->err = "vote_slots must be 4 or 6"; return GMX_ERR_INVALID; }
             ctx->vote_slots = (int)value; return GMX_OK;
-        case GMX_OPT_VOTE_COMPACT: ctx->vote_compact = value != 0; return GMX_OK;
+        case GMX_OPT_VOTE_COMPACT: ctx->vote_compact = value < 0 ? 0 : (value > 2 ? 2 : (int)value); return GMX_OK;
         case GMX_OPT_CIGAR_STRIDE:
             if (value < 16 || value > 2048 || (value & 15)) { ctx->err = "cigar_stride must be a multiple of 16 in 16..2048"; return GMX_ERR_INVALID; }
             ctx->cigar_stride = (int)value; ctx->mapped = false; ctx->scored = false; ctx->cs.valid = false; return GMX_OK;

@@ -462,8 +462,12 @@ typedef FilterSmemT<GMX_FILTER_MAX_SEEDS> FilterSmem;
 
 __host__ __device__ constexpr size_t gmx_filter_warp_bytes(int f_log2) { return ((size_t)1 << f_log2) + sizeof(FilterSmem); }
 // the compact variant: filter bytes need not be a power of two, at most 32 k-mers per task
-#define GMX_FILTER_COMPACT_BYTES 7552
-__host__ __device__ constexpr size_t gmx_filter_warp_bytes_compact() { return (size_t)GMX_FILTER_COMPACT_BYTES + sizeof(FilterSmemT<32>); }
+// COMPACT 1: 7552 bytes, two bits per diagonal, six CTAs per SM; COMPACT 2: 5120 bytes, three bits, eight CTAs per SM
+// (tasks of up to ~2 k hits: 0.8 false positives per task); COMPACT 3: 7552 bytes, three bits, six CTAs per SM (tasks of
+// up to ~8 k hits: 150-bp reads on a 156 Mb genome have 4.2 k, which leaves 9 false positives per task where two bits
+// in 8 KB leave 22 -- every one of them costs an exact verification against the genome)
+__host__ __device__ constexpr uint32_t gmx_filter_compact_bytes(int compact) { return compact == 2 ? 5120u : 7552u; }
+__host__ __device__ constexpr size_t gmx_filter_warp_bytes_compact(int compact) { return (size_t)gmx_filter_compact_bytes(compact) + sizeof(FilterSmemT<32>); }
 
 // exact vote mask of diagonal d > 0 over the k-mers of the walk (bit s <=> k-mer s hits d), from its window words.
 // Lane l holds k-mers l and l + 32 of the walk in registers: offset, code, and the last diagonal at which the
@@ -534,11 +538,11 @@ __device__ int gmx_round_diag0(const DevIndex &ix, int ns, int mer, int kmin, co
 // COMPACT (BITS only): the occupancy variant for tasks of at most 32 k-mers -- a 7552-byte filter (the word index is a
 // multiply-high instead of a shift, so the size need not be a power of two), half the k-mer arrays in shared memory and
 // in registers, and a register budget for six CTAs of four warps per SM: 24 warps instead of 20.
-template <int F_LOG2, int WARPS, bool BITS, int U = GMX_VOTE_UNROLL, bool COMPACT = false>
-__global__ void __launch_bounds__(WARPS * 32, COMPACT ? 6 : 1) k_vote_filter(DevIndex ix, uint32_t pac_words, SeedStore S, ClassLists F, ClassLists E,
+template <int F_LOG2, int WARPS, bool BITS, int U = GMX_VOTE_UNROLL, int COMPACT = 0>
+__global__ void __launch_bounds__(WARPS * 32, COMPACT == 2 ? 8 : (COMPACT ? 6 : 1)) k_vote_filter(DevIndex ix, uint32_t pac_words, SeedStore S, ClassLists F, ClassLists E,
                                                             int cls, int kmin, int mer, CandSink sink)
 {
-    constexpr uint32_t FBYTES = COMPACT ? (uint32_t)GMX_FILTER_COMPACT_BYTES : (1u << F_LOG2);
+    constexpr uint32_t FBYTES = COMPACT ? gmx_filter_compact_bytes(COMPACT) : (1u << F_LOG2);
     constexpr int SEEDS = COMPACT ? 32 : GMX_FILTER_MAX_SEEDS;
     constexpr int H = SEEDS / 32;                                   // k-mers per lane
     typedef FilterSmemT<SEEDS> FS;
@@ -752,6 +756,7 @@ __global__ void __launch_bounds__(WARPS * 32, COMPACT ? 6 : 1) k_vote_filter(Dev
                     const uint32_t idx = COMPACT ? __umulhi((uint32_t)pr, FBYTES / 4u) : (uint32_t)pr >> (32 - (F_LOG2 - 2));
                     asm("mad.lo.u32 %0, %1, 4, %2;" : "=r"(w[u]) : "r"(idx), "r"(fbase));
                     b[u] = (1u << (diag[u] & 31u)) | (1u << ((uint32_t)(pr >> 32) & 31u));
+                    if (COMPACT >= 2) b[u] |= 1u << ((uint32_t)(pr >> 37) & 31u);       // third bit: fewer false positives per filter byte
                 }
                 // one returning shared-memory atomic per hit: it sets the diagonal's two bits and tells whether both
                 // were there already (measured on B200: 9.3 ms per step against 9.6 for load + reduction and 10.6 for

@@ -361,7 +361,8 @@ int gmx_snp_call(const float counts[5], int genome_base, int snp_monoploid, floa
                                     which some alignment needs more text than the slot fails with GMX_ERR_OVERFLOW instead of
                                     returning a cut string */
 #define GMX_OPT_VOTE_SLOTS   6   /* tuning: 32-hit slots per step of the vote kernel, 4 or 6 (default: from seq_len / 4^mer)  */
-#define GMX_OPT_VOTE_COMPACT 7   /* tuning: 1 (default) = the 24-warps-per-SM variant of the vote kernel for tasks of <= 32 k-mers      */
+#define GMX_OPT_VOTE_COMPACT 7   /* tuning: occupancy variants of the vote kernel for tasks of <= 32 k-mers: 0 off, 1 two bits per
+                                    diagonal (24 warps / SM), 2 (default) three bits (32 or 24 warps / SM by hits per task)         */
 int gmx_set_option(gmx_ctx *ctx, int option, int64_t value);
 
 /* ---- instrumentation ---------------------------------------------------------------------- */
