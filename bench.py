@@ -655,12 +655,15 @@ def own_arm(a):
         assert n_out.value == n and int((res_np["status"] == 0).sum()) == mapped
         # SAM row: native formatting of the batch just scored
         sam_cap = n * (2 * L + 96)
-        sam_buf = np.empty(sam_cap, dtype=np.uint8)
+        sam_buf = torch.empty(sam_cap, dtype=torch.uint8).pin_memory()
         names_c = (C.c_char_p * len(ix.names))(*[nm.encode() for nm in ix.names])
         sam_len = C.c_int64(0)
-        t0 = time.time()
-        rc = m.L.gmx_format_sam(m._ctx, text_h.data_ptr(), recs_h.data_ptr(), res_h.data_ptr(), n, names_c, sam_buf.ctypes.data, sam_cap, C.byref(sam_len))
-        sam_s = time.time() - t0
+        sam_s = None
+        for _ in range(3):                      # first call allocates the formatter's device buffers
+            t0 = time.time()
+            rc = m.L.gmx_format_sam(m._ctx, text_h.data_ptr(), recs_h.data_ptr(), res_h.data_ptr(), n, names_c, sam_buf.data_ptr(), sam_cap, C.byref(sam_len))
+            dt = time.time() - t0
+            sam_s = dt if sam_s is None else min(sam_s, dt)
         if rc != 0:
             raise RuntimeError(f"gmx_format_sam: {rc} {m.L.gmx_last_error(m._ctx).decode()}")
         # accumulator output row: .sgr text of the accumulators as they stand (device row selection + host text)
@@ -682,8 +685,9 @@ def own_arm(a):
         fastq = {"value": n * world * a.steps / (fq_ms * 1e-3), "unit": "reads/s", "h2d_bytes_per_step": int(text_h.numel()),
                  "d2h_bytes_per_step": int(n * (_abi.READ_RESULT_DTYPE.itemsize + 64 + _abi.FASTQ_REC_DTYPE.itemsize)),
                  "what": "gmx_process_fastq: FASTQ text in pinned host memory -> device record indexer -> reads used in place -> results (wall clock)",
-                 "sam": {"value": n / sam_s, "unit": "reads/s", "bytes": int(sam_len.value), "host_threads": min(os.cpu_count() or 1, 32),
-                         "what": "gmx_format_sam: SAM body of the batch (ScoredSeq::get_SAM + writer)"},
+                 "sam": {"value": n / sam_s, "unit": "reads/s", "bytes": int(sam_len.value),
+                         "what": "gmx_format_sam: SAM body of the batch (ScoredSeq::get_SAM + writer) formatted on the GPU from the resident text / results / CIGARs, "
+                                 "finished text copied to pinned host memory (wall clock, best of 3)"},
                  "sgr": {"seconds": sgr_s, "rows": sgr_rows, "bytes": int(sgr_len.value), "bins_scanned": int(job.acc[0].numel()),
                          "what": "gmx_format_sgr: GenomeBwt::PrintFinalSGR of the accumulators (device scan + select, host text)"}}
 

@@ -17,6 +17,7 @@
 #include "pair_hmm.cuh"
 #include "fastq.cuh"
 #include "gmp_out.cuh"
+#include "sam_out.cuh"
 
 struct gmx_comm;
 
@@ -141,7 +142,13 @@ struct gmx_ctx {
     uint32_t multi_cap = 0; bool multi_overflow = false;
     std::vector<MultiPos> h_multi;
     std::vector<int64_t> h_seq_offset;         // host copy of the sequence offsets (+ l_pac) for pos -> chromosome
-    DevBuf d_best_cigar[2], d_out_results[2];  // staging of the fast download path, double-buffered
+    DevBuf d_batch_cigar, d_batch_results;     // fast download path: per-read records + best CIGARs of the WHOLE batch (they also
+                                               // feed the device SAM formatter)
+    bool batch_dev_valid = false;              // ... hold the batch last scored
+    bool fq_batch = false;                     // the batch last scored came from gmx_process_fastq: text + record index are resident
+    const char *fq_d_text = nullptr; int64_t fq_len = 0;
+    bool sam_on_device = true;                 // GMX_OPT_SAM_DEVICE
+    DevBuf d_sam_pieces, d_sam_cigar, d_sam_lens, d_sam_offs, d_sam_extra, d_sam_out, d_sam_names, d_sam_tmp;
     cudaStream_t d2h_stream = nullptr;
     cudaEvent_t gather_ev[2] = {nullptr, nullptr}, dl_ev[2] = {nullptr, nullptr};
     int dl_slot = 0;
@@ -433,7 +440,7 @@ extern "C" void gmx_destroy(gmx_ctx *ctx)
                       &ctx->d_seed_off, &ctx->d_seed_n, &ctx->d_seed_hits, &ctx->d_cls_list, &ctx->d_cls_meta,
                       &ctx->d_keys, &ctx->d_keys_alt, &ctx->d_sort_tmp, &ctx->d_score, &ctx->d_leader, &ctx->d_slot, &ctx->d_lead_cand,
                       &ctx->d_hashes, &ctx->d_expv, &ctx->d_counters, &ctx->d_results, &ctx->d_alen, &ctx->d_aligned, &ctx->d_cigar,
-                      &ctx->d_hmm, &ctx->d_moves, &ctx->d_arena, &ctx->d_phmm_scratch, &ctx->d_best_cigar[0], &ctx->d_best_cigar[1], &ctx->d_out_results[0], &ctx->d_out_results[1], &ctx->d_kmer_tab, &ctx->d_multi, &ctx->d_multi_count, &ctx->d_ranges, &ctx->d_groups, &ctx->d_read_base, &ctx->d_fq_text, &ctx->d_fq_nl, &ctx->d_fq_tmp, &ctx->d_fq_seq_off, &ctx->d_fq_qual_off, &ctx->d_fq_len, &ctx->d_fq_recs, &ctx->d_fq_flags, &ctx->d_fq_count};
+                      &ctx->d_hmm, &ctx->d_moves, &ctx->d_arena, &ctx->d_phmm_scratch, &ctx->d_batch_cigar, &ctx->d_batch_results, &ctx->d_sam_pieces, &ctx->d_sam_cigar, &ctx->d_sam_lens, &ctx->d_sam_offs, &ctx->d_sam_extra, &ctx->d_sam_out, &ctx->d_sam_names, &ctx->d_sam_tmp, &ctx->d_kmer_tab, &ctx->d_multi, &ctx->d_multi_count, &ctx->d_ranges, &ctx->d_groups, &ctx->d_read_base, &ctx->d_fq_text, &ctx->d_fq_nl, &ctx->d_fq_tmp, &ctx->d_fq_seq_off, &ctx->d_fq_qual_off, &ctx->d_fq_len, &ctx->d_fq_recs, &ctx->d_fq_flags, &ctx->d_fq_count};
     for (DevBuf *b : bufs) b->release();
     ctx->h_best_cigar.release();
     ctx->h_counters.release();
@@ -1154,27 +1161,26 @@ static int download_chunk(gmx_ctx *ctx, bool scored, gmx_read_result *results_ou
     }
     stage_begin(ctx, ST_DOWNLOAD);
     if (!ctx->collect_hits) {
-        // fast path: fixed-size records only, staged and copied out on a second stream while the next chunk computes
-        const int sl = ctx->dl_slot; ctx->dl_slot ^= 1;
-        CK(ctx->d_best_cigar[sl].ensure((size_t)std::max(n, 1) * GMX_CIGAR_STRIDE));
-        CK(ctx->d_out_results[sl].ensure((size_t)std::max(n, 1) * sizeof(gmx_read_result)));
-        CK(cudaStreamWaitEvent(ctx->stream, ctx->dl_ev[sl], 0));            // the staging slot's previous copy has left
+        // fast path: fixed-size records only, gathered into the batch's device arrays and copied out on a second stream
+        // while the next chunk computes
+        gmx_read_result *d_res = ctx->d_batch_results.as<gmx_read_result>() + lo;
+        char *d_cig = ctx->d_batch_cigar.as<char>() + (size_t)lo * GMX_CIGAR_STRIDE;
         if (scored && n_cand && ctx->multi_cap) {                           // positions of multi-position best groups (SAM row)
             k_gather_multi<<<nblk(n_cand, 256), 256, 0, ctx->stream>>>(cs.keys, ctx->d_leader.as<int32_t>(), n_cand, ctx->d_results.as<gmx_read_result>(),
                                                                       lo, ctx->d_multi.as<MultiPos>(), ctx->d_multi_count.as<uint32_t>(), ctx->multi_cap);
             CK(cudaGetLastError());
         }
-        k_gather_best<<<nblk(n, 128), 128, 0, ctx->stream>>>(ctx->d_results.as<gmx_read_result>(), ctx->d_out_results[sl].as<gmx_read_result>(), n,
-                                                           ctx->d_slot.as<int32_t>(), L, ctx->d_best_cigar[sl].as<char>(), GMX_CIGAR_STRIDE,
+        k_gather_best<<<nblk(n, 128), 128, 0, ctx->stream>>>(ctx->d_results.as<gmx_read_result>(), d_res, n,
+                                                           ctx->d_slot.as<int32_t>(), L, d_cig, GMX_CIGAR_STRIDE,
                                                            scored && n_leaders ? 1 : 0);
         CK(cudaGetLastError());
+        const int sl = ctx->dl_slot; ctx->dl_slot ^= 1;
         CK(cudaEventRecord(ctx->gather_ev[sl], ctx->stream));
         CK(cudaStreamWaitEvent(ctx->d2h_stream, ctx->gather_ev[sl], 0));
         gmx_read_result *dst = results_out ? results_out + lo : ctx->h_results.data() + lo;
-        CK(cudaMemcpyAsync(dst, ctx->d_out_results[sl].p, (size_t)n * sizeof(gmx_read_result), cudaMemcpyDeviceToHost, ctx->d2h_stream));
-        CK(cudaMemcpyAsync(ctx->h_best_cigar.as<char>() + (size_t)lo * GMX_CIGAR_STRIDE, ctx->d_best_cigar[sl].p, (size_t)n * GMX_CIGAR_STRIDE,
+        CK(cudaMemcpyAsync(dst, d_res, (size_t)n * sizeof(gmx_read_result), cudaMemcpyDeviceToHost, ctx->d2h_stream));
+        CK(cudaMemcpyAsync(ctx->h_best_cigar.as<char>() + (size_t)lo * GMX_CIGAR_STRIDE, d_cig, (size_t)n * GMX_CIGAR_STRIDE,
                            cudaMemcpyDeviceToHost, ctx->d2h_stream));
-        CK(cudaEventRecord(ctx->dl_ev[sl], ctx->d2h_stream));
         stage_end(ctx, ST_DOWNLOAD, (uint64_t)n, (uint64_t)n * (sizeof(gmx_read_result) + GMX_CIGAR_STRIDE), 1);
         return GMX_OK;                                                      // run_batch / gmx_score_batch drain d2h_stream
     }
@@ -1304,6 +1310,11 @@ static int run_batch_impl(gmx_ctx *ctx, const gmx_reads *reads, gmx_read_result 
         CK(ctx->d_multi.ensure((size_t)ctx->multi_cap * sizeof(MultiPos)));
     }
     ctx->h_a_stride = max_len + 2 * ctx->params.max_gap + 8;
+    ctx->batch_dev_valid = false; ctx->fq_batch = false;
+    if (!ctx->collect_hits) {
+        CK(ctx->d_batch_results.ensure((size_t)std::max(n, 1) * sizeof(gmx_read_result)));
+        CK(ctx->d_batch_cigar.ensure((size_t)std::max(n, 1) * GMX_CIGAR_STRIDE));
+    }
     CK(ctx->h_best_cigar.ensure((size_t)std::max(n, 1) * GMX_CIGAR_STRIDE));
     if (ctx->collect_hits) {
         memset(ctx->h_best_cigar.p, 0, (size_t)std::max(n, 1) * GMX_CIGAR_STRIDE);
@@ -1358,6 +1369,7 @@ static int run_batch_impl(gmx_ctx *ctx, const gmx_reads *reads, gmx_read_result 
     int r = collect_batch_counters(ctx);
     if (r != GMX_OK) return r;
     ctx->mapped = true; ctx->scored = do_score;
+    ctx->batch_dev_valid = do_score && !ctx->collect_hits;
     return GMX_OK;
 }
 
@@ -1398,9 +1410,12 @@ extern "C" int gmx_score_batch(gmx_ctx *ctx, gmx_read_result *results)
         ctx->h_multi.clear(); ctx->multi_overflow = false; ctx->multi_cap = 0;
         CK(ctx->d_multi_count.ensure(16));
         CK(cudaMemsetAsync(ctx->d_multi_count.p, 0, 16, ctx->stream));
+        ctx->batch_dev_valid = false; ctx->fq_batch = false;
         if (!ctx->collect_hits) {
             ctx->multi_cap = (uint32_t)std::min<int64_t>(4ll * ctx->last_n_reads + 65536, 0x7fffffffll);
             CK(ctx->d_multi.ensure((size_t)ctx->multi_cap * sizeof(MultiPos)));
+            CK(ctx->d_batch_results.ensure((size_t)std::max(ctx->last_n_reads, 1) * sizeof(gmx_read_result)));
+            CK(ctx->d_batch_cigar.ensure((size_t)std::max(ctx->last_n_reads, 1) * GMX_CIGAR_STRIDE));
         }
         int r = phase_b(ctx);
         if (r != GMX_OK) return r;
@@ -1412,6 +1427,7 @@ extern "C" int gmx_score_batch(gmx_ctx *ctx, gmx_read_result *results)
         r = collect_batch_counters(ctx);
         if (r != GMX_OK) return r;
         ctx->cs.valid = false; ctx->scored = true;
+        ctx->batch_dev_valid = !ctx->collect_hits;
         return GMX_OK;
     }
     if (!ctx->keep_valid) { ctx->err = "the mapped batch is no longer available"; return GMX_ERR_STATE; }
@@ -1432,6 +1448,7 @@ extern "C" int gmx_set_option(gmx_ctx *ctx, int option, int64_t value)
         case GMX_OPT_VOTE_SLOTS:
             if (value != 4 && value != 6) { ctx->err = "vote_slots must be 4 or 6"; return GMX_ERR_INVALID; }
             ctx->vote_slots = (int)value; return GMX_OK;
+        case GMX_OPT_SAM_DEVICE: ctx->sam_on_device = value != 0; return GMX_OK;
         case GMX_OPT_VOTE_COMPACT: ctx->vote_compact = value < 0 ? 0 : (value > 2 ? 2 : (int)value); return GMX_OK;
         case GMX_OPT_CIGAR_STRIDE:
             if (value < 16 || value > 2048 || (value & 15)) { ctx->err = "cigar_stride must be a multiple of 16 in 16..2048"; return GMX_ERR_INVALID; }
@@ -1643,7 +1660,9 @@ extern "C" int gmx_process_fastq(gmx_ctx *ctx, const char *text, int64_t len, in
     in.seq = reinterpret_cast<const uint8_t *>(d_text); in.qual = reinterpret_cast<const uint8_t *>(d_text);
     in.qual_offsets = ctx->d_fq_qual_off.as<int64_t>(); in.lens = ctx->d_fq_len.as<int32_t>();
     in.on_device = 1; in.max_len = std::max(max_len, 1);
-    return run_batch(ctx, &in, results, true);
+    r = run_batch(ctx, &in, results, true);
+    if (r == GMX_OK && ctx->batch_dev_valid) { ctx->fq_batch = true; ctx->fq_d_text = d_text; ctx->fq_len = len; }
+    return r;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1745,12 +1764,114 @@ void sam_format_range(const gmx_ctx *ctx, const char *text, const gmx_fastq_rec 
 }
 }  // namespace
 
+// The batch last run by gmx_process_fastq, formatted where its text, record index, results and CIGARs already are
+// (sam_out.cuh); reads whose best group holds several positions are written by the host formatter into the place the
+// device reserved for them.
+static int format_sam_device(gmx_ctx *ctx, const char *text, const gmx_fastq_rec *recs, const gmx_read_result *results, int64_t n_reads,
+                             const char *const *chrom_names, char *out, int64_t cap, int64_t *len)
+{
+    CK(cudaSetDevice(ctx->device));
+    const int n = (int)n_reads;
+    *len = 0;
+    if (n == 0) return GMX_OK;
+    const int n_seqs = ctx->ix.n_seqs;
+    // chromosome names: chars | offsets | lengths
+    std::vector<int32_t> noff((size_t)n_seqs), nlen((size_t)n_seqs);
+    std::string chars;
+    for (int i = 0; i < n_seqs; ++i) { noff[i] = (int32_t)chars.size(); nlen[i] = (int32_t)strlen(chrom_names[i]); chars += chrom_names[i]; }
+    const size_t chars_pad = (chars.size() + 15) & ~(size_t)15;
+    CK(ctx->d_sam_names.ensure(chars_pad + (size_t)n_seqs * 8 + 16));
+    CK(cudaMemcpyAsync(ctx->d_sam_names.p, chars.data(), chars.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_sam_names.as<char>() + chars_pad, noff.data(), (size_t)n_seqs * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_sam_names.as<char>() + chars_pad + (size_t)n_seqs * 4, nlen.data(), (size_t)n_seqs * 4, cudaMemcpyHostToDevice, ctx->stream));
+    SamNames names;
+    names.chars = ctx->d_sam_names.as<char>(); names.off = reinterpret_cast<const int32_t *>(ctx->d_sam_names.as<char>() + chars_pad);
+    names.len = names.off + n_seqs; names.n = n_seqs;
+
+    CK(ctx->d_sam_pieces.ensure((size_t)n * sizeof(SamPiece)));
+    CK(ctx->d_sam_cigar.ensure((size_t)n * GMX_CIGAR_STRIDE));
+    CK(ctx->d_sam_lens.ensure(((size_t)n + 1) * 8)); CK(ctx->d_sam_offs.ensure(((size_t)n + 1) * 8));
+    CK(ctx->d_sam_extra.ensure((size_t)n * 8 + 16));
+    uint32_t *d_unc = reinterpret_cast<uint32_t *>(ctx->d_sam_extra.as<char>() + (size_t)n * 8);
+    CK(cudaMemsetAsync(ctx->d_sam_extra.p, 0, (size_t)n * 8 + 16, ctx->stream));
+    long long *d_lens = ctx->d_sam_lens.as<long long>(), *d_offs = ctx->d_sam_offs.as<long long>();
+    const gmx_fastq_rec *d_recs = ctx->d_fq_recs.as<gmx_fastq_rec>();
+    k_sam_measure<<<nblk(n, 128), 128, 0, ctx->stream>>>(ctx->d_batch_results.as<gmx_read_result>(), d_recs, ctx->d_batch_cigar.as<char>(), GMX_CIGAR_STRIDE, n,
+                                                        ctx->ix, names, 1.0 / (double)ctx->params.adjust, ctx->d_sam_pieces.as<SamPiece>(),
+                                                        ctx->d_sam_cigar.as<char>(), d_lens, d_unc);
+    CK(cudaGetLastError());
+    const uint32_t n_multi = (uint32_t)ctx->h_multi.size();
+    if (n_multi) {
+        k_sam_multi_len<<<nblk(n_multi, 256), 256, 0, ctx->stream>>>(ctx->d_multi.as<MultiPos>(), n_multi, ctx->ix, names, d_lens,
+                                                                    ctx->d_sam_extra.as<unsigned long long>());
+        CK(cudaGetLastError());
+    }
+    k_sam_fix_lens<<<nblk(n, 256), 256, 0, ctx->stream>>>(d_lens, ctx->d_sam_extra.as<unsigned long long>(), n);
+    CK(cudaGetLastError());
+    CK(cudaMemsetAsync(d_lens + n, 0, 8, ctx->stream));
+    size_t tmp_bytes = 0;
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_lens, d_offs, n + 1, ctx->stream));
+    CK(ctx->d_sam_tmp.ensure(tmp_bytes));
+    CK(cub::DeviceScan::ExclusiveSum(ctx->d_sam_tmp.p, tmp_bytes, d_lens, d_offs, n + 1, ctx->stream));
+    long long total = 0; uint32_t unc = 0;
+    CK(cudaMemcpyAsync(&total, d_offs + n, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(&unc, d_unc, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (unc) return GMX_ERR_STATE;
+    *len = total;
+    if (total > cap) return GMX_ERR_OVERFLOW;
+    CK(ctx->d_sam_out.ensure((size_t)total + 16));
+    k_sam_write<<<nblk((int64_t)n * 32, 256), 256, 0, ctx->stream>>>(ctx->fq_d_text, d_recs, ctx->d_sam_pieces.as<SamPiece>(), ctx->d_sam_cigar.as<char>(),
+                                                                    GMX_CIGAR_STRIDE, d_offs, n, names, ctx->d_sam_out.as<char>());
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, ctx->d_sam_out.p, (size_t)total, cudaMemcpyDeviceToHost, ctx->stream));
+    // the reads with several positions: their records from the host formatter, into the reserved places
+    std::vector<int64_t> multi_index((size_t)n_reads, -1);
+    std::vector<std::vector<SamPos>> multi_of;
+    for (const MultiPos &m : ctx->h_multi)
+        if (m.read >= 0 && m.read < n_reads) {
+            if (multi_index[m.read] < 0) { multi_index[m.read] = (int64_t)multi_of.size(); multi_of.emplace_back(); }
+            multi_of[multi_index[m.read]].push_back(SamPos{m.pos, m.strand});
+        }
+    for (auto &v : multi_of) std::sort(v.begin(), v.end(), [](const SamPos &a, const SamPos &b) { return a.pos != b.pos ? a.pos < b.pos : a.strand < b.strand; });
+    std::vector<long long> offs;
+    if (!multi_of.empty()) {
+        offs.resize((size_t)n + 1);
+        CK(cudaMemcpyAsync(offs.data(), d_offs, ((size_t)n + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    std::string one;
+    for (int64_t r = 0; r < n_reads; ++r) {
+        if (multi_index[r] < 0 || !GMX_READ_PRINTS_SAM(results[r])) continue;
+        one.clear();
+        sam_format_range(ctx, text, recs, results, r, r + 1, chrom_names, &multi_of, multi_index, one);
+        if ((long long)one.size() != offs[r + 1] - offs[r]) { ctx->err = "device SAM formatter: a multi-position read's size differs from the host's"; return GMX_ERR_CUDA; }
+        memcpy(out + offs[r], one.data(), one.size());
+    }
+    return GMX_OK;
+}
+
+// "%g" as the device SAM formatter writes it (sam_out.cuh), callable on the host
+extern "C" int gmx_format_g(double v, char *out, int cap)
+{
+    char b[40];
+    const int n = gmx_fmt_g6(v, b);
+    if (n < 0) return GMX_ERR_UNSUPPORTED;
+    if (!out || n + 1 > cap) return GMX_ERR_OVERFLOW;
+    memcpy(out, b, (size_t)n); out[n] = 0;
+    return n;
+}
+
 extern "C" int gmx_format_sam(gmx_ctx *ctx, const char *text, const gmx_fastq_rec *recs, const gmx_read_result *results, int64_t n_reads,
                               const char *const *chrom_names, char *out, int64_t cap, int64_t *len)
 {
     if (!ctx || !text || !recs || !results || !chrom_names || !len || n_reads < 0 || (cap > 0 && !out)) return GMX_ERR_INVALID;
     if (!ctx->scored || n_reads != ctx->last_n_reads) { ctx->err = "gmx_format_sam formats the batch last scored"; return GMX_ERR_STATE; }
     if (!ctx->collect_hits && ctx->multi_overflow) { ctx->err = "more multi-position hits than the fast path keeps (4 per read): set GMX_OPT_COLLECT_HITS"; return GMX_ERR_OVERFLOW; }
+    if (ctx->sam_on_device && ctx->fq_batch && ctx->batch_dev_valid && !ctx->collect_hits) {
+        int r = format_sam_device(ctx, text, recs, results, n_reads, chrom_names, out, cap, len);
+        if (r != GMX_ERR_STATE) return r;                  // GMX_ERR_STATE: a number the device formatter does not cover -- host path
+    }
     // positions of the multi-position best groups: from the hit list (collect mode) or from the device list (fast path)
     std::vector<int64_t> multi_index((size_t)n_reads, -1);
     std::vector<std::vector<SamPos>> multi_of;

@@ -310,11 +310,18 @@ int gmx_process_fastq(gmx_ctx *ctx, const char *text, int64_t len, int text_on_d
 /* ---- next row: SAM emission ------------------------------------------------------
  * ScoredSeq::get_SAM (reference inc/ScoredSeq.h:293-404) + the SAM writer (src/Driver.cpp:2146-2217): the body
  * lines of the last scored batch, in read order, one per (position, strand) of each read's best group, byte for
- * byte as the reference prints them.  Works with GMX_OPT_COLLECT_HITS 0 or 1.  names / seq / qual come from
+ * byte as the reference prints them.  Works with GMX_OPT_COLLECT_HITS 0 or 1.  After gmx_process_fastq with
+ * GMX_OPT_COLLECT_HITS = 0 the records are formatted on the GPU (text, record index, results and CIGARs are resident
+ * there) and only the finished text crosses to `out`; any other batch is formatted by host threads.  names / seq / qual come from
  * `recs` into `text` (gmx_fastq_rec: name_off/len, seq_off/len, qual_off/qual_len); chrom_names[i] is the name of
  * sequence i of the index.  Returns GMX_ERR_OVERFLOW with *len = bytes needed when `cap` is short. */
 int gmx_format_sam(gmx_ctx *ctx, const char *text, const gmx_fastq_rec *recs, const gmx_read_result *results, int64_t n_reads,
                    const char *const *chrom_names, char *out, int64_t cap, int64_t *len);
+
+/* "%g" of a double exactly as printf prints it -- the writer the device SAM formatter uses for XA:f / XP:f (the reference
+ * streams floats with the default ostream format), exported so that it can be checked on the host.  Returns the length,
+ * GMX_ERR_UNSUPPORTED for values outside ~1e-17 .. 1e21 (not finite included), GMX_ERR_OVERFLOW when cap is short. */
+int gmx_format_g(double v, char *out, int cap);
 
 /* ---- next row: .sgr output (Normal-mode part) ----------------------------------
  * GenomeBwt::PrintFinalSGR (reference src/GenomeBwt.cpp:1212-1273): one line "chrom\tpos\t%.5f" per accumulator bin
@@ -361,6 +368,8 @@ int gmx_snp_call(const float counts[5], int genome_base, int snp_monoploid, floa
                                     which some alignment needs more text than the slot fails with GMX_ERR_OVERFLOW instead of
                                     returning a cut string */
 #define GMX_OPT_VOTE_SLOTS   6   /* tuning: 32-hit slots per step of the vote kernel, 4 or 6 (default: from seq_len / 4^mer)  */
+#define GMX_OPT_SAM_DEVICE   8   /* 1 (default): gmx_format_sam formats the batch of the last gmx_process_fastq on the GPU (the text, the
+                                    record index, the results and the CIGARs are resident there); 0: always the host formatter     */
 #define GMX_OPT_VOTE_COMPACT 7   /* tuning: occupancy variants of the vote kernel for tasks of <= 32 k-mers: 0 off, 1 two bits per
                                     diagonal (24 warps / SM), 2 (default) three bits (32 or 24 warps / SM by hits per task)         */
 int gmx_set_option(gmx_ctx *ctx, int option, int64_t value);

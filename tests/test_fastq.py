@@ -243,3 +243,56 @@ def test_native_gmp_rows_and_calls(mode):
     with pytest.raises(api.GmxError):
         m0.format_gmp()                      # Normal mode has no .gmp
     m0.close()
+
+
+@pytest.mark.gpu
+def test_device_sam_formatter_equals_host_formatter():
+    """gmx_format_sam after gmx_process_fastq formats on the GPU (csrc/sam_out.cuh): the bytes, in read order, must be the
+    host formatter's -- both strands, indels, three contigs, multi-position best groups (written by the host into the
+    places the device reserved), reads that print nothing."""
+    from gnumap_b200 import synth
+    contigs = synth.make_genome(300_000, 61, n_contigs=3)
+    codes = np.concatenate([c for _, c in contigs])
+    codes[200_000:200_600] = codes[50_000:50_600]
+    codes[260_000:260_400] = 3 - codes[90_000:90_400][::-1]
+    b = np.cumsum([0] + [len(c) for _, c in contigs])
+    contigs = [(n, codes[b[i]:b[i + 1]]) for i, (n, _) in enumerate(contigs)]
+    n_reads, L = 20000, 100
+    reads = synth.simulate_reads(codes, n_reads, L, 62, indel_rate=0.2, n_rate=0.002, qlo=5)
+    k = n_reads // 10
+    reads["pos"][:k] = np.random.default_rng(61).integers(50_000, 50_600 - L, size=k)
+    fwd = codes[reads["pos"][:k, None] + np.arange(L)[None, :]]
+    reads["bases"][:k] = np.where((reads["strand"][:k] == 1)[:, None], 3 - fwd[:, ::-1], fwd)
+    reads["bases"][k:k + 50] = 4                                             # all-N reads: unmapped
+    lut = np.frombuffer(b"ACGTN", dtype=np.uint8)
+    text = b"".join(b"@read_%d/%d\n" % (i, i % 7) + lut[reads["bases"][i]].tobytes() + b"\n+\n" + (reads["quals"][i] + 33).astype(np.uint8).tobytes() + b"\n"
+                    for i in range(n_reads))
+    ix = index.build_index(contigs)
+    m = api.Mapper(ix)
+    m.set_option(api.OPT_COLLECT_HITS, 0)
+    m.set_option(api.OPT_CHUNK_READS, 6000)
+    _, got = m.process_fastq(text, fetch=False)
+    recs = api.fastq_scan_host(text)
+    dev = m.format_sam(text, recs, got["results"])
+    m.set_option(api.OPT_SAM_DEVICE, 0)
+    host = m.format_sam(text, recs, got["results"])
+    assert dev == host
+    lines = host.decode().split("\n")[:-1]
+    assert len(lines) > 0.9 * n_reads and any(ln.split("\t")[1] == "16" for ln in lines)
+    assert max(int(ln.split("X0:i:")[1]) for ln in lines) > 1 and any("I" in ln.split("\t")[5] or "D" in ln.split("\t")[5] for ln in lines)
+    m.close()
+
+
+def test_g_format_of_the_device_sam_writer_is_printf_g():
+    """The "%g" writer the device SAM formatter uses (exact 128-bit decimal conversion) against printf, through the
+    host-callable copy exported for this test."""
+    import ctypes as C
+    L = api.load_library()
+    L.gmx_format_g.argtypes = [C.c_double, C.c_char_p, C.c_int]
+    rng = np.random.default_rng(5)
+    vals = np.concatenate([rng.random(20000).astype(np.float32).astype(np.float64), (rng.random(20000) * 300).astype(np.float32).astype(np.float64) * 4,
+                           10.0 ** (-rng.random(5000) * 15), np.array([0.0, 1.0, 0.5, 999999.5, 999999.49, 1e6, 1e-5, 9.9999995e-5, 123456.5, 1234565.0, 131.322, -2.5])])
+    buf = C.create_string_buffer(64)
+    for v in vals:
+        n = L.gmx_format_g(float(v), buf, 64)
+        assert n > 0 and buf.raw[:n].decode() == "%g" % v, (v, buf.raw[:n])
