@@ -17,7 +17,7 @@ from gnumap_b200._abi import GmxIndex, GmxParams, GmxReads, HIT_DTYPE, READ_RESU
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "liboracle.so")
-REF_DIR = os.path.join(HERE, "_ref")
+REF_DIR = os.environ.get("GMX_REF_DIR") or os.path.join(HERE, "_ref")     # GMX_REF_DIR: another build of the reference (e.g. against real GSL)
 REF_BIN = os.path.join(REF_DIR, "gnumap")
 REF_PROBE = os.path.join(REF_DIR, "libref_probe.so")
 

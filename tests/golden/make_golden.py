@@ -229,9 +229,16 @@ def make_program_snpdepth(tmp):
 
 def make_snp_calls(tmp):
     """Call columns of GenomeBwt::PrintSNPCall (reference src/GenomeBwt.cpp:1011-1092 over is_snp / LRT / dipLRT
-    :739-898) for random read-count vectors, through the unmodified reference objects.  gsl_cdf_chisq_P comes from
-    oracle/gsl_stub (the reference build's GSL differs from it only in the last digits of 1 - P)."""
+    :739-898) for random read-count vectors, through the unmodified reference objects LINKED WITH THE REFERENCE'S OWN
+    GSL 1.9 (built once from /root/reference/lib/gsl-1.9.tar.gz; `make -C oracle ref OUT=<dir> GSL=<prefix>` and
+    GMX_REF_DIR=<dir> for this script).  Count vectors for which GSL's error handler fires -- the unmodified program
+    aborts there, e.g. gsl_cdf_chisq_P(inf, 1) after a likelihood ratio underflowed -- are left out."""
+    import ctypes as C
     R = O.RefProbe()
+    gsl_errors = C.CDLL(O.REF_PROBE).refp_gsl_errors
+    real_gsl = gsl_errors() >= 0
+    if not real_gsl:
+        raise SystemExit("ref_snp_calls.json.gz is generated against the real GSL: build it and set GMX_REF_DIR (see the docstring)")
     R.set_mode(2)
     contigs = synth.make_genome(2000, 5, n_contigs=1)
     fa = os.path.join(tmp, "lrt.fa")
@@ -252,8 +259,10 @@ def make_snp_calls(tmp):
         pos = int(rng.integers(0, 2000))
         monop = bool(t % 3 == 0)
         pval = float(rng.choice([0.001, 0.05]))
-        cases.append({"counts": [float(x) for x in c], "base": int(codes[pos]), "monop": monop, "pval": pval,
-                      "call": R.snp_call(pos, c, monop, pval).decode()})
+        call = R.snp_call(pos, c, monop, pval).decode()
+        if gsl_errors() > 0:
+            continue                                   # the reference aborts on this input
+        cases.append({"counts": [float(x) for x in c], "base": int(codes[pos]), "monop": monop, "pval": pval, "call": call})
     R.set_mode(0)
     with gzip.GzipFile(os.path.join(HERE, "ref_snp_calls.json.gz"), "wb", mtime=0) as f:
         f.write(json.dumps(cases).encode())
