@@ -314,6 +314,8 @@ class Job:
             m.set_option(api.OPT_CHUNK_READS, int(os.environ["GMX_CHUNK_READS"]))
         if os.environ.get("GMX_FILTER_SHIFT"):
             m.set_option(api.OPT_FILTER_SHIFT, int(os.environ["GMX_FILTER_SHIFT"]))
+        if os.environ.get("GMX_FASTQ_PIECE"):
+            m.set_option(api.OPT_FASTQ_PIECE, int(os.environ["GMX_FASTQ_PIECE"]))
         if os.environ.get("GMX_VOTE_COMPACT"):
             m.set_option(api.OPT_VOTE_COMPACT, int(os.environ["GMX_VOTE_COMPACT"]))
         if os.environ.get("GMX_VOTE_SLOTS"):

@@ -36,7 +36,7 @@ EXPORTS = [
     "gmx_comm_create", "gmx_comm_reduce", "gmx_comm_stats", "gmx_comm_destroy", "gmx_measure_alu_peak", "gmx_format_g",
 ]
 
-OPT_COLLECT_HITS, OPT_CHUNK_READS, OPT_VOTE_FILTER, OPT_FILTER_SHIFT, OPT_CIGAR_STRIDE, OPT_VOTE_SLOTS, OPT_VOTE_COMPACT, OPT_SAM_DEVICE = 1, 2, 3, 4, 5, 6, 7, 8
+OPT_COLLECT_HITS, OPT_CHUNK_READS, OPT_VOTE_FILTER, OPT_FILTER_SHIFT, OPT_CIGAR_STRIDE, OPT_VOTE_SLOTS, OPT_VOTE_COMPACT, OPT_SAM_DEVICE, OPT_FASTQ_PIECE = 1, 2, 3, 4, 5, 6, 7, 8, 9
 COMM_AUTO, COMM_PEER, COMM_NCCL = 0, 1, 2
 
 
@@ -291,6 +291,17 @@ class Mapper:
         results = np.zeros(cap, dtype=READ_RESULT_DTYPE); recs = np.zeros(cap, dtype=_abi.FASTQ_REC_DTYPE)
         n = C.c_int64(0)
         rc = self.L.gmx_process_fastq(self._ctx, buf.ctypes.data if len(buf) else recs.ctypes.data, len(buf), 0, results.ctypes.data, cap, C.byref(n), recs.ctypes.data)
+        if rc == _abi.GMX_ERR_FORMAT and n.value > 0:
+            # a pipelined text whose later part needs the reference's recovery path: the first n reads are done (mapped and
+            # scored); the rest goes through the host scan
+            done = n.value
+            cut = int(recs[done - 1]["qual_off"]) + int(recs[done - 1]["qual_len"]) + 1
+            rest = text[cut:]
+            recs2 = fastq_scan_host(rest, self.params.illumina)
+            names2, batch2 = batch_from_fastq(rest, recs2)
+            out2 = self.process_batch(batch2, fetch=False)
+            names1, _ = batch_from_fastq(text, recs[:done])
+            return names1 + names2, dict(results=np.concatenate([results[:done], out2["results"]]))
         if rc == _abi.GMX_ERR_FORMAT:
             recs = fastq_scan_host(text, self.params.illumina)
             names, batch = batch_from_fastq(text, recs)

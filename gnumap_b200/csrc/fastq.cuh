@@ -65,7 +65,8 @@ __device__ __forceinline__ void gmx_fastq_line(const uint32_t *nl, uint32_t n_nl
     e = l < n_nl ? (int64_t)nl[l] : len;
 }
 
-__global__ void k_fastq_records(const char *text, int64_t len, const uint32_t *nl, uint32_t n_nl, uint32_t n_recs, int qmin, FastqDev out)
+// `base`: offset of `text` inside the whole text when a piece of it is indexed (all stored offsets are global)
+__global__ void k_fastq_records(const char *text, int64_t len, const uint32_t *nl, uint32_t n_nl, uint32_t n_recs, int qmin, FastqDev out, int64_t base)
 {
     uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_recs) return;
@@ -79,9 +80,9 @@ __global__ void k_fastq_records(const char *text, int64_t len, const uint32_t *n
     if (ok) for (int i = 0; i < n; ++i) if ((int)(unsigned char)text[b3 + i] < qmin) { ok = false; break; }   // Q < 0: the reference throws
     if (!ok) { atomicAdd(&out.flags[0], 1u); atomicMin(&out.flags[2], r); }
     atomicMax(&out.flags[1], (uint32_t)n);
-    out.seq_off[r] = b1; out.qual_off[r] = b3; out.seq_len[r] = n;
+    out.seq_off[r] = base + b1; out.qual_off[r] = base + b3; out.seq_len[r] = n;
     gmx_fastq_rec rec;
-    rec.name_off = b0 + 1; rec.seq_off = b1; rec.qual_off = b3;
+    rec.name_off = base + b0 + 1; rec.seq_off = base + b1; rec.qual_off = base + b3;
     rec.name_len = (int32_t)(e0 - b0 - 1); rec.seq_len = n; rec.qual_len = (int32_t)(e3 - b3); rec.pad = 0;
     out.recs[r] = rec;
 }

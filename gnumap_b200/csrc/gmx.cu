@@ -148,6 +148,7 @@ struct gmx_ctx {
     bool fq_batch = false;                     // the batch last scored came from gmx_process_fastq: text + record index are resident
     const char *fq_d_text = nullptr; int64_t fq_len = 0;
     bool sam_on_device = true;                 // GMX_OPT_SAM_DEVICE
+    int64_t fq_piece_bytes = 96ll << 20;       // GMX_OPT_FASTQ_PIECE: bytes per piece of a pipelined host FASTQ text (0 = whole text)
     DevBuf d_sam_pieces, d_sam_cigar, d_sam_lens, d_sam_offs, d_sam_extra, d_sam_out, d_sam_names, d_sam_tmp;
     cudaStream_t d2h_stream = nullptr;
     cudaEvent_t gather_ev[2] = {nullptr, nullptr}, dl_ev[2] = {nullptr, nullptr};
@@ -1293,12 +1294,10 @@ static int run_batch(gmx_ctx *ctx, const gmx_reads *reads, gmx_read_result *resu
     return r;
 }
 
-static int run_batch_impl(gmx_ctx *ctx, const gmx_reads *reads, gmx_read_result *results, bool do_score)
+// per-batch state before the first chunk runs: `n` = reads of the batch (an upper bound for a FASTQ text that is indexed
+// piece by piece), `max_len` = longest read where it is known up front
+static int batch_begin(gmx_ctx *ctx, int32_t n, int32_t max_len, gmx_read_result *results, bool do_score)
 {
-    CK(cudaSetDevice(ctx->device));
-    const int32_t n = reads->n_reads;
-    int32_t max_len = 0;       // of the whole batch: only the hit-collecting download needs it before the first chunk runs
-    if (n > 0 && (ctx->collect_hits || reads->on_device)) { int r = batch_max_len(ctx, reads, &max_len); if (r != GMX_OK) return r; }
     ctx->h_results.assign(ctx->collect_hits || !results ? (size_t)n : 0, gmx_read_result());
     ctx->h_hits.clear();
     ctx->h_multi.clear();
@@ -1323,6 +1322,29 @@ static int run_batch_impl(gmx_ctx *ctx, const gmx_reads *reads, gmx_read_result 
     ctx->last_n_reads = n; ctx->last_max_len = 0;
     ctx->mapped = false; ctx->scored = false; ctx->cs.valid = false;
     stage_reset(ctx);
+    return GMX_OK;
+}
+
+// after the last chunk has been issued: drain, fold the counters, mark the batch
+static int batch_end(gmx_ctx *ctx, bool do_score)
+{
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaStreamSynchronize(ctx->d2h_stream));
+    stage_collect(ctx);
+    int r = collect_batch_counters(ctx);
+    if (r != GMX_OK) return r;
+    ctx->mapped = true; ctx->scored = do_score;
+    ctx->batch_dev_valid = do_score && !ctx->collect_hits;
+    return GMX_OK;
+}
+
+static int run_batch_impl(gmx_ctx *ctx, const gmx_reads *reads, gmx_read_result *results, bool do_score)
+{
+    CK(cudaSetDevice(ctx->device));
+    const int32_t n = reads->n_reads;
+    int32_t max_len = 0;       // of the whole batch: only the hit-collecting download needs it before the first chunk runs
+    if (n > 0 && (ctx->collect_hits || reads->on_device)) { int r = batch_max_len(ctx, reads, &max_len); if (r != GMX_OK) return r; }
+    { int r = batch_begin(ctx, n, max_len, results, do_score); if (r != GMX_OK) return r; }
     // Chunk schedule.  A chunk's upload rides under its predecessor's kernels and its download under its successor's,
     // so what a batch exposes is the first upload and the last download.  When PHASE A and B run together, a host
     // batch therefore starts and every batch ends with a short chunk of 1/8 of the regular size (measured at 1 M reads:
@@ -1363,14 +1385,7 @@ static int run_batch_impl(gmx_ctx *ctx, const gmx_reads *reads, gmx_read_result 
         if (!last_and_split && !do_score) ctx->cs.valid = false;
     }
     if (do_score) ctx->cs.valid = false;
-    CK(cudaStreamSynchronize(ctx->stream));
-    CK(cudaStreamSynchronize(ctx->d2h_stream));
-    stage_collect(ctx);
-    int r = collect_batch_counters(ctx);
-    if (r != GMX_OK) return r;
-    ctx->mapped = true; ctx->scored = do_score;
-    ctx->batch_dev_valid = do_score && !ctx->collect_hits;
-    return GMX_OK;
+    return batch_end(ctx, do_score);
 }
 
 extern "C" int gmx_process_batch(gmx_ctx *ctx, const gmx_reads *reads, gmx_read_result *results) { return run_batch(ctx, reads, results, true); }
@@ -1449,6 +1464,9 @@ extern "C" int gmx_set_option(gmx_ctx *ctx, int option, int64_t value)
             if (value != 4 && value != 6) { ctx->err = "vote_slots must be 4 or 6"; return GMX_ERR_INVALID; }
             ctx->vote_slots = (int)value; return GMX_OK;
         case GMX_OPT_SAM_DEVICE: ctx->sam_on_device = value != 0; return GMX_OK;
+        case GMX_OPT_FASTQ_PIECE:
+            if (value < 0) { ctx->err = "fastq piece bytes must be >= 0"; return GMX_ERR_INVALID; }
+            ctx->fq_piece_bytes = value; return GMX_OK;
         case GMX_OPT_VOTE_COMPACT: ctx->vote_compact = value < 0 ? 0 : (value > 2 ? 2 : (int)value); return GMX_OK;
         case GMX_OPT_CIGAR_STRIDE:
             if (value < 16 || value > 2048 || (value & 15)) { ctx->err = "cigar_stride must be a multiple of 16 in 16..2048"; return GMX_ERR_INVALID; }
@@ -1612,7 +1630,7 @@ static int fastq_scan_device(gmx_ctx *ctx, const char *text, int64_t len, int te
     FastqDev out;
     out.seq_off = ctx->d_fq_seq_off.as<int64_t>(); out.qual_off = ctx->d_fq_qual_off.as<int64_t>(); out.seq_len = ctx->d_fq_len.as<int32_t>();
     out.recs = ctx->d_fq_recs.as<gmx_fastq_rec>(); out.flags = ctx->d_fq_flags.as<uint32_t>();
-    k_fastq_records<<<nblk(n, 256), 256, 0, ctx->stream>>>(d_text, len, ctx->d_fq_nl.as<uint32_t>(), n_nl, n, ctx->params.illumina ? 64 : 33, out);
+    k_fastq_records<<<nblk(n, 256), 256, 0, ctx->stream>>>(d_text, len, ctx->d_fq_nl.as<uint32_t>(), n_nl, n, ctx->params.illumina ? 64 : 33, out, 0);
     CK(cudaGetLastError());
     uint32_t flags[4];
     CK(cudaMemcpyAsync(flags, ctx->d_fq_flags.p, 16, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1642,11 +1660,185 @@ extern "C" int gmx_fastq_scan(gmx_ctx *ctx, const char *text, int64_t len, int t
     return GMX_OK;
 }
 
+// ---- FASTQ text from the host, pipelined ---------------------------------------------------------------
+// The text is cut at record boundaries into pieces; piece p + 1 crosses PCIe and is indexed while piece p is mapped, so
+// that only the first piece's upload + index stay exposed (the whole-text path below exposes all of it: 3.9 ms of PCIe
+// + the indexer per 1 M x 100 bp reads, a quarter of the path's own time).
+
+// First record start at or after `from`: a line that starts with '@' whose next-but-one line starts with '+'.  A quality
+// line may start with '@' too, but the line two below a quality line is a sequence line, which never starts with '+'.
+static int64_t fastq_record_cut(const char *text, int64_t len, int64_t from)
+{
+    if (from <= 0) return 0;
+    const char *q = (const char *)memchr(text + from - 1, '\n', (size_t)(len - (from - 1)));
+    for (int tries = 0; tries < 16 && q; ++tries) {
+        const int64_t l0 = (q - text) + 1;
+        if (l0 >= len) return len;
+        const char *q1 = (const char *)memchr(text + l0, '\n', (size_t)(len - l0));
+        if (!q1) return -1;
+        const char *q2 = (const char *)memchr(q1 + 1, '\n', (size_t)(len - (q1 + 1 - text)));
+        if (!q2) return -1;
+        const int64_t l2 = (q2 - text) + 1;
+        if (text[l0] == '@' && l2 < len && text[l2] == '+') return l0;
+        q = q1;
+    }
+    return -1;
+}
+
+// index one piece [at, at + plen) of the device text on `st`; appends its reads at `first`.  Host-synchronous on `st`.
+static int fastq_index_piece(gmx_ctx *ctx, const char *d_text, int64_t at, int64_t plen, int64_t first, int64_t n_cap, cudaStream_t st,
+                             int64_t *n_out, int32_t *max_len_out)
+{
+    *n_out = 0; *max_len_out = 0;
+    if (plen <= 0) return GMX_OK;
+    if (plen >= 0x7fffffffll) { ctx->err = "FASTQ piece of 2 GiB or more"; return GMX_ERR_UNSUPPORTED; }
+    const char *pt = d_text + at;
+    CK(ctx->d_fq_count.ensure(16));
+    CK(cudaMemsetAsync(ctx->d_fq_count.p, 0, 16, st));
+    k_count_newlines<<<ctx->n_sm * 8, 256, 0, st>>>(pt, plen, ctx->d_fq_count.as<unsigned long long>() + 1);
+    CK(cudaGetLastError());
+    unsigned long long h = 0;
+    CK(cudaMemcpyAsync(&h, ctx->d_fq_count.as<unsigned long long>() + 1, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const uint32_t n_expect = (uint32_t)h;
+    CK(ctx->d_fq_nl.ensure(((size_t)n_expect + 16) * 4));
+    thrust::counting_iterator<uint32_t> idx(0);
+    IsNewline pred{pt};
+    size_t tmp_bytes = 0;
+    CK(cub::DeviceSelect::If(nullptr, tmp_bytes, idx, ctx->d_fq_nl.as<uint32_t>(), ctx->d_fq_count.as<uint32_t>(), (int)plen, pred, st));
+    CK(ctx->d_fq_tmp.ensure(tmp_bytes));
+    CK(cub::DeviceSelect::If(ctx->d_fq_tmp.p, tmp_bytes, idx, ctx->d_fq_nl.as<uint32_t>(), ctx->d_fq_count.as<uint32_t>(), (int)plen, pred, st));
+    char last = 0;
+    CK(cudaMemcpyAsync(&last, pt + plen - 1, 1, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const uint32_t n_nl = n_expect;
+    const uint64_t n_lines = (uint64_t)n_nl + (last != '\n' ? 1 : 0);
+    if (n_lines % 4 != 0) { ctx->err = "FASTQ text is not a whole number of 4-line records (blank or missing lines): use gmx_fastq_scan_host"; return GMX_ERR_FORMAT; }
+    const uint32_t n = (uint32_t)(n_lines / 4);
+    if (n == 0) return GMX_OK;
+    if (first + (int64_t)n > n_cap) { *n_out = n; return GMX_ERR_OVERFLOW; }
+    CK(ctx->d_fq_flags.ensure(16));
+    const uint32_t init[4] = {0u, 0u, 0xffffffffu, 0u};
+    CK(cudaMemcpyAsync(ctx->d_fq_flags.p, init, 16, cudaMemcpyHostToDevice, st));
+    FastqDev out;
+    out.seq_off = ctx->d_fq_seq_off.as<int64_t>() + first; out.qual_off = ctx->d_fq_qual_off.as<int64_t>() + first; out.seq_len = ctx->d_fq_len.as<int32_t>() + first;
+    out.recs = ctx->d_fq_recs.as<gmx_fastq_rec>() + first; out.flags = ctx->d_fq_flags.as<uint32_t>();
+    k_fastq_records<<<nblk(n, 256), 256, 0, st>>>(pt, plen, ctx->d_fq_nl.as<uint32_t>(), n_nl, n, ctx->params.illumina ? 64 : 33, out, at);
+    CK(cudaGetLastError());
+    uint32_t flags[4];
+    CK(cudaMemcpyAsync(flags, ctx->d_fq_flags.p, 16, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (flags[0]) {
+        char b[200];
+        snprintf(b, sizeof(b), "%u malformed FASTQ record(s), first at record %lld: use gmx_fastq_scan_host", flags[0], (long long)first + flags[2]);
+        ctx->err = b;
+        return GMX_ERR_FORMAT;
+    }
+    *n_out = n; *max_len_out = (int32_t)flags[1];
+    return GMX_OK;
+}
+
+// GMX_ERR_STATE: the text cannot be cut (caller takes the whole-text path)
+static int process_fastq_pipelined(gmx_ctx *ctx, const char *text, int64_t len, gmx_read_result *results, int64_t capacity, int64_t *n_reads, gmx_fastq_rec *recs)
+{
+    const int64_t piece = ctx->fq_piece_bytes;
+    std::vector<int64_t> cuts(1, 0);
+    while (true) {                                         // a short first piece: its upload and index are the exposed ones
+        const int64_t want = cuts.back() + (cuts.size() == 1 ? std::max<int64_t>(piece / 4, 1) : piece);
+        if (want >= len - piece / 8) break;
+        const int64_t c = fastq_record_cut(text, len, want);
+        if (c < 0) return GMX_ERR_STATE;
+        if (c >= len || c <= cuts.back()) break;
+        cuts.push_back(c);
+    }
+    cuts.push_back(len);
+    const size_t P = cuts.size() - 1;
+    if (P < 2) return GMX_ERR_STATE;
+    const int64_t n_cap = std::min<int64_t>((results || recs) ? capacity : len / 6 + 1, 0x7ffffff0ll);
+    if (n_cap <= 0) return GMX_ERR_STATE;
+    CK(ctx->d_fq_text.ensure((size_t)len + 16));
+    CK(ctx->d_fq_seq_off.ensure((size_t)n_cap * 8)); CK(ctx->d_fq_qual_off.ensure((size_t)n_cap * 8)); CK(ctx->d_fq_len.ensure((size_t)n_cap * 4));
+    CK(ctx->d_fq_recs.ensure((size_t)n_cap * sizeof(gmx_fastq_rec)));
+    char *d_text = ctx->d_fq_text.as<char>();
+    { int r = batch_begin(ctx, (int32_t)n_cap, 0, results, true); if (r != GMX_OK) return r; }
+    CK(cudaStreamSynchronize(ctx->stream));               // batch_begin's resets precede everything issued on the copy stream
+    auto upload = [&](size_t p) -> int {
+        CK(cudaMemcpyAsync(d_text + cuts[p], text + cuts[p], (size_t)(cuts[p + 1] - cuts[p]), cudaMemcpyHostToDevice, ctx->copy_stream));
+        return GMX_OK;
+    };
+    int64_t first = 0, n_p = 0;
+    int32_t max_p = 0;
+    int rc = upload(0);
+    if (rc == GMX_OK) rc = fastq_index_piece(ctx, d_text, cuts[0], cuts[1] - cuts[0], 0, n_cap, ctx->copy_stream, &n_p, &max_p);
+    if (rc != GMX_OK) { *n_reads = rc == GMX_ERR_OVERFLOW ? n_p : 0; return rc; }
+    // the record index of a piece leaves for the host as soon as the piece is indexed (the host has waited for its kernels)
+    auto send_recs = [&](int64_t at, int64_t cnt) -> int {
+        if (recs && cnt) CK(cudaMemcpyAsync(recs + at, ctx->d_fq_recs.as<gmx_fastq_rec>() + at, (size_t)cnt * sizeof(gmx_fastq_rec), cudaMemcpyDeviceToHost, ctx->d2h_stream));
+        return GMX_OK;
+    };
+    rc = send_recs(0, n_p);
+    if (rc != GMX_OK) return rc;
+    gmx_reads in;
+    memset(&in, 0, sizeof(in));
+    in.offsets = ctx->d_fq_seq_off.as<int64_t>(); in.qual_offsets = ctx->d_fq_qual_off.as<int64_t>(); in.lens = ctx->d_fq_len.as<int32_t>();
+    in.seq = reinterpret_cast<const uint8_t *>(d_text); in.qual = reinterpret_cast<const uint8_t *>(d_text);
+    in.on_device = 1;
+    int slot = 0;
+    for (size_t p = 0; p < P; ++p) {
+        if (p + 1 < P) { rc = upload(p + 1); if (rc != GMX_OK) return rc; }       // crosses PCIe while piece p is mapped
+        in.n_reads = (int32_t)(first + n_p); in.max_len = std::max(max_p, 1);
+        const int64_t step = (int64_t)ctx->chunk_reads;
+        for (int64_t lo = first; lo < first + n_p; lo += step, slot ^= 1) {
+            const int64_t hi = std::min(first + n_p, lo + step);
+            rc = issue_upload(ctx, &in, (int32_t)lo, (int32_t)hi, slot, ctx->stream);      // device-resident: a view, no copy
+            if (rc == GMX_OK) rc = phase_a(ctx, &in, (int32_t)lo, (int32_t)hi, slot);
+            if (rc == GMX_OK) rc = phase_b(ctx);
+            if (rc == GMX_OK) rc = download_chunk(ctx, true, results);
+            if (rc != GMX_OK) return rc;
+        }
+        first += n_p;
+        if (p + 1 < P) {                                   // its kernels and host waits run beside piece p's PHASE B and download
+            rc = fastq_index_piece(ctx, d_text, cuts[p + 1], cuts[p + 2] - cuts[p + 1], first, n_cap, ctx->copy_stream, &n_p, &max_p);
+            if (rc != GMX_OK) {
+                // the reads before this piece have been mapped AND scored: the caller continues from there
+                ctx->cs.valid = false;
+                const std::string why = ctx->err;
+                ctx->last_n_reads = (int32_t)first;
+                int r2 = batch_end(ctx, true);
+                *n_reads = first;
+                ctx->err = why + " (the reads before it have been mapped and scored)";
+                if (r2 == GMX_OK) { ctx->fq_batch = ctx->batch_dev_valid; ctx->fq_d_text = d_text; ctx->fq_len = len; }
+                return rc;
+            }
+            rc = send_recs(first, n_p);
+            if (rc != GMX_OK) return rc;
+        }
+    }
+    ctx->cs.valid = false;
+    ctx->last_n_reads = (int32_t)first;
+    rc = batch_end(ctx, true);
+    if (rc != GMX_OK) return rc;
+    *n_reads = first;
+    if (ctx->batch_dev_valid) { ctx->fq_batch = true; ctx->fq_d_text = d_text; ctx->fq_len = len; }
+    return GMX_OK;
+}
+
 extern "C" int gmx_process_fastq(gmx_ctx *ctx, const char *text, int64_t len, int text_on_device, gmx_read_result *results, int64_t capacity,
                                  int64_t *n_reads, gmx_fastq_rec *recs)
 {
     if (!ctx || !text || len < 0 || !n_reads) return GMX_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
+    if (!text_on_device && !ctx->collect_hits && ctx->fq_piece_bytes > 0 && len >= 2 * ctx->fq_piece_bytes) {
+        int r = process_fastq_pipelined(ctx, text, len, results, capacity, n_reads, recs);
+        if (r != GMX_OK && r != GMX_ERR_STATE) {           // every error leaves through the drain of run_batch's error exit
+            const std::string why = ctx->err;
+            cudaStreamSynchronize(ctx->stream); cudaStreamSynchronize(ctx->copy_stream); cudaStreamSynchronize(ctx->d2h_stream);
+            cudaGetLastError();
+            ctx->cs.valid = false;
+            ctx->err = why;
+        }
+        if (r != GMX_ERR_STATE) return r;
+    }
     int32_t max_len = 0; const char *d_text = nullptr;
     int r = fastq_scan_device(ctx, text, len, text_on_device, n_reads, &max_len, &d_text);
     if (r != GMX_OK) return r;

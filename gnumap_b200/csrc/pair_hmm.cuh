@@ -212,37 +212,60 @@ __device__ void gmx_pair_hmm_warp(const ReadView &rd, const WindowView &win, con
 // tolerance kernel: 1e-5 relative; the generic path below keeps the reference's operation order).
 #define GMX_PHMM_FAST_MAXC 5
 
-// Parked forward values: (fM, fY) of the C cells a lane computes in one step, as two FLOATS per cell scaled by a power of
-// two chosen per (lane, step) so that the largest of the 2C values lands in [1, 2), plus that exponent (one int per
-// lane and step).  The forward matrix spans 1e-300 .. 1e+66 over a 150 x 150 alignment, far outside float range, but
+// Parked forward values: (fM, fY) of the C cells a lane computes in one step, as two float bit patterns per cell scaled
+// by a power of two chosen per (lane, step) so that the largest of the 2C values lands in [1, 2), plus that exponent
+// offset (one int per lane and step).  The forward matrix spans 1e-300 .. 1e+66 over a 150 x 150 alignment, far outside float range, but
 // within one lane-step the values that matter sit within a few decades of the largest: a cell more than 2^-126 below
 // it flushes to zero, and its posterior f * b / fE is then below 1e-25 (b varies by at most (1 / (q * Tmg))^(C-1) ~ 1e13
 // across the C adjacent columns while f * b / fE <= 1 holds for the largest) -- far under the 1e-7 absolute tolerance of
 // this kernel.  The stored mantissa keeps 24 bits (relative 6e-8 against the kernel's 1e-5).  This halves the one
 // HBM-bound stream of the kernel (ncu before: DRAM 4.06 TB/s = 50 % of peak next to 49 % issue utilisation) and frees
 // twenty registers of prefetched forward values.
+// scaled float bits of a non-negative double: the float of x * 2^(1023 - eb) with the mantissa truncated to 24 bits, by
+// integer arithmetic on the bit pattern (hi word minus the exponent offset, then a funnel shift by 3) -- the conversion
+// unit (F2F, a quarter-rate pipe) was the busiest pipe of this kernel (ncu: xu 46 %) while it packed with DMUL + F2F.
+// Values more than 2^-127 below the scale come out as (sub)normal-range garbage below 1e-38 of it: inert.
+__device__ __forceinline__ uint32_t gmx_phmm_pack(double x, int c_off)
+{
+    const int t = max(__double2hiint(x) - c_off, 0);
+    return __funnelshift_l((uint32_t)__double2loint(x), (uint32_t)t, 3);
+}
+__device__ __forceinline__ double gmx_phmm_unpack(uint32_t f, int c_off)
+{
+    return __hiloint2double((int)(f >> 3) + c_off, (int)(f << 29));
+}
+
+#define GMX_PHMM_ESTRIDE(C) (32 * (C) + 4)      // doubles per genome base in the emission table (rows 0 .. n, padded)
+
 template <int C>
-__device__ void gmx_pair_hmm_warp_fast(const ReadView &rd, const uint8_t *pac, int64_t pos, const DevTables &T, float2 *F, int *E, float *post,
-                                       float *acc_s /* [C][5][32] */, float4 *erow_s /* [32*C] */, uint8_t *code_s /* [32*C] */)
+__device__ void gmx_pair_hmm_warp_fast(const ReadView &rd, const uint8_t *pac, int64_t pos, const DevTables &T, uint2 *F, int *E, float *post,
+                                       float *acc_s /* [C][5][32] */, double *e_s /* [4][ESTRIDE] */, uint8_t *code_s /* [32*C] */)
 {
     const int lane = threadIdx.x & 31;
     const int n = rd.n, m = rd.n;
     constexpr int MP = 32 * C;                                   // padded row length
-    // per-row operands of the read, staged once: emission row p_seq(pwm[i], g) for g = a,c,g,t and the consensus code
-    for (int i = lane; i < n; i += 32) {
-        erow_s[i] = rd.phmm_row(T, i);
-        const char ch = gmx_max_char(rd.pwm_row(T, i));
-        code_s[i] = (uint8_t)(ch == 'a' ? 0 : ch == 'c' ? 1 : ch == 'g' ? 2 : ch == 't' ? 3 : 4);
+    constexpr int ES = GMX_PHMM_ESTRIDE(C);
+    // per-row operands of the read, staged once: the emission p_seq(pwm[i], g) as a DOUBLE per genome base g (one
+    // shared-memory load per cell instead of a four-way select and a conversion; rows past the read are zero, so the
+    // backward sweep's "row i + 1" needs no range test) and the consensus code
+    for (int i = lane; i < ES; i += 32) {
+        float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < n) {
+            r4 = rd.phmm_row(T, i);
+            const char ch = gmx_max_char(rd.pwm_row(T, i));
+            code_s[i] = (uint8_t)(ch == 'a' ? 0 : ch == 'c' ? 1 : ch == 'g' ? 2 : ch == 't' ? 3 : 4);
+        }
+        e_s[i] = (double)r4.x; e_s[ES + i] = (double)r4.y; e_s[2 * ES + i] = (double)r4.z; e_s[3 * ES + i] = (double)r4.w;
     }
     __syncwarp();
     const PhmmConst K = gmx_phmm_const();
     const int j0 = lane * C;
-    int gb[C], gbn[C];
+    const double *ep[C], *epn[C];             // emission column of genome base j, and of base j + 1 (zero column when past the window)
 #pragma unroll
     for (int c = 0; c < C; ++c) {
         const int j = j0 + c;
-        gb[c] = j < m ? gmx_pac_base(pac, pos + j) : 0;
-        gbn[c] = j + 1 < m ? gmx_pac_base(pac, pos + j + 1) : 0;
+        ep[c] = e_s + (j < m ? gmx_pac_base(pac, pos + j) : 0) * ES;
+        epn[c] = e_s + (j + 1 < m ? gmx_pac_base(pac, pos + j + 1) : 0) * ES;
     }
 #pragma unroll
     for (int x = 0; x < C * 5; ++x) acc_s[x * 32 + lane] = 0.f;
@@ -259,20 +282,19 @@ __device__ void gmx_pair_hmm_warp_fast(const ReadView &rd, const uint8_t *pac, i
         const int i = s - lane;                                  // 1-based read row
         if (lane == 0) { rM = 0; rX = 0; rY = 0; }
         if (i >= 1 && i <= n) {
-            const float4 row = erow_s[i - 1];
             if (lane == 0) { dM = (i == 1) ? 1.0 : 0.0; dX = 0; dY = 0; }
             double cM = dM, cX = dX, cY = dY;                    // (i-1, j-1)
             double leftM = rM, leftY = rY;                       // (i, j-1)
-            // parked by STEP, slot-major: at any step the 32 lanes write 32 adjacent double2 (the backward sweep reads
-            // the block of forward step n + 31 - s_b at its step s_b: the skew cancels, both sides are coalesced)
-            float2 *frow = F + (size_t)s * MP + lane;
+            // parked by STEP, slot-major: at any step the 32 lanes write 32 adjacent pairs (the backward sweep reads the
+            // block of forward step n + 31 - s_b at its step s_b: the skew cancels, both sides are coalesced)
+            uint2 *frow = F + (size_t)s * MP + lane;
             int eh = 0;                                           // largest high word = largest value (all are >= 0)
 #pragma unroll
             for (int c = 0; c < C; ++c) {
-                const float e = gmx_sel4(row, gb[c], 0.f);
+                const double e = ep[c][i - 1];
                 // fused multiply-adds: this is the tolerance kernel (posteriors within 1e-5), and FMA only removes roundings
                 const double sum = fma(K.Tmm, cM, fma(K.Tgm, cX, K.Tgm * cY));
-                const double fM = (double)e * sum;
+                const double fM = e * sum;
                 const double fX = fma(dqTmg, pM[c], dqTgg * pX[c]);
                 const double fY = fma(dqTmg, leftM, dqTgg * leftY);
                 cM = pM[c]; cX = pX[c]; cY = pY[c];
@@ -282,10 +304,10 @@ __device__ void gmx_pair_hmm_warp_fast(const ReadView &rd, const uint8_t *pac, i
             }
             int eb = eh >> 20;                                    // biased exponent of the largest value of this lane-step
             if (eb == 0) eb = 1023;                               // all zero (or denormal): any scale will do
-            const double scale = __hiloint2double((2046 - eb) << 20, 0);      // 2^(1023 - eb), exact
+            const int c_off = (eb - 127) << 20;                   // double exponent field -> float exponent field of x * 2^(1023 - eb)
 #pragma unroll
-            for (int c = 0; c < C; ++c) frow[c * 32] = make_float2((float)(pM[c] * scale), (float)(pY[c] * scale));
-            E[s * 32 + lane] = eb;
+            for (int c = 0; c < C; ++c) frow[c * 32] = make_uint2(gmx_phmm_pack(pM[c], c_off), gmx_phmm_pack(pY[c], c_off));
+            E[s * 32 + lane] = c_off;
             outM = pM[C - 1]; outX = pX[C - 1]; outY = pY[C - 1];
             dM = rM; dX = rX; dY = rY;
         }
@@ -304,10 +326,10 @@ __device__ void gmx_pair_hmm_warp_fast(const ReadView &rd, const uint8_t *pac, i
 #pragma unroll
     for (int c = 0; c < C; ++c) { qM[c] = 0; qX[c] = 0; }
     double eM = 0, sndM = 0, sndY = 0;
-    float2 fv_nxt[C];                                            // forward values of the row handled in the next step
-    int e_nxt = 1023;
+    uint2 fv_nxt[C];                                             // parked forward values of the row handled in the next step
+    int e_nxt = 0;
 #pragma unroll
-    for (int c = 0; c < C; ++c) fv_nxt[c] = make_float2(0.f, 0.f);
+    for (int c = 0; c < C; ++c) fv_nxt[c] = make_uint2(0u, 0u);
     if (lane == 31) {                                            // row n-1 of lane 31 was written at forward step n + 31
 #pragma unroll
         for (int c = 0; c < C; ++c) fv_nxt[c] = F[(size_t)(n + 31) * MP + c * 32 + lane];
@@ -317,19 +339,17 @@ __device__ void gmx_pair_hmm_warp_fast(const ReadView &rd, const uint8_t *pac, i
         double rM = gmx_shfl_d(sndM, lane + 1), rY = gmx_shfl_d(sndY, lane + 1);
         if (lane == 31) { rM = 0; rY = 0; }
         const int i = (n - 1) - (s - (31 - lane));               // 0-based read row
-        float2 fv[C];
+        uint2 fv[C];
 #pragma unroll
         for (int c = 0; c < C; ++c) fv[c] = fv_nxt[c];
-        // 1 / fE and the power of two the parked values of this lane-step were scaled by, in one factor
-        const double inv_s = inv_fE * __hiloint2double(e_nxt << 20, 0);
+        const int c_off = e_nxt;
         if (i - 1 >= 0 && i - 1 <= n - 1) {                      // request the next step's row before this one's chain
-            const float2 *fnext = F + (size_t)(n + 31 - (s + 1)) * MP + lane;
+            const uint2 *fnext = F + (size_t)(n + 31 - (s + 1)) * MP + lane;
 #pragma unroll
             for (int c = 0; c < C; ++c) fv_nxt[c] = fnext[c * 32];
             e_nxt = E[(n + 31 - (s + 1)) * 32 + lane];
         }
         if (i >= 0 && i <= n - 1) {
-            const float4 row = (i + 1 <= n - 1) ? erow_s[i + 1] : make_float4(0, 0, 0, 0);
             const int code = code_s[i];
             float *acc = acc_s + code * 32 + lane;
             double diagM = eM, rightY = rY;
@@ -340,20 +360,22 @@ __device__ void gmx_pair_hmm_warp_fast(const ReadView &rd, const uint8_t *pac, i
                     double bM = __dmul_rn(dqTmg, rightY), bX = 0, bY = __dmul_rn(dqTgg, rightY);
                     if (j == m - 1) { bM = K.t; bX = K.t; bY = K.t; }
                     if (j > m - 1) { bM = 0; bX = 0; bY = 0; }
-                    const double add = __dadd_rn(__dmul_rn(__dmul_rn((double)fv[c].y, bY), inv_s), __dmul_rn(__dmul_rn((double)fv[c].x, bM), inv_s));
+                    const double fMv = gmx_phmm_unpack(fv[c].x, c_off), fYv = gmx_phmm_unpack(fv[c].y, c_off);
+                    const double add = __dadd_rn(__dmul_rn(__dmul_rn(fYv, bY), inv_fE), __dmul_rn(__dmul_rn(fMv, bM), inv_fE));
                     if (j <= m - 1) acc[c * 160] = (float)__dadd_rn((double)acc[c * 160], add);
                     qM[c] = bM; qX[c] = bX; rightY = bY;
                 }
             } else {
 #pragma unroll
                 for (int c = C - 1; c >= 0; --c) {
-                    const float e = gmx_sel4(row, gbn[c], 0.f);
-                    const double eTmm = (double)__fmul_rn(e, K.fTmm), eTgm = (double)__fmul_rn(e, K.fTgm);
+                    const double e = epn[c][i + 1];              // zero past the read's last row / the window's last column
+                    const double eTmm = e * K.Tmm, eTgm = e * K.Tgm;
                     const double bM = fma(eTmm, diagM, fma(dqTmg, qX[c], dqTmg * rightY));
                     const double gd = eTgm * diagM;
                     const double bX = fma(dqTgg, qX[c], gd);
                     const double bY = fma(dqTgg, rightY, gd);
-                    const double add = fma((double)fv[c].y, bY, (double)fv[c].x * bM) * inv_s;
+                    const double fMv = gmx_phmm_unpack(fv[c].x, c_off), fYv = gmx_phmm_unpack(fv[c].y, c_off);
+                    const double add = fma(fYv, bY, fMv * bM) * inv_fE;
                     acc[c * 160] = (float)__dadd_rn((double)acc[c * 160], add);
                     diagM = qM[c];
                     qM[c] = bM; qX[c] = bX; rightY = bY;
@@ -397,8 +419,8 @@ __global__ void __launch_bounds__(GMX_PHMM_THREADS) k_pair_hmm_leaders(DevIndex 
 {
     constexpr int CS = C_T > 0 ? C_T : 1;
     __shared__ float acc_s[CS * 5 * 32];
-    __shared__ float4 erow_s[CS * 32];
-    __shared__ uint8_t code_s[CS * 32];
+    __shared__ double e_s[4 * GMX_PHMM_ESTRIDE(CS)];
+    __shared__ uint8_t code_s[CS * 32 + 32];
     double *my = scratch + (size_t)blockIdx.x * per_task;
     while (true) {
         uint32_t s = 0;
@@ -410,10 +432,10 @@ __global__ void __launch_bounds__(GMX_PHMM_THREADS) k_pair_hmm_leaders(DevIndex 
         ReadView rd = gmx_read_view(R, (int)(task >> 1), (int)(task & 1));
         float *out = L.hmm + (size_t)s * L.max_len * 5;
         if (C_T > 0) {
-            // scratch slot: float2 [n + 32][32 * C] followed by int [n + 32][32]
-            float2 *F = reinterpret_cast<float2 *>(my);
+            // scratch slot: packed pairs [n + 32][32 * C] followed by int [n + 32][32]
+            uint2 *F = reinterpret_cast<uint2 *>(my);
             int *E = reinterpret_cast<int *>(F + (size_t)(L.max_len + 32) * (32 * CS));
-            gmx_pair_hmm_warp_fast<CS>(rd, ix.pac, diag, T, F, E, out, acc_s, erow_s, code_s);
+            gmx_pair_hmm_warp_fast<CS>(rd, ix.pac, diag, T, F, E, out, acc_s, e_s, code_s);
         } else {
             WindowView win; win.pac = ix.pac; win.pos = diag; win.chars = nullptr;
             gmx_pair_hmm_warp<GMX_PHMM_MAXC>(rd, win, T, my, out);

@@ -303,7 +303,10 @@ int gmx_fastq_scan_host(const char *text, int64_t len, int illumina, gmx_fastq_r
  * need the reference's recovery path gives GMX_ERR_FORMAT: fall back to gmx_fastq_scan_host.  recs may be NULL. */
 int gmx_fastq_scan(gmx_ctx *ctx, const char *text, int64_t len, int text_on_device, gmx_fastq_rec *recs, int64_t capacity, int64_t *n_recs);
 
-/* gmx_fastq_scan + gmx_process_batch with the reads used in place inside the (device copy of the) text. */
+/* gmx_fastq_scan + gmx_process_batch with the reads used in place inside the (device copy of the) text.  A large host text
+ * is pipelined piece by piece (GMX_OPT_FASTQ_PIECE): should a LATER piece turn out malformed, the call returns GMX_ERR_FORMAT
+ * with *n_reads = the reads before that piece -- they have been mapped and scored, results / recs hold them -- and the
+ * caller continues with gmx_fastq_scan_host from the end of record *n_reads - 1 (*n_reads == 0: nothing was done). */
 int gmx_process_fastq(gmx_ctx *ctx, const char *text, int64_t len, int text_on_device, gmx_read_result *results, int64_t capacity,
                       int64_t *n_reads, gmx_fastq_rec *recs);
 
@@ -368,6 +371,9 @@ int gmx_snp_call(const float counts[5], int genome_base, int snp_monoploid, floa
                                     which some alignment needs more text than the slot fails with GMX_ERR_OVERFLOW instead of
                                     returning a cut string */
 #define GMX_OPT_VOTE_SLOTS   6   /* tuning: 32-hit slots per step of the vote kernel, 4 or 6 (default: from seq_len / 4^mer)  */
+#define GMX_OPT_FASTQ_PIECE  9   /* bytes per piece of a host FASTQ text in gmx_process_fastq (default 96 MiB; 0 = upload and index the
+                                    whole text first).  Texts of two pieces or more are cut at record boundaries and piece p + 1
+                                    crosses PCIe and is indexed while piece p is mapped                                          */
 #define GMX_OPT_SAM_DEVICE   8   /* 1 (default): gmx_format_sam formats the batch of the last gmx_process_fastq on the GPU (the text, the
                                     record index, the results and the CIGARs are resident there); 0: always the host formatter     */
 #define GMX_OPT_VOTE_COMPACT 7   /* tuning: occupancy variants of the vote kernel for tasks of <= 32 k-mers: 0 off, 1 two bits per

@@ -296,3 +296,60 @@ def test_g_format_of_the_device_sam_writer_is_printf_g():
     for v in vals:
         n = L.gmx_format_g(float(v), buf, 64)
         assert n > 0 and buf.raw[:n].decode() == "%g" % v, (v, buf.raw[:n])
+
+
+@pytest.mark.gpu
+def test_pipelined_fastq_text_equals_whole_text_path():
+    """A host FASTQ text of several pieces (GMX_OPT_FASTQ_PIECE) is cut at record boundaries and piece p + 1 is uploaded and
+    indexed while piece p is mapped: per-read results, record index, accumulators and the device-formatted SAM must be
+    those of the whole-text path; a text whose LATER part is malformed reports the reads done so far and the wrapper
+    finishes it through the host scan."""
+    from gnumap_b200 import synth
+    contigs = synth.make_genome(250_000, 91, n_contigs=2)
+    codes = np.concatenate([c for _, c in contigs])
+    n_reads = 6000
+    rng = np.random.default_rng(92)
+    lut = np.frombuffer(b"ACGTN", dtype=np.uint8)
+    recs_txt = []
+    for i in range(n_reads):
+        L = int(rng.integers(40, 121))
+        r = synth.simulate_reads(codes, 1, L, 1000 + i, indel_rate=0.2, qlo=0)      # Q0 -> '!' ... quality lines may start with '@' (Q31)
+        q = (r["quals"][0] + 33).astype(np.uint8)
+        if i % 5 == 0:
+            q[0] = ord("@")                                                          # a quality line that looks like a name line
+        recs_txt.append(b"@r%d\n" % i + lut[r["bases"][0]].tobytes() + b"\n+\n" + q.tobytes() + b"\n")
+    text = b"".join(recs_txt)
+    ix = index.build_index(contigs)
+    m = api.Mapper(ix)
+    m.set_option(api.OPT_COLLECT_HITS, 0)
+    m.set_option(api.OPT_FASTQ_PIECE, 0)
+    names0, whole = m.process_fastq(text, fetch=False)
+    recs0 = api.fastq_scan_host(text)
+    sam0 = m.format_sam(text, recs0, whole["results"])
+    amount0, _ = m.finish()
+    for piece, chunk in ((100_000, 1 << 19), (150_000, 700)):
+        m.reset_accumulators()
+        m.set_option(api.OPT_FASTQ_PIECE, piece); m.set_option(api.OPT_CHUNK_READS, chunk)
+        names1, piped = m.process_fastq(text, fetch=False)
+        assert names1 == names0
+        for f in whole["results"].dtype.names:
+            assert np.array_equal(piped["results"][f], whole["results"][f]), f
+        assert m.format_sam(text, recs0, piped["results"]) == sam0
+        assert np.allclose(m.finish()[0], amount0, rtol=1e-5, atol=1e-6)
+    # malformed late in the text: a record with a quality line shorter than its sequence
+    k = 4000
+    bad = recs_txt[k].split(b"\n")
+    bad[3] = bad[3][:-3]
+    messy = b"".join(recs_txt[:k]) + b"\n".join(bad) + b"".join(recs_txt[k + 1:])
+    m.set_option(api.OPT_FASTQ_PIECE, 0); m.set_option(api.OPT_CHUNK_READS, 1 << 19)
+    m.reset_accumulators()
+    names_a, res_a = m.process_fastq(messy, fetch=False)              # whole text: device indexer refuses, host scan does it all
+    amount_a, _ = m.finish()
+    m.set_option(api.OPT_FASTQ_PIECE, 100_000)
+    m.reset_accumulators()
+    names_b, res_b = m.process_fastq(messy, fetch=False)              # pipelined: the first pieces on the device, the rest through the host scan
+    assert names_b == names_a and len(names_a) in (n_reads - 1, n_reads)
+    for f in ("status", "best_first_pos", "best_score", "n_groups", "best_first_strand"):
+        assert np.array_equal(res_b["results"][f], res_a["results"][f]), f
+    assert np.allclose(m.finish()[0], amount_a, rtol=1e-5, atol=1e-6)
+    m.close()
