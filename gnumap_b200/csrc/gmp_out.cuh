@@ -55,6 +55,63 @@ __global__ void k_gmp_gather(const float *amount, const float *p0, const float *
     base[k] = count < l_pac ? (uint8_t)gmx_pac_base(pac, (int64_t)count) : 4;
 }
 
+// ---- .sgr rows formatted on the device -----------------------------------------------------------------
+// GenomeBwt::PrintFinalSGR (reference src/GenomeBwt.cpp:1212-1273): "chrom\tpos\t%.5f\n" per selected bin.  A float times
+// 10^5 is exact in a double, so rint() (round-half-even) gives printf's digits; one thread per row sizes it, a scan places
+// it, one thread per row writes it.  8 M rows = 196 MB of text that the host used to format on all its threads.
+struct SgrNames { const char *chars; const int32_t *off; const int32_t *len; };
+
+__device__ __forceinline__ int gmx_dev_digits(unsigned long long v) { int d = 1; while (v >= 10) { v /= 10; d++; } return d; }
+__device__ __forceinline__ char *gmx_dev_put_uint(char *o, unsigned long long v)
+{
+    const int d = gmx_dev_digits(v);
+    for (int i = d - 1; i >= 0; --i) { o[i] = (char)('0' + v % 10); v /= 10; }
+    return o + d;
+}
+
+// row k: bin idx[k] with value val[k]; lens[k] = bytes of its line (0 when the bin starts past the genome)
+__global__ void __launch_bounds__(256) k_sgr_measure(const uint32_t *idx, const float *val, uint32_t n, uint64_t gen_size, const int64_t *seq_offset, int n_seqs,
+                                                     SgrNames names, long long *lens, uint32_t *uncovered)
+{
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int64_t count = (int64_t)((uint64_t)idx[k] * gen_size);
+    long long len = 0;
+    if (count < seq_offset[n_seqs]) {
+        int lo = 0, hi = n_seqs;
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (seq_offset[mid] <= count) lo = mid; else hi = mid; }
+        const float v = val[k];
+        if (!(v >= 0.0f && v < 1.0e9f)) atomicAdd(uncovered, 1u);          // the host's snprintf takes the whole file then
+        const unsigned long long q = (unsigned long long)rint((double)v * 100000.0);
+        len = names.len[lo] + 1 + gmx_dev_digits((unsigned long long)(count - seq_offset[lo] + 1)) + 1 + gmx_dev_digits(q / 100000ull) + 1 + 5 + 1;
+    }
+    lens[k] = len;
+}
+
+__global__ void __launch_bounds__(256) k_sgr_write(const uint32_t *idx, const float *val, uint32_t n, uint64_t gen_size, const int64_t *seq_offset, int n_seqs,
+                                                   SgrNames names, const long long *offs, char *out)
+{
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    if (offs[k + 1] == offs[k]) return;
+    const int64_t count = (int64_t)((uint64_t)idx[k] * gen_size);
+    int lo = 0, hi = n_seqs;
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (seq_offset[mid] <= count) lo = mid; else hi = mid; }
+    char *o = out + offs[k];
+    const char *nm = names.chars + names.off[lo];
+    for (int i = 0; i < names.len[lo]; ++i) *o++ = nm[i];
+    *o++ = '\t';
+    o = gmx_dev_put_uint(o, (unsigned long long)(count - seq_offset[lo] + 1));
+    *o++ = '\t';
+    const unsigned long long q = (unsigned long long)rint((double)val[k] * 100000.0);
+    o = gmx_dev_put_uint(o, q / 100000ull);
+    *o++ = '.';
+    unsigned long long f = q % 100000ull;
+    for (int d = 4; d >= 0; --d) { o[d] = (char)('0' + f % 10); f /= 10; }
+    o += 5;
+    *o++ = '\n';
+}
+
 // ---- host side ------------------------------------------------------------------------------------
 
 // "%.{dec}f" of a non-negative float below 1e9, digit for digit as printf rounds it (ties to even on the exact

@@ -2129,11 +2129,49 @@ extern "C" int gmx_format_sgr(gmx_ctx *ctx, const char *const *chrom_names, doub
     uint32_t n = 0;
     CK(cudaMemcpyAsync(&n, d_cnt.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    std::vector<uint32_t> idx(n); std::vector<float> val(n);
+    std::vector<uint32_t> idx; std::vector<float> val;
     if (n) {
         CK(d_val.ensure((size_t)n * 4));
         k_gather_f32<<<nblk(n, 256), 256, 0, ctx->stream>>>(ctx->acc.amount, d_idx.as<uint32_t>(), n, d_val.as<float>());
         CK(cudaGetLastError());
+        // the lines themselves on the device: size, place, write (gmp_out.cuh); only the finished text crosses to the host
+        const int n_seqs = ctx->ix.n_seqs;
+        std::vector<int32_t> noff((size_t)n_seqs), nlen((size_t)n_seqs);
+        std::string chars;
+        for (int i = 0; i < n_seqs; ++i) { noff[i] = (int32_t)chars.size(); nlen[i] = (int32_t)strlen(chrom_names[i]); chars += chrom_names[i]; }
+        const size_t chars_pad = (chars.size() + 15) & ~(size_t)15;
+        ScratchBuf d_names, d_lens, d_offs, d_text;
+        CK(d_names.ensure(chars_pad + (size_t)n_seqs * 8 + 16)); CK(d_lens.ensure(((size_t)n + 1) * 8 + 16)); CK(d_offs.ensure(((size_t)n + 1) * 8));
+        CK(cudaMemcpyAsync(d_names.p, chars.data(), chars.size(), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(d_names.as<char>() + chars_pad, noff.data(), (size_t)n_seqs * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(d_names.as<char>() + chars_pad + (size_t)n_seqs * 4, nlen.data(), (size_t)n_seqs * 4, cudaMemcpyHostToDevice, ctx->stream));
+        SgrNames names;
+        names.chars = d_names.as<char>(); names.off = reinterpret_cast<const int32_t *>(d_names.as<char>() + chars_pad); names.len = names.off + n_seqs;
+        long long *dl = d_lens.as<long long>(), *dof = d_offs.as<long long>();
+        uint32_t *d_unc = reinterpret_cast<uint32_t *>(dl + n + 1);
+        CK(cudaMemsetAsync(dl + n, 0, 16, ctx->stream));
+        k_sgr_measure<<<nblk(n, 256), 256, 0, ctx->stream>>>(d_idx.as<uint32_t>(), d_val.as<float>(), n, ctx->params.gen_size, ctx->ix.seq_offset, n_seqs, names, dl, d_unc);
+        CK(cudaGetLastError());
+        size_t scan_bytes = 0;
+        CK(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, dl, dof, (int)n + 1, ctx->stream));
+        CK(d_tmp.ensure(scan_bytes));
+        CK(cub::DeviceScan::ExclusiveSum(d_tmp.p, scan_bytes, dl, dof, (int)n + 1, ctx->stream));
+        long long total = 0; uint32_t unc = 0;
+        CK(cudaMemcpyAsync(&total, dof + n, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(&unc, d_unc, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (!unc) {
+            *len = total;
+            if (total > cap) return GMX_ERR_OVERFLOW;
+            CK(d_text.ensure((size_t)total + 16));
+            k_sgr_write<<<nblk(n, 256), 256, 0, ctx->stream>>>(d_idx.as<uint32_t>(), d_val.as<float>(), n, ctx->params.gen_size, ctx->ix.seq_offset, n_seqs, names, dof, d_text.as<char>());
+            CK(cudaGetLastError());
+            CK(cudaMemcpyAsync(out, d_text.p, (size_t)total, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            return GMX_OK;
+        }
+        // a value outside the fixed-point writer's range: the host formats the file (snprintf)
+        idx.resize(n); val.resize(n);
         CK(cudaMemcpyAsync(idx.data(), d_idx.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaMemcpyAsync(val.data(), d_val.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
