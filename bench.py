@@ -567,33 +567,6 @@ def extra_row(spec, a, rank, world, local, dev, peaks, alu):
     return row
 
 
-def bind_to_gpu_cores(local: int, world: int):
-    """One rank per GPU on one host: keep the rank's threads (and so its pinned buffers, first touched by them) on the CPU
-    cores next to its GPU, and give the ranks that share those cores disjoint slices of them -- eight ranks otherwise
-    wander over both sockets and pull 344 MB per step each across the inter-socket link."""
-    try:
-        import pynvml
-        pynvml.nvmlInit()
-        ncpu = os.cpu_count() or 1
-        words = (ncpu + 63) // 64
-
-        def cores_of(i):
-            h = pynvml.nvmlDeviceGetHandleByIndex(i)
-            mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
-            return [c for c in range(ncpu) if (mask[c // 64] >> (c % 64)) & 1]
-
-        mine = cores_of(local)
-        avail = sorted(os.sched_getaffinity(0))
-        mine = [c for c in mine if c in avail] or avail
-        peers = [g for g in range(world) if cores_of(g) == cores_of(local)]
-        k = peers.index(local)
-        share = mine[k * len(mine) // len(peers):(k + 1) * len(mine) // len(peers)] or mine
-        os.sched_setaffinity(0, share)
-        return {"cores": share, "ranks_sharing_the_socket": len(peers)}
-    except Exception as e:          # no NVML / no permission: run unbound
-        return {"error": str(e)}
-
-
 def own_arm(a):
     import torch
     import torch.distributed as dist
@@ -605,7 +578,6 @@ def own_arm(a):
         raise SystemExit("bench.py needs a CUDA device: gnumap_b200 has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    affinity = bind_to_gpu_cores(local, world) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -805,7 +777,7 @@ def own_arm(a):
             "config": {"workload": workload_name(a.genome, n, L, a.mode, main_tag(a)), "reads_per_gpu_per_step": n,
                        "l2": f"inputs exceed L2: reads {2 * n * L // 1_000_000} MB + suffix array {4 * a.genome // 1_000_000} MB streamed per step (L2 126 MB)",
                        "collective": (f"one ncclAllReduce(sum, f32) of {job.acc_bytes / 1e6:.0f} MB per GPU after the last step, inside the timed region ({red_ms:.2f} ms)") if world > 1 else "none (1 GPU)",
-                       "mapped_fraction": mapped / n, "nw_gcups": gcups, "cpu_affinity_rank0": affinity},
+                       "mapped_fraction": mapped / n, "nw_gcups": gcups},
             "clocks": clocks,
             "e2e": {"value": total_reads / (wall_e2e * 1e-3), "unit": "reads/s", "h2d_bytes_per_step": int(2 * n * L + 8 * (n + 1)),
                     "d2h_bytes_per_step": int(n * (_abi.READ_RESULT_DTYPE.itemsize + 64)), "ms_per_step": wall_e2e / a.steps,
