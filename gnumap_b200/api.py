@@ -33,7 +33,7 @@ EXPORTS = [
     "gmx_nw_score", "gmx_nw_traceback", "gmx_pair_hmm", "gmx_map_batch", "gmx_score_batch", "gmx_process_batch",
     "gmx_get_hits", "gmx_get_best_alignments", "gmx_accumulators_device", "gmx_reset_accumulators", "gmx_finish",
     "gmx_get_stage_stats", "gmx_set_option", "gmx_fastq_scan_host", "gmx_fastq_scan", "gmx_process_fastq", "gmx_format_sam", "gmx_format_sgr", "gmx_format_gmp", "gmx_snp_call",
-    "gmx_comm_create", "gmx_comm_reduce", "gmx_comm_stats", "gmx_comm_destroy", "gmx_measure_alu_peak", "gmx_format_g",
+    "gmx_comm_create", "gmx_comm_reduce", "gmx_comm_stats", "gmx_comm_destroy", "gmx_measure_alu_peak", "gmx_format_g", "gmx_index_sizes", "gmx_index_build",
 ]
 
 OPT_COLLECT_HITS, OPT_CHUNK_READS, OPT_VOTE_FILTER, OPT_FILTER_SHIFT, OPT_CIGAR_STRIDE, OPT_VOTE_SLOTS, OPT_VOTE_COMPACT, OPT_SAM_DEVICE, OPT_FASTQ_PIECE = 1, 2, 3, 4, 5, 6, 7, 8, 9
@@ -87,6 +87,9 @@ def load_library():
         L.gmx_snp_call.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double), C.c_char_p, C.c_int]
         L.gmx_format_gmp.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_float, C.c_int, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
         L.gmx_process_fastq.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.c_void_p]
+        L.gmx_index_sizes.argtypes = [C.c_int64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.gmx_index_build.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.POINTER(C.c_int32), C.c_char_p, C.c_int]
         L.gmx_measure_alu_peak.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
         L.gmx_comm_create.argtypes = [C.POINTER(C.c_void_p), C.c_void_p, C.c_int, C.c_int]
         L.gmx_comm_reduce.argtypes = [C.c_void_p, C.c_int]
@@ -135,6 +138,26 @@ def batch_from_fastq(text: bytes, recs: np.ndarray):
     seqs = [text[int(r["seq_off"]): int(r["seq_off"]) + int(r["seq_len"])] for r in recs]
     quals = [text[int(r["qual_off"]): int(r["qual_off"]) + int(r["seq_len"])] for r in recs]
     return names, ReadBatch(seqs, quals)
+
+
+def index_build(codes: np.ndarray, device: int = 0):
+    """bwa_index on the GPU (gmx_index_build): codes uint8[n] in 0..3 -> dict(bwt uint32[], primary, L2 uint64[5], sa uint64[],
+    pac uint8[], rounds)."""
+    L = load_library()
+    codes = np.ascontiguousarray(codes, dtype=np.uint8)
+    n = len(codes)
+    w, ns, pb = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+    rc = L.gmx_index_sizes(n, C.byref(w), C.byref(ns), C.byref(pb))
+    if rc != 0:
+        raise GmxError(rc, "gmx_index_sizes", L.gmx_strerror(rc).decode())
+    bwt = np.zeros(w.value, dtype=np.uint32); sa = np.zeros(ns.value, dtype=np.uint64); pac = np.zeros(pb.value, dtype=np.uint8)
+    L2 = np.zeros(5, dtype=np.uint64)
+    primary = C.c_uint64(0); rounds = C.c_int32(0)
+    err = C.create_string_buffer(512)
+    rc = L.gmx_index_build(ptr(codes), n, device, ptr(bwt), C.byref(primary), ptr(L2), ptr(sa), ptr(pac), C.byref(rounds), err, 512)
+    if rc != 0:
+        raise GmxError(rc, "gmx_index_build", err.value.decode() or L.gmx_strerror(rc).decode())
+    return dict(bwt=bwt, primary=int(primary.value), L2=L2, sa=sa, pac=pac, rounds=int(rounds.value))
 
 
 class Mapper:

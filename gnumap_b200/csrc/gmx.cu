@@ -2312,6 +2312,117 @@ extern "C" int gmx_snp_call(const float counts[5], int genome_base, int snp_mono
 }
 
 // ------------------------------------------------------------------------------------------------
+// next row: index construction
+// ------------------------------------------------------------------------------------------------
+#include "index_build.cuh"
+
+extern "C" int gmx_index_sizes(int64_t l_pac, uint64_t *bwt_words, uint64_t *n_sa, uint64_t *pac_bytes)
+{
+    if (l_pac < 1) return GMX_ERR_INVALID;
+    const uint64_t n = (uint64_t)l_pac, n_blocks = (n + GMX_IDX_OCC - 1) / GMX_IDX_OCC;
+    if (bwt_words) *bwt_words = ((n + 15) >> 4) + (n_blocks + 1) * 8;
+    if (n_sa) *n_sa = (n + GMX_IDX_SA_INTV) / GMX_IDX_SA_INTV;
+    if (pac_bytes) *pac_bytes = (n + 3) / 4;
+    return GMX_OK;
+}
+
+#define ICK(call)                                                                                    \
+    do {                                                                                             \
+        cudaError_t e__ = (call);                                                                    \
+        if (e__ != cudaSuccess) {                                                                    \
+            if (err && err_cap > 0) snprintf(err, (size_t)err_cap, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            return (e__ == cudaErrorMemoryAllocation) ? GMX_ERR_NOMEM : GMX_ERR_CUDA;                \
+        }                                                                                            \
+    } while (0)
+
+extern "C" int gmx_index_build(const uint8_t *codes, int64_t l_pac, int device, uint32_t *bwt, uint64_t *primary_out, uint64_t L2[5],
+                               uint64_t *sa, uint8_t *pac, int32_t *rounds, char *err, int err_cap)
+{
+    if (!codes || l_pac < 1 || !bwt || !primary_out || !L2 || !sa || !pac) return GMX_ERR_INVALID;
+    if (l_pac >= 0x7fffff00ll) { if (err && err_cap > 0) snprintf(err, (size_t)err_cap, "genomes of 2^31 bases or more are not supported by the builder"); return GMX_ERR_UNSUPPORTED; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return GMX_ERR_NO_DEVICE;
+    if (device < 0 || device >= ndev) return GMX_ERR_INVALID;
+    ICK(cudaSetDevice(device));
+    const int64_t n = l_pac;
+    cudaStream_t st = nullptr;
+    ICK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    struct Guard { cudaStream_t s; ~Guard() { if (s) cudaStreamDestroy(s); } } guard{st};
+    ScratchBuf d_codes, d_key[2], d_idx[2], d_rank, d_flag, d_tmp;
+    ICK(d_codes.ensure((size_t)n + 32)); ICK(d_key[0].ensure((size_t)n * 8)); ICK(d_key[1].ensure((size_t)n * 8));
+    ICK(d_idx[0].ensure((size_t)n * 4)); ICK(d_idx[1].ensure((size_t)n * 4)); ICK(d_rank.ensure((size_t)n * 4)); ICK(d_flag.ensure((size_t)n * 4));
+    ICK(cudaMemcpyAsync(d_codes.p, codes, (size_t)n, cudaMemcpyHostToDevice, st));
+    cub::DoubleBuffer<unsigned long long> keys(d_key[0].as<unsigned long long>(), d_key[1].as<unsigned long long>());
+    cub::DoubleBuffer<uint32_t> vals(d_idx[0].as<uint32_t>(), d_idx[1].as<uint32_t>());
+    size_t sort_bytes = 0, scan_bytes = 0;
+    ICK(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, keys, vals, (int)n, 0, 64, st));
+    ICK(cub::DeviceScan::InclusiveSum(nullptr, scan_bytes, d_flag.as<uint32_t>(), d_flag.as<uint32_t>(), (int)n, st));
+    ICK(d_tmp.ensure(std::max(sort_bytes, scan_bytes)));
+    int rank_bits = 1; while ((1ll << rank_bits) <= n) rank_bits++;
+    int n_rounds = 0;
+    int64_t h = 16;
+    uint32_t n_ranks = 0;
+    k_idx_key16<<<nblk(n, 256), 256, 0, st>>>(d_codes.as<uint8_t>(), n, keys.Current(), vals.Current());
+    ICK(cudaGetLastError());
+    while (true) {
+        size_t tb = d_tmp.cap;
+        ICK(cub::DeviceRadixSort::SortPairs(d_tmp.p, tb, keys, vals, (int)n, 0, n_rounds == 0 ? 48 : 32 + rank_bits, st));
+        k_idx_flags<<<nblk(n, 256), 256, 0, st>>>(keys.Current(), n, d_flag.as<uint32_t>());
+        ICK(cudaGetLastError());
+        tb = d_tmp.cap;
+        ICK(cub::DeviceScan::InclusiveSum(d_tmp.p, tb, d_flag.as<uint32_t>(), d_flag.as<uint32_t>(), (int)n, st));
+        k_idx_scatter_rank<<<nblk(n, 256), 256, 0, st>>>(vals.Current(), d_flag.as<uint32_t>(), n, d_rank.as<uint32_t>());
+        ICK(cudaGetLastError());
+        ICK(cudaMemcpyAsync(&n_ranks, d_flag.as<uint32_t>() + (n - 1), 4, cudaMemcpyDeviceToHost, st));
+        ICK(cudaStreamSynchronize(st));
+        n_rounds++;
+        if ((int64_t)n_ranks >= n) break;
+        if (h >= n) { if (err && err_cap > 0) snprintf(err, (size_t)err_cap, "suffix sort did not converge"); return GMX_ERR_CUDA; }
+        k_idx_pair_key<<<nblk(n, 256), 256, 0, st>>>(d_rank.as<uint32_t>(), n, h, keys.Current(), vals.Current());
+        ICK(cudaGetLastError());
+        h *= 2;
+    }
+    if (rounds) *rounds = n_rounds;
+    const uint32_t *d_sa = vals.Current();                       // suffix array of the n suffixes (augmented rank R >= 1 <-> d_sa[R - 1])
+    uint32_t rank0 = 0;
+    ICK(cudaMemcpyAsync(&rank0, d_rank.p, 4, cudaMemcpyDeviceToHost, st));
+    ICK(cudaStreamSynchronize(st));
+    const int64_t primary = (int64_t)rank0;                       // rank of suffix 0 among the '$'-augmented suffixes
+    const int64_t n_blocks = (n + GMX_IDX_OCC - 1) / GMX_IDX_OCC, n_words = (n + 15) >> 4;
+    uint64_t bwt_words = 0, n_sa = 0, pac_bytes = 0;
+    gmx_index_sizes(n, &bwt_words, &n_sa, &pac_bytes);
+    // counts per block -> exclusive prefix sums (the key buffers are free now: reuse them)
+    d_key[0].release(); d_key[1].release();
+    ScratchBuf d_c, d_out, d_sas, d_pac;
+    ICK(d_c.ensure((size_t)(n_blocks + 1) * 8 * 4)); ICK(d_out.ensure((size_t)bwt_words * 4)); ICK(d_sas.ensure((size_t)n_sa * 8)); ICK(d_pac.ensure((size_t)pac_bytes));
+    unsigned long long *c[4];
+    for (int k = 0; k < 4; ++k) c[k] = d_c.as<unsigned long long>() + (size_t)k * (n_blocks + 1);
+    ICK(cudaMemsetAsync(d_c.p, 0, (size_t)(n_blocks + 1) * 8 * 4, st));
+    ICK(cudaMemsetAsync(d_out.p, 0, (size_t)bwt_words * 4, st));
+    k_idx_block_counts<<<nblk(n_blocks, 4), 128, 0, st>>>(d_codes.as<uint8_t>(), d_sa, n, primary, n_blocks, c[0], c[1], c[2], c[3]);
+    ICK(cudaGetLastError());
+    size_t sb = 0;
+    ICK(cub::DeviceScan::ExclusiveSum(nullptr, sb, c[0], c[0], (int)(n_blocks + 1), st));
+    ICK(d_tmp.ensure(sb));
+    for (int k = 0; k < 4; ++k) { size_t tb = d_tmp.cap; ICK(cub::DeviceScan::ExclusiveSum(d_tmp.p, tb, c[k], c[k], (int)(n_blocks + 1), st)); }
+    k_idx_interleave<<<nblk(n_words + 1, 256), 256, 0, st>>>(d_codes.as<uint8_t>(), d_sa, n, primary, n_blocks, c[0], c[1], c[2], c[3], d_out.as<uint32_t>());
+    ICK(cudaGetLastError());
+    k_idx_sample_sa<<<nblk((int64_t)n_sa, 256), 256, 0, st>>>(d_sa, (int64_t)n_sa, d_sas.as<unsigned long long>());
+    ICK(cudaGetLastError());
+    k_idx_pack_pac<<<nblk((int64_t)pac_bytes, 256), 256, 0, st>>>(d_codes.as<uint8_t>(), n, d_pac.as<uint8_t>(), (int64_t)pac_bytes);
+    ICK(cudaGetLastError());
+    unsigned long long tot[4];
+    for (int k = 0; k < 4; ++k) ICK(cudaMemcpyAsync(&tot[k], c[k] + n_blocks, 8, cudaMemcpyDeviceToHost, st));
+    ICK(cudaMemcpyAsync(bwt, d_out.p, (size_t)bwt_words * 4, cudaMemcpyDeviceToHost, st));
+    ICK(cudaMemcpyAsync(sa, d_sas.p, (size_t)n_sa * 8, cudaMemcpyDeviceToHost, st));
+    ICK(cudaMemcpyAsync(pac, d_pac.p, (size_t)pac_bytes, cudaMemcpyDeviceToHost, st));
+    ICK(cudaStreamSynchronize(st));
+    *primary_out = (uint64_t)primary;
+    L2[0] = 0; L2[1] = tot[0]; L2[2] = L2[1] + tot[1]; L2[3] = L2[2] + tot[2]; L2[4] = L2[3] + tot[3];
+    return GMX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // measured ALU ceilings for the roofline of the NW kernels ("measure with a mul/add micro-kernel")
 // ------------------------------------------------------------------------------------------------
 // K2a / K2b are bit-exact FP32 with separate multiplies and adds (no FMA); K2c runs on the FP64 pipe.  Eight independent

@@ -12,10 +12,11 @@ built by either side is usable by the other.
 
 `build_index` constructs the same arrays from scratch.  The BWT of a text is unique, so any
 correct suffix sorter reproduces the reference's files bit-for-bit (tests compare against
-indexes written by the compiled reference).  The sorter here is prefix doubling expressed with
-torch sort / cumsum so that it runs on the GPU for the 100-156 Mb benchmark genomes (seconds)
-and on the CPU for the small test genomes.  Index construction is a one-off input-preparation
-step, outside the hot path.
+indexes written by the compiled reference).  On a GPU (`device="cuda"`) it is the library's
+own builder, `gmx_index_build` (CUDA, csrc/index_build.cuh: prefix doubling over radix sorts,
+then streaming kernels for the BWT, the occ interleave, the SA sample and the pac); on the CPU
+the same construction is expressed with torch sort / cumsum / numpy, for the small genomes of
+the CPU tests and fixtures.  SURVEY.md §8f rank 4.
 """
 from __future__ import annotations
 
@@ -162,6 +163,18 @@ def build_index(contigs, device: str | torch.device = "cpu") -> FMIndex:
     (reference src/bwtindex.c:187-293) for a FASTA holding those sequences (no N)."""
     codes = np.concatenate([c for _, c in contigs]).astype(np.uint8)
     n = len(codes)
+    dev = torch.device(device)
+    if dev.type == "cuda":
+        # the product's builder: gmx_index_build (csrc/index_build.cuh), CUDA behind the C ABI
+        from . import api
+        r = api.index_build(codes, dev.index or 0)
+        offs, lens, names = [], [], []
+        o = 0
+        for name, c in contigs:
+            names.append(name); offs.append(o); lens.append(len(c)); o += len(c)
+        return FMIndex(bwt=r["bwt"], primary=r["primary"], L2=r["L2"], seq_len=n, sa=r["sa"], sa_intv=SA_INTV, pac=r["pac"], l_pac=n,
+                       names=names, seq_offset=np.asarray(offs, dtype=np.int64), seq_len_arr=np.asarray(lens, dtype=np.int32))
+    # CPU: the same construction with torch / numpy (tests without a GPU, fixtures)
     sa = suffix_array(codes, device)                       # int64[n], ranks 1..n of the $-augmented SA
     # full SA including '$' suffix at rank 0
     prev = sa - 1                                           # position of the preceding symbol

@@ -359,6 +359,17 @@ int gmx_format_gmp(gmx_ctx *ctx, const char *const *chrom_names, int target_base
 int gmx_snp_call(const float counts[5], int genome_base, int snp_monoploid, float snp_pval, int *first, int *second, int *diploid,
                  double *pval, char *text, int text_cap);
 
+/* ---- next row: index construction ------------------------------------------------
+ * bwa_index (reference src/bwtindex.c:187-293) on the GPU, from the base codes (0..3, one byte per base, the sequences of
+ * the FASTA concatenated; the synthetic genomes hold no N) to what the reference keeps in `.gnumap.bwt` / `.sa` / `.pac`:
+ * the occ-interleaved BWT (bwt_bwtupdate_core :128-150), primary, L2, the 1/32-sampled suffix array (bwt_cal_sa,
+ * src/bwt.c:62-84; sa[0] = (uint64_t)-1) and the 2-bit pac.  The suffixes are sorted by prefix doubling over radix sorts
+ * (csrc/index_build.cuh); the BWT of a text is unique, so the arrays are the reference's bit for bit.  Needs no context;
+ * output arrays are host memory sized by gmx_index_sizes.  *rounds (may be NULL) = sorting rounds used. */
+int gmx_index_sizes(int64_t l_pac, uint64_t *bwt_words, uint64_t *n_sa, uint64_t *pac_bytes);
+int gmx_index_build(const uint8_t *codes, int64_t l_pac, int device, uint32_t *bwt, uint64_t *primary, uint64_t L2[5],
+                    uint64_t *sa, uint8_t *pac, int32_t *rounds, char *err, int err_cap);
+
 /* ---- options ----------------------------------------------------------------------------- */
 #define GMX_OPT_COLLECT_HITS 1   /* 1 (default): keep every accepted (pos,strand) for gmx_get_hits; 0: only the
                                     per-read results and the best group's CIGAR leave the device           */
