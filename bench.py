@@ -316,6 +316,8 @@ class Job:
             m.set_option(api.OPT_FILTER_SHIFT, int(os.environ["GMX_FILTER_SHIFT"]))
         if os.environ.get("GMX_FASTQ_PIECE"):
             m.set_option(api.OPT_FASTQ_PIECE, int(os.environ["GMX_FASTQ_PIECE"]))
+        if os.environ.get("GMX_OPTIMISTIC"):
+            m.set_option(api.OPT_OPTIMISTIC, int(os.environ["GMX_OPTIMISTIC"]))
         if os.environ.get("GMX_VOTE_COMPACT"):
             m.set_option(api.OPT_VOTE_COMPACT, int(os.environ["GMX_VOTE_COMPACT"]))
         if os.environ.get("GMX_VOTE_SLOTS"):
@@ -785,6 +787,7 @@ def own_arm(a):
             "gpu_launches": int(sum(st["launches"].values())),
             "roofline": roofline,
             "small_calls": small,
+            "chunks": dict(zip(("issued_without_host_wait", "run_again"), job.m.chunk_stats())),
             "alu_peaks": alu,
             "cpu_baseline": cpu,
             "parity_sample": parity,

@@ -33,10 +33,10 @@ EXPORTS = [
     "gmx_nw_score", "gmx_nw_traceback", "gmx_pair_hmm", "gmx_map_batch", "gmx_score_batch", "gmx_process_batch",
     "gmx_get_hits", "gmx_get_best_alignments", "gmx_accumulators_device", "gmx_reset_accumulators", "gmx_finish",
     "gmx_get_stage_stats", "gmx_set_option", "gmx_fastq_scan_host", "gmx_fastq_scan", "gmx_process_fastq", "gmx_format_sam", "gmx_format_sgr", "gmx_format_gmp", "gmx_snp_call",
-    "gmx_comm_create", "gmx_comm_reduce", "gmx_comm_stats", "gmx_comm_destroy", "gmx_measure_alu_peak", "gmx_format_g", "gmx_index_sizes", "gmx_index_build",
+    "gmx_comm_create", "gmx_comm_reduce", "gmx_comm_stats", "gmx_comm_destroy", "gmx_measure_alu_peak", "gmx_chunk_stats", "gmx_format_g", "gmx_index_sizes", "gmx_index_build",
 ]
 
-OPT_COLLECT_HITS, OPT_CHUNK_READS, OPT_VOTE_FILTER, OPT_FILTER_SHIFT, OPT_CIGAR_STRIDE, OPT_VOTE_SLOTS, OPT_VOTE_COMPACT, OPT_SAM_DEVICE, OPT_FASTQ_PIECE = 1, 2, 3, 4, 5, 6, 7, 8, 9
+OPT_COLLECT_HITS, OPT_CHUNK_READS, OPT_VOTE_FILTER, OPT_FILTER_SHIFT, OPT_CIGAR_STRIDE, OPT_VOTE_SLOTS, OPT_VOTE_COMPACT, OPT_SAM_DEVICE, OPT_FASTQ_PIECE, OPT_OPTIMISTIC = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10
 COMM_AUTO, COMM_PEER, COMM_NCCL = 0, 1, 2
 
 
@@ -91,6 +91,7 @@ def load_library():
         L.gmx_index_build.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.POINTER(C.c_int32), C.c_char_p, C.c_int]
         L.gmx_measure_alu_peak.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
+        L.gmx_chunk_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.gmx_comm_create.argtypes = [C.POINTER(C.c_void_p), C.c_void_p, C.c_int, C.c_int]
         L.gmx_comm_reduce.argtypes = [C.c_void_p, C.c_int]
         L.gmx_comm_stats.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_uint64), C.POINTER(C.c_int)]
@@ -410,6 +411,12 @@ class Mapper:
         v = C.c_double(0.0)
         self._ck(self.L.gmx_measure_alu_peak(self._ctx, kind, C.byref(v)), "gmx_measure_alu_peak")
         return v.value
+
+    def chunk_stats(self):
+        """(chunks issued without a host wait, of those run again) since the context was created -- GMX_OPT_OPTIMISTIC."""
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        self._ck(self.L.gmx_chunk_stats(self._ctx, C.byref(a), C.byref(b)), "gmx_chunk_stats")
+        return a.value, b.value
 
     def stage_stats(self):
         s = GmxStageStats()

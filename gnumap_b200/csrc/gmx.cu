@@ -109,7 +109,7 @@ struct gmx_ctx {
     std::vector<gmx_hit> h_hits;
     int cigar_stride = 64;                     // GMX_OPT_CIGAR_STRIDE
     HostBuf h_best_cigar;                      // pinned [n_reads][cigar_stride]
-    HostBuf h_counters;                        // pinned staging of the per-chunk device counters
+    HostBuf h_counters;                        // pinned staging of the per-chunk device counters, one per chunk parity
     std::vector<uint8_t> h_best_aligned;       // [n_reads][a_stride]  (collect_hits only)
     int h_a_stride = 0;
     // state of the chunk whose PHASE A results are resident on the device
@@ -117,13 +117,29 @@ struct gmx_ctx {
         bool valid = false;
         int32_t lo = 0, n = 0, max_len = 0;
         int64_t total_bases = 0;
-        uint32_t n_cand = 0, n_leaders = 0, n_accepted = 0;
+        uint32_t n_cand = 0, n_leaders = 0, n_accepted = 0;     // optimistic chunk: the bounds its grids and buffers cover
+        const uint32_t *live_cand = nullptr, *live_lead = nullptr;   // optimistic chunk: device words holding the real counts
+        bool opt = false;
         unsigned long long *keys = nullptr;    // sorted candidate keys (d_keys or d_keys_alt)
         LeaderStore L;
     } cs;
-    // instrumentation
-    cudaEvent_t ev[ST_COUNT][2];
-    bool ev_used[ST_COUNT];
+    // Optimistic chunks (phase_a): issued end to end without a host wait, over bounds predicted from the last settled
+    // chunk; the host looks at a chunk's counters one chunk later (settle_chunk) and runs it again, synchronously, if it
+    // did not fit.  Two may be in flight: the one just issued and its predecessor.
+    struct Pending {
+        bool active = false;
+        int32_t lo = 0, hi = 0, max_len = 0; int slot = 0;
+        gmx_reads reads; gmx_read_result *results = nullptr;
+    } pend[2];
+    cudaEvent_t settle_ev[2] = {nullptr, nullptr};
+    double pred_cand = -1, pred_lead = -1;     // candidates / group leaders per read of the last settled chunk (< 0: none yet)
+    double pred_margin = 1.0 / 16;             // head room over the prediction; doubled by every re-run
+    int optimistic = 1;                        // GMX_OPT_OPTIMISTIC: 0 off, 1 on, 2 on with bounds that are too small (tests)
+    uint64_t n_optimistic = 0, n_rerun = 0;
+    // instrumentation (event pairs per chunk parity: a chunk's times are folded in when it is settled)
+    int par = 0;
+    cudaEvent_t ev[2][ST_COUNT][2];
+    bool ev_used[2][ST_COUNT];
     float stage_ms[ST_COUNT];
     uint64_t stage_units[ST_COUNT], stage_bytes[ST_COUNT];
     int32_t stage_launches[ST_COUNT];
@@ -172,26 +188,30 @@ struct gmx_ctx {
 
 static inline unsigned nblk(int64_t n, int b) { return (unsigned)((n + b - 1) / b); }
 
-static void stage_begin(gmx_ctx *ctx, int st) { cudaEventRecord(ctx->ev[st][0], ctx->stream); }
+static void stage_begin(gmx_ctx *ctx, int st) { cudaEventRecord(ctx->ev[ctx->par][st][0], ctx->stream); }
 static void stage_end(gmx_ctx *ctx, int st, uint64_t units, uint64_t bytes, int launches)
 {
-    cudaEventRecord(ctx->ev[st][1], ctx->stream);
-    ctx->ev_used[st] = true;
+    cudaEventRecord(ctx->ev[ctx->par][st][1], ctx->stream);
+    ctx->ev_used[ctx->par][st] = true;
     ctx->stage_units[st] += units; ctx->stage_bytes[st] += bytes; ctx->stage_launches[st] += launches;
 }
-// fold the event pairs of the chunk just finished into the running totals (stream must be idle)
-static void stage_collect(gmx_ctx *ctx)
+// fold the event pairs of a finished chunk (parity `par`, default: the current one) into the running totals
+static void stage_collect(gmx_ctx *ctx, int par = -1)
 {
+    if (par < 0) par = ctx->par;
     for (int s = 0; s < ST_COUNT; ++s)
-        if (ctx->ev_used[s]) {
+        if (ctx->ev_used[par][s]) {
             float ms = 0;
-            if (cudaEventElapsedTime(&ms, ctx->ev[s][0], ctx->ev[s][1]) == cudaSuccess) ctx->stage_ms[s] += ms;
-            ctx->ev_used[s] = false;
+            if (cudaEventElapsedTime(&ms, ctx->ev[par][s][0], ctx->ev[par][s][1]) == cudaSuccess) ctx->stage_ms[s] += ms;
+            ctx->ev_used[par][s] = false;
         }
 }
 static void stage_reset(gmx_ctx *ctx)
 {
-    for (int s = 0; s < ST_COUNT; ++s) { ctx->stage_ms[s] = 0; ctx->stage_units[s] = 0; ctx->stage_bytes[s] = 0; ctx->stage_launches[s] = 0; ctx->ev_used[s] = false; }
+    for (int s = 0; s < ST_COUNT; ++s) {
+        ctx->stage_ms[s] = 0; ctx->stage_units[s] = 0; ctx->stage_bytes[s] = 0; ctx->stage_launches[s] = 0;
+        ctx->ev_used[0][s] = ctx->ev_used[1][s] = false;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -352,7 +372,10 @@ extern "C" int gmx_create(gmx_ctx **out, const gmx_index *index, const gmx_param
     for (int b = 0; b < 2; ++b) { CK(cudaEventCreateWithFlags(&ctx->up_ev[b], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&ctx->done_ev[b], cudaEventDisableTiming)); }
     CK(cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
     for (int b = 0; b < 2; ++b) { CK(cudaEventCreateWithFlags(&ctx->gather_ev[b], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&ctx->dl_ev[b], cudaEventDisableTiming)); }
-    for (int s = 0; s < ST_COUNT; ++s) { CK(cudaEventCreate(&ctx->ev[s][0])); CK(cudaEventCreate(&ctx->ev[s][1])); }
+    for (int b = 0; b < 2; ++b) {
+        for (int s = 0; s < ST_COUNT; ++s) { CK(cudaEventCreate(&ctx->ev[b][s][0])); CK(cudaEventCreate(&ctx->ev[b][s][1])); }
+        CK(cudaEventCreateWithFlags(&ctx->settle_ev[b], cudaEventDisableTiming));
+    }
     stage_reset(ctx);
     cudaDeviceGetAttribute(&ctx->n_sm, cudaDevAttrMultiProcessorCount, device);
 
@@ -445,7 +468,10 @@ extern "C" void gmx_destroy(gmx_ctx *ctx)
     for (DevBuf *b : bufs) b->release();
     ctx->h_best_cigar.release();
     ctx->h_counters.release();
-    if (ctx->ev[0][0]) for (int s = 0; s < ST_COUNT; ++s) { cudaEventDestroy(ctx->ev[s][0]); cudaEventDestroy(ctx->ev[s][1]); }
+    for (int b = 0; b < 2; ++b) {
+        for (int s = 0; s < ST_COUNT; ++s) { if (ctx->ev[b][s][0]) cudaEventDestroy(ctx->ev[b][s][0]); if (ctx->ev[b][s][1]) cudaEventDestroy(ctx->ev[b][s][1]); }
+        if (ctx->settle_ev[b]) cudaEventDestroy(ctx->settle_ev[b]);
+    }
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
     if (ctx->d2h_stream) { cudaStreamSynchronize(ctx->d2h_stream); cudaStreamDestroy(ctx->d2h_stream); }
     for (int b = 0; b < 2; ++b) { if (ctx->done_ev[b]) cudaEventDestroy(ctx->done_ev[b]); if (ctx->up_ev[b]) cudaEventDestroy(ctx->up_ev[b]); if (ctx->gather_ev[b]) cudaEventDestroy(ctx->gather_ev[b]); if (ctx->dl_ev[b]) cudaEventDestroy(ctx->dl_ev[b]); }
@@ -793,7 +819,8 @@ extern "C" int gmx_pair_hmm(gmx_ctx *ctx, const gmx_reads *reads, int64_t n_task
 // batch pipeline
 // ------------------------------------------------------------------------------------------------
 struct Counters {            // device-resident scalars, reset before every vote attempt
-    uint32_t n_cand, cand_overflow, n_leaders, n_accepted, arena_overflow, pad[3];
+    uint32_t n_cand, cand_overflow, n_leaders, n_accepted, arena_overflow;
+    uint32_t live_cand, live_lead, bad;                                  // optimistic chunks: k_seal_candidates / k_seal_leaders
     unsigned long long arena_used;
     uint32_t cls_count[GMX_N_CLASSES], cls_cursor[GMX_N_CLASSES];        // exact classes
     uint32_t fcls_count[GMX_N_CLASSES], fcls_cursor[GMX_N_CLASSES];      // filter classes
@@ -801,6 +828,29 @@ struct Counters {            // device-resident scalars, reset before every vote
 struct ChunkStats {          // device-resident, reset once per chunk: lookups, search steps, SA hits
     unsigned long long v[4];
 };
+struct HostCounters { Counters c; ChunkStats s; };
+
+__global__ void k_publish_words(const uint32_t *src, uint32_t *dst, int n)
+{
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+}
+
+static int settle_chunk(gmx_ctx *ctx, int par);
+static int settle_all(gmx_ctx *ctx) { for (int b = 0; b < 2; ++b) { int r = settle_chunk(ctx, b); if (r != GMX_OK) return r; } return GMX_OK; }
+
+// algorithmic work of the seed / vote stages (DESIGN.md "Roofline"): every backward-search step reads two 64-byte occ
+// blocks; every SA hit reads one 4-byte entry of the de-sampled suffix array
+static void account_seed_vote(gmx_ctx *ctx, const ChunkStats &s)
+{
+    ctx->stage_units[ST_SEED] += s.v[0]; ctx->stage_bytes[ST_SEED] += s.v[1] * 128ull + (ctx->ix.tab_len > 0 ? s.v[0] * 8ull : 0ull);
+    ctx->stage_units[ST_VOTE] += s.v[2]; ctx->stage_bytes[ST_VOTE] += s.v[2] * 4ull;
+}
+static uint64_t scatter_bytes_per_hit(const DevParams &P, int max_len)
+{
+    // per accepted (position, strand): one float RMW per aligned base and plane, Normal mode after bin
+    // aggregation: ceil(len / gen_size) RMWs
+    return P.mode == GMX_MODE_NORMAL ? 8ull * ((uint64_t)(max_len + P.gen_size - 1) / P.gen_size) : (P.mode == GMX_MODE_BS ? 16ull : 48ull) * (uint64_t)max_len;
+}
 
 template <int SL, int WARPS>
 static cudaError_t launch_vote(gmx_ctx *ctx, const SeedStore &S, const ClassLists &C, int cls, const CandSink &sink, int n_sm)
@@ -833,10 +883,17 @@ static cudaError_t launch_filter(gmx_ctx *ctx, const SeedStore &S, const ClassLi
 }
 
 // PHASE A for reads [lo, hi) of the batch; leaves its results resident on the device (ctx->cs).
-static int phase_a(gmx_ctx *ctx, const gmx_reads *reads, int32_t lo, int32_t hi, int slot)
+//
+// `opt`: issue the chunk without waiting for its counts.  Needs a prediction (ctx->pred_*) from a settled chunk; the
+// candidate list, the sort and every grid behind it are sized by the predicted bound, the kernels read the real counts on
+// the device, and settle_chunk() checks one chunk later that the bounds held.
+static int phase_a(gmx_ctx *ctx, const gmx_reads *reads, int32_t lo, int32_t hi, int slot, bool opt = false)
 {
     gmx_ctx::ChunkState &cs = ctx->cs;
     cs.valid = false;
+    if (!opt) { int r = settle_all(ctx); if (r != GMX_OK) return r; }      // a synchronous chunk reads the counters in place
+    ctx->par = ctx->pend[0].active ? 1 : 0;
+    if (ctx->pend[ctx->par].active) { int r = settle_chunk(ctx, ctx->par); if (r != GMX_OK) return r; }
     const int32_t n = hi - lo;
     const int64_t n_tasks = 2 * (int64_t)n;
     int32_t max_len = 0;
@@ -894,10 +951,16 @@ static int phase_a(gmx_ctx *ctx, const gmx_reads *reads, int32_t lo, int32_t hi,
     CK(cudaGetLastError());
     stage_end(ctx, ST_SEED, 0, 0, 1);
 
-    struct HostCounters { Counters c; ChunkStats s; };
-    CK(ctx->h_counters.ensure(sizeof(HostCounters)));
-    HostCounters &hc = *ctx->h_counters.as<HostCounters>();          // pinned: the two small D2H copies per chunk stay asynchronous
-    uint32_t n_cand = 0;
+    CK(ctx->h_counters.ensure(2 * sizeof(HostCounters)));
+    HostCounters &hc = ctx->h_counters.as<HostCounters>()[ctx->par];   // pinned: the small D2H copies per chunk stay asynchronous
+    uint32_t n_cand = 0, lead_cap = 0;
+    if (opt) {
+        const double room = ctx->optimistic == 2 ? 0.5 : 1.0 + ctx->pred_margin;
+        const double slack = ctx->optimistic == 2 ? 0 : 16384;
+        n_cand = (uint32_t)std::min<double>(0x7ffffff0, (double)n * ctx->pred_cand * room + slack + 2);
+        lead_cap = (uint32_t)std::min<double>(n_cand, (double)n * ctx->pred_lead * room + slack + 1);
+        ctx->cand_cap = std::max<size_t>(ctx->cand_cap, n_cand);
+    }
     for (int attempt = 0;; ++attempt) {
         CK(cudaMemsetAsync(dc, 0, sizeof(Counters), ctx->stream));
         CK(ctx->d_keys.ensure(ctx->cand_cap * 8));
@@ -908,8 +971,9 @@ static int phase_a(gmx_ctx *ctx, const gmx_reads *reads, int32_t lo, int32_t hi,
         stage_end(ctx, ST_CLASSIFY, (uint64_t)n_tasks, (uint64_t)n_tasks * 8, 1);
 
         // K1b + K1c.  Twelve kernels cover the task classes (6 filter + 6 exact); a uniform workload fills one or two of
-        // them.  Only the classes that held tasks in the previous chunk are launched up front; once the counters are back
-        // (the host needs them anyway), a class that turned out non-empty without having been launched is launched then.
+        // them.  Only the classes that held tasks in the previous chunk are launched up front.  A synchronous chunk then
+        // reads the counters back and launches any class that turned out non-empty without having been launched; an
+        // optimistic chunk lets k_seal_candidates void it in that case.
         CandSink sink; sink.keys = ctx->d_keys.as<unsigned long long>(); sink.count = &dc->n_cand; sink.overflow = &dc->cand_overflow; sink.cap = (uint32_t)ctx->cand_cap;
         auto launch_class = [&](int k) -> cudaError_t {         // k: 0..5 filter classes, 6..11 exact classes
             if (k < GMX_N_CLASSES) {
@@ -970,6 +1034,14 @@ static int phase_a(gmx_ctx *ctx, const gmx_reads *reads, int32_t lo, int32_t hi,
         for (int k = 0; k < 2 * GMX_N_CLASSES; ++k)
             if ((ctx->class_hint >> k) & 1u) { CK(launch_class(k)); launched |= 1u << k; n_launch++; }
         stage_end(ctx, ST_VOTE, 0, 0, n_launch);
+        if (opt) {
+            SealIn in;
+            in.n_cand = &dc->n_cand; in.cand_overflow = &dc->cand_overflow; in.arena_overflow = &dc->arena_overflow;
+            in.cls_count = dc->cls_count; in.fcls_count = dc->fcls_count; in.launched = launched; in.bound = n_cand;
+            k_seal_candidates<<<nblk(n_cand, 256), 256, 0, ctx->stream>>>(in, sink.keys, &dc->live_cand, &dc->bad);
+            CK(cudaGetLastError());
+            break;
+        }
         CK(cudaMemcpyAsync(&hc, dc, sizeof(hc), cudaMemcpyDeviceToHost, ctx->stream));
         { int r = finish_scan(ctx, slot ^ 1); if (r != GMX_OK) return r; }      // host work for the next chunk while the vote runs
         CK(cudaStreamSynchronize(ctx->stream));
@@ -1008,11 +1080,11 @@ static int phase_a(gmx_ctx *ctx, const gmx_reads *reads, int32_t lo, int32_t hi,
         n_cand = hc.c.n_cand;
         break;
     }
-    if (hc.s.v[3]) { ctx->err = "device-resident gmx_reads: a read is longer than gmx_reads.max_len (or has a negative length)"; return GMX_ERR_INVALID; }
-    // algorithmic work of the seed / vote stages (DESIGN.md "Roofline"): every backward-search step reads two
-    // 64-byte occ blocks; every SA hit reads one 4-byte entry of the de-sampled suffix array
-    ctx->stage_units[ST_SEED] += hc.s.v[0]; ctx->stage_bytes[ST_SEED] += hc.s.v[1] * 128ull + (ctx->ix.tab_len > 0 ? hc.s.v[0] * 8ull : 0ull);
-    ctx->stage_units[ST_VOTE] += hc.s.v[2]; ctx->stage_bytes[ST_VOTE] += hc.s.v[2] * 4ull;
+    const uint32_t *live_c = opt ? &dc->live_cand : nullptr, *live_l = opt ? &dc->live_lead : nullptr;
+    if (!opt) {
+        if (hc.s.v[3]) { ctx->err = "device-resident gmx_reads: a read is longer than gmx_reads.max_len (or has a negative length)"; return GMX_ERR_INVALID; }
+        account_seed_vote(ctx, hc.s);
+    }
 
     // restore the reference's processing order: (task, round, position)
     unsigned long long *keys = ctx->d_keys.as<unsigned long long>();
@@ -1024,7 +1096,7 @@ static int phase_a(gmx_ctx *ctx, const gmx_reads *reads, int32_t lo, int32_t hi,
         CK(ctx->d_sort_tmp.ensure(tmp_bytes));
         CK(cub::DeviceRadixSort::SortKeys(ctx->d_sort_tmp.p, tmp_bytes, keys, ctx->d_keys_alt.as<unsigned long long>(), (int)n_cand, 0, 40 + task_bits, ctx->stream));
         keys = ctx->d_keys_alt.as<unsigned long long>();
-        stage_end(ctx, ST_SORT, n_cand, (uint64_t)n_cand * 16, 1);
+        stage_end(ctx, ST_SORT, opt ? 0 : n_cand, opt ? 0 : (uint64_t)n_cand * 16, 1);
     }
 
     size_t nc = std::max<uint32_t>(n_cand, 1);
@@ -1034,10 +1106,11 @@ static int phase_a(gmx_ctx *ctx, const gmx_reads *reads, int32_t lo, int32_t hi,
     // GetString + K2a
     if (n_cand) {
         stage_begin(ctx, ST_NW);
-        k_cand_score<<<nblk(n_cand, 128), 128, 0, ctx->stream>>>(ctx->ix, ctx->dreads, ctx->tab, P, keys, n_cand, ctx->d_score.as<float>());
+        k_cand_score<<<nblk(n_cand, 128), 128, 0, ctx->stream>>>(ctx->ix, ctx->dreads, ctx->tab, P, keys, n_cand, ctx->d_score.as<float>(), live_c);
         CK(cudaGetLastError());
         // per candidate: 2-bit window (n/4 B) + read bases and qualities (2n B) + key (8 B) + score (4 B)
-        stage_end(ctx, ST_NW, (uint64_t)n_cand * (uint64_t)std::max(7 * max_len - 12, 0), (uint64_t)n_cand * (uint64_t)(max_len / 4 + 2 * max_len + 12), 1);
+        const uint32_t nc_acc = opt ? 0 : n_cand;
+        stage_end(ctx, ST_NW, (uint64_t)nc_acc * (uint64_t)std::max(7 * max_len - 12, 0), (uint64_t)nc_acc * (uint64_t)(max_len / 4 + 2 * max_len + 12), 1);
     }
 
     // acceptance, grouping, denominator, best group
@@ -1052,7 +1125,7 @@ static int phase_a(gmx_ctx *ctx, const gmx_reads *reads, int32_t lo, int32_t hi,
     stage_begin(ctx, ST_FINALIZE);
     CK(cudaMemsetAsync(ctx->d_groups.p, 0, (size_t)n * 4, ctx->stream));
     CK(cudaMemsetAsync(ctx->d_ranges.p, 0, (size_t)n * 8, ctx->stream));
-    if (n_cand) { k_cand_ranges<<<nblk(n_cand, 256), 256, 0, ctx->stream>>>(keys, n_cand, ctx->d_ranges.as<uint32_t>()); CK(cudaGetLastError()); }
+    if (n_cand) { k_cand_ranges<<<nblk(n_cand, 256), 256, 0, ctx->stream>>>(keys, n_cand, ctx->d_ranges.as<uint32_t>(), live_c); CK(cudaGetLastError()); }
     k_finalize_reads<<<nblk((int64_t)n * 32, 128), 128, 0, ctx->stream>>>(ctx->ix, ctx->dreads, P, ctx->d_prep.as<ReadPrep>(), keys, ctx->d_score.as<float>(), n_cand, O);
     CK(cudaGetLastError());
     if (n_cand) {
@@ -1061,17 +1134,23 @@ static int phase_a(gmx_ctx *ctx, const gmx_reads *reads, int32_t lo, int32_t hi,
         CK(ctx->d_sort_tmp.ensure(scan_bytes));
         CK(cub::DeviceScan::ExclusiveSum(ctx->d_sort_tmp.p, scan_bytes, ctx->d_groups.as<uint32_t>(), ctx->d_read_base.as<uint32_t>(), (int)n, ctx->stream));
         k_assign_slots<<<nblk(n_cand, 256), 256, 0, ctx->stream>>>(keys, ctx->d_leader.as<int32_t>(), ctx->d_slot.as<int32_t>(), ctx->d_read_base.as<uint32_t>(),
-                                                                  ctx->d_lead_cand.as<uint32_t>(), n_cand, &dc->n_leaders, &dc->n_accepted);
+                                                                  ctx->d_lead_cand.as<uint32_t>(), n_cand, &dc->n_leaders, &dc->n_accepted,
+                                                                  live_c, opt ? lead_cap : 0xffffffffu);
         CK(cudaGetLastError());
     }
+    if (opt) { k_seal_leaders<<<1, 1, 0, ctx->stream>>>(&dc->n_leaders, lead_cap, &dc->live_cand, &dc->live_lead, &dc->bad); CK(cudaGetLastError()); }
     stage_end(ctx, ST_FINALIZE, (uint64_t)n, 0, 4);
 
-    CK(cudaMemcpyAsync(&hc.c, dc, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    stage_collect(ctx);
+    if (!opt) {
+        CK(cudaMemcpyAsync(&hc.c, dc, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        stage_collect(ctx);
+        if (n > 0) { ctx->pred_cand = (double)n_cand / n; ctx->pred_lead = (double)hc.c.n_leaders / n; }
+    }
 
     cs.lo = lo; cs.n = n; cs.max_len = max_len; cs.total_bases = total_bases;
-    cs.n_cand = n_cand; cs.n_leaders = hc.c.n_leaders; cs.n_accepted = hc.c.n_accepted; cs.keys = keys;
+    cs.n_cand = n_cand; cs.n_leaders = opt ? lead_cap : hc.c.n_leaders; cs.n_accepted = opt ? 0 : hc.c.n_accepted; cs.keys = keys;
+    cs.opt = opt; cs.live_cand = live_c; cs.live_lead = live_l;
     LeaderStore &L = cs.L;
     L.lead_cand = ctx->d_lead_cand.as<uint32_t>();
     L.a_stride = max_len + 2 * P.max_gap + 8; L.c_stride = GMX_CIGAR_STRIDE; L.max_len = max_len;
@@ -1098,9 +1177,10 @@ static int phase_b(gmx_ctx *ctx)
     const int want_aligned = (P.mode == GMX_MODE_BS || ctx->collect_hits) ? 1 : 0;
     stage_begin(ctx, ST_TRACEBACK);
     k_traceback<<<nblk(n_leaders, 128), 128, 0, ctx->stream>>>(ctx->ix, ctx->dreads, ctx->tab, P, cs.keys, n_leaders, L,
-                                                              ctx->d_moves.as<uint32_t>(), want_aligned, ctx->d_multi_count.as<uint32_t>() + 1);
+                                                              ctx->d_moves.as<uint32_t>(), want_aligned, ctx->d_multi_count.as<uint32_t>() + 1, cs.live_lead);
     CK(cudaGetLastError());
-    stage_end(ctx, ST_TRACEBACK, (uint64_t)n_leaders * (uint64_t)std::max(7 * max_len - 12, 0), 0, 1);
+    const uint32_t nl_acc = cs.opt ? 0 : n_leaders;        // an optimistic chunk's work is accounted when it is settled
+    stage_end(ctx, ST_TRACEBACK, (uint64_t)nl_acc * (uint64_t)std::max(7 * max_len - 12, 0), 0, 1);
     if (P.mode == GMX_MODE_SNP) {
         if (max_len > 32 * GMX_PHMM_MAXC) { ctx->err = "SNP mode: reads longer than 256 bp are not supported by the pair-HMM kernel"; return GMX_ERR_UNSUPPORTED; }
         CK(ctx->d_hmm.ensure((size_t)n_leaders * max_len * 5 * 4));
@@ -1120,7 +1200,7 @@ static int phase_b(gmx_ctx *ctx)
         CK(cudaMemsetAsync(cursor, 0, 4, ctx->stream));
         int launches = 1;
         double *scr = ctx->d_phmm_scratch.as<double>();
-#define GMX_PHMM_LAUNCH(CT) k_pair_hmm_leaders<CT><<<grid, GMX_PHMM_THREADS, 0, ctx->stream>>>(ctx->ix, ctx->dreads, ctx->tab, cs.keys, L, n_leaders, cursor, scr, per_task)
+#define GMX_PHMM_LAUNCH(CT) k_pair_hmm_leaders<CT><<<grid, GMX_PHMM_THREADS, 0, ctx->stream>>>(ctx->ix, ctx->dreads, ctx->tab, cs.keys, L, n_leaders, cursor, scr, per_task, cs.live_lead)
         switch (C) {
             case 1: GMX_PHMM_LAUNCH(1); break;
             case 2: GMX_PHMM_LAUNCH(2); break;
@@ -1131,17 +1211,13 @@ static int phase_b(gmx_ctx *ctx)
         }
 #undef GMX_PHMM_LAUNCH
         CK(cudaGetLastError());
-        stage_end(ctx, ST_PHMM, (uint64_t)n_leaders * (uint64_t)max_len * (uint64_t)max_len, 0, launches);
+        stage_end(ctx, ST_PHMM, (uint64_t)nl_acc * (uint64_t)max_len * (uint64_t)max_len, 0, launches);
     }
     stage_begin(ctx, ST_SCATTER);
     k_scatter<<<nblk(n_cand, 128), 128, 0, ctx->stream>>>(ctx->ix, ctx->dreads, P, cs.keys, ctx->d_score.as<float>(), ctx->d_leader.as<int32_t>(),
-                                                                        ctx->d_slot.as<int32_t>(), n_cand, ctx->d_results.as<gmx_read_result>(), L, ctx->acc);
+                                                                        ctx->d_slot.as<int32_t>(), n_cand, ctx->d_results.as<gmx_read_result>(), L, ctx->acc, cs.live_cand);
     CK(cudaGetLastError());
-    // per accepted (position, strand): one float RMW per aligned base and plane, Normal mode
-    // after bin aggregation: ceil(len / gen_size) RMWs
-    uint64_t per_hit = P.mode == GMX_MODE_NORMAL ? 8ull * ((uint64_t)(max_len + P.gen_size - 1) / P.gen_size)
-                                                  : (P.mode == GMX_MODE_BS ? 16ull : 48ull) * (uint64_t)max_len;
-    stage_end(ctx, ST_SCATTER, cs.n_accepted, (uint64_t)cs.n_accepted * per_hit, 1);
+    stage_end(ctx, ST_SCATTER, cs.n_accepted, (uint64_t)cs.n_accepted * scatter_bytes_per_hit(P, max_len), 1);
     return GMX_OK;
 }
 
@@ -1168,12 +1244,12 @@ static int download_chunk(gmx_ctx *ctx, bool scored, gmx_read_result *results_ou
         char *d_cig = ctx->d_batch_cigar.as<char>() + (size_t)lo * GMX_CIGAR_STRIDE;
         if (scored && n_cand && ctx->multi_cap) {                           // positions of multi-position best groups (SAM row)
             k_gather_multi<<<nblk(n_cand, 256), 256, 0, ctx->stream>>>(cs.keys, ctx->d_leader.as<int32_t>(), n_cand, ctx->d_results.as<gmx_read_result>(),
-                                                                      lo, ctx->d_multi.as<MultiPos>(), ctx->d_multi_count.as<uint32_t>(), ctx->multi_cap);
+                                                                      lo, ctx->d_multi.as<MultiPos>(), ctx->d_multi_count.as<uint32_t>(), ctx->multi_cap, cs.live_cand);
             CK(cudaGetLastError());
         }
         k_gather_best<<<nblk(n, 128), 128, 0, ctx->stream>>>(ctx->d_results.as<gmx_read_result>(), d_res, n,
                                                            ctx->d_slot.as<int32_t>(), L, d_cig, GMX_CIGAR_STRIDE,
-                                                           scored && n_leaders ? 1 : 0);
+                                                           scored && n_leaders ? 1 : 0, cs.live_lead);
         CK(cudaGetLastError());
         const int sl = ctx->dl_slot; ctx->dl_slot ^= 1;
         CK(cudaEventRecord(ctx->gather_ev[sl], ctx->stream));
@@ -1249,6 +1325,77 @@ static int download_chunk(gmx_ctx *ctx, bool scored, gmx_read_result *results_ou
     return GMX_OK;
 }
 
+// ---- optimistic chunks ----------------------------------------------------------------------------
+static bool chunk_can_be_optimistic(const gmx_ctx *ctx, bool do_score)
+{
+    return do_score && ctx->optimistic && !ctx->collect_hits && ctx->pred_cand >= 0;
+}
+
+// behind the last kernel of an optimistic chunk: its counters leave for the host, the chunk waits to be settled
+static int chunk_mark_pending(gmx_ctx *ctx, const gmx_reads *reads, int slot, gmx_read_result *results)
+{
+    const int par = ctx->par;
+    gmx_ctx::Pending &pd = ctx->pend[par];
+    // stored by a kernel straight into the pinned host words: a copy would queue on the D2H engine behind the chunk's own
+    // result download, and the next chunk's kernels behind the copy (measured: 0.6 ms of idle GPU per chunk)
+    static_assert(sizeof(HostCounters) % 4 == 0, "word copy");
+    k_publish_words<<<1, 64, 0, ctx->stream>>>(ctx->d_counters.as<uint32_t>(), reinterpret_cast<uint32_t *>(&ctx->h_counters.as<HostCounters>()[par]),
+                                              (int)(sizeof(HostCounters) / 4));
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->settle_ev[par], ctx->stream));
+    pd.active = true; pd.lo = ctx->cs.lo; pd.hi = ctx->cs.lo + ctx->cs.n; pd.max_len = ctx->cs.max_len; pd.slot = slot;
+    pd.reads = *reads; pd.results = results;
+    ctx->n_optimistic++;
+    return GMX_OK;
+}
+
+// one chunk, PHASE A + B + download, in whichever way is possible
+static int run_chunk(gmx_ctx *ctx, const gmx_reads *reads, int32_t lo, int32_t hi, int slot, gmx_read_result *results, bool opt)
+{
+    int r = phase_a(ctx, reads, lo, hi, slot, opt);
+    if (r == GMX_OK) r = phase_b(ctx);
+    if (r == GMX_OK) r = download_chunk(ctx, true, results);
+    if (r == GMX_OK && opt) r = chunk_mark_pending(ctx, reads, slot, results);
+    return r;
+}
+
+// Wait for the optimistic chunk of parity `par`, fold its counters into the statistics and the next prediction -- or, when
+// k_seal_* voided it (nothing of it reached the accumulators or the multi-position list), run it again the synchronous
+// way.  Its reads are still where they were: the caller issues the upload that reuses their buffers after this.
+static int settle_chunk(gmx_ctx *ctx, int par)
+{
+    gmx_ctx::Pending &pd = ctx->pend[par];
+    if (!pd.active) return GMX_OK;
+    pd.active = false;
+    CK(cudaEventSynchronize(ctx->settle_ev[par]));
+    stage_collect(ctx, par);
+    const HostCounters hc = ctx->h_counters.as<HostCounters>()[par];
+    if (hc.s.v[3]) { ctx->err = "device-resident gmx_reads: a read is longer than gmx_reads.max_len (or has a negative length)"; return GMX_ERR_INVALID; }
+    const int32_t n = pd.hi - pd.lo;
+    if (hc.c.bad) {
+        ctx->n_rerun++;
+        ctx->pred_margin = std::min(4.0, ctx->pred_margin * 2);
+        uint32_t need = 0;
+        for (int c = 0; c < GMX_N_CLASSES; ++c) { if (hc.c.fcls_count[c]) need |= 1u << c; if (hc.c.cls_count[c]) need |= 1u << (GMX_N_CLASSES + c); }
+        ctx->class_hint |= need;
+        const gmx_reads again = pd.reads;
+        return run_chunk(ctx, &again, pd.lo, pd.hi, pd.slot, pd.results, false);
+    }
+    account_seed_vote(ctx, hc.s);
+    const DevParams &P = ctx->dparams;
+    const uint64_t nc = hc.c.n_cand, nl = hc.c.n_leaders, na = hc.c.n_accepted, L = (uint64_t)pd.max_len;
+    ctx->stage_units[ST_SORT] += nc; ctx->stage_bytes[ST_SORT] += nc * 16;
+    ctx->stage_units[ST_NW] += nc * (uint64_t)std::max(7 * pd.max_len - 12, 0); ctx->stage_bytes[ST_NW] += nc * (L / 4 + 2 * L + 12);
+    ctx->stage_units[ST_TRACEBACK] += nl * (uint64_t)std::max(7 * pd.max_len - 12, 0);
+    if (P.mode == GMX_MODE_SNP) ctx->stage_units[ST_PHMM] += nl * L * L;
+    ctx->stage_units[ST_SCATTER] += na; ctx->stage_bytes[ST_SCATTER] += na * scatter_bytes_per_hit(P, pd.max_len);
+    if (n > 0) { ctx->pred_cand = (double)nc / n; ctx->pred_lead = (double)nl / n; }
+    uint32_t need = 0;
+    for (int c = 0; c < GMX_N_CLASSES; ++c) { if (hc.c.fcls_count[c]) need |= 1u << c; if (hc.c.cls_count[c]) need |= 1u << (GMX_N_CLASSES + c); }
+    if (need) ctx->class_hint = need;
+    return GMX_OK;
+}
+
 static int batch_max_len(gmx_ctx *ctx, const gmx_reads *reads, int32_t *out)
 {
     return scan_max_len(ctx, reads, 0, reads->n_reads, out);
@@ -1288,6 +1435,7 @@ static int run_batch(gmx_ctx *ctx, const gmx_reads *reads, gmx_read_result *resu
         cudaStreamSynchronize(ctx->stream); cudaStreamSynchronize(ctx->copy_stream); cudaStreamSynchronize(ctx->d2h_stream);
         cudaGetLastError();
         ctx->cs.valid = false; ctx->mapped = false; ctx->scored = false; ctx->keep_valid = false;
+        ctx->pend[0].active = ctx->pend[1].active = false;
         ctx->up_scan[0].reads = nullptr; ctx->up_scan[1].reads = nullptr;
         ctx->err = why;
     }
@@ -1328,6 +1476,7 @@ static int batch_begin(gmx_ctx *ctx, int32_t n, int32_t max_len, gmx_read_result
 // after the last chunk has been issued: drain, fold the counters, mark the batch
 static int batch_end(gmx_ctx *ctx, bool do_score)
 {
+    { int r = settle_all(ctx); if (r != GMX_OK) return r; }
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaStreamSynchronize(ctx->d2h_stream));
     stage_collect(ctx);
@@ -1370,18 +1519,30 @@ static int run_batch_impl(gmx_ctx *ctx, const gmx_reads *reads, gmx_read_result 
     int slot = 0;
     for (size_t c = 0; c + 1 < cuts.size(); ++c, slot ^= 1) {
         const int32_t lo = cuts[c], hi = cuts[c + 1];
-        if (hi < n) {   // buffer set slot^1 was last read by chunk i-1: its kernels must have drained first
+        auto next_upload = [&]() -> int {
+            if (hi >= n) return GMX_OK;
+            // buffer set slot^1 was last read by chunk c-1: its kernels must have drained first
             CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->done_ev[slot ^ 1], 0));
-            int r = issue_upload(ctx, reads, hi, cuts[c + 2], slot ^ 1, ctx->copy_stream);
-            if (r != GMX_OK) return r;
-        }
-        int r = phase_a(ctx, reads, lo, hi, slot);
+            return issue_upload(ctx, reads, hi, cuts[c + 2], slot ^ 1, ctx->copy_stream);
+        };
+        // chunk c-1 may still be waiting to be settled, and a chunk that has to be run again needs its reads where they
+        // are: then the upload that overwrites them is issued after the settling, below
+        const int prev = ctx->pend[0].active ? 0 : (ctx->pend[1].active ? 1 : -1);
+        if (prev < 0) { int r = next_upload(); if (r != GMX_OK) return r; }
+        const bool opt = chunk_can_be_optimistic(ctx, do_score);
+        int r = phase_a(ctx, reads, lo, hi, slot, opt);
         if (r != GMX_OK) return r;
         const bool last_and_split = !do_score && hi == n && lo == 0;       // single-chunk map_batch: PHASE B may follow
         if (do_score) { r = phase_b(ctx); if (r != GMX_OK) return r; }
         r = download_chunk(ctx, do_score, results);
         if (r != GMX_OK) return r;
         CK(cudaEventRecord(ctx->done_ev[slot], ctx->stream));
+        if (opt) { r = chunk_mark_pending(ctx, reads, slot, results); if (r != GMX_OK) return r; }
+        if (prev >= 0) {                                                   // the GPU has chunk c queued while the host waits for c-1
+            r = settle_chunk(ctx, prev);
+            if (r == GMX_OK) r = next_upload();
+            if (r != GMX_OK) return r;
+        }
         if (!last_and_split && !do_score) ctx->cs.valid = false;
     }
     if (do_score) ctx->cs.valid = false;
@@ -1451,6 +1612,14 @@ extern "C" int gmx_score_batch(gmx_ctx *ctx, gmx_read_result *results)
     return run_batch(ctx, &again, results, true);
 }
 
+extern "C" int gmx_chunk_stats(gmx_ctx *ctx, uint64_t *optimistic, uint64_t *rerun)
+{
+    if (!ctx) return GMX_ERR_INVALID;
+    if (optimistic) *optimistic = ctx->n_optimistic;
+    if (rerun) *rerun = ctx->n_rerun;
+    return GMX_OK;
+}
+
 extern "C" int gmx_set_option(gmx_ctx *ctx, int option, int64_t value)
 {
     if (!ctx) return GMX_ERR_INVALID;
@@ -1467,6 +1636,7 @@ extern "C" int gmx_set_option(gmx_ctx *ctx, int option, int64_t value)
         case GMX_OPT_FASTQ_PIECE:
             if (value < 0) { ctx->err = "fastq piece bytes must be >= 0"; return GMX_ERR_INVALID; }
             ctx->fq_piece_bytes = value; return GMX_OK;
+        case GMX_OPT_OPTIMISTIC: ctx->optimistic = value < 0 ? 0 : (value > 2 ? 2 : (int)value); return GMX_OK;
         case GMX_OPT_VOTE_COMPACT: ctx->vote_compact = value < 0 ? 0 : (value > 2 ? 2 : (int)value); return GMX_OK;
         case GMX_OPT_CIGAR_STRIDE:
             if (value < 16 || value > 2048 || (value & 15)) { ctx->err = "cigar_stride must be a multiple of 16 in 16..2048"; return GMX_ERR_INVALID; }
@@ -1790,10 +1960,10 @@ static int process_fastq_pipelined(gmx_ctx *ctx, const char *text, int64_t len, 
         const int64_t step = (int64_t)ctx->chunk_reads;
         for (int64_t lo = first; lo < first + n_p; lo += step, slot ^= 1) {
             const int64_t hi = std::min(first + n_p, lo + step);
+            const int prev = ctx->pend[0].active ? 0 : (ctx->pend[1].active ? 1 : -1);
             rc = issue_upload(ctx, &in, (int32_t)lo, (int32_t)hi, slot, ctx->stream);      // device-resident: a view, no copy
-            if (rc == GMX_OK) rc = phase_a(ctx, &in, (int32_t)lo, (int32_t)hi, slot);
-            if (rc == GMX_OK) rc = phase_b(ctx);
-            if (rc == GMX_OK) rc = download_chunk(ctx, true, results);
+            if (rc == GMX_OK) rc = run_chunk(ctx, &in, (int32_t)lo, (int32_t)hi, slot, results, chunk_can_be_optimistic(ctx, true));
+            if (rc == GMX_OK && prev >= 0) rc = settle_chunk(ctx, prev);                   // before the next view takes its slot
             if (rc != GMX_OK) return rc;
         }
         first += n_p;
@@ -1835,6 +2005,7 @@ extern "C" int gmx_process_fastq(gmx_ctx *ctx, const char *text, int64_t len, in
             cudaStreamSynchronize(ctx->stream); cudaStreamSynchronize(ctx->copy_stream); cudaStreamSynchronize(ctx->d2h_stream);
             cudaGetLastError();
             ctx->cs.valid = false;
+            ctx->pend[0].active = ctx->pend[1].active = false;
             ctx->err = why;
         }
         if (r != GMX_ERR_STATE) return r;

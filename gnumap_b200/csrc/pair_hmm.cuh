@@ -415,9 +415,11 @@ __global__ void __launch_bounds__(GMX_PHMM_THREADS) k_pair_hmm_tasks(DevReads R,
 // (one launch per chunk instead of one per wave: no tail of half-empty SMs between waves).
 template <int C_T>
 __global__ void __launch_bounds__(GMX_PHMM_THREADS) k_pair_hmm_leaders(DevIndex ix, DevReads R, DevTables T, const unsigned long long *keys,
-                                                                       LeaderStore L, uint32_t n_leaders, uint32_t *cursor, double *scratch, size_t per_task)
+                                                                       LeaderStore L, uint32_t n_leaders, uint32_t *cursor, double *scratch, size_t per_task,
+                                                                       const uint32_t *live)
 {
     constexpr int CS = C_T > 0 ? C_T : 1;
+    n_leaders = gmx_live(live, n_leaders);
     __shared__ float acc_s[CS * 5 * 32];
     __shared__ double e_s[4 * GMX_PHMM_ESTRIDE(CS)];
     __shared__ uint8_t code_s[CS * 32 + 32];

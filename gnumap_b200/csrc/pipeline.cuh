@@ -849,6 +849,48 @@ __global__ void __launch_bounds__(128) k_vote_gmem(DevIndex ix, SeedStore S, Cla
     }
 }
 
+// ---- counts that live on the device ---------------------------------------------------------------
+// A chunk issued without waiting for its candidate / leader counts (gmx.cu "optimistic chunk") launches its kernels over
+// host-side BOUNDS and hands them the address of the real count: k_seal_candidates / k_seal_leaders store it there, or 0
+// when the chunk has to be run again (a bound was exceeded, a task class was not launched), which turns every kernel behind
+// them into a no-op.  A null address means the bound is the count.
+__device__ __forceinline__ uint32_t gmx_live(const uint32_t *live, uint32_t bound)
+{
+    return live ? min(__ldg(live), bound) : bound;
+}
+
+struct SealIn {
+    const uint32_t *n_cand, *cand_overflow, *arena_overflow;
+    const uint32_t *cls_count, *fcls_count;     // [GMX_N_CLASSES] each
+    uint32_t launched;                           // bit k: filter class k, bit GMX_N_CLASSES + k: exact class k
+    uint32_t bound;                              // candidates the buffers and grids of this chunk cover
+};
+
+// pads the key list up to the sort's element count with keys that sort last, and decides whether the chunk stands
+__global__ void __launch_bounds__(256) k_seal_candidates(SealIn in, unsigned long long *keys, uint32_t *live_cand, uint32_t *bad)
+{
+    const uint32_t n = *in.n_cand;
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n && c < in.bound) keys[c] = ~0ull;
+    if (c == 0) {
+        uint32_t need = 0;
+        for (int k = 0; k < GMX_N_CLASSES; ++k) {
+            if (in.fcls_count[k]) need |= 1u << k;
+            if (in.cls_count[k]) need |= 1u << (GMX_N_CLASSES + k);
+        }
+        const bool ok = n <= in.bound && !*in.cand_overflow && !*in.arena_overflow && !(need & ~in.launched);
+        *live_cand = ok ? n : 0u;
+        *bad = ok ? 0u : 1u;
+    }
+}
+
+__global__ void k_seal_leaders(const uint32_t *n_leaders, uint32_t lead_cap, uint32_t *live_cand, uint32_t *live_lead, uint32_t *bad)
+{
+    const uint32_t n = *n_leaders;
+    if (*bad || n > lead_cap) { *live_cand = 0; *live_lead = 0; *bad = 1; }
+    else *live_lead = n;
+}
+
 // ---- candidate scoring -------------------------------------------------------------------------
 __device__ __forceinline__ void gmx_decode_key(unsigned long long key, uint32_t &task, uint32_t &round, uint32_t &diag)
 {
@@ -857,10 +899,10 @@ __device__ __forceinline__ void gmx_decode_key(unsigned long long key, uint32_t 
 
 // One thread per candidate (inter-task parallelism; the band lives in registers).
 __global__ void __launch_bounds__(128) k_cand_score(DevIndex ix, DevReads R, DevTables T, DevParams P,
-                                                    const unsigned long long *keys, uint32_t n_cand, float *score)
+                                                    const unsigned long long *keys, uint32_t n_cand, float *score, const uint32_t *live)
 {
     uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= n_cand) return;
+    if (c >= gmx_live(live, n_cand)) return;
     uint32_t task, round, diag;
     gmx_decode_key(keys[c], task, round, diag);
     ReadView rd = gmx_read_view(R, (int)(task >> 1), (int)(task & 1));
@@ -902,9 +944,10 @@ __device__ int gmx_key_compare(const DevIndex &ix, uint32_t da, int na, uint32_t
 
 // candidate range of every read in the sorted key list (replaces two binary searches per read): range[2r], range[2r+1];
 // the array is zeroed first, so reads without candidates keep the empty range [0, 0)
-__global__ void k_cand_ranges(const unsigned long long *keys, uint32_t n_cand, uint32_t *range)
+__global__ void k_cand_ranges(const unsigned long long *keys, uint32_t n_cand, uint32_t *range, const uint32_t *live)
 {
     uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    n_cand = gmx_live(live, n_cand);
     if (c >= n_cand) return;
     const uint32_t r = (uint32_t)(keys[c] >> 41);                     // task >> 1
     if (c == 0 || (uint32_t)(keys[c - 1] >> 41) != r) range[2 * r] = c;
@@ -927,17 +970,18 @@ __device__ __forceinline__ double gmx_shfl_xor_f64(double v, int mask)
 // leader rank within the read -> leader slot: slot = read_base[read] + rank (read_base = exclusive scan of the reads'
 // group counts); also counts the leaders and the accepted candidates of the chunk
 __global__ void __launch_bounds__(256) k_assign_slots(const unsigned long long *keys, const int32_t *leader, int32_t *slot, const uint32_t *read_base,
-                                                      uint32_t *lead_cand, uint32_t n_cand, uint32_t *n_leaders, uint32_t *n_accepted)
+                                                      uint32_t *lead_cand, uint32_t n_cand, uint32_t *n_leaders, uint32_t *n_accepted,
+                                                      const uint32_t *live, uint32_t lead_cap)
 {
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool in = c < n_cand;
+    const bool in = c < gmx_live(live, n_cand);
     const bool acc = in && leader[c] >= 0;
     const bool lead = acc && slot[c] >= 0;
     if (lead) {
         const uint32_t r = (uint32_t)(keys[c] >> 41);
         const uint32_t s = read_base[r] + (uint32_t)slot[c];
         slot[c] = (int32_t)s;
-        lead_cand[s] = c;
+        if (s < lead_cap) lead_cand[s] = c;              // beyond the bound: k_seal_leaders voids the chunk
     }
     const uint32_t am = __ballot_sync(0xffffffffu, acc), lm = __ballot_sync(0xffffffffu, lead);
     if ((threadIdx.x & 31) == 0) {
@@ -1248,10 +1292,10 @@ struct LeaderStore {
 // adjacent words (404 MB per million 100-bp groups: noise next to the ALU work)
 __global__ void __launch_bounds__(128) k_traceback(DevIndex ix, DevReads R, DevTables T, DevParams P,
                                                    const unsigned long long *keys, uint32_t n_leaders, LeaderStore L,
-                                                   uint32_t *moves, int want_aligned, uint32_t *truncated)
+                                                   uint32_t *moves, int want_aligned, uint32_t *truncated, const uint32_t *live)
 {
     uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n_leaders) return;
+    if (s >= gmx_live(live, n_leaders)) return;
     uint32_t task, round, diag;
     gmx_decode_key(keys[L.lead_cand[s]], task, round, diag);
     ReadView rd = gmx_read_view(R, (int)(task >> 1), (int)(task & 1));
@@ -1276,8 +1320,9 @@ struct Accum {
 
 __global__ void __launch_bounds__(128) k_scatter(DevIndex ix, DevReads R, DevParams P, const unsigned long long *keys,
                                                  const float *score, const int32_t *leader, const int32_t *slot, uint32_t n_cand,
-                                                 const gmx_read_result *results, LeaderStore L, Accum A)
+                                                 const gmx_read_result *results, LeaderStore L, Accum A, const uint32_t *live)
 {
+    n_cand = gmx_live(live, n_cand);
     // a warp owns 32 consecutive candidates and scatters the accepted ones in turn with all its lanes (most
     // candidates are not accepted: a warp per candidate would launch four idle warps for every working one)
     const uint32_t c_lane = (blockIdx.x * blockDim.x + threadIdx.x);
@@ -1338,10 +1383,11 @@ __global__ void __launch_bounds__(128) k_scatter(DevIndex ix, DevReads R, DevPar
 // One thread per read: copies the CIGAR of the best group next to the per-read result so that only
 // [n_reads] fixed-size records leave the device when the caller does not ask for the hit list.
 __global__ void __launch_bounds__(128) k_gather_best(const gmx_read_result *results, gmx_read_result *out, int n_reads, const int32_t *slot,
-                                                     LeaderStore L, char *best_cigar, int stride, int have_traceback)
+                                                     LeaderStore L, char *best_cigar, int stride, int have_traceback, const uint32_t *live_lead)
 {
     int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_reads) return;
+    if (live_lead && __ldg(live_lead) == 0) have_traceback = 0;
     uint4 *dst = reinterpret_cast<uint4 *>(best_cigar + (size_t)r * stride);
     gmx_read_result res = results[r];
     const bool has = have_traceback && res.status == GMX_READ_MAPPED && res.best_group >= 0;
@@ -1365,10 +1411,11 @@ __global__ void __launch_bounds__(128) k_gather_best(const gmx_read_result *resu
 struct MultiPos { uint64_t pos; int32_t read; int32_t strand; };
 
 __global__ void __launch_bounds__(256) k_gather_multi(const unsigned long long *keys, const int32_t *leader, uint32_t n_cand,
-                                                      const gmx_read_result *results, int32_t read_base, MultiPos *out, uint32_t *count, uint32_t cap)
+                                                      const gmx_read_result *results, int32_t read_base, MultiPos *out, uint32_t *count, uint32_t cap,
+                                                      const uint32_t *live)
 {
     uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= n_cand) return;
+    if (c >= gmx_live(live, n_cand)) return;
     const int32_t ld = leader[c];
     if (ld < 0) return;
     uint32_t task, round, diag;

@@ -389,7 +389,14 @@ int gmx_index_build(const uint8_t *codes, int64_t l_pac, int device, uint32_t *b
                                     record index, the results and the CIGARs are resident there); 0: always the host formatter     */
 #define GMX_OPT_VOTE_COMPACT 7   /* tuning: occupancy variants of the vote kernel for tasks of <= 32 k-mers: 0 off, 1 two bits per
                                     diagonal (24 warps / SM), 2 (default) three bits (32 or 24 warps / SM by hits per task)         */
+#define GMX_OPT_OPTIMISTIC   10  /* 1 (default): chunks of gmx_process_batch / gmx_process_fastq are issued without a host wait, over
+                                    candidate / group-leader bounds predicted from the previous chunk; the counters are looked at one
+                                    chunk later and a chunk that did not fit its bounds is run again the synchronous way (results are
+                                    the same either way).  0: every chunk waits for its counts.  2: testing -- bounds that are too
+                                    small on purpose, so that every optimistic chunk is run again                              */
 int gmx_set_option(gmx_ctx *ctx, int option, int64_t value);
+/* chunks issued optimistically / of those, run again -- since the context was created */
+int gmx_chunk_stats(gmx_ctx *ctx, uint64_t *optimistic, uint64_t *rerun);
 
 /* ---- instrumentation ---------------------------------------------------------------------- */
 #define GMX_N_STAGES 12

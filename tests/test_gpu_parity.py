@@ -458,3 +458,45 @@ def test_boundary_misuse_is_safe(api, O, plain):
     m.reset_accumulators()
     common.compare_batches(m.process_batch(gapped), want_g)
     m.close()
+
+
+@pytest.mark.parametrize("mode", [_abi.MODE_NORMAL, _abi.MODE_BS, _abi.MODE_SNP])
+def test_optimistic_chunks_equal_synchronous_chunks(api, O, repeats, mode):
+    """GMX_OPT_OPTIMISTIC: chunks issued without a host wait (bounds predicted from the previous chunk), chunks whose bounds
+    did not hold and were run again (value 2 forces that for every chunk), and chunks that wait for their counts give the
+    same per-read results, CIGARs, multi-position lists and accumulators -- over calls that keep the prediction, too."""
+    ix, batch, _ = repeats
+    po = common.set_mode(O.default_params(), mode)
+    want = O.process_batch(O.OracleIndex(ix), po, batch)
+    m = api.Mapper(ix, common.set_mode(api.default_params(), mode))
+    m.set_option(api.OPT_COLLECT_HITS, 0)
+    m.set_option(api.OPT_CHUNK_READS, 193)
+    runs = {}
+    for opt in (0, 1, 2):
+        m.set_option(api.OPT_OPTIMISTIC, opt)
+        m.reset_accumulators()
+        before = m.chunk_stats()
+        out = m.process_batch(batch, fetch=False)
+        half = batch.n_reads // 2
+        m.process_batch(batch.slice(0, half), fetch=False)                # a second and third call: single-chunk and multi-chunk
+        m.process_batch(batch.slice(half, batch.n_reads), fetch=False)
+        after = m.chunk_stats()
+        issued, rerun = after[0] - before[0], after[1] - before[1]
+        if opt == 0:
+            assert issued == 0
+        elif opt == 1:
+            assert issued > 0 and rerun <= issued
+        else:
+            assert issued > 0 and rerun >= issued // 2          # a chunk with half the candidates of its predecessor still fits
+        runs[opt] = (out["results"].copy(), m.finish())
+    for f in ("status", "n_groups", "top_score", "best_score", "best_first_pos", "best_n_positions", "best_first_strand",
+              "best_aligned_len", "n_candidates", "denominator", "best_posterior"):
+        assert f in ("denominator", "best_posterior") or np.array_equal(runs[0][0][f], want["results"][f]), f
+        for opt in (1, 2):
+            assert np.array_equal(runs[opt][0][f], runs[0][0][f]), (opt, f)
+    for opt in (1, 2):
+        assert np.allclose(runs[opt][1][0], runs[0][1][0], rtol=1e-5, atol=1e-6)
+        if runs[0][1][1] is not None:
+            assert np.allclose(runs[opt][1][1], runs[0][1][1], rtol=1e-5, atol=1e-6)
+    assert runs[0][1][0].sum() > 0
+    m.close()
