@@ -365,16 +365,23 @@ class Job:
             s.on_device = 0; s.max_len = self.L
             b.struct = s; b.n_reads = n
             batches.append((b, self.res_np[c * n:(c + 1) * n]))
-        for b, r in batches[:2]:
-            self.m.process_batch(b, fetch=False, results=r)
-        torch.cuda.synchronize()
-        t0 = time.time()
-        for b, r in batches:
-            self.m.process_batch(b, fetch=False, results=r)
-        torch.cuda.synchronize()
-        dt = time.time() - t0
+        def run():
+            for b, r in batches[:2]:
+                self.m.process_batch(b, fetch=False, results=r)
+            torch.cuda.synchronize()
+            t0 = time.time()
+            for b, r in batches:
+                self.m.process_batch(b, fetch=False, results=r)
+            torch.cuda.synchronize()
+            return time.time() - t0
+        dt_timed = run()
+        self.m.set_option(self.api.OPT_STAGE_TIMING, 0)         # what a caller that does not read gmx_get_stage_stats sets
+        dt = run()
+        self.m.set_option(self.api.OPT_STAGE_TIMING, 1)
         return {"reads_per_call": n, "calls": calls, "value": n * calls / dt, "unit": "reads/s", "ms_per_call": 1e3 * dt / calls,
-                "what": "gmx_process_batch from pinned host buffers at the reference's call granularity (2048 reads x 16 worker threads per round), wall clock"}
+                "with_stage_timing": {"value": n * calls / dt_timed, "ms_per_call": 1e3 * dt_timed / calls},
+                "what": "gmx_process_batch from pinned host buffers at the reference's call granularity (2048 reads x 16 worker threads per round), "
+                        "wall clock, GMX_OPT_STAGE_TIMING 0 (the per-stage CUDA events off, as the reference-side binding sets it)"}
 
     def reduce(self, timed=True):
         """The path's one collective (MPI Allreduce / Reduce of the accumulators, reference src/Driver.cpp:1615-1811)."""

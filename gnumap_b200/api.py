@@ -36,7 +36,7 @@ EXPORTS = [
     "gmx_comm_create", "gmx_comm_reduce", "gmx_comm_stats", "gmx_comm_destroy", "gmx_measure_alu_peak", "gmx_chunk_stats", "gmx_format_g", "gmx_index_sizes", "gmx_index_build",
 ]
 
-OPT_COLLECT_HITS, OPT_CHUNK_READS, OPT_VOTE_FILTER, OPT_FILTER_SHIFT, OPT_CIGAR_STRIDE, OPT_VOTE_SLOTS, OPT_VOTE_COMPACT, OPT_SAM_DEVICE, OPT_FASTQ_PIECE, OPT_OPTIMISTIC = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10
+OPT_COLLECT_HITS, OPT_CHUNK_READS, OPT_VOTE_FILTER, OPT_FILTER_SHIFT, OPT_CIGAR_STRIDE, OPT_VOTE_SLOTS, OPT_VOTE_COMPACT, OPT_SAM_DEVICE, OPT_FASTQ_PIECE, OPT_OPTIMISTIC, OPT_STAGE_TIMING = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11
 COMM_AUTO, COMM_PEER, COMM_NCCL = 0, 1, 2
 
 

@@ -109,6 +109,7 @@ struct gmx_ctx {
     std::vector<gmx_hit> h_hits;
     int cigar_stride = 64;                     // GMX_OPT_CIGAR_STRIDE
     HostBuf h_best_cigar;                      // pinned [n_reads][cigar_stride]
+    HostBuf h_batch_counts;                    // pinned: batch-level device counters (publish_batch_counts)
     HostBuf h_counters;                        // pinned staging of the per-chunk device counters, one per chunk parity
     std::vector<uint8_t> h_best_aligned;       // [n_reads][a_stride]  (collect_hits only)
     int h_a_stride = 0;
@@ -134,6 +135,7 @@ struct gmx_ctx {
     cudaEvent_t settle_ev[2] = {nullptr, nullptr};
     double pred_cand = -1, pred_lead = -1;     // candidates / group leaders per read of the last settled chunk (< 0: none yet)
     double pred_margin = 1.0 / 16;             // head room over the prediction; doubled by every re-run
+    bool stage_timing = true;                  // GMX_OPT_STAGE_TIMING: CUDA-event pairs around every stage
     int optimistic = 1;                        // GMX_OPT_OPTIMISTIC: 0 off, 1 on, 2 on with bounds that are too small (tests)
     uint64_t n_optimistic = 0, n_rerun = 0;
     // instrumentation (event pairs per chunk parity: a chunk's times are folded in when it is settled)
@@ -188,11 +190,10 @@ struct gmx_ctx {
 
 static inline unsigned nblk(int64_t n, int b) { return (unsigned)((n + b - 1) / b); }
 
-static void stage_begin(gmx_ctx *ctx, int st) { cudaEventRecord(ctx->ev[ctx->par][st][0], ctx->stream); }
+static void stage_begin(gmx_ctx *ctx, int st) { if (ctx->stage_timing) cudaEventRecord(ctx->ev[ctx->par][st][0], ctx->stream); }
 static void stage_end(gmx_ctx *ctx, int st, uint64_t units, uint64_t bytes, int launches)
 {
-    cudaEventRecord(ctx->ev[ctx->par][st][1], ctx->stream);
-    ctx->ev_used[ctx->par][st] = true;
+    if (ctx->stage_timing) { cudaEventRecord(ctx->ev[ctx->par][st][1], ctx->stream); ctx->ev_used[ctx->par][st] = true; }
     ctx->stage_units[st] += units; ctx->stage_bytes[st] += bytes; ctx->stage_launches[st] += launches;
 }
 // fold the event pairs of a finished chunk (parity `par`, default: the current one) into the running totals
@@ -468,6 +469,7 @@ extern "C" void gmx_destroy(gmx_ctx *ctx)
     for (DevBuf *b : bufs) b->release();
     ctx->h_best_cigar.release();
     ctx->h_counters.release();
+    ctx->h_batch_counts.release();
     for (int b = 0; b < 2; ++b) {
         for (int s = 0; s < ST_COUNT; ++s) { if (ctx->ev[b][s][0]) cudaEventDestroy(ctx->ev[b][s][0]); if (ctx->ev[b][s][1]) cudaEventDestroy(ctx->ev[b][s][1]); }
         if (ctx->settle_ev[b]) cudaEventDestroy(ctx->settle_ev[b]);
@@ -1403,11 +1405,19 @@ static int batch_max_len(gmx_ctx *ctx, const gmx_reads *reads, int32_t *out)
 
 static int run_batch_impl(gmx_ctx *ctx, const gmx_reads *reads, gmx_read_result *results, bool do_score);
 
+// behind the batch's last kernel: [0] multi-position entries, [1] truncated CIGARs -> pinned host words
+static int publish_batch_counts(gmx_ctx *ctx)
+{
+    CK(ctx->h_batch_counts.ensure(16));
+    k_publish_words<<<1, 32, 0, ctx->stream>>>(ctx->d_multi_count.as<uint32_t>(), ctx->h_batch_counts.as<uint32_t>(), 2);
+    CK(cudaGetLastError());
+    return GMX_OK;
+}
+
 // end of a batch (streams idle): the multi-position list of the fast download path and the truncated-CIGAR count
 static int collect_batch_counters(gmx_ctx *ctx)
 {
-    uint32_t c[2] = {0, 0};
-    CK(cudaMemcpy(c, ctx->d_multi_count.p, 8, cudaMemcpyDeviceToHost));
+    const uint32_t *c = ctx->h_batch_counts.as<uint32_t>();            // published by batch_end / gmx_score_batch before their drain
     if (ctx->multi_cap) {
         uint32_t nm = c[0];
         if (nm > ctx->multi_cap) { ctx->multi_overflow = true; nm = ctx->multi_cap; }
@@ -1477,6 +1487,7 @@ static int batch_begin(gmx_ctx *ctx, int32_t n, int32_t max_len, gmx_read_result
 static int batch_end(gmx_ctx *ctx, bool do_score)
 {
     { int r = settle_all(ctx); if (r != GMX_OK) return r; }
+    { int r = publish_batch_counts(ctx); if (r != GMX_OK) return r; }
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaStreamSynchronize(ctx->d2h_stream));
     stage_collect(ctx);
@@ -1597,6 +1608,8 @@ extern "C" int gmx_score_batch(gmx_ctx *ctx, gmx_read_result *results)
         if (r != GMX_OK) return r;
         r = download_chunk(ctx, true, results);
         if (r != GMX_OK) return r;
+        r = publish_batch_counts(ctx);
+        if (r != GMX_OK) return r;
         CK(cudaStreamSynchronize(ctx->stream));
         CK(cudaStreamSynchronize(ctx->d2h_stream));
         stage_collect(ctx);
@@ -1636,6 +1649,7 @@ extern "C" int gmx_set_option(gmx_ctx *ctx, int option, int64_t value)
         case GMX_OPT_FASTQ_PIECE:
             if (value < 0) { ctx->err = "fastq piece bytes must be >= 0"; return GMX_ERR_INVALID; }
             ctx->fq_piece_bytes = value; return GMX_OK;
+        case GMX_OPT_STAGE_TIMING: ctx->stage_timing = value != 0; return GMX_OK;
         case GMX_OPT_OPTIMISTIC: ctx->optimistic = value < 0 ? 0 : (value > 2 ? 2 : (int)value); return GMX_OK;
         case GMX_OPT_VOTE_COMPACT: ctx->vote_compact = value < 0 ? 0 : (value > 2 ? 2 : (int)value); return GMX_OK;
         case GMX_OPT_CIGAR_STRIDE:

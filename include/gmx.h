@@ -394,6 +394,8 @@ int gmx_index_build(const uint8_t *codes, int64_t l_pac, int device, uint32_t *b
                                     chunk later and a chunk that did not fit its bounds is run again the synchronous way (results are
                                     the same either way).  0: every chunk waits for its counts.  2: testing -- bounds that are too
                                     small on purpose, so that every optimistic chunk is run again                              */
+#define GMX_OPT_STAGE_TIMING 11  /* 1 (default): a CUDA-event pair around every stage of every chunk feeds gmx_get_stage_stats; 0: no
+                                    events are recorded (units / bytes / launches are still counted, ms stay 0)                 */
 int gmx_set_option(gmx_ctx *ctx, int option, int64_t value);
 /* chunks issued optimistically / of those, run again -- since the context was created */
 int gmx_chunk_stats(gmx_ctx *ctx, uint64_t *optimistic, uint64_t *rerun);

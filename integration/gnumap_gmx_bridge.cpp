@@ -137,6 +137,7 @@ void gmx_attach(GenomeBwt &gen, unsigned n_threads)
             gmx_destroy(c);
             break;
         }
+        gmx_set_option(c, GMX_OPT_STAGE_TIMING, 0);                                 // nobody reads gmx_get_stage_stats here
         pthread_mutex_init(&gGmxLock[d], NULL);
         gGmx[gGmxN++] = c;
     }

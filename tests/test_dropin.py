@@ -77,7 +77,10 @@ CASES = {
     "max_kmer_and_matches": (["-h", "40", "-T", "3"], 2, {}),
     "up_strand_raw": (["--up_strand", "-r", "-a", "60"], 2, {}),
     "read_quality_fast": (["-q", "70", "--fast", "-k", "1"], 2, {}),      # --fast stops at the first k-mer that hits: one seed must do
+    "subst_file": (["-S", "@SUBST@"], 2, {}),                             # readPWM, reference src/Driver.cpp:768-859: own score table, gADJUST = 1
 }
+
+SUBST_TABLE = "\tA\tC\tG\tT\nA\t2.5\t-1.75\t-0.5\t-1.75\nC\t-1.75\t2.5\t-1.75\t-0.5\nG\t-0.5\t-1.75\t2.5\t-1.75\nT\t-1.75\t-0.5\t-1.75\t2.5\nN\t0.25\t0.25\t0.25\t0.25\n"
 
 
 @pytest.mark.parametrize("case", list(CASES))
@@ -86,6 +89,9 @@ def test_patched_reference_binary_matches_unmodified(tmp_path, case):
         pytest.skip("oracle/_ref/gnumap_gmx has not been built (needs /root/reference at build time)")
     opts, threads, world = CASES[case]
     fa, fq = _world(tmp_path, **world)
+    if "@SUBST@" in opts:
+        open(str(tmp_path / "subst.txt"), "w").write(SUBST_TABLE)
+        opts = [str(tmp_path / "subst.txt") if o == "@SUBST@" else o for o in opts]
     empty = str(tmp_path / "empty.fq"); open(empty, "w").close()
     _run(REF, fa, empty, str(tmp_path / "warm"), opts, 1)               # builds the index; later runs start from zero pages
     ref_log = _run(REF, fa, fq, str(tmp_path / "ref"), opts, 1)
