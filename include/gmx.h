@@ -380,7 +380,9 @@ int gmx_index_build(const uint8_t *codes, int64_t l_pac, int device, uint32_t *b
 #define GMX_OPT_CIGAR_STRIDE  5   /* bytes per CIGAR slot of the batch pipeline (default 64, a multiple of 16 up to 2048).  The
                                     reference builds CIGARs unbounded (TopReadOutput::CIGAR holds MAX_CIGAR_SZ = 1024); a batch in
                                     which some alignment needs more text than the slot fails with GMX_ERR_OVERFLOW instead of
-                                    returning a cut string */
+                                    returning a cut string -- after the batch has reached the accumulators, so a caller that
+                                    cannot rule long CIGARs out sizes the slot up front: 4 * read length + 16 bytes hold any
+                                    alignment (integration/gnumap_gmx_bridge.cpp does that per slice) */
 #define GMX_OPT_VOTE_SLOTS   6   /* tuning: 32-hit slots per step of the vote kernel, 4 or 6 (default: from seq_len / 4^mer)  */
 #define GMX_OPT_FASTQ_PIECE  9   /* bytes per piece of a host FASTQ text in gmx_process_fastq (default 96 MiB; 0 = upload and index the
                                     whole text first).  Texts of two pieces or more are cut at record boundaries and piece p + 1

@@ -63,6 +63,7 @@ extern bool gPRINT_ALL_SAM;
 #define GMX_BRIDGE_MAX_GPUS 16
 static gmx_ctx *gGmx[GMX_BRIDGE_MAX_GPUS];
 static pthread_mutex_t gGmxLock[GMX_BRIDGE_MAX_GPUS];        // worker threads that share a GPU take turns on its context
+static int gGmxCigar[GMX_BRIDGE_MAX_GPUS];                   // CIGAR slot bytes of each context (GMX_OPT_CIGAR_STRIDE)
 static int gGmxN = 0;
 static gmx_comm *gGmxComm = 0;
 static int gGmxIllumina = 0;                                  // gILLUMINA when the contexts were created
@@ -139,6 +140,7 @@ void gmx_attach(GenomeBwt &gen, unsigned n_threads)
         }
         gmx_set_option(c, GMX_OPT_STAGE_TIMING, 0);                                 // nobody reads gmx_get_stage_stats here
         pthread_mutex_init(&gGmxLock[d], NULL);
+        gGmxCigar[d] = 64;                                                          // the library's default
         gGmx[gGmxN++] = c;
     }
     if (gGmxN > 1) {
@@ -186,17 +188,28 @@ void gmx_run_slice(GenomeBwt &gen, unsigned thread_id, unsigned read_begin, unsi
     in.pwm = as_pwm && !pwm.empty() ? &pwm[0] : 0;
     std::vector<gmx_read_result> res(n);
     std::vector<gmx_hit> hits;
-    std::vector<char> cigar((size_t)n * 64 + 64);
 
     const int g = (int)(thread_id % (unsigned)gGmxN);
     gmx_ctx *ctx = gGmx[g];
     pthread_mutex_lock(&gGmxLock[g]);
+    // The reference builds CIGARs unbounded; the library writes them into fixed slots and fails the batch rather than cut
+    // one.  No alignment of an n-base read needs more than 4 n + 16 bytes ("1I1D" per base), so the slot is sized for the
+    // longest read seen so far (a cheap score table makes gap-rich alignments real: -S with gap > mismatch).
+    size_t longest = 0;
+    for (unsigned i = 0; i < n; ++i) longest = std::max(longest, (size_t)(off[i + 1] - off[i]));
+    int want = (int)std::min<size_t>(2048, (4 * longest + 16 + 15) / 16 * 16);
+    if (want > gGmxCigar[g]) {
+        if (gmx_set_option(ctx, GMX_OPT_CIGAR_STRIDE, want) != GMX_OK) gmx_die("gmx_set_option(CIGAR_STRIDE)", ctx);
+        gGmxCigar[g] = want;
+    }
+    const size_t cs = (size_t)gGmxCigar[g];
+    std::vector<char> cigar((size_t)n * cs + cs);
     if (n && gmx_process_batch(ctx, &in, &res[0]) != GMX_OK) gmx_die("gmx_process_batch", ctx);
     int64_t nh = 0;
     if (n && gmx_get_hits(ctx, 0, 0, &nh) != GMX_OK) gmx_die("gmx_get_hits", ctx);
     hits.resize((size_t)nh + 1);
     if (n && gmx_get_hits(ctx, &hits[0], nh + 1, &nh) != GMX_OK) gmx_die("gmx_get_hits", ctx);
-    if (n && gmx_get_best_alignments(ctx, &cigar[0], 64, 0, 0) != GMX_OK) gmx_die("gmx_get_best_alignments", ctx);
+    if (n && gmx_get_best_alignments(ctx, &cigar[0], (int)cs, 0, 0) != GMX_OK) gmx_die("gmx_get_best_alignments", ctx);
     pthread_mutex_unlock(&gGmxLock[g]);
 
     for (unsigned i = 0; i < n; ++i) {
@@ -224,7 +237,7 @@ void gmx_run_slice(GenomeBwt &gen, unsigned thread_id, unsigned read_begin, unsi
             out.CHR_POS = seq_pos.second + 1;
             out.strand = hits[h].strand == GMX_NEG_STRAND ? NEG_STRAND : POS_STRAND;
             out.MAPQ = mapq;
-            strncpy(out.CIGAR, &cigar[(size_t)i * 64], MAX_CIGAR_SZ - 1); out.CIGAR[MAX_CIGAR_SZ - 1] = '\0';
+            strncpy(out.CIGAR, &cigar[(size_t)i * cs], MAX_CIGAR_SZ - 1); out.CIGAR[MAX_CIGAR_SZ - 1] = '\0';
             out.readIndex = k;
             out.consensus = seq.substr((size_t)off[i], (size_t)(off[i + 1] - off[i]));        // GetConsensus(read)
             out.qual = str2qual(*gReadArray[k]);
