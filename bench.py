@@ -208,6 +208,34 @@ class ReferenceRunner:
         return n / max(time.time() - t0 - load, 1e-6), n
 
 
+    def run_patched(self, threads: int, n_reads: int, gpus: int = 1):
+        """The reference program itself with integration/driver_gmx.patch applied (oracle/_ref/gnumap_gmx): its own option parser,
+        FASTQ reader, worker threads and SAM writer around gmx_process_batch.  Returns None when that binary was not built."""
+        exe = os.path.join(os.path.dirname(self.bin), "gnumap_gmx")
+        if not os.path.exists(exe):
+            return None
+        n = min(n_reads, len(self.reads["pos"]))
+        fq = os.path.join(self.dir, "dropin.fq")
+        self._fastq(fq, 0, n)
+        env = dict(self.env, GMX_GPUS=str(gpus))
+        cmd = [exe, "-g", self.prefix, "-a", ".9", "-c", str(threads), "--no_gmp", *self.extra]
+        empty = os.path.join(self.dir, "empty.fq")
+        open(empty, "w").close()
+        load = None
+        for _ in range(2):                             # start-up: index load, context creation, index upload
+            t = time.time()
+            subprocess.run(cmd + ["-o", os.path.join(self.dir, "de"), empty], env=env, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            load = time.time() - t
+        t0 = time.time()
+        p = subprocess.run(cmd + ["-o", os.path.join(self.dir, "do"), fq], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        wall = time.time() - t0
+        if p.returncode != 0:
+            raise RuntimeError(f"patched binary failed ({p.returncode}): {p.stdout[-400:]}")
+        return {"value": n / max(wall - load, 1e-6), "unit": "reads/s", "reads": n, "threads": threads, "gpus": gpus, "seconds": wall, "startup_seconds": load,
+                "what": f"`gnumap_gmx -c {threads}` (the reference binary with integration/driver_gmx.patch: its FASTQ reader, worker threads and SAM "
+                        "writer around gmx_process_batch in 65 536-read slices), wall clock minus the start-up measured on an empty read file"}
+
+
 def reference_arm(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -758,6 +786,10 @@ def own_arm(a):
                                                      "what": f"one `gnumap -c {rr.cores}` process on 2048 x {rr.cores} reads (every thread gets one slice)"}
                     except Exception as e:
                         cpu["single_process_c_n"] = {"value": None, "what": f"unavailable: {e}"}
+                    try:       # the same program with its hot path on the GPU (the drop-in): bounded by the reference's own reader / writer
+                        cpu["e2e_dropin"] = rr.run_patched(rr.cores, min(a.reads, 1 << 19)) or {"value": None, "what": "oracle/_ref/gnumap_gmx was not built"}
+                    except Exception as e:
+                        cpu["e2e_dropin"] = {"value": None, "what": f"unavailable: {e}"}
                 finally:
                     rr.close()
             except Exception as e:  # the baseline is reported, never required

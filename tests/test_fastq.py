@@ -327,10 +327,14 @@ def test_pipelined_fastq_text_equals_whole_text_path():
     recs0 = api.fastq_scan_host(text)
     sam0 = m.format_sam(text, recs0, whole["results"])
     amount0, _ = m.finish()
-    for piece, chunk in ((100_000, 1 << 19), (150_000, 700)):
+    # chunks issued without a host wait (default), every such chunk voided and run again (2), every chunk waiting (0)
+    for piece, chunk, optimistic in ((100_000, 1 << 19, 1), (150_000, 700, 1), (150_000, 700, 2), (120_000, 900, 0)):
         m.reset_accumulators()
-        m.set_option(api.OPT_FASTQ_PIECE, piece); m.set_option(api.OPT_CHUNK_READS, chunk)
+        m.set_option(api.OPT_FASTQ_PIECE, piece); m.set_option(api.OPT_CHUNK_READS, chunk); m.set_option(api.OPT_OPTIMISTIC, optimistic)
+        before = m.chunk_stats()
         names1, piped = m.process_fastq(text, fetch=False)
+        issued, rerun = (x - y for x, y in zip(m.chunk_stats(), before))
+        assert (issued == 0) if optimistic == 0 else (issued > 0 and (optimistic == 1 or rerun >= issued // 2))
         assert names1 == names0
         for f in whole["results"].dtype.names:
             assert np.array_equal(piped["results"][f], whole["results"][f]), f
@@ -341,7 +345,7 @@ def test_pipelined_fastq_text_equals_whole_text_path():
     bad = recs_txt[k].split(b"\n")
     bad[3] = bad[3][:-3]
     messy = b"".join(recs_txt[:k]) + b"\n".join(bad) + b"".join(recs_txt[k + 1:])
-    m.set_option(api.OPT_FASTQ_PIECE, 0); m.set_option(api.OPT_CHUNK_READS, 1 << 19)
+    m.set_option(api.OPT_FASTQ_PIECE, 0); m.set_option(api.OPT_CHUNK_READS, 1 << 19); m.set_option(api.OPT_OPTIMISTIC, 1)
     m.reset_accumulators()
     names_a, res_a = m.process_fastq(messy, fetch=False)              # whole text: device indexer refuses, host scan does it all
     amount_a, _ = m.finish()
