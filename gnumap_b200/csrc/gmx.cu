@@ -798,11 +798,12 @@ extern "C" int gmx_pair_hmm(gmx_ctx *ctx, const gmx_reads *reads, int64_t n_task
     int32_t max_len = 0;
     int r = upload_tasks(ctx, u, reads, n_tasks, read_idx, strand, windows, win_stride, nullptr, &max_len);
     if (r != GMX_OK) return r;
-    if (max_len > 32 * GMX_PHMM_MAXC) { ctx->err = "reads longer than 256 bp are not supported by the pair-HMM kernel"; return GMX_ERR_UNSUPPORTED; }
+    if (max_len > 32 * GMX_PHMM_LONGC) { ctx->err = "reads longer than 1024 bp are not supported by the pair-HMM kernel"; return GMX_ERR_UNSUPPORTED; }
     CK(out.ensure((size_t)n_tasks * win_stride * 5 * 4));
     CK(cudaMemsetAsync(out.p, 0, (size_t)n_tasks * win_stride * 5 * 4, ctx->stream));
     size_t per_task = gmx_phmm_scratch_doubles(max_len);
     int64_t wave = std::min<int64_t>(n_tasks, 148 * 16);
+    wave = std::max<int64_t>(1, std::min<int64_t>(wave, (int64_t)((4ull << 30) / (per_task * 8))));      // long reads: 17 MB of scratch per task at 1024 bp
     CK(scratch.ensure((size_t)wave * per_task * 8));
     for (int64_t t0 = 0; t0 < n_tasks; t0 += wave) {
         int64_t cnt = std::min<int64_t>(wave, n_tasks - t0);
@@ -1184,7 +1185,7 @@ static int phase_b(gmx_ctx *ctx)
     const uint32_t nl_acc = cs.opt ? 0 : n_leaders;        // an optimistic chunk's work is accounted when it is settled
     stage_end(ctx, ST_TRACEBACK, (uint64_t)nl_acc * (uint64_t)std::max(7 * max_len - 12, 0), 0, 1);
     if (P.mode == GMX_MODE_SNP) {
-        if (max_len > 32 * GMX_PHMM_MAXC) { ctx->err = "SNP mode: reads longer than 256 bp are not supported by the pair-HMM kernel"; return GMX_ERR_UNSUPPORTED; }
+        if (max_len > 32 * GMX_PHMM_LONGC) { ctx->err = "SNP mode: reads longer than 1024 bp are not supported by the pair-HMM kernel"; return GMX_ERR_UNSUPPORTED; }
         CK(ctx->d_hmm.ensure((size_t)n_leaders * max_len * 5 * 4));
         L.hmm = ctx->d_hmm.as<float>();
         size_t per_task = gmx_phmm_scratch_doubles(max_len);
@@ -1193,9 +1194,10 @@ static int phase_b(gmx_ctx *ctx)
         int per_sm = 1;
 #define GMX_PHMM_OCC(CT) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pair_hmm_leaders<CT>, GMX_PHMM_THREADS, 0))
         switch (C) { case 1: GMX_PHMM_OCC(1); break; case 2: GMX_PHMM_OCC(2); break; case 3: GMX_PHMM_OCC(3); break; case 4: GMX_PHMM_OCC(4); break;
-                     case 5: GMX_PHMM_OCC(5); break; default: GMX_PHMM_OCC(0); break; }
+                     case 5: GMX_PHMM_OCC(5); break; default: if (C <= GMX_PHMM_MAXC) GMX_PHMM_OCC(0); else GMX_PHMM_OCC(-1); break; }
 #undef GMX_PHMM_OCC
-        const uint32_t grid = std::min<uint32_t>(n_leaders, (uint32_t)ctx->n_sm * (uint32_t)std::max(per_sm, 1));
+        uint32_t grid = std::min<uint32_t>(n_leaders, (uint32_t)ctx->n_sm * (uint32_t)std::max(per_sm, 1));
+        grid = std::max<uint32_t>(1, std::min<uint32_t>(grid, (uint32_t)((4ull << 30) / (per_task * 8))));      // long reads: at most 4 GB of scratch
         CK(ctx->d_phmm_scratch.ensure((size_t)grid * per_task * 8 + 16));
         uint32_t *cursor = reinterpret_cast<uint32_t *>(ctx->d_phmm_scratch.as<char>() + (size_t)grid * per_task * 8);
         stage_begin(ctx, ST_PHMM);
@@ -1209,7 +1211,7 @@ static int phase_b(gmx_ctx *ctx)
             case 3: GMX_PHMM_LAUNCH(3); break;
             case 4: GMX_PHMM_LAUNCH(4); break;
             case 5: GMX_PHMM_LAUNCH(5); break;
-            default: GMX_PHMM_LAUNCH(0); break;
+            default: if (C <= GMX_PHMM_MAXC) GMX_PHMM_LAUNCH(0); else GMX_PHMM_LAUNCH(-1); break;
         }
 #undef GMX_PHMM_LAUNCH
         CK(cudaGetLastError());

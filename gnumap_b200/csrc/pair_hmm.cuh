@@ -17,7 +17,8 @@
 #include "pipeline.cuh"
 
 #define GMX_PHMM_THREADS 32
-#define GMX_PHMM_MAXC 8                       // columns per lane -> read length <= 256 in SNP mode
+#define GMX_PHMM_MAXC 8                       // columns per lane of the generic path's register strips: reads <= 256 bp
+#define GMX_PHMM_LONGC 32                     // ... of its long-read instantiation (strips in local memory): reads <= 1024 bp
 
 // forward matrix parked in global memory: (fM, fY) per cell -- the X state never enters the posterior
 __host__ __device__ inline size_t gmx_phmm_scratch_doubles(int max_len) { return (size_t)(max_len + 33) * (size_t)(((max_len + 31) / 32) * 32) * 2; }
@@ -406,11 +407,13 @@ __global__ void __launch_bounds__(GMX_PHMM_THREADS) k_pair_hmm_tasks(DevReads R,
     ReadView rd = gmx_read_view(R, read_idx[t], strand ? strand[t] : 0);
     WindowView win; win.pac = nullptr; win.pos = 0; win.chars = windows + t * win_stride;
     if (rd.n <= 160) gmx_pair_hmm_warp<5>(rd, win, T, scratch + (size_t)blockIdx.x * per_task, post + (size_t)t * win_stride * 5);
-    else gmx_pair_hmm_warp<GMX_PHMM_MAXC>(rd, win, T, scratch + (size_t)blockIdx.x * per_task, post + (size_t)t * win_stride * 5);
+    else if (rd.n <= 32 * GMX_PHMM_MAXC) gmx_pair_hmm_warp<GMX_PHMM_MAXC>(rd, win, T, scratch + (size_t)blockIdx.x * per_task, post + (size_t)t * win_stride * 5);
+    else gmx_pair_hmm_warp<GMX_PHMM_LONGC>(rd, win, T, scratch + (size_t)blockIdx.x * per_task, post + (size_t)t * win_stride * 5);
 }
 
 // one group leader per warp (SNPScoredSeq::score, reference src/SNPScoredSeq.cpp:44-67).  C_T > 0: every read of the
-// chunk fits 32 * C_T columns (fast path, padded); C_T == 0: generic path.  Persistent: the grid is what the SMs hold
+// chunk fits 32 * C_T columns (fast path, padded); C_T == 0: generic path, reads up to 256 bp; C_T < 0: generic path with
+// 32 columns per lane, reads up to 1024 bp (bin_seq::pairHMM has no length limit; GMX_MAX_READ_LEN is the library's).  Persistent: the grid is what the SMs hold
 // at once, every CTA (one warp) owns one scratch slot and takes group leaders from a shared cursor until none is left
 // (one launch per chunk instead of one per wave: no tail of half-empty SMs between waves).
 template <int C_T>
@@ -440,7 +443,7 @@ __global__ void __launch_bounds__(GMX_PHMM_THREADS) k_pair_hmm_leaders(DevIndex 
             gmx_pair_hmm_warp_fast<CS>(rd, ix.pac, diag, T, F, E, out, acc_s, e_s, code_s);
         } else {
             WindowView win; win.pac = ix.pac; win.pos = diag; win.chars = nullptr;
-            gmx_pair_hmm_warp<GMX_PHMM_MAXC>(rd, win, T, my, out);
+            gmx_pair_hmm_warp<(C_T < 0 ? GMX_PHMM_LONGC : GMX_PHMM_MAXC)>(rd, win, T, my, out);
         }
         __syncwarp();
     }

@@ -109,7 +109,11 @@ void gmx_default_params(gmx_params *p);
  *              read r occupies [offsets[r], offsets[r+1]).  The PWM of a FASTQ read is a pure
  *              function of (base, quality char) -- reference src/SeqReader.cpp:1155-1240.
  *   pwm      : optional float[total_len][4] for reads whose PWM is not such a function
- *              (PRB / INT inputs, SeqReader.cpp:541-571,901-978); NULL for FASTQ. */
+ *              (PRB / INT inputs, SeqReader.cpp:541-571,901-978); NULL for FASTQ.
+ * A read may be up to 1024 bases long in every mode (GMX_ERR_UNSUPPORTED beyond; the reference has no limit of its own
+ * but its float scores leave the range of exp() near 940 bases).  The kernels are tuned for reads of up to 160 bases;
+ * longer ones take generic paths (exact vote tables beyond 448, register strips of the pair-HMM up to 256, local-memory
+ * strips up to 1024). */
 typedef struct gmx_reads {
     int32_t        n_reads;
     const int64_t *offsets;   /* [n_reads + 1] */

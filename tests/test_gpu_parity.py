@@ -358,7 +358,7 @@ def test_raw_pwm_reads_match_fastq_reads(api, O, plain):
 
 def test_long_reads_take_the_exact_vote_path(api, O):
     """Reads beyond the filter kernel's span (k-mer offset + mer > 448) fall back to the exact hash-table kernels; the
-    generic band / traceback paths handle lengths up to GMX_MAX_READ_LEN; SNP mode refuses reads over 256 bp loudly."""
+    generic band / traceback / pair-HMM paths handle lengths up to GMX_MAX_READ_LEN."""
     from gnumap_b200 import synth
     contigs = synth.make_genome(400_000, 41, n_contigs=2)
     codes = np.concatenate([c for _, c in contigs])
@@ -378,17 +378,23 @@ def test_long_reads_take_the_exact_vote_path(api, O):
     assert np.allclose(amount, want["amount"], rtol=1e-5, atol=1e-6)
     assert (want["results"]["status"] == _abi.READ_MAPPED).sum() > 80
     m.close()
+    # SNP mode: the pair-HMM's generic path -- register strips up to 256 bp, local-memory strips (32 columns per lane) up
+    # to GMX_MAX_READ_LEN; bin_seq::pairHMM itself has no length limit (reference src/bin_seq.cpp:60-244)
     ps = common.set_mode(api.default_params(), _abi.MODE_SNP)
+    po = common.set_mode(O.default_params(), _abi.MODE_SNP)
     m = api.Mapper(ix, ps)
-    with pytest.raises(api_mod(api).GmxError) as e:
-        m.process_batch(batch)
-    assert e.value.code == _abi.GMX_ERR_UNSUPPORTED
-    short = _abi.ReadBatch(seqs[60:], quals[60:])                 # 120, 200 and 256 bp: generic pair-HMM path above 160 bp
-    got = m.process_batch(short)
-    amount, planes = m.finish()
-    want = O.process_batch(O.OracleIndex(ix), common.set_mode(O.default_params(), _abi.MODE_SNP), short)
-    common.compare_batches(got, want)
-    assert np.allclose(planes, want["planes"], rtol=1e-5, atol=1e-6)
+    for sub in (_abi.ReadBatch(seqs[60:], quals[60:]),            # 120, 200 and 256 bp
+                batch):                                           # ... and 300 to 900 bp
+        m.reset_accumulators()
+        got = m.process_batch(sub)
+        amount, planes = m.finish()
+        want = O.process_batch(O.OracleIndex(ix), po, sub)
+        common.compare_batches(got, want)
+        # the reference's unscaled FP64 forward pass underflows for the 900-bp reads (fE = 0, posteriors 0 / 0): the same
+        # NaNs must come out of the kernel
+        assert np.allclose(planes, want["planes"], rtol=1e-5, atol=1e-6, equal_nan=True)
+        assert np.nansum(np.abs(want["planes"])) > 0
+    assert np.isnan(want["planes"]).any() and not np.isnan(want["planes"]).all()
     m.close()
 
 
