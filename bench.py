@@ -687,6 +687,7 @@ def own_arm(a):
             fq_step()
         torch.cuda.synchronize()
         fq_ms = (time.time() - t0) * 1e3
+        fq_stages = {k: round(v["ms"], 3) for k, v in m.stage_stats().items()}          # of the last call
         if world > 1:
             tt = torch.tensor([fq_ms], device=dev, dtype=torch.float64)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -724,6 +725,7 @@ def own_arm(a):
         fastq = {"value": n * world * a.steps / (fq_ms * 1e-3), "unit": "reads/s", "h2d_bytes_per_step": int(text_h.numel()),
                  "d2h_bytes_per_step": int(n * (_abi.READ_RESULT_DTYPE.itemsize + 64 + _abi.FASTQ_REC_DTYPE.itemsize)),
                  "what": "gmx_process_fastq: FASTQ text in pinned host memory -> device record indexer -> reads used in place -> results (wall clock)",
+                 "ms_per_step": fq_ms / a.steps, "stages_ms_last_step": fq_stages,
                  "sam": {"value": n / sam_s, "unit": "reads/s", "bytes": int(sam_len.value),
                          "what": "gmx_format_sam: SAM body of the batch (ScoredSeq::get_SAM + writer) formatted on the GPU from the resident text / results / CIGARs, "
                                  "finished text copied to pinned host memory (wall clock, best of 3)"},

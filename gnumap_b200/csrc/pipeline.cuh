@@ -53,19 +53,22 @@ __device__ __forceinline__ ReadView gmx_read_view(const DevReads &R, int r, int 
 #define GMX_PREP_STAGE_BYTES (GMX_PREP_THREADS * 176)        // reads of up to 176 bases on average per block
 __global__ void __launch_bounds__(GMX_PREP_THREADS) k_prep_reads(DevReads R, DevTables T, DevParams P, ReadPrep *prep, unsigned long long *bad_len)
 {
-    __shared__ __align__(16) uint8_t s_seq[GMX_PREP_STAGE_BYTES + 8], s_qual[GMX_PREP_STAGE_BYTES + 8];
+    __shared__ __align__(16) uint8_t s_buf[2 * GMX_PREP_STAGE_BYTES + 16];
+    uint8_t *s_seq = s_buf, *s_qual = s_buf + GMX_PREP_STAGE_BYTES + 8;
     const int r0 = blockIdx.x * blockDim.x;
     const int r = r0 + threadIdx.x;
     const int r1 = min(r0 + (int)blockDim.x, R.n_reads);
-    // contiguous layout (no raw PWM, no in-place FASTQ offsets): the block's reads are one byte range
-    bool staged = false;
-    int64_t lead = 0;
+    // staged = 1, contiguous layout (no raw PWM, no in-place FASTQ offsets): the block's reads are one byte range of seq and
+    // one of qual.  staged = 2, reads used in place in a FASTQ text (seq == qual == the text, per-read offsets of the two
+    // lines): the block's records are one byte range of the text, staged whole (names and '+' lines included)
+    int staged = 0;
+    int64_t lead = 0, t0 = 0, t1 = 0;
     if (!R.pwm && !R.qoffsets && !R.lens && R.qual) {
         const int64_t b0 = R.offsets[r0], b1 = R.offsets[r1];
         const uintptr_t a_seq = (uintptr_t)(R.seq + b0), a_qual = (uintptr_t)(R.qual + b0);
         lead = (int64_t)(a_seq & 3u);
         if ((a_qual & 3u) == (uintptr_t)lead && b1 - b0 + lead <= GMX_PREP_STAGE_BYTES) {
-            staged = true;
+            staged = 1;
             const uint32_t *g_seq = reinterpret_cast<const uint32_t *>(a_seq - lead), *g_qual = reinterpret_cast<const uint32_t *>(a_qual - lead);
             const int words = (int)((b1 - b0 + lead + 3) >> 2);
             for (int w = threadIdx.x; w < words; w += blockDim.x) {
@@ -74,6 +77,18 @@ __global__ void __launch_bounds__(GMX_PREP_THREADS) k_prep_reads(DevReads R, Dev
             }
         }
         lead -= b0;                                        // shared index of genome-order byte x is x + lead
+    } else if (!R.pwm && R.qoffsets && R.lens && R.qual == R.seq && r1 > r0) {
+        t0 = R.offsets[r0];
+        t1 = R.qoffsets[r1 - 1] + (int64_t)max(R.lens[r1 - 1], 0);
+        const uintptr_t a = (uintptr_t)(R.seq + t0);
+        lead = (int64_t)(a & 3u);
+        if (t1 > t0 && t1 - t0 + lead <= 2 * GMX_PREP_STAGE_BYTES + 8) {
+            staged = 2;
+            const uint32_t *g = reinterpret_cast<const uint32_t *>(a - lead);
+            const int words = (int)((t1 - t0 + lead + 3) >> 2);
+            for (int w = threadIdx.x; w < words; w += blockDim.x) reinterpret_cast<uint32_t *>(s_buf)[w] = g[w];
+        }
+        lead -= t0;
     }
     __syncthreads();
     if (r >= R.n_reads) return;
@@ -88,11 +103,20 @@ __global__ void __launch_bounds__(GMX_PREP_THREADS) k_prep_reads(DevReads R, Dev
     if ((unsigned)rd.n < (unsigned)P.mer) { out.status = GMX_READ_TOO_SHORT; prep[r] = out; return; }
     // get_align_score(read, consensus, 0, n-1) == get_align_score_mid  (reference src/bin_seq.cpp:860-893)
     float score = 0.f;
-    if (staged) {
+    if (staged == 2) {
+        // a caller's own record index need not be in text order: a read outside the staged range is walked in place
+        const int64_t so = R.offsets[r], qo = R.qoffsets[r];
+        if (so < t0 || so + rd.n > t1 || qo < t0 || qo + rd.n > t1) staged = 0;
+        else {
+            const uint8_t *sq = s_buf + (so + lead), *ql = s_buf + (qo + lead);
+            for (int i = 0; i < rd.n; ++i) score = __fadd_rn(score, __ldg(T.self + (int)sq[i] * GMX_NQ + gmx_qidx(ql[i], 0)));
+        }
+    }
+    if (staged == 1) {
         const int64_t at = R.offsets[r] + lead;
         for (int i = 0; i < rd.n; ++i)
             score = __fadd_rn(score, __ldg(T.self + (int)s_seq[at + i] * GMX_NQ + gmx_qidx(s_qual[at + i], 0)));
-    } else {
+    } else if (staged == 0) {
         for (int i = 0; i < rd.n; ++i) {
             float4 p = rd.pwm_row(T, i);
             uint8_t ch = rd.seq[i];                  // GetConsensus(): read.seq (reference src/Driver.cpp:352-356)

@@ -390,7 +390,8 @@ int gmx_index_build(const uint8_t *codes, int64_t l_pac, int device, uint32_t *b
 #define GMX_OPT_VOTE_SLOTS   6   /* tuning: 32-hit slots per step of the vote kernel, 4 or 6 (default: from seq_len / 4^mer)  */
 #define GMX_OPT_FASTQ_PIECE  9   /* bytes per piece of a host FASTQ text in gmx_process_fastq (default 96 MiB; 0 = upload and index the
                                     whole text first).  Texts of two pieces or more are cut at record boundaries and piece p + 1
-                                    crosses PCIe and is indexed while piece p is mapped                                          */
+                                    crosses PCIe and is indexed while piece p is mapped; the first piece is a quarter of the
+                                    regular size (its upload is the exposed one)                                                */
 #define GMX_OPT_SAM_DEVICE   8   /* 1 (default): gmx_format_sam formats the batch of the last gmx_process_fastq on the GPU (the text, the
                                     record index, the results and the CIGARs are resident there); 0: always the host formatter     */
 #define GMX_OPT_VOTE_COMPACT 7   /* tuning: occupancy variants of the vote kernel for tasks of <= 32 k-mers: 0 off, 1 two bits per
