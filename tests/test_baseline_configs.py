@@ -103,6 +103,11 @@ CONFIGS = {
     "cfg2_normal_156Mb_150bp": (156_000_000, 156, 150, 157, "normal", []),
     "cfg3_snp_156Mb_150bp": (156_000_000, 156, 150, 157, "snp", ["--snp"]),
     "cfg4_bs_100Mb_100bp": (100_000_000, 500, 100, 501, "bs", ["-b"]),
+    # the same regime (95 SA hits per k-mer) through the vote paths the defaults do not take: three agreeing k-mers (the
+    # byte-counter filter classes), a cap on the hits of a k-mer (half of the k-mers are skipped), a 12-mer with jump 3
+    "cfg1_min_seed_hits_3": (100_000_000, 100, 100, 101, "normal", ["-k", "3"], {"min_seed_hits": 3}),
+    "cfg1_max_kmer_hits_95": (100_000_000, 100, 100, 101, "normal", ["-h", "95"], {"max_kmer_hits": 95}),
+    "cfg1_mer12_jump3": (100_000_000, 100, 100, 101, "normal", ["-m", "12", "-j", "3"], {"mer": 12, "jump": 3}),
 }
 N_SAMPLE = 8192
 
@@ -162,7 +167,8 @@ def test_full_size_config_matches_reference_binary(cfg):
     if not os.path.exists(REF_BIN):
         pytest.skip("oracle/_ref/gnumap has not been built (needs /root/reference at build time)")
     from gnumap_b200 import api
-    length, gseed, L, rseed, mode, flags = CONFIGS[cfg]
+    length, gseed, L, rseed, mode, flags = CONFIGS[cfg][:6]
+    edits = CONFIGS[cfg][6] if len(CONFIGS[cfg]) > 6 else {}
     ix, prefix = _index_for(length, gseed)
     codes = ix.codes()
     reads = synth.simulate_reads(codes, N_SAMPLE, L, rseed, sub_rate=0.01, qlo=15, qhi=40, bisulfite=0.95 if mode == "bs" else 0.0)
@@ -181,6 +187,9 @@ def test_full_size_config_matches_reference_binary(cfg):
             fqs.append(fq); outs.append(os.path.join(tmp, f"o{p}"))
         logs = _run_reference(prefix, fqs, outs, flags)
         params = common.set_mode(api.default_params(), {"normal": _abi.MODE_NORMAL, "bs": _abi.MODE_BS, "snp": _abi.MODE_SNP}[mode])
+        for k, v in edits.items():
+            assert hasattr(params, k), k
+            setattr(params, k, v)
         m = api.Mapper(ix, params)
         total_nw_ref = total_nw = 0
         n_sam = n_rows = 0
