@@ -452,7 +452,14 @@ class Job:
             dist.barrier()
         ms = max(e0.elapsed_time(e1), 0.0)
         red = sum(a.elapsed_time(b) for a, b in self._reduce_events)
+        self.last_ranks = None
         if self.world > 1:
+            # what every rank measured on its own: the line's figures are the maxima, this is where they come from
+            mine = torch.tensor([ms, red, sum(st["ms"].values())], device=self.dev, dtype=torch.float64)
+            every = [torch.zeros_like(mine) for _ in range(self.world)]
+            dist.all_gather(every, mine)
+            self.last_ranks = [{"rank": r, "ms_per_step": float(t[0]) / steps, "of_which_inside_the_collective_ms_per_step": float(t[1]) / steps,
+                                "stage_ms_per_step": float(t[2]) / steps} for r, t in enumerate(every)]
             tt = torch.tensor([ms, wall_ms, red], device=self.dev, dtype=torch.float64)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             ms, wall_ms, red = (float(x) for x in tt.tolist())
@@ -647,6 +654,7 @@ def own_arm(a):
     m.reset_accumulators()
 
     ms_dev, wall_dev, st, red_ms = job.timed(job.dev_batch, a.steps, False)
+    ranks_dev = job.last_ranks
     clocks = sampler.stop() if sampler else None
     ms_e2e, wall_e2e, _, _ = job.timed(job.host_batch, a.steps, False)
     mapped = int((res_np["status"] == 0).sum())
@@ -827,6 +835,7 @@ def own_arm(a):
                     "clock": "wall, max over ranks", "cuda_event_ms_per_step": ms_e2e / a.steps},
             "gpu_launches": int(sum(st["launches"].values())),
             "roofline": roofline,
+            "ranks": ranks_dev,
             "small_calls": small,
             "chunks": dict(zip(("issued_without_host_wait", "run_again"), job.m.chunk_stats())),
             "alu_peaks": alu,
